@@ -1,0 +1,311 @@
+"""ctypes binding of libhgwarp.so — the same symbols an N-API addon binds (include/hgwarp.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or no GPU is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhgwarp.so")
+
+HG_OK, HG_ERR_INVALID, HG_ERR_CUDA, HG_ERR_NOMEM, HG_ERR_UNSUPPORTED, HG_ERR_STATE = range(6)
+HG_AFFINE, HG_PROJECTIVE = 0, 1
+
+# every symbol include/hgwarp.h declares (tests check the .so exports exactly these)
+SYMBOLS = [
+    "hg_abi_version", "hg_device_count", "hg_ctx_create", "hg_ctx_destroy", "hg_last_error",
+    "hg_ctx_synchronize", "hg_ctx_stream", "hg_timer_start", "hg_timer_stop", "hg_launch_count",
+    "hg_image_set", "hg_image_set_device",
+    "hg_solve_affine", "hg_solve_projective", "hg_inverse_affine", "hg_transform_limits", "hg_solve_with_limits",
+    "hg_warp_inverse_matrix", "hg_warp_inverse_points", "hg_warp_forward_matrix",
+    "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_build_index_map",
+    "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
+    "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
+    "hg_dev_alloc", "hg_dev_free", "hg_host_alloc_pinned", "hg_host_free_pinned",
+    "hg_memcpy_h2d", "hg_memcpy_d2h", "hg_output_device",
+]
+
+
+class HgFrame(C.Structure):
+    _fields_ = [("src_dev", C.c_void_p), ("out_dev", C.c_void_p),
+                ("src_w", C.c_int32), ("src_h", C.c_int32),
+                ("x_off", C.c_int32), ("y_off", C.c_int32), ("o_w", C.c_int32), ("o_h", C.c_int32)]
+
+
+class HgError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__(f"hgwarp status {status}: {text}")
+        self.status = status
+        self.text = text
+
+
+_lib = None
+
+
+def load():
+    """dlopen libhgwarp.so; raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    L.hg_abi_version.restype = i
+    L.hg_device_count.argtypes = [C.POINTER(i)]
+    L.hg_ctx_create.argtypes = [i, C.POINTER(vp)]
+    L.hg_ctx_destroy.argtypes = [vp]
+    L.hg_last_error.argtypes = [vp]
+    L.hg_last_error.restype = C.c_char_p
+    L.hg_ctx_synchronize.argtypes = [vp]
+    L.hg_ctx_stream.argtypes = [vp, C.POINTER(vp)]
+    L.hg_timer_start.argtypes = [vp]
+    L.hg_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.hg_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.hg_image_set.argtypes = [vp, vp, i, i]
+    L.hg_image_set_device.argtypes = [vp, vp, i, i]
+    L.hg_solve_affine.argtypes = [vp, vp, vp, vp]
+    L.hg_solve_projective.argtypes = [vp, vp, vp, vp]
+    L.hg_inverse_affine.argtypes = [vp, vp, vp]
+    L.hg_transform_limits.argtypes = [vp, i, vp, d, d, vp]
+    L.hg_solve_with_limits.argtypes = [vp, i, vp, vp, d, d, vp, vp]
+    L.hg_warp_inverse_matrix.argtypes = [vp, i, vp, i, i, i, i, vp, vp]
+    L.hg_warp_inverse_points.argtypes = [vp, i, vp, vp, i, i, i, i, vp, vp]
+    L.hg_warp_forward_matrix.argtypes = [vp, i, vp, i, i, i, i, vp, vp]
+    L.hg_piecewise_set_mesh.argtypes = [vp, vp, i, vp, i]
+    L.hg_piecewise_matrices.argtypes = [vp, vp, vp, vp]
+    L.hg_build_index_map.argtypes = [vp, vp, d, d, C.c_int64, vp]
+    L.hg_warp_piecewise_inverse.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp]
+    L.hg_warp_piecewise_forward.argtypes = [vp, vp, i, i, i, i, i, i, i, i, i, vp, vp]
+    L.hg_warp_inverse_batch.argtypes = [vp, i, vp, C.POINTER(HgFrame), i]
+    L.hg_warp_piecewise_inverse_batch.argtypes = [vp, vp, C.POINTER(HgFrame), i, i, i]
+    L.hg_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.hg_dev_free.argtypes = [vp, vp]
+    L.hg_host_alloc_pinned.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.hg_host_free_pinned.argtypes = [vp, vp]
+    L.hg_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.hg_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.hg_output_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One GPU + one CUDA stream (hg_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        h = C.c_void_p()
+        st = self.L.hg_ctx_create(device, C.byref(h))
+        if st != HG_OK:
+            raise HgError(st, (self.L.hg_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != HG_OK:
+            raise HgError(st, (self.L.hg_last_error(self.h) or b"").decode())
+
+    # ---- plumbing
+    def synchronize(self):
+        self._ck(self.L.hg_ctx_synchronize(self.h))
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        self._ck(self.L.hg_ctx_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def timer_start(self):
+        self._ck(self.L.hg_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._ck(self.L.hg_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self._ck(self.L.hg_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def dev_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.hg_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, p: int):
+        self._ck(self.L.hg_dev_free(self.h, p))
+
+    def host_alloc_pinned(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.hg_host_alloc_pinned(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def host_free_pinned(self, p: int):
+        self._ck(self.L.hg_host_free_pinned(self.h, p))
+
+    def memcpy_h2d(self, dst_dev: int, src_host: int, nbytes: int):
+        self._ck(self.L.hg_memcpy_h2d(self.h, dst_dev, src_host, nbytes))
+
+    def memcpy_d2h(self, dst_host: int, src_dev: int, nbytes: int):
+        self._ck(self.L.hg_memcpy_d2h(self.h, dst_host, src_dev, nbytes))
+
+    def output_device(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.hg_output_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    # ---- image
+    def image_set(self, rgba: np.ndarray, w: int, h: int):
+        a = np.ascontiguousarray(rgba, dtype=np.uint8).reshape(-1)
+        if a.size != w * h * 4:
+            raise ValueError(f"image buffer has {a.size} bytes, expected {w}x{h}x4")
+        self._ck(self.L.hg_image_set(self.h, a.ctypes.data, w, h))
+
+    def image_set_host_ptr(self, host_ptr: int, w: int, h: int):
+        self._ck(self.L.hg_image_set(self.h, host_ptr, w, h))
+
+    def image_set_device(self, dev_ptr: int, w: int, h: int):
+        self._ck(self.L.hg_image_set_device(self.h, dev_ptr, w, h))
+
+    # ---- solves
+    def solve_affine(self, src, dst) -> np.ndarray:
+        s = np.ascontiguousarray(src, dtype=np.float64).reshape(-1)
+        d = np.ascontiguousarray(dst, dtype=np.float64).reshape(-1)
+        assert s.size == 6 and d.size == 6
+        out = np.empty(6, np.float32)
+        self._ck(self.L.hg_solve_affine(self.h, _ptr(s), _ptr(d), _ptr(out)))
+        return out
+
+    def solve_projective(self, src, dst) -> np.ndarray:
+        s = np.ascontiguousarray(src, dtype=np.float64).reshape(-1)
+        d = np.ascontiguousarray(dst, dtype=np.float64).reshape(-1)
+        assert s.size == 8 and d.size == 8
+        out = np.empty(8, np.float64)
+        self._ck(self.L.hg_solve_projective(self.h, _ptr(s), _ptr(d), _ptr(out)))
+        return out
+
+    def inverse_affine(self, m) -> np.ndarray:
+        a = np.ascontiguousarray(m, dtype=np.float32).reshape(-1)
+        assert a.size == 6
+        out = np.empty(6, np.float32)
+        self._ck(self.L.hg_inverse_affine(self.h, _ptr(a), _ptr(out)))
+        return out
+
+    def transform_limits(self, matrix, w, h) -> np.ndarray:
+        m = np.ascontiguousarray(matrix)
+        kind = HG_AFFINE if m.size == 6 else HG_PROJECTIVE
+        m = m.astype(np.float32 if kind == HG_AFFINE else np.float64).reshape(-1)
+        out = np.empty(4, np.float64)
+        self._ck(self.L.hg_transform_limits(self.h, kind, _ptr(m), float(w), float(h), _ptr(out)))
+        return out
+
+    def solve_with_limits(self, kind, src, dst, w, h):
+        s = np.ascontiguousarray(src, dtype=np.float64).reshape(-1)
+        d = np.ascontiguousarray(dst, dtype=np.float64).reshape(-1)
+        m = np.empty(6, np.float32) if kind == HG_AFFINE else np.empty(8, np.float64)
+        lim = np.empty(4, np.float64)
+        self._ck(self.L.hg_solve_with_limits(self.h, kind, _ptr(s), _ptr(d), float(w), float(h), _ptr(m), _ptr(lim)))
+        return m, lim
+
+    # ---- warps
+    def warp_inverse_matrix(self, inv, x_off, y_off, o_w, o_h, to_host=True, out_dev=None):
+        m = np.ascontiguousarray(inv)
+        kind = HG_AFFINE if m.size == 6 else HG_PROJECTIVE
+        m = m.astype(np.float32 if kind == HG_AFFINE else np.float64).reshape(-1)
+        out = np.empty(o_w * o_h * 4, np.uint8) if to_host else None
+        self._ck(self.L.hg_warp_inverse_matrix(self.h, kind, _ptr(m), x_off, y_off, o_w, o_h, _ptr(out), out_dev))
+        return out
+
+    def warp_inverse_points(self, kind, dst_pts, src_pts, x_off, y_off, o_w, o_h, to_host=True, out_dev=None,
+                            out_host_ptr=None):
+        d = np.ascontiguousarray(dst_pts, dtype=np.float64).reshape(-1)
+        s = np.ascontiguousarray(src_pts, dtype=np.float64).reshape(-1)
+        out = None
+        hp = out_host_ptr
+        if hp is None and to_host:
+            out = np.empty(o_w * o_h * 4, np.uint8)
+            hp = out.ctypes.data
+        self._ck(self.L.hg_warp_inverse_points(self.h, kind, _ptr(d), _ptr(s), x_off, y_off, o_w, o_h, hp, out_dev))
+        return out
+
+    def warp_forward_matrix(self, fwd, x_off, y_off, o_w, o_h, to_host=True, out_dev=None):
+        m = np.ascontiguousarray(fwd)
+        kind = HG_AFFINE if m.size == 6 else HG_PROJECTIVE
+        m = m.astype(np.float32 if kind == HG_AFFINE else np.float64).reshape(-1)
+        out = np.empty(o_w * o_h * 4, np.uint8) if to_host else None
+        self._ck(self.L.hg_warp_forward_matrix(self.h, kind, _ptr(m), x_off, y_off, o_w, o_h, _ptr(out), out_dev))
+        return out
+
+    def warp_inverse_batch(self, kind, inv_matrices: np.ndarray, frames):
+        m = np.ascontiguousarray(inv_matrices, dtype=np.float32 if kind == HG_AFFINE else np.float64)
+        arr = (HgFrame * len(frames))(*frames)
+        self._ck(self.L.hg_warp_inverse_batch(self.h, kind, _ptr(m), arr, len(frames)))
+
+    # ---- piecewise
+    def piecewise_set_mesh(self, src_pts, tris):
+        p = np.ascontiguousarray(src_pts, dtype=np.float32).reshape(-1)
+        t = np.ascontiguousarray(tris, dtype=np.uint32).reshape(-1)
+        self._n_tris = t.size // 3
+        self._n_pts = p.size // 2
+        self._ck(self.L.hg_piecewise_set_mesh(self.h, _ptr(p), p.size // 2, _ptr(t), t.size // 3))
+
+    def piecewise_matrices(self, dst_pts, want_inverse=False):
+        d = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(-1)
+        fwd = np.empty((self._n_tris, 6), np.float32)
+        inv = np.empty((self._n_tris, 6), np.float32) if want_inverse else None
+        self._ck(self.L.hg_piecewise_matrices(self.h, _ptr(d), _ptr(fwd), _ptr(inv)))
+        return (fwd, inv) if want_inverse else fwd
+
+    def build_index_map(self, pts, map_width, y_offset, map_len) -> np.ndarray:
+        p = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1)
+        out = np.empty(max(int(map_len), 0), np.int16)
+        self._ck(self.L.hg_build_index_map(self.h, _ptr(p), float(map_width), float(y_offset), int(map_len), _ptr(out)))
+        return out
+
+    def warp_piecewise_inverse(self, dst_pts, x_off, y_off, o_w, o_h, min_src_x, min_src_y, to_host=True,
+                               out_dev=None):
+        d = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(-1)
+        out = np.empty(o_w * o_h * 4, np.uint8) if to_host else None
+        self._ck(self.L.hg_warp_piecewise_inverse(self.h, _ptr(d), x_off, y_off, o_w, o_h, min_src_x, min_src_y,
+                                                  _ptr(out), out_dev))
+        return out
+
+    def warp_piecewise_forward(self, dst_pts, x_off, y_off, o_w, o_h, min_src_x, min_src_y, max_src_x, max_src_y,
+                               use_inverse_map=False, to_host=True, out_dev=None):
+        d = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(-1)
+        out = np.empty(o_w * o_h * 4, np.uint8) if to_host else None
+        self._ck(self.L.hg_warp_piecewise_forward(self.h, _ptr(d), x_off, y_off, o_w, o_h, min_src_x, min_src_y,
+                                                  max_src_x, max_src_y, int(use_inverse_map), _ptr(out), out_dev))
+        return out
+
+    def warp_piecewise_inverse_batch(self, dst_pts, frames, min_src_x, min_src_y):
+        d = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(-1)
+        arr = (HgFrame * len(frames))(*frames)
+        self._ck(self.L.hg_warp_piecewise_inverse_batch(self.h, _ptr(d), arr, len(frames), min_src_x, min_src_y))
+
+
+def device_count() -> int:
+    n = C.c_int()
+    load().hg_device_count(C.byref(n))
+    return n.value

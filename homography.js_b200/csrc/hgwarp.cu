@@ -1,0 +1,806 @@
+// hgwarp.cu — context, memory and the extern "C" surface declared in include/hgwarp.h.
+// Build (see __graft_entry__.build / homography.js_b200/build.py):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared -Xcompiler -fPIC
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/hgwarp.h"
+#include "jsnum.cuh"
+#include "piecewise.cuh"
+#include "solve.cuh"
+#include "warp_geo.cuh"
+
+using namespace hg;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct hg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // image (this._image)
+    const uint32_t *img = nullptr;
+    DevBuf img_own;
+    int W = 0, H = 0;
+
+    // output of the last non-batched warp
+    DevBuf out;
+    size_t out_bytes = 0;
+
+    // small device scratch: matrices, limits, points (doubles)
+    DevBuf scratch;       // 4 KiB
+    void *pinned = nullptr;  // 4 KiB pinned host mirror
+
+    // mesh
+    DevBuf src_pts, dst_pts, tris, rec, map32, map16, frames, mats;
+    int n_pts = 0, n_tris = 0;
+    long long map_len = 0;  // length of the map currently in map32 (for the aliasing forward read)
+};
+
+namespace {
+
+int fail(hg_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(c, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail((c), HG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                     \
+    } while (0)
+
+#define NEED(c, cond, msg)                                          \
+    do {                                                            \
+        if (!(cond)) return fail((c), HG_ERR_INVALID, "%s", (msg)); \
+    } while (0)
+
+int ensure(hg_ctx *c, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return HG_OK;
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (b.p) CU(c, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, HG_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return HG_OK;
+}
+
+int bind(hg_ctx *c)
+{
+    CU(c, cudaSetDevice(c->device));
+    return HG_OK;
+}
+
+#define BIND(c)                                   \
+    do {                                          \
+        if (!(c)) return HG_ERR_INVALID;          \
+        int r_ = bind(c);                         \
+        if (r_) return r_;                        \
+    } while (0)
+
+#define TRY(expr)                 \
+    do {                          \
+        int r_ = (expr);          \
+        if (r_) return r_;        \
+    } while (0)
+
+int check_window(hg_ctx *c, int x_off, int y_off, int o_w, int o_h)
+{
+    if (o_w < 1 || o_h < 1) return fail(c, HG_ERR_INVALID, "output size %dx%d must be >= 1x1", o_w, o_h);
+    if (o_w > 65536 || o_h > 65536 || (long long)o_w * o_h >= (1LL << 31))
+        return fail(c, HG_ERR_UNSUPPORTED, "output size %dx%d outside the supported range", o_w, o_h);
+    if (x_off > (1 << 18) || x_off < -(1 << 18) || y_off > (1 << 18) || y_off < -(1 << 18))
+        return fail(c, HG_ERR_UNSUPPORTED, "output offset (%d,%d) outside the supported range", x_off, y_off);
+    return HG_OK;
+}
+
+int check_image_dims(hg_ctx *c, int w, int h)
+{
+    if (w < 1 || h < 1) return fail(c, HG_ERR_INVALID, "image size %dx%d must be >= 1x1", w, h);
+    if (w > 65536 || h > 65536 || (long long)w * h >= (1LL << 31))
+        return fail(c, HG_ERR_UNSUPPORTED, "image size %dx%d outside the supported range", w, h);
+    return HG_OK;
+}
+
+// where a non-batched warp writes: caller's device buffer or the context's own
+int pick_out(hg_ctx *c, void *out_dev, size_t bytes, uint32_t **dst)
+{
+    if (out_dev) {
+        if (((uintptr_t)out_dev & 15) != 0) return fail(c, HG_ERR_INVALID, "out_dev must be 16-byte aligned");
+        *dst = (uint32_t *)out_dev;
+    } else {
+        TRY(ensure(c, c->out, bytes));
+        *dst = (uint32_t *)c->out.p;
+        c->out_bytes = bytes;
+    }
+    return HG_OK;
+}
+
+int finish_out(hg_ctx *c, const uint32_t *dst, size_t bytes, uint8_t *out_host)
+{
+    CU(c, cudaGetLastError());
+    if (out_host) {
+        CU(c, cudaMemcpyAsync(out_host, dst, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return HG_OK;
+}
+
+unsigned grid_for(hg_ctx *c, long long npix, int n_frames)
+{
+    const long long nquad = (npix + 3) / 4;
+    long long blocks = (nquad + 255) / 256;
+    // enough resident CTAs to cover HBM latency; whole multiples of the SM count per frame
+    long long cap = (long long)c->sm_count * 8;
+    if (n_frames > 1) cap = (long long)c->sm_count * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+int launch_geo(hg_ctx *c, int kind, const GeoParams &P, long long max_npix, int n_frames)
+{
+    dim3 grid(grid_for(c, max_npix, n_frames), (unsigned)n_frames);
+    if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, 256, 0, c->stream>>>(P);
+    else warp_inverse_geo_kernel<1><<<grid, 256, 0, c->stream>>>(P);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return HG_OK;
+}
+
+int launch_solve(hg_ctx *c, const SolveArgs &a)
+{
+    solve_kernel<<<(a.n + 63) / 64, 64, 0, c->stream>>>(a);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return HG_OK;
+}
+
+// scratch layout (bytes): [0,128) src pts, [128,256) dst pts, [256,320) matrix, [320,352) limits, [384,..) misc
+constexpr size_t SC_SRC = 0, SC_DST = 128, SC_MAT = 256, SC_LIM = 320, SC_MISC = 384;
+
+int upload_small(hg_ctx *c, size_t off, const void *host, size_t bytes)
+{
+    // pageable -> device; tiny, goes through the driver's staging buffer, ordered on the stream
+    CU(c, cudaMemcpyAsync((char *)c->scratch.p + off, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return HG_OK;
+}
+
+int download_small(hg_ctx *c, void *host, size_t off, size_t bytes)
+{
+    CU(c, cudaMemcpyAsync(host, (char *)c->scratch.p + off, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return HG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hg_abi_version(void) { return HGWARP_ABI_VERSION; }
+
+int hg_device_count(int *count)
+{
+    if (!count) return HG_ERR_INVALID;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(nullptr, HG_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return HG_OK;
+}
+
+int hg_ctx_create(int device, hg_ctx **out)
+{
+    if (!out) return HG_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, HG_ERR_CUDA, "no CUDA device available: %s", cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(nullptr, HG_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    hg_ctx *c = new hg_ctx();
+    c->device = device;
+#define CUC(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            fail(nullptr, HG_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                 \
+            delete c;                                                                                   \
+            return HG_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->ev0));
+    CUC(cudaEventCreate(&c->ev1));
+    CUC(cudaMalloc(&c->scratch.p, 4096));
+    c->scratch.cap = 4096;
+    CUC(cudaHostAlloc(&c->pinned, 4096, cudaHostAllocDefault));
+#undef CUC
+    *out = c;
+    return HG_OK;
+}
+
+int hg_ctx_destroy(hg_ctx *c)
+{
+    if (!c) return HG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->img_own, &c->out, &c->scratch, &c->src_pts, &c->dst_pts, &c->tris,
+                      &c->rec, &c->map32, &c->map16, &c->frames, &c->mats};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return HG_OK;
+}
+
+const char *hg_last_error(hg_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int hg_ctx_synchronize(hg_ctx *c)
+{
+    BIND(c);
+    CU(c, cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+int hg_ctx_stream(hg_ctx *c, void **s)
+{
+    if (!c || !s) return HG_ERR_INVALID;
+    *s = (void *)c->stream;
+    return HG_OK;
+}
+
+int hg_timer_start(hg_ctx *c)
+{
+    BIND(c);
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    return HG_OK;
+}
+
+int hg_timer_stop(hg_ctx *c, float *ms)
+{
+    BIND(c);
+    NEED(c, ms, "elapsed_ms is NULL");
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaEventSynchronize(c->ev1));
+    CU(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return HG_OK;
+}
+
+int hg_launch_count(hg_ctx *c, uint64_t *n)
+{
+    if (!c || !n) return HG_ERR_INVALID;
+    *n = c->launches;
+    return HG_OK;
+}
+
+/* ------------------------------------------------------------------ image */
+int hg_image_set(hg_ctx *c, const uint8_t *rgba, int w, int h)
+{
+    BIND(c);
+    NEED(c, rgba, "rgba_host is NULL");
+    TRY(check_image_dims(c, w, h));
+    const size_t bytes = (size_t)w * h * 4;
+    TRY(ensure(c, c->img_own, bytes));
+    CU(c, cudaMemcpyAsync(c->img_own.p, rgba, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->img = (const uint32_t *)c->img_own.p;
+    c->W = w;
+    c->H = h;
+    return HG_OK;
+}
+
+int hg_image_set_device(hg_ctx *c, const void *rgba_dev, int w, int h)
+{
+    BIND(c);
+    NEED(c, rgba_dev, "rgba_dev is NULL");
+    NEED(c, ((uintptr_t)rgba_dev & 3) == 0, "rgba_dev must be 4-byte aligned");
+    TRY(check_image_dims(c, w, h));
+    c->img = (const uint32_t *)rgba_dev;
+    c->W = w;
+    c->H = h;
+    return HG_OK;
+}
+
+/* ------------------------------------------------------------------ solves */
+int hg_solve_affine(hg_ctx *c, const double src[6], const double dst[6], float out[6])
+{
+    BIND(c);
+    NEED(c, src && dst && out, "NULL argument");
+    TRY(upload_small(c, SC_SRC, src, 48));
+    TRY(upload_small(c, SC_DST, dst, 48));
+    SolveArgs a{};
+    a.src = (const double *)((char *)c->scratch.p + SC_SRC);
+    a.dst = (const double *)((char *)c->scratch.p + SC_DST);
+    a.out_f = (float *)((char *)c->scratch.p + SC_MAT);
+    a.n = 1;
+    a.op = 0;
+    TRY(launch_solve(c, a));
+    TRY(download_small(c, out, SC_MAT, 24));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+int hg_solve_projective(hg_ctx *c, const double src[8], const double dst[8], double out[8])
+{
+    BIND(c);
+    NEED(c, src && dst && out, "NULL argument");
+    TRY(upload_small(c, SC_SRC, src, 64));
+    TRY(upload_small(c, SC_DST, dst, 64));
+    SolveArgs a{};
+    a.src = (const double *)((char *)c->scratch.p + SC_SRC);
+    a.dst = (const double *)((char *)c->scratch.p + SC_DST);
+    a.out_d = (double *)((char *)c->scratch.p + SC_MAT);
+    a.n = 1;
+    a.op = 1;
+    TRY(launch_solve(c, a));
+    TRY(download_small(c, out, SC_MAT, 64));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+int hg_inverse_affine(hg_ctx *c, const float m[6], float out[6])
+{
+    BIND(c);
+    NEED(c, m && out, "NULL argument");
+    TRY(upload_small(c, SC_MISC, m, 24));
+    SolveArgs a{};
+    a.in_f = (const float *)((char *)c->scratch.p + SC_MISC);
+    a.out_f = (float *)((char *)c->scratch.p + SC_MAT);
+    a.n = 1;
+    a.op = 2;
+    TRY(launch_solve(c, a));
+    TRY(download_small(c, out, SC_MAT, 24));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+int hg_transform_limits(hg_ctx *c, int kind, const void *matrix, double w, double h, double out[4])
+{
+    BIND(c);
+    NEED(c, matrix && out, "NULL argument");
+    NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
+    TRY(upload_small(c, SC_MAT, matrix, kind == HG_AFFINE ? 24 : 64));
+    limits_kernel<<<1, 32, 0, c->stream>>>(kind, (char *)c->scratch.p + SC_MAT, w, h,
+                                           (double *)((char *)c->scratch.p + SC_LIM));
+    c->launches++;
+    CU(c, cudaGetLastError());
+    TRY(download_small(c, out, SC_LIM, 32));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+int hg_solve_with_limits(hg_ctx *c, int kind, const double *src, const double *dst, double w, double h,
+                         void *matrix_out, double limits_out[4])
+{
+    BIND(c);
+    NEED(c, src && dst && matrix_out && limits_out, "NULL argument");
+    NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
+    const size_t pb = kind == HG_AFFINE ? 48 : 64;
+    const size_t mb = kind == HG_AFFINE ? 24 : 64;
+    TRY(upload_small(c, SC_SRC, src, pb));
+    TRY(upload_small(c, SC_DST, dst, pb));
+    SolveArgs a{};
+    a.src = (const double *)((char *)c->scratch.p + SC_SRC);
+    a.dst = (const double *)((char *)c->scratch.p + SC_DST);
+    a.out_f = (float *)((char *)c->scratch.p + SC_MAT);
+    a.out_d = (double *)((char *)c->scratch.p + SC_MAT);
+    a.n = 1;
+    a.op = kind == HG_AFFINE ? 0 : 1;
+    TRY(launch_solve(c, a));
+    limits_kernel<<<1, 32, 0, c->stream>>>(kind, (char *)c->scratch.p + SC_MAT, w, h,
+                                           (double *)((char *)c->scratch.p + SC_LIM));
+    c->launches++;
+    CU(c, cudaGetLastError());
+    // one D2H for matrix + limits (contiguous in scratch: [SC_MAT, SC_LIM+32))
+    char *pin = (char *)c->pinned;
+    CU(c, cudaMemcpyAsync(pin, (char *)c->scratch.p + SC_MAT, SC_LIM + 32 - SC_MAT, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    memcpy(matrix_out, pin, mb);
+    memcpy(limits_out, pin + (SC_LIM - SC_MAT), 32);
+    return HG_OK;
+}
+
+/* ------------------------------------------------------------------ affine / projective warps */
+static int warp_inverse_common(hg_ctx *c, int kind, const void *inv_host, bool solve_on_device, int x_off,
+                               int y_off, int o_w, int o_h, uint8_t *out_host, void *out_dev)
+{
+    NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
+    if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
+    TRY(check_window(c, x_off, y_off, o_w, o_h));
+    const size_t bytes = (size_t)o_w * o_h * 4;
+    uint32_t *dst = nullptr;
+    TRY(pick_out(c, out_dev, bytes, &dst));
+    GeoParams P{};
+    P.one.src = c->img;
+    P.one.out = dst;
+    P.one.W = c->W;
+    P.one.H = c->H;
+    P.one.xOff = x_off;
+    P.one.yOff = y_off;
+    P.one.oW = o_w;
+    P.one.oH = o_h;
+    P.many = nullptr;
+    if (solve_on_device) {
+        P.mats_dev = (char *)c->scratch.p + SC_MAT;
+    } else {
+        P.mats_dev = nullptr;
+        if (kind == HG_AFFINE)
+            for (int k = 0; k < 6; ++k) P.mat_val[k] = (double)((const float *)inv_host)[k];
+        else
+            for (int k = 0; k < 8; ++k) P.mat_val[k] = ((const double *)inv_host)[k];
+    }
+    TRY(launch_geo(c, kind, P, (long long)o_w * o_h, 1));
+    return finish_out(c, dst, bytes, out_host);
+}
+
+int hg_warp_inverse_matrix(hg_ctx *c, int kind, const void *inv_matrix, int x_off, int y_off, int o_w, int o_h,
+                           uint8_t *out_host, void *out_dev)
+{
+    BIND(c);
+    NEED(c, inv_matrix, "inv_matrix is NULL");
+    return warp_inverse_common(c, kind, inv_matrix, false, x_off, y_off, o_w, o_h, out_host, out_dev);
+}
+
+int hg_warp_inverse_points(hg_ctx *c, int kind, const double *dst_pts, const double *src_pts, int x_off,
+                           int y_off, int o_w, int o_h, uint8_t *out_host, void *out_dev)
+{
+    BIND(c);
+    NEED(c, dst_pts && src_pts, "NULL points");
+    NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
+    const size_t pb = kind == HG_AFFINE ? 48 : 64;
+    // inverse matrix = calculateTransformMatrix(kind, dstPoints, srcPoints)  (H.js:994)
+    TRY(upload_small(c, SC_SRC, dst_pts, pb));
+    TRY(upload_small(c, SC_DST, src_pts, pb));
+    SolveArgs a{};
+    a.src = (const double *)((char *)c->scratch.p + SC_SRC);
+    a.dst = (const double *)((char *)c->scratch.p + SC_DST);
+    a.out_f = (float *)((char *)c->scratch.p + SC_MAT);
+    a.out_d = (double *)((char *)c->scratch.p + SC_MAT);
+    a.n = 1;
+    a.op = kind == HG_AFFINE ? 0 : 1;
+    TRY(launch_solve(c, a));
+    return warp_inverse_common(c, kind, nullptr, true, x_off, y_off, o_w, o_h, out_host, out_dev);
+}
+
+int hg_warp_forward_matrix(hg_ctx *c, int, const void *, int, int, int, int, uint8_t *, void *)
+{
+    return fail(c, HG_ERR_UNSUPPORTED, "forward scatter (_geometricWarp) is not built yet");
+}
+
+int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const hg_frame *frames, int n_frames)
+{
+    BIND(c);
+    NEED(c, inv_matrices && frames, "NULL argument");
+    NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
+    NEED(c, n_frames >= 1, "n_frames must be >= 1");
+    std::vector<GeoFrame> gf((size_t)n_frames);
+    long long max_npix = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        const hg_frame &h = frames[f];
+        TRY(check_window(c, h.x_off, h.y_off, h.o_w, h.o_h));
+        NEED(c, h.out_dev && ((uintptr_t)h.out_dev & 15) == 0, "frame out_dev must be a 16-byte aligned device pointer");
+        GeoFrame &g = gf[(size_t)f];
+        if (h.src_dev) {
+            TRY(check_image_dims(c, h.src_w, h.src_h));
+            g.src = (const uint32_t *)h.src_dev;
+            g.W = h.src_w;
+            g.H = h.src_h;
+        } else {
+            if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
+            g.src = c->img;
+            g.W = c->W;
+            g.H = c->H;
+        }
+        g.out = (uint32_t *)h.out_dev;
+        g.xOff = h.x_off;
+        g.yOff = h.y_off;
+        g.oW = h.o_w;
+        g.oH = h.o_h;
+        const long long np = (long long)h.o_w * h.o_h;
+        if (np > max_npix) max_npix = np;
+    }
+    const size_t mstride = kind == HG_AFFINE ? 24 : 64;
+    TRY(ensure(c, c->frames, sizeof(GeoFrame) * (size_t)n_frames));
+    TRY(ensure(c, c->mats, mstride * (size_t)n_frames));
+    CU(c, cudaMemcpyAsync(c->frames.p, gf.data(), sizeof(GeoFrame) * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->mats.p, inv_matrices, mstride * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
+    // the staging vector must outlive the (pageable) async copy
+    CU(c, cudaStreamSynchronize(c->stream));
+    const int chunk = 32768;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        GeoParams P{};
+        P.many = (const GeoFrame *)c->frames.p + f0;
+        P.mats_dev = (const char *)c->mats.p + mstride * (size_t)f0;
+        TRY(launch_geo(c, kind, P, max_npix, nf));
+    }
+    return HG_OK;
+}
+
+/* ------------------------------------------------------------------ piecewise */
+static int check_points(hg_ctx *c, const float *p, int n, const char *what)
+{
+    for (int i = 0; i < 2 * n; ++i) {
+        const float v = p[i];
+        if (!(v >= -1048576.f && v <= 1048576.f))  // also rejects NaN / Inf
+            return fail(c, HG_ERR_UNSUPPORTED, "%s[%d] = %g: piecewise points must be finite and |v| <= 2^20", what, i, (double)v);
+    }
+    return HG_OK;
+}
+
+int hg_piecewise_set_mesh(hg_ctx *c, const float *src_pts, int n_pts, const uint32_t *tris, int n_tris)
+{
+    BIND(c);
+    NEED(c, src_pts && tris, "NULL argument");
+    NEED(c, n_pts >= 3 && n_tris >= 0, "need >= 3 points");
+    for (int i = 0; i < 3 * n_tris; ++i)
+        if (tris[i] >= (uint32_t)n_pts) return fail(c, HG_ERR_INVALID, "triangle index %u out of range", tris[i]);
+    TRY(check_points(c, src_pts, n_pts, "src_pts"));
+    TRY(ensure(c, c->src_pts, sizeof(float) * 2 * (size_t)n_pts));
+    TRY(ensure(c, c->tris, sizeof(uint32_t) * 3 * (size_t)(n_tris > 0 ? n_tris : 1)));
+    TRY(ensure(c, c->rec, sizeof(TriRec) * (size_t)(n_tris > 0 ? n_tris : 1)));
+    CU(c, cudaMemcpyAsync(c->src_pts.p, src_pts, sizeof(float) * 2 * (size_t)n_pts, cudaMemcpyHostToDevice, c->stream));
+    if (n_tris)
+        CU(c, cudaMemcpyAsync(c->tris.p, tris, sizeof(uint32_t) * 3 * (size_t)n_tris, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->n_pts = n_pts;
+    c->n_tris = n_tris;
+    return HG_OK;
+}
+
+static int upload_dst_points(hg_ctx *c, const float *dst_pts, size_t n_frames)
+{
+    const size_t bytes = sizeof(float) * 2 * (size_t)c->n_pts * n_frames;
+    TRY(ensure(c, c->dst_pts, bytes));
+    CU(c, cudaMemcpyAsync(c->dst_pts.p, dst_pts, bytes, cudaMemcpyHostToDevice, c->stream));
+    return HG_OK;
+}
+
+static int launch_setup(hg_ctx *c, const float *dst_dev, const float *map_pts_dev, float *fwd_out, float *inv_out)
+{
+    if (c->n_tris == 0) return HG_OK;
+    PwSetupArgs a{};
+    a.src_pts = (const float *)c->src_pts.p;
+    a.dst_pts = dst_dev;
+    a.map_pts = map_pts_dev;
+    a.tris = (const uint32_t *)c->tris.p;
+    a.rec = (TriRec *)c->rec.p;
+    a.fwd_out = fwd_out;
+    a.inv_out = inv_out;
+    a.n_tris = c->n_tris;
+    a.dst_stride = 0;
+    a.rec_stride = 0;
+    pw_setup_kernel<<<dim3((c->n_tris + 127) / 128, 1), 128, 0, c->stream>>>(a);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return HG_OK;
+}
+
+static int launch_fill(hg_ctx *c, double map_width, double y_offset, long long map_len)
+{
+    TRY(ensure(c, c->map32, sizeof(int) * (size_t)(map_len > 0 ? map_len : 1)));
+    if (map_len > 0) CU(c, cudaMemsetAsync(c->map32.p, 0xFF, sizeof(int) * (size_t)map_len, c->stream));
+    c->map_len = map_len;
+    if (c->n_tris == 0 || map_len <= 0) return HG_OK;
+    PwFillArgs a{};
+    a.rec = (const TriRec *)c->rec.p;
+    a.map32 = (int *)c->map32.p;
+    a.map_len = map_len;
+    a.map_width = map_width;
+    a.y_offset = y_offset;
+    a.n_tris = c->n_tris;
+    // rows of one triangle are spread over row_split blocks; any value is correct
+    double rows_guess = map_width > 0 ? (double)map_len / map_width : 1.0;
+    int split = (int)(rows_guess / 64.0) + 1;
+    if (split > 64) split = 64;
+    if ((long long)split * c->n_tris > (1 << 20)) split = (1 << 20) / c->n_tris + 1;
+    a.row_split = split;
+    pw_fill_kernel<<<dim3((unsigned)c->n_tris, (unsigned)split), dim3(32, 8), 0, c->stream>>>(a);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return HG_OK;
+}
+
+int hg_piecewise_matrices(hg_ctx *c, const float *dst_pts, float *fwd_out, float *inv_out)
+{
+    BIND(c);
+    NEED(c, dst_pts, "dst_pts is NULL");
+    if (c->n_pts == 0) return fail(c, HG_ERR_STATE, "no mesh set (hg_piecewise_set_mesh)");
+    TRY(check_points(c, dst_pts, c->n_pts, "dst_pts"));
+    TRY(upload_dst_points(c, dst_pts, 1));
+    const size_t mb = sizeof(float) * 6 * (size_t)(c->n_tris > 0 ? c->n_tris : 1);
+    TRY(ensure(c, c->mats, 2 * mb));
+    float *fd = (float *)c->mats.p, *id = (float *)((char *)c->mats.p + mb);
+    TRY(launch_setup(c, (const float *)c->dst_pts.p, (const float *)c->dst_pts.p, fd, id));
+    if (c->n_tris) {
+        if (fwd_out) CU(c, cudaMemcpyAsync(fwd_out, fd, sizeof(float) * 6 * (size_t)c->n_tris, cudaMemcpyDeviceToHost, c->stream));
+        if (inv_out) CU(c, cudaMemcpyAsync(inv_out, id, sizeof(float) * 6 * (size_t)c->n_tris, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+int hg_build_index_map(hg_ctx *c, const float *pts, double map_width, double y_offset, int64_t map_len,
+                       int16_t *map_out_host)
+{
+    BIND(c);
+    NEED(c, pts, "pts is NULL");
+    if (c->n_pts == 0) return fail(c, HG_ERR_STATE, "no mesh set (hg_piecewise_set_mesh)");
+    NEED(c, map_len >= 0 && map_len < (1LL << 31), "map_len out of range");
+    TRY(check_points(c, pts, c->n_pts, "pts"));
+    TRY(upload_dst_points(c, pts, 1));
+    TRY(launch_setup(c, nullptr, (const float *)c->dst_pts.p, nullptr, nullptr));
+    TRY(launch_fill(c, map_width, y_offset, map_len));
+    if (map_out_host && map_len > 0) {
+        TRY(ensure(c, c->map16, sizeof(short) * (size_t)map_len));
+        map32_to_int16_kernel<<<(unsigned)((map_len + 255) / 256), 256, 0, c->stream>>>((const int *)c->map32.p,
+                                                                                      (short *)c->map16.p, map_len);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        CU(c, cudaMemcpyAsync(map_out_host, c->map16.p, sizeof(short) * (size_t)map_len, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+int hg_warp_piecewise_inverse(hg_ctx *c, const float *dst_pts, int x_off, int y_off, int o_w, int o_h,
+                              int min_src_x, int min_src_y, uint8_t *out_host, void *out_dev)
+{
+    BIND(c);
+    NEED(c, dst_pts, "dst_pts is NULL");
+    if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
+    if (c->n_pts == 0) return fail(c, HG_ERR_STATE, "no mesh set (hg_piecewise_set_mesh)");
+    TRY(check_window(c, x_off, y_off, o_w, o_h));
+    if (min_src_x > (1 << 18) || min_src_x < -(1 << 18) || min_src_y > (1 << 18) || min_src_y < -(1 << 18))
+        return fail(c, HG_ERR_UNSUPPORTED, "min_src (%d,%d) outside the supported range", min_src_x, min_src_y);
+    TRY(check_points(c, dst_pts, c->n_pts, "dst_pts"));
+    const size_t bytes = (size_t)o_w * o_h * 4;
+    uint32_t *dst = nullptr;
+    TRY(pick_out(c, out_dev, bytes, &dst));
+    TRY(upload_dst_points(c, dst_pts, 1));
+    TRY(launch_setup(c, (const float *)c->dst_pts.p, (const float *)c->dst_pts.p, nullptr, nullptr));
+    const long long map_len = (long long)o_w * o_h;
+    TRY(launch_fill(c, (double)o_w, (double)y_off, map_len));
+    PwWarpArgs a{};
+    a.src = c->img;
+    a.out = dst;
+    a.map32 = (const int *)c->map32.p;
+    a.rec = (const TriRec *)c->rec.p;
+    a.W = c->W;
+    a.H = c->H;
+    a.xOff = x_off;
+    a.yOff = y_off;
+    a.oW = o_w;
+    a.oH = o_h;
+    a.minSrcX = min_src_x;
+    a.minSrcY = min_src_y;
+    a.n_tris = c->n_tris;
+    pw_warp_inverse_kernel<<<grid_for(c, map_len, 1), 256, 0, c->stream>>>(a);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return finish_out(c, dst, bytes, out_host);
+}
+
+int hg_warp_piecewise_forward(hg_ctx *c, const float *, int, int, int, int, int, int, int, int, int, uint8_t *, void *)
+{
+    return fail(c, HG_ERR_UNSUPPORTED, "forward scatter (_piecewiseAffineWarp) is not built yet");
+}
+
+int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *, const hg_frame *, int, int, int)
+{
+    return fail(c, HG_ERR_UNSUPPORTED, "batched piecewise warp is not built yet");
+}
+
+/* ------------------------------------------------------------------ memory helpers */
+int hg_dev_alloc(hg_ctx *c, size_t bytes, void **p)
+{
+    BIND(c);
+    NEED(c, p, "dev_ptr is NULL");
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return fail(c, HG_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return HG_OK;
+}
+
+int hg_dev_free(hg_ctx *c, void *p)
+{
+    BIND(c);
+    if (p) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, cudaFree(p));
+    }
+    return HG_OK;
+}
+
+int hg_host_alloc_pinned(hg_ctx *c, size_t bytes, void **p)
+{
+    BIND(c);
+    NEED(c, p, "host_ptr is NULL");
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return fail(c, HG_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return HG_OK;
+}
+
+int hg_host_free_pinned(hg_ctx *c, void *p)
+{
+    BIND(c);
+    if (p) CU(c, cudaFreeHost(p));
+    return HG_OK;
+}
+
+int hg_memcpy_h2d(hg_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    BIND(c);
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return HG_OK;
+}
+
+int hg_memcpy_d2h(hg_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    BIND(c);
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return HG_OK;
+}
+
+int hg_output_device(hg_ctx *c, void **p, size_t *bytes)
+{
+    if (!c || !p || !bytes) return HG_ERR_INVALID;
+    *p = c->out.p;
+    *bytes = c->out_bytes;
+    return HG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+/*
+ * hgwarp.h — C ABI of libhgwarp.so, the sm_100a image-warp engine behind the
+ * Homography.js class surface.
+ *
+ * The reference (Eric-Canas/Homography.js, one ES module, cited as H.js:<line>) has no FFI:
+ * its replaceable seam is the set of private methods / free functions that `warp()` (H.js:408)
+ * and the setters call once the state is prepared.  Each entry point below names the reference
+ * function it replaces.  Signatures are plain C (pointers + sizes, no CUDA / torch types) so an
+ * N-API addon, cgo, JNI or ctypes can bind them directly.
+ *
+ * Conventions
+ *   - every function returns an hg_status (0 = ok); hg_last_error(ctx) gives the text;
+ *   - inputs are borrowed for the duration of the call, nothing host-side is retained;
+ *   - images are row-major RGBA8 (the layout of ImageData.data / Uint8ClampedArray);
+ *   - "points" are [x0,y0,x1,y1,...]; affine / projective solves take doubles (the reference
+ *     accepts Float32Array or Float64Array, H.js:220), piecewise takes floats (the reference
+ *     copies every triangle through a Float32Array(6) scratch, H.js:121-122,791-800);
+ *   - `out_host` (may be NULL) receives oW*oH*4 bytes after a stream sync; `out_dev` (may be
+ *     NULL) is a caller-owned, 16-byte-aligned device buffer written instead of the context's
+ *     own output buffer.  With both NULL the result stays device-resident in the context;
+ *   - a context is bound to one GPU and one CUDA stream and is not thread-safe; use one per GPU;
+ *   - degenerate transforms (NaN / Inf matrices) are NOT errors: like the reference they give an
+ *     all-transparent image.
+ * Supported ranges (anything else returns HG_ERR_UNSUPPORTED, never a wrong image):
+ *   1 <= W,H,oW,oH <= 65536, W*H and oW*oH < 2^31, |xOff|,|yOff|,|minSrc*| <= 2^18.
+ */
+#ifndef HGWARP_H
+#define HGWARP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define HGWARP_ABI_VERSION 1
+
+typedef struct hg_ctx hg_ctx;
+
+typedef enum {
+    HG_OK = 0,
+    HG_ERR_INVALID = 1,     /* bad argument */
+    HG_ERR_CUDA = 2,        /* CUDA runtime failure (text in hg_last_error) */
+    HG_ERR_NOMEM = 3,
+    HG_ERR_UNSUPPORTED = 4, /* outside the supported ranges above */
+    HG_ERR_STATE = 5        /* e.g. warp before hg_image_set */
+} hg_status;
+
+typedef enum { HG_AFFINE = 0, HG_PROJECTIVE = 1 } hg_kind;
+
+/* one frame of a batched warp: where it reads, where it writes, its output window */
+typedef struct {
+    const void *src_dev;  /* RGBA8 source image on the device (NULL = the context image) */
+    void *out_dev;        /* 16-byte aligned device buffer of o_w*o_h*4 bytes */
+    int32_t src_w, src_h; /* ignored when src_dev is NULL */
+    int32_t x_off, y_off, o_w, o_h;
+} hg_frame;
+
+/* ------------------------------------------------------------------ context */
+int hg_abi_version(void);
+int hg_device_count(int *count);
+int hg_ctx_create(int device, hg_ctx **out);
+int hg_ctx_destroy(hg_ctx *ctx);
+const char *hg_last_error(hg_ctx *ctx); /* ctx may be NULL: error of the last failed create */
+int hg_ctx_synchronize(hg_ctx *ctx);
+int hg_ctx_stream(hg_ctx *ctx, void **cuda_stream); /* the cudaStream_t all work is enqueued on */
+/* CUDA-event stopwatch on the context stream (device time, not wall clock) */
+int hg_timer_start(hg_ctx *ctx);
+int hg_timer_stop(hg_ctx *ctx, float *elapsed_ms);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int hg_launch_count(hg_ctx *ctx, uint64_t *count);
+
+/* ------------------------------------------------------------------ image (this._image, H.js:298) */
+int hg_image_set(hg_ctx *ctx, const uint8_t *rgba_host, int w, int h);      /* H2D copy, stays resident */
+int hg_image_set_device(hg_ctx *ctx, const void *rgba_dev, int w, int h);   /* borrow a device buffer */
+
+/* ------------------------------------------------------------------ transform solves (one in-register kernel) */
+/* affineMatrixFromTriangles, H.js:1265 (f64 math, result rounded to Float32Array(6)) */
+int hg_solve_affine(hg_ctx *ctx, const double src[6], const double dst[6], float out[6]);
+/* projectiveMatrixFromSquares + numeric.js LU/LUsolve, H.js:1320 + 1650-1751 (Array(8) of f64) */
+int hg_solve_projective(hg_ctx *ctx, const double src[8], const double dst[8], double out[8]);
+/* inverseAffineMatrix, H.js:1345 */
+int hg_inverse_affine(hg_ctx *ctx, const float m[6], float out[6]);
+/* calculateTransformLimits, H.js:1503: out = [xOff, yOff, oW, oH] as JS Numbers (may be NaN) */
+int hg_transform_limits(hg_ctx *ctx, int kind, const void *matrix, double w, double h, double out[4]);
+/* calculateTransformMatrix(kind, src, dst) + calculateTransformLimits in one submission
+ * (what setDestinyPoints needs, H.js:357 + 365); matrix_out: float[6] or double[8] */
+int hg_solve_with_limits(hg_ctx *ctx, int kind, const double *src, const double *dst, double w, double h,
+                         void *matrix_out, double limits_out[4]);
+
+/* ------------------------------------------------------------------ affine / projective warps */
+/* pixel loop of _inverseGeometricWarp, H.js:997-1011, with a given inverse (dst->src) matrix
+ * (float[6] for HG_AFFINE, double[8] for HG_PROJECTIVE) */
+int hg_warp_inverse_matrix(hg_ctx *ctx, int kind, const void *inv_matrix, int x_off, int y_off, int o_w, int o_h,
+                           uint8_t *out_host, void *out_dev);
+/* the whole of _inverseGeometricWarp, H.js:987-1013: solve calculateTransformMatrix(kind, dst, src)
+ * on the device, then the pixel loop, with no host round trip in between */
+int hg_warp_inverse_points(hg_ctx *ctx, int kind, const double *dst_pts, const double *src_pts, int x_off,
+                           int y_off, int o_w, int o_h, uint8_t *out_host, void *out_dev);
+/* _geometricWarp, H.js:911-932 (forward scatter, source raster order, last writer wins),
+ * matrix = forward (src->dst) matrix */
+int hg_warp_forward_matrix(hg_ctx *ctx, int kind, const void *fwd_matrix, int x_off, int y_off, int o_w, int o_h,
+                           uint8_t *out_host, void *out_dev);
+
+/* ------------------------------------------------------------------ piecewise affine */
+/* mesh = this._srcPoints (pixel range) + this._triangles (H.js:1216 / setTriangles H.js:517) */
+int hg_piecewise_set_mesh(hg_ctx *ctx, const float *src_pts, int n_pts, const uint32_t *tris, int n_tris);
+/* _calculatePiecewiseAffineTransformMatrices, H.js:785: T forward 2x3 float matrices; optionally
+ * also their inverses (inverseAffineMatrix, H.js:1036-1038).  Either output may be NULL. */
+int hg_piecewise_matrices(hg_ctx *ctx, const float *dst_pts, float *fwd_out, float *inv_out);
+/* _build(Inverse)TrianglesCorrespondencesMatrix + fillTriangle, H.js:817/845/1111: Int16 map of
+ * map_len entries built from `pts` (n_pts of the mesh) with row stride map_width and row origin
+ * y_offset; copied to map_out_host */
+int hg_build_index_map(hg_ctx *ctx, const float *pts, double map_width, double y_offset, int64_t map_len,
+                       int16_t *map_out_host);
+/* the whole of _inversePiecewiseAffineWarp, H.js:1029-1058: per-triangle forward+inverse matrices,
+ * the inverse index map and the pixel loop, all on the device */
+int hg_warp_piecewise_inverse(hg_ctx *ctx, const float *dst_pts, int x_off, int y_off, int o_w, int o_h,
+                              int min_src_x, int min_src_y, uint8_t *out_host, void *out_dev);
+/* _piecewiseAffineWarp, H.js:948-972 (forward scatter over the source-point bounding box).
+ * use_inverse_map != 0 reproduces the reference's map aliasing (the forward loop reading the map
+ * left by the last inverse warp, H.js:759/847/957): the map is then the one built by the last
+ * hg_warp_piecewise_inverse / hg_build_index_map call on this context. */
+int hg_warp_piecewise_forward(hg_ctx *ctx, const float *dst_pts, int x_off, int y_off, int o_w, int o_h,
+                              int min_src_x, int min_src_y, int max_src_x, int max_src_y, int use_inverse_map,
+                              uint8_t *out_host, void *out_dev);
+
+/* ------------------------------------------------------------------ batched / streamed frames */
+/* n_frames independent inverse warps in ONE launch (grid.y = frame).  matrices: n_frames x
+ * (float[6] | double[8]) on the HOST; frames on the HOST.  Results stay on the device. */
+int hg_warp_inverse_batch(hg_ctx *ctx, int kind, const void *inv_matrices, const hg_frame *frames, int n_frames);
+/* n_frames inverse piecewise warps sharing the context mesh, frame f using dst_pts + f*2*n_pts
+ * (HOST floats); per-frame extents come from frames[f]; min_src_* as in the single call. */
+int hg_warp_piecewise_inverse_batch(hg_ctx *ctx, const float *dst_pts, const hg_frame *frames, int n_frames,
+                                    int min_src_x, int min_src_y);
+
+/* ------------------------------------------------------------------ device memory helpers (benchmarks / bindings) */
+int hg_dev_alloc(hg_ctx *ctx, size_t bytes, void **dev_ptr);
+int hg_dev_free(hg_ctx *ctx, void *dev_ptr);
+int hg_host_alloc_pinned(hg_ctx *ctx, size_t bytes, void **host_ptr);
+int hg_host_free_pinned(hg_ctx *ctx, void *host_ptr);
+int hg_memcpy_h2d(hg_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on the ctx stream */
+int hg_memcpy_d2h(hg_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async on the ctx stream */
+/* the context's own output buffer of the last non-batched warp (device pointer + byte size) */
+int hg_output_device(hg_ctx *ctx, void **dev_ptr, size_t *bytes);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGWARP_H */

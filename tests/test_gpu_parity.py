@@ -1,0 +1,346 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: bit-exact for every byte.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import math
+
+import numpy as np
+import pytest
+
+import flows
+import homography_js_b200 as hg
+from oracle import oracle as O
+from oracle.homography_ref import RefHomography, RefImageData
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_img(seed, w, h):
+    return np.random.default_rng(seed).integers(0, 256, (h, w, 4), dtype=np.uint8)
+
+
+def _diff(a, b):
+    a = a.reshape(-1, 4)
+    b = b.reshape(-1, 4)
+    return int((a != b).any(axis=1).sum())
+
+
+# ------------------------------------------------------------------ solves (K5)
+def test_affine_solve_bit_exact(ctx):
+    rng = np.random.default_rng(21)
+    for k in range(400):
+        s = rng.uniform(-500, 4000, 6)
+        d = rng.uniform(-500, 4000, 6)
+        if k % 4 == 0:
+            s, d = s.astype(np.float32).astype(np.float64), d.astype(np.float32).astype(np.float64)
+        if k % 50 == 7:
+            s[2:4] = s[0:2]  # degenerate: zero determinant -> Inf / NaN entries, not an error
+        got, want = ctx.solve_affine(s, d), O.affine_from_triangles(s, d)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (k, got, want)
+
+
+def test_inverse_affine_bit_exact(ctx):
+    rng = np.random.default_rng(22)
+    for k in range(300):
+        m = rng.uniform(-3, 3, 6).astype(np.float32)
+        m[4:] *= 500
+        if k % 60 == 3:
+            m[:4] = [1, 2, 2, 4]  # singular
+        assert np.array_equal(ctx.inverse_affine(m).view(np.uint32), O.inverse_affine(m).view(np.uint32)), k
+
+
+def test_projective_solve_bit_exact(ctx):
+    rng = np.random.default_rng(23)
+    for k in range(400):
+        s = rng.uniform(0, 4000, 8)
+        d = rng.uniform(0, 4000, 8)
+        if k % 3 == 0:
+            s, d = s.astype(np.float32).astype(np.float64), d.astype(np.float32).astype(np.float64)
+        if k % 5 == 0:  # axis-aligned rectangle as source: many exact zeros / pivot ties
+            w, h = rng.integers(100, 4000, 2)
+            s = np.array([0, 0, 0, h, w, 0, w, h], np.float64)
+        if k % 67 == 11:
+            s[6:8] = s[0:2]  # degenerate quad
+        got, want = ctx.solve_projective(s, d), O.projective_from_squares(s, d)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (k, got, want)
+
+
+def test_limits_bit_exact(ctx):
+    rng = np.random.default_rng(24)
+    for k in range(200):
+        if k % 2:
+            m = rng.uniform(-2, 2, 6).astype(np.float32)
+            m[4:] *= 300
+        else:
+            m = np.concatenate([rng.uniform(-2, 2, 6), rng.uniform(-1e-3, 1e-3, 2)])
+            m[2] *= 300
+            m[5] *= 300
+        w, h = rng.integers(1, 4000, 2)
+        got, want = ctx.transform_limits(m, w, h), O.transform_limits(m, w, h)
+        assert np.array_equal(got, want, equal_nan=True), (k, got, want)
+    nan_m = np.full(6, np.nan, np.float32)
+    assert np.isnan(ctx.transform_limits(nan_m, 10, 10)).all()
+
+
+def test_solve_with_limits_matches_separate_calls(ctx):
+    s = np.array([0, 0, 0, 1080, 1920, 0, 1920, 1080], np.float64)
+    d = np.array([192, 0, 192, 1080, 1920, 270, 1920, 810], np.float64)
+    m, lim = ctx.solve_with_limits(hg._abi.HG_PROJECTIVE, s, d, 1920, 1080)
+    assert np.array_equal(m, O.projective_from_squares(s, d))
+    assert np.array_equal(lim, O.transform_limits(m, 1920, 1080))
+    assert list(lim) == [192.0, 0.0, 1728.0, 1080.0]
+
+
+# ------------------------------------------------------------------ inverse affine / projective warp (K1/K2)
+def _geo_case(ctx, img, inv, xo, yo, oW, oH):
+    H, W = img.shape[:2]
+    ctx.image_set(img, W, H)
+    got = ctx.warp_inverse_matrix(inv, xo, yo, oW, oH)
+    want = O.warp_inverse_geometric(img, W, H, inv, xo, yo, oW, oH, threads=4)
+    assert _diff(got, want) == 0, f"{_diff(got, want)} of {oW * oH} pixels differ"
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_affine_inverse_warp_random(ctx, seed):
+    rng = np.random.default_rng(100 + seed)
+    W, H = int(rng.integers(5, 300)), int(rng.integers(5, 300))
+    img = _rand_img(seed, W, H)
+    ang = rng.uniform(0, 2 * math.pi)
+    sc = rng.uniform(0.3, 3.0)
+    inv = np.array([math.cos(ang) * sc, math.sin(ang) * sc, -math.sin(ang) * sc * rng.uniform(0.5, 1.5),
+                    math.cos(ang) * sc, rng.uniform(-W, W), rng.uniform(-H, H)], np.float32)
+    _geo_case(ctx, img, inv, int(rng.integers(-50, 50)), int(rng.integers(-50, 50)),
+              int(rng.integers(1, 400)), int(rng.integers(1, 400)))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_projective_inverse_warp_random(ctx, seed):
+    rng = np.random.default_rng(200 + seed)
+    W, H = int(rng.integers(5, 300)), int(rng.integers(5, 300))
+    img = _rand_img(seed, W, H)
+    s = np.array([0, 0, 0, H, W, 0, W, H], np.float64)
+    d = s + rng.uniform(-0.3, 0.3, 8) * max(W, H)
+    inv = O.projective_from_squares(d, s)
+    lim = O.transform_limits(O.projective_from_squares(s, d), W, H)
+    xo, yo, oW, oH = [int(v) for v in lim]
+    oW, oH = max(1, min(oW, 1500)), max(1, min(oH, 1500))
+    _geo_case(ctx, img, inv, xo, yo, oW, oH)
+
+
+def test_half_integer_and_boundary_coordinates(ctx):
+    """Coordinates that land EXACTLY on k+0.5 (Math.round ties up), on 0 and on W (Q1/Q2): scale 0.5 and
+    integer shifts make every decision boundary exact; also exercises the projective exact-division path."""
+    img = _rand_img(5, 64, 48)
+    for inv in (np.array([0.5, 0, 0, 0.5, 0, 0], np.float32),
+                np.array([0.5, 0, 0, 0.5, -0.5, 31.5], np.float32),
+                np.array([-1, 0, 0, -1, 64, 48], np.float32),
+                np.array([0.25, 0, 0, 0.75, 0.125, -0.25], np.float32)):
+        _geo_case(ctx, img, inv, -8, -8, 160, 130)
+        h8 = np.array([inv[0], inv[2], inv[4], inv[1], inv[3], inv[5], 0.0, 0.0], np.float64)
+        _geo_case(ctx, img, h8, -8, -8, 160, 130)
+    # a projective map with exact dyadic quotients: denominators are powers of two
+    _geo_case(ctx, img, np.array([1, 0, 0, 0, 1, 0, 0, 0.0], np.float64), 0, 0, 64, 48)
+    _geo_case(ctx, img, np.array([0.5, 0, 0.5, 0, 0.5, 0.5, 0, 0.0], np.float64), -3, -3, 140, 110)
+
+
+def test_degenerate_matrices_give_transparent_output(ctx):
+    img = _rand_img(6, 32, 32)
+    for inv in (np.full(6, np.nan, np.float32), np.array([np.inf, 0, 0, 1, 0, 0], np.float32),
+                np.full(8, np.nan), np.array([1, 0, 0, 0, 1, 0, 1e308, 1e308]), np.zeros(8)):
+        _geo_case(ctx, img, inv, 0, 0, 40, 40)
+
+
+def test_horizon_crossing_projective(ctx):
+    """Denominator changes sign inside the output window (huge / negative / infinite quotients)."""
+    img = _rand_img(7, 200, 100)
+    inv = np.array([1.0, 0.1, 5.0, 0.05, 1.0, 3.0, -0.01, 0.002], np.float64)
+    _geo_case(ctx, img, inv, -20, -20, 300, 200)
+
+
+def test_output_tail_not_multiple_of_four(ctx):
+    img = _rand_img(8, 17, 13)
+    inv = np.array([1, 0, 0, 1, 0, 0], np.float32)
+    for oW, oH in ((1, 1), (3, 1), (5, 7), (17, 13), (19, 3)):
+        _geo_case(ctx, img, inv, 0, 0, oW, oH)
+
+
+def test_inverse_points_entry_solves_on_device(ctx, golden):
+    src = (golden["src_points"].reshape(-1) * 400).astype(np.float32).astype(np.float64)
+    dst = (golden["dst_points"].reshape(-1) * 400).astype(np.float32).astype(np.float64)
+    ctx.image_set(golden["src"], 400, 400)
+    got = ctx.warp_inverse_points(hg._abi.HG_PROJECTIVE, dst, src, 0, 200, 400, 200)
+    assert np.array_equal(got.reshape(200, 400, 4), golden["out"])
+
+
+def test_config2_full_size_projective_1080p(ctx):
+    """BASELINE config 2 at full size (1920x1080 -> 1728x1080), every pixel compared."""
+    w, h = 1920, 1080
+    img = _rand_img(2, w, h)
+    s = np.array([0, 0, 0, h, w, 0, w, h], np.float64)
+    d = np.array([w / 10, 0, w / 10, h, w, h / 4, w, 3 * h / 4], np.float64)
+    fwd, lim = ctx.solve_with_limits(hg._abi.HG_PROJECTIVE, s, d, w, h)
+    assert list(lim) == [192.0, 0.0, 1728.0, 1080.0]
+    ctx.image_set(img, w, h)
+    got = ctx.warp_inverse_points(hg._abi.HG_PROJECTIVE, d, s, 192, 0, 1728, 1080)
+    want = O.warp_inverse_geometric(img, w, h, O.projective_from_squares(d, s), 192, 0, 1728, 1080, threads=8)
+    assert _diff(got, want) == 0
+
+
+def test_identity_at_4k_is_a_copy(ctx):
+    """Size-independent property at 3840x2160: the identity warp returns the image."""
+    w, h = 3840, 2160
+    img = _rand_img(3, w, h)
+    ctx.image_set(img, w, h)
+    out = ctx.warp_inverse_matrix(np.array([1, 0, 0, 1, 0, 0], np.float32), 0, 0, w, h)
+    assert np.array_equal(out.reshape(h, w, 4), img)
+    out = ctx.warp_inverse_matrix(np.array([1, 0, 0, 0, 1, 0, 0, 0], np.float64), 0, 0, w, h)
+    assert np.array_equal(out.reshape(h, w, 4), img)
+    # integer translation: out[y, x] = img[y + 5, x + 7] inside, transparent outside
+    out = ctx.warp_inverse_matrix(np.array([1, 0, 0, 1, 7, 5], np.float32), 0, 0, w, h).reshape(h, w, 4)
+    assert np.array_equal(out[: h - 5, : w - 7], img[5:, 7:])
+    assert not out[h - 5:].any() and not out[:, w - 7:].any()
+
+
+def test_batch_entry_matches_single_frames(ctx):
+    rng = np.random.default_rng(31)
+    W, H = 160, 120
+    imgs = [_rand_img(40 + k, W, H) for k in range(3)]
+    n = 6
+    dev_src = [ctx.dev_alloc(W * H * 4) for _ in imgs]
+    for p, im in zip(dev_src, imgs):
+        ctx.memcpy_h2d(p, im.ctypes.data, im.nbytes)
+    mats, frames, outs, shapes = [], [], [], []
+    for f in range(n):
+        s = np.array([0, 0, 0, H, W, 0, W, H], np.float64)
+        d = s + rng.uniform(-0.2, 0.2, 8) * W
+        mats.append(O.projective_from_squares(d, s))
+        xo, yo, oW, oH = [int(v) for v in O.transform_limits(O.projective_from_squares(s, d), W, H)]
+        p = ctx.dev_alloc(oW * oH * 4)
+        outs.append(p)
+        shapes.append((xo, yo, oW, oH))
+        frames.append(hg.HgFrame(dev_src[f % 3], p, W, H, xo, yo, oW, oH))
+    ctx.warp_inverse_batch(hg._abi.HG_PROJECTIVE, np.stack(mats), frames)
+    for f in range(n):
+        xo, yo, oW, oH = shapes[f]
+        got = np.empty(oW * oH * 4, np.uint8)
+        ctx.memcpy_d2h(got.ctypes.data, outs[f], got.nbytes)
+        ctx.synchronize()
+        want = O.warp_inverse_geometric(imgs[f % 3], W, H, mats[f], xo, yo, oW, oH)
+        assert _diff(got, want) == 0, f
+    for p in dev_src + outs:
+        ctx.dev_free(p)
+
+
+# ------------------------------------------------------------------ piecewise (K3/K4/K5)
+def _grid_mesh(nx, ny, w, h):
+    xs = np.arange(nx) * (w / (nx - 1))
+    ys = np.arange(ny) * (h / (ny - 1))
+    pts = np.array([[x, y] for y in ys for x in xs], np.float32)
+    tris = []
+    for j in range(ny - 1):
+        for i in range(nx - 1):
+            p00, p10, p01, p11 = j * nx + i, j * nx + i + 1, (j + 1) * nx + i, (j + 1) * nx + i + 1
+            tris += [[p00, p10, p01], [p10, p11, p01]]
+    return pts, np.array(tris, np.uint32)
+
+
+def test_piecewise_matrices_bit_exact(ctx):
+    rng = np.random.default_rng(51)
+    src, tris = _grid_mesh(9, 7, 640, 480)
+    dst = (src + rng.uniform(-20, 20, src.shape)).astype(np.float32)
+    ctx.piecewise_set_mesh(src, tris)
+    fwd, inv = ctx.piecewise_matrices(dst, want_inverse=True)
+    want = O.piecewise_matrices(src, dst, tris)
+    assert np.array_equal(fwd.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(inv.view(np.uint32), O.inverse_matrices(want).view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_index_map_bit_exact(ctx, seed):
+    """A5 incl. the quirks: no x offset (Q4), negative relative fill index (Q5), overlaps (Q7)."""
+    rng = np.random.default_rng(300 + seed)
+    if seed < 4:
+        src, tris = _grid_mesh(6, 5, 200, 150)
+        pts = (src + rng.uniform(-12, 12, src.shape) + rng.uniform(-30, 30, 2)).astype(np.float32)
+    else:
+        pts = rng.uniform(-20, 220, (12, 2)).astype(np.float32)
+        if seed % 2:
+            pts = np.round(pts)
+        tris = rng.integers(0, 12, (15, 3)).astype(np.uint32)  # arbitrary, overlapping, possibly degenerate
+    ctx.piecewise_set_mesh(pts, tris)
+    mm = O.minmax_xy(pts)
+    mw = float(mm[2] - mm[0]) if seed % 2 == 0 else 211.0
+    yoff = float(mm[1])
+    length = int(mw * (mm[3] - mm[1] + 3))
+    got = ctx.build_index_map(pts, mw, yoff, length)
+    want = O.build_index_map(pts, tris, mw, yoff, length)
+    assert np.array_equal(got, want), f"{(got != want).sum()} map entries differ"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_piecewise_inverse_warp_bit_exact(ctx, seed):
+    rng = np.random.default_rng(400 + seed)
+    W, H = 320, 200
+    img = _rand_img(60 + seed, W, H)
+    src, tris = _grid_mesh(7, 5, W, H)
+    dst = src.copy()
+    dst[:, 0] = dst[:, 0] * rng.uniform(0.8, 2.2) + rng.uniform(-15, 15, len(dst))
+    dst[:, 1] = dst[:, 1] * rng.uniform(0.8, 2.2) + rng.uniform(-15, 15, len(dst)) + rng.uniform(0, 40)
+    dst = dst.astype(np.float32)
+    mm = O.minmax_xy(dst)
+    xo, yo, oW, oH = int(mm[0]), int(mm[1]), int(mm[2] - mm[0]), int(mm[3] - mm[1])
+    smm = O.minmax_xy(src)
+    ctx.image_set(img, W, H)
+    ctx.piecewise_set_mesh(src, tris)
+    got = ctx.warp_piecewise_inverse(dst, xo, yo, oW, oH, int(smm[0]), int(smm[1]))
+    fwd = O.piecewise_matrices(src, dst, tris)
+    imap = O.build_index_map(dst, tris, oW, yo, oW * oH)
+    want = O.warp_inverse_piecewise(img, W, H, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, int(smm[0]), int(smm[1]), threads=4)
+    assert _diff(got, want) == 0, f"{_diff(got, want)} of {oW * oH} pixels differ"
+
+
+def test_config3_full_size_piecewise_4k(ctx):
+    """BASELINE config 3: 10x10 grid (162 triangles), 3840x2160, sinusoidal destiny points, all pixels."""
+    w, h = 3840, 2160
+    img = _rand_img(3, w, h)
+    src, tris = _grid_mesh(10, 10, w, h)
+    A = 108.0
+    dst = src.copy()
+    dst[:, 1] = (A + src[:, 1] + A * np.sin(2 * np.pi * 2 * src[:, 0].astype(np.float64) / w)).astype(np.float32)
+    mm = O.minmax_xy(dst)
+    xo, yo, oW, oH = int(mm[0]), int(mm[1]), int(mm[2] - mm[0]), int(mm[3] - mm[1])
+    assert oH > h
+    ctx.image_set(img, w, h)
+    ctx.piecewise_set_mesh(src, tris)
+    got = ctx.warp_piecewise_inverse(dst, xo, yo, oW, oH, 0, 0)
+    fwd = O.piecewise_matrices(src, dst, tris)
+    imap = O.build_index_map(dst, tris, oW, yo, oW * oH)
+    want = O.warp_inverse_piecewise(img, w, h, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, 0, 0, threads=8)
+    assert _diff(got, want) == 0
+
+
+# ------------------------------------------------------------------ the class surface over CUDA
+@pytest.mark.parametrize("flow", flows.INVERSE_ONLY, ids=lambda f: f.__name__)
+def test_reference_test_page_flows_over_cuda(ctx, flow, golden):
+    ref_res, ref = flow(lambda *a: RefHomography(*a), RefImageData(golden["src"].reshape(-1).copy(), 400, 400))
+    got_res, got = flow(lambda *a: hg.Homography(*a, context=ctx), hg.ImageData(golden["src"].reshape(-1).copy(), 400, 400))
+    assert got.last_path == ref.last_path
+    for r, g in zip(ref_res, got_res):
+        assert (g.width, g.height) == (r.width, r.height)
+        assert _diff(g.data, r.data) == 0
+
+
+def test_node_golden_over_cuda(ctx, golden):
+    res, _ = flows.node_test(lambda *a: hg.Homography(*a, context=ctx), hg.ImageData(golden["src"].reshape(-1).copy(), 400, 400))
+    assert np.array_equal(res[0].as_array(), golden["out"])
+
+
+def test_unsupported_and_state_errors(ctx):
+    c2 = hg.Context(0)
+    with pytest.raises(hg.HgError, match="no image set"):
+        c2.warp_inverse_matrix(np.array([1, 0, 0, 1, 0, 0], np.float32), 0, 0, 4, 4)
+    c2.image_set(_rand_img(1, 8, 8), 8, 8)
+    with pytest.raises(hg.HgError) as e:
+        c2.warp_inverse_matrix(np.array([1, 0, 0, 1, 0, 0], np.float32), 1 << 20, 0, 4, 4)
+    assert e.value.status == hg._abi.HG_ERR_UNSUPPORTED
+    with pytest.raises(hg.HgError):
+        c2.warp_inverse_matrix(np.array([1, 0, 0, 1, 0, 0], np.float32), 0, 0, 0, 4)
+    c2.close()

@@ -1,0 +1,207 @@
+"""JS-number semantics and solver behaviour of the oracle, checked against independent statements
+(pure-Python restatements for small cases, numpy.linalg for the solves).  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+@pytest.mark.parametrize("x,want", [(0.5, 1), (1.5, 2), (2.5, 3), (-0.5, 0), (-1.5, -1), (-2.5, -2), (0.49999999999999994, 0),
+                                     (-0.49999999999999994, 0), (2.4, 2), (-2.6, -3), (4503599627370497.0, 4503599627370497.0),
+                                     (1e300, 1e300)])
+def test_math_round(x, want):
+    assert O.js_round(x) == want
+
+
+def test_math_round_nan_inf():
+    assert math.isnan(O.js_round(float("nan")))
+    assert O.js_round(float("inf")) == float("inf") and O.js_round(float("-inf")) == float("-inf")
+
+
+@pytest.mark.parametrize("x,want", [(2.9, 2), (-2.9, -2), (float("nan"), 0), (float("inf"), 0), (4294967296.0 + 5.5, 5),
+                                     (2147483648.0, -2147483648), (-2147483649.0, 2147483647)])
+def test_toint32(x, want):
+    assert O.js_toint32(x) == want
+
+
+def _py_lu_solve(A, b):
+    """numeric.js LU + LUsolve (H.js:1664-1749) in plain Python floats (IEEE double, unfused)."""
+    n = len(A)
+    A = [list(r) for r in A]
+    P = [0] * n
+    for k in range(n):
+        Pk, mx = k, abs(A[k][k])
+        for j in range(k + 1, n):
+            if mx < abs(A[j][k]):
+                mx, Pk = abs(A[j][k]), j
+        P[k] = Pk
+        if Pk != k:
+            A[k], A[Pk] = A[Pk], A[k]
+        for i in range(k + 1, n):
+            A[i][k] /= A[k][k]
+        for i in range(k + 1, n):
+            for j in range(k + 1, n):
+                A[i][j] -= A[i][k] * A[k][j]
+    x = list(b)
+    for i in range(n):
+        if P[i] != i:
+            x[i], x[P[i]] = x[P[i]], x[i]
+        for j in range(i):
+            x[i] -= x[j] * A[i][j]
+    for i in range(n - 1, -1, -1):
+        for j in range(i + 1, n):
+            x[i] -= x[j] * A[i][j]
+        x[i] /= A[i][i]
+    return x
+
+
+def _py_projective(s, d):
+    A = []
+    for p in range(4):
+        sx, sy, dx, dy = s[2 * p], s[2 * p + 1], d[2 * p], d[2 * p + 1]
+        A.append([sx, sy, 1, 0, 0, 0, -dx * sx, -dx * sy])
+        A.append([0, 0, 0, sx, sy, 1, -dy * sx, -dy * sy])
+    return _py_lu_solve(A, list(d))
+
+
+def test_projective_solve_matches_python_restatement_bitwise():
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        s = rng.uniform(0, 2000, 8).astype(np.float32).astype(np.float64)
+        d = rng.uniform(0, 2000, 8).astype(np.float32).astype(np.float64)
+        got = O.projective_from_squares(s, d)
+        want = np.array(_py_projective(list(s), list(d)))
+        assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_projective_solve_maps_points():
+    s = np.array([0, 0, 0, 1080, 1920, 0, 1920, 1080], np.float64)
+    d = np.array([192, 0, 192, 1080, 1920, 270, 1920, 810], np.float64)
+    h = O.projective_from_squares(s, d)
+    Hm = np.array([[h[0], h[1], h[2]], [h[3], h[4], h[5]], [h[6], h[7], 1.0]])
+    for k in range(4):
+        q = Hm @ np.array([s[2 * k], s[2 * k + 1], 1.0])
+        assert np.allclose(q[:2] / q[2], d[2 * k:2 * k + 2], atol=1e-8)
+
+
+def test_affine_solve_matches_python_restatement_bitwise():
+    rng = np.random.default_rng(8)
+    for _ in range(500):
+        s = rng.uniform(-500, 3000, 6).astype(np.float32).astype(np.float64)
+        d = rng.uniform(-500, 3000, 6).astype(np.float32).astype(np.float64)
+        sE, sF = s[4], s[5]
+        sA, sB, sC, sD = s[0] - sE, s[1] - sF, s[2] - sE, s[3] - sF
+        dE, dF = d[4], d[5]
+        dA, dB, dC, dD = d[0] - dE, d[1] - dF, d[2] - dE, d[3] - dF
+        den = sA * sD - sB * sC
+        iA, iB, iC, iD = sD / den, sB / -den, sC / -den, sA / den
+        iE, iF = (sD * sE - sC * sF) / -den, (sB * sE - sA * sF) / den
+        want = np.array([dA * iA + dC * iB, dB * iA + dD * iB, dA * iC + dC * iD, dB * iC + dD * iD,
+                         dA * iE + dC * iF + dE, dB * iE + dD * iF + dF]).astype(np.float32)
+        assert np.array_equal(O.affine_from_triangles(s, d), want)
+
+
+def test_inverse_warp_matches_python_loop_small():
+    """_inverseGeometricWarp restated as the literal double loop in Python, 37x23 image, both kinds."""
+    rng = np.random.default_rng(3)
+    W, H = 37, 23
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    flat = img.reshape(-1)
+    cases = [np.array([0.9, 0.1, -0.2, 1.1, 3.0, -2.0], np.float32),
+             np.array([1.01, 0.02, -3.0, 0.03, 0.98, 2.0, 1e-4, -2e-4], np.float64)]
+    for m in cases:
+        xo, yo, oW, oH = -3, -4, 45, 31
+        want = np.zeros(oW * oH * 4, np.uint8)
+        for y in range(yo, yo + oH):
+            for x in range(xo, xo + oW):
+                if m.size == 6:
+                    mm = [float(v) for v in m]
+                    sx = mm[0] * x + mm[2] * y + mm[4]
+                    sy = mm[1] * x + mm[3] * y + mm[5]
+                else:
+                    den = m[6] * x + m[7] * y + 1
+                    sx = (m[0] * x + m[1] * y + m[2]) / den
+                    sy = (m[3] * x + m[4] * y + m[5]) / den
+                if 0 <= sx < W and 0 <= sy < H:
+                    si = int(math.floor(sy + 0.5)) * W * 4 + int(math.floor(sx + 0.5)) * 4
+                    di = ((y - yo) * oW + (x - xo)) * 4
+                    for c in range(4):
+                        want[di + c] = flat[si + c] if si + c < flat.size else 0
+        got = O.warp_inverse_geometric(img, W, H, m, xo, yo, oW, oH)
+        assert np.array_equal(got, want)
+
+
+def _py_fill(tri, idx, mw, yoff, arr):
+    """fillTriangle (H.js:1111) in plain Python with TypedArray.fill semantics."""
+    x0, y0, x1, y1, x2, y2 = [float(np.float32(v)) for v in tri]
+    minY = int(math.trunc(min(y0, y1, y2)))
+    maxY = math.ceil(max(y0, y1, y2))
+
+    def seg(xa, ya, xb, yb):
+        if xb != xa:
+            m = (yb - ya) / (xb - xa)
+            return m, ya - xa * m, min(ya, yb), max(ya, yb)
+        return math.inf, xa, min(ya, yb), max(ya, yb)
+
+    segs = [seg(x0, y0, x1, y1), seg(x0, y0, x2, y2), seg(x1, y1, x2, y2)]
+    n = len(arr)
+
+    def bound(v):
+        if v != v:
+            v = 0
+        if v == math.inf:
+            return n
+        if v == -math.inf:
+            return 0
+        v = math.trunc(v)
+        return max(n + v, 0) if v < 0 else min(v, n)
+
+    def jsround(v):
+        if v in (math.inf, -math.inf) or v != v:
+            return v
+        return math.floor(v + 0.5)
+
+    for y in range(minY, maxY):
+        mn, mx = math.inf, -math.inf
+        for m, b, lo, hi in segs:
+            if lo <= y <= hi:
+                if m == math.inf:
+                    x = b
+                elif m == 0:
+                    continue
+                else:
+                    x = (y - b) / m
+                mn, mx = min(mn, x), max(mx, x)
+        k0, k1 = bound((y - yoff) * mw + jsround(mn)), bound((y - yoff) * mw + jsround(mx))
+        for k in range(k0, k1):
+            arr[k] = idx
+
+
+def test_index_map_matches_python_restatement_including_quirks():
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        n_pts = 7
+        pts = rng.uniform(-4, 40, (n_pts, 2)).astype(np.float32)
+        if trial % 3 == 0:
+            pts = np.round(pts)  # integer vertices: horizontal / vertical edges, shared rows
+        tris = np.array([[0, 1, 2], [2, 3, 4], [4, 5, 6], [0, 3, 6], [1, 4, 5]], np.uint32)
+        mw = 30 + trial % 5
+        yoff = float(O.js_round(float(pts[:, 1].min())))   # Q5: ~~minY can be yoff-1 -> negative relative index
+        length = mw * 36
+        want = [-1] * length
+        for t, tri in enumerate(tris):
+            _py_fill(pts[tri].reshape(-1), t, mw, yoff, want)
+        got = O.build_index_map(pts, tris, mw, yoff, length)
+        assert np.array_equal(got, np.array(want, np.int16)), trial
+
+
+def test_index_map_last_triangle_wins_and_x_offset_is_ignored():
+    # two identical triangles: the later id wins everywhere (Q7)
+    pts = np.array([[2, 1], [12, 1], [2, 9]], np.float32)
+    m = O.build_index_map(pts, np.array([0, 1, 2, 0, 1, 2], np.uint32), 16, 1, 16 * 10)
+    assert set(np.unique(m)) == {-1, 1}
+    # Q4: columns are absolute x, no x offset is subtracted -> span starts at column round(xmin) = 2
+    row1 = m[16:32]
+    assert row1[2] == 1 and row1[1] == -1
