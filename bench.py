@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — Mpix/s warped on B200 for BASELINE.json's headline config, with roofline + CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU loop (oracle port), rank 0 only
+
+Workload at every N: config 2 of BASELINE.json — projective 4-point warp of 1920x1080 RGBA8 frames into their
+1728x1080 output window.  One step = one batch of FRAMES independent frames (distinct source + distinct output
+buffer per frame: a ring far larger than the 126 MB L2, so every step streams from / to HBM).  Frames are
+independent, so N GPUs each warp their own batch (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_PIXEL = 8  # 4 B RGBA8 read + 4 B RGBA8 write per output pixel (SURVEY §8d / north_star)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample_once(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                     "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample_once()
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        self.sample_once()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_port_rate(wl, threads: int, budget_s: float, frames_per_round: int = 4, seed: int = 2):
+    """The reference's loop (oracle port, C, -O2, unfused doubles) on the host cores: Mpix/s over a bounded sample."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (wl["H"], wl["W"], 4), dtype=np.uint8)
+    px = 0
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        for _ in range(frames_per_round):
+            inv = O.projective_from_squares(wl["dst"], wl["src"])  # per-frame solve, like _inverseGeometricWarp
+            O.warp_inverse_geometric(img, wl["W"], wl["H"], inv, wl["x_off"], wl["y_off"], wl["o_w"], wl["o_h"], threads=threads)
+            px += wl["o_w"] * wl["o_h"]
+            n += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s:
+            break
+    return px / dt / 1e6, n, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Node.js is not in this image and
+    the reference is JavaScript (nothing gcc could compile into oracle/_ref), so this is the oracle PORT of
+    _inverseGeometricWarp with all host threads (the real reference is single-threaded; see cpu_baseline.single_thread)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import homography_js_b200 as hg
+    from oracle import oracle as O
+    O.build()
+    wl = hg.workloads.projective_1080p()
+    threads = os.cpu_count() or 1
+    frames = args.ref_frames
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (wl["H"], wl["W"], 4), dtype=np.uint8)
+
+    def step():
+        for _ in range(frames):
+            inv = O.projective_from_squares(wl["dst"], wl["src"])
+            O.warp_inverse_geometric(img, wl["W"], wl["H"], inv, wl["x_off"], wl["y_off"], wl["o_w"], wl["o_h"], threads=threads)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    px = frames * wl["o_w"] * wl["o_h"] * args.steps
+    val = px / dt / 1e6
+    one_t, _, _ = cpu_port_rate(wl, 1, 1.5, 1)
+    line = {
+        "impl": "reference", "metric": "Mpix/s warped", "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "frames_per_step": frames,
+                   "note": "oracle port of Homography.js _inverseGeometricWarp (C, unfused doubles); Node.js absent"},
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": threads, "kind": "port",
+                         "sample": f"{frames} frames x {args.steps} steps of 1728x1080, OpenMP over output rows",
+                         "single_thread": one_t},
+        "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="frames per step (per GPU)")
+    ap.add_argument("--e2e-frames", type=int, default=16, help="frames per end-to-end step (per GPU)")
+    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
+    ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU baseline work")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    import torch.distributed as dist
+    import homography_js_b200 as hg
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = hg.Context(local_rank)
+    wl = hg.workloads.projective_1080p()
+    W, H, oW, oH = wl["W"], wl["H"], wl["o_w"], wl["o_h"]
+    F = args.frames
+    npix_frame = oW * oH
+
+    # ---- device-resident rings (torch = device-memory plumbing only)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2 + rank)
+    src_ring = torch.randint(0, 256, (F, H * W * 4), dtype=torch.uint8, device=dev, generator=g)
+    out_ring = torch.zeros((F, npix_frame * 4), dtype=torch.uint8, device=dev)
+    # inverse matrix: calculateTransformMatrix('projective', dst, src) on the device (K5)
+    inv = ctx.solve_projective(wl["dst"], wl["src"])
+    mats = np.tile(inv, (F, 1))
+    frames = [hg.HgFrame(src_ring[f].data_ptr(), out_ring[f].data_ptr(), W, H, wl["x_off"], wl["y_off"], oW, oH)
+              for f in range(F)]
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.warp_inverse_batch(hg._abi.HG_PROJECTIVE, mats, frames)
+
+    # ---- parity gate inside the run: frame 0 of the batch against the oracle (not timed)
+    step()
+    ctx.synchronize()
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        want = O.warp_inverse_geometric(src_ring[0].cpu().numpy(), W, H, O.projective_from_squares(wl["dst"], wl["src"]),
+                                        wl["x_off"], wl["y_off"], oW, oH, threads=os.cpu_count() or 1)
+        parity = bool(np.array_equal(out_ring[0].cpu().numpy(), want))
+        if not parity:
+            raise SystemExit("parity gate failed: CUDA output differs from the oracle")
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = ctx.launch_count()
+    ctx.profile_enable(True)
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms_local = ctx.timer_stop()
+    sampler.sample_once()
+    barrier()
+    sampler.stop()
+    kern_ms, kern_n = ctx.profile_read()
+    ctx.profile_enable(False)
+    launches = ctx.launch_count() - l0
+    ms = max_over_ranks(ms_local)
+    value = world * F * npix_frame * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (warp_inverse_geo_kernel<projective>), live CUDA events
+    peak, peak_src = measured_peak_gbs()
+    px_per_launch = F * npix_frame
+    avg_kernel_s = (kern_ms / max(kern_n, 1)) * 1e-3
+    achieved = ALG_BYTES_PER_PIXEL * px_per_launch / avg_kernel_s / 1e9
+
+    # ---- end to end through the host-buffer ABI (the calls a binding makes per frame):
+    #      hg_image_set (H2D from pinned host memory) + hg_warp_inverse_points (solve + warp + D2H)
+    Fe = args.e2e_frames
+    h_src = torch.randint(0, 256, (Fe, H * W * 4), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty((Fe, npix_frame * 4), dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        for f in range(Fe):
+            ctx.image_set_host_ptr(h_src[f].data_ptr(), W, H)
+            ctx.warp_inverse_points(hg._abi.HG_PROJECTIVE, wl["dst"], wl["src"], wl["x_off"], wl["y_off"], oW, oH,
+                                    out_host_ptr=h_out[f].data_ptr())
+
+    e2e_steps = args.steps
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_ms_dev = ctx.timer_stop()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(max(e2e_ms_dev, e2e_wall))
+    e2e_val = world * Fe * npix_frame * e2e_steps / (e2e_ms * 1e-3) / 1e6
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v_all, n_all, dt_all = cpu_port_rate(wl, threads, args.cpu_budget * 0.8)
+        v_one, n_one, dt_one = cpu_port_rate(wl, 1, args.cpu_budget * 0.2, 1)
+        cpu = {"value": v_all, "unit": "Mpix/s", "cores": threads, "kind": "port",
+               "sample": f"{n_all} frames of 1728x1080 in {dt_all:.1f} s, OpenMP over output rows "
+                         "(oracle port of Homography.js _inverseGeometricWarp; Node.js absent from the image)",
+               "single_thread": v_one}
+
+    if rank == 0:
+        line = {
+            "metric": "Mpix/s warped", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "frames_per_step_per_gpu": F,
+                       "l2": f"ring of {F} distinct sources + {F} distinct outputs per GPU "
+                             f"({(src_ring.numel() + out_ring.numel()) / 1e6:.0f} MB) > 126 MB L2",
+                       "parity_gate": parity},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "warp_inverse_geo_kernel<projective>",
+                         "alg_bytes_per_launch": ALG_BYTES_PER_PIXEL * px_per_launch,
+                         "avg_kernel_ms": avg_kernel_s * 1e3, "kernels_timed": kern_n, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": Fe * H * W * 4,
+                    "d2h_bytes_per_step": Fe * npix_frame * 4, "frames_per_step_per_gpu": Fe, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "hg_image_set + hg_warp_inverse_points per frame, pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

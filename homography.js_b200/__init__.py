@@ -7,8 +7,8 @@ Layout: csrc/ (hand-written CUDA kernels + the C ABI of include/hgwarp.h), _abi.
 that ABI), homography.py (host mirror of the reference class), js/ (the Node.js shim + N-API addon
 source a maintainer would ship), build.py (nvcc recipe).
 """
-from . import _abi
+from . import _abi, workloads
 from ._abi import Context, HgError, HgFrame, device_count
 from .homography import Homography, HomographyError, ImageData
 
-__all__ = ["Homography", "HomographyError", "ImageData", "Context", "HgError", "HgFrame", "device_count", "_abi"]
+__all__ = ["Homography", "HomographyError", "ImageData", "Context", "HgError", "HgFrame", "device_count", "_abi", "workloads"]

@@ -19,6 +19,7 @@ HG_AFFINE, HG_PROJECTIVE = 0, 1
 SYMBOLS = [
     "hg_abi_version", "hg_device_count", "hg_ctx_create", "hg_ctx_destroy", "hg_last_error",
     "hg_ctx_synchronize", "hg_ctx_stream", "hg_timer_start", "hg_timer_stop", "hg_launch_count",
+    "hg_profile_enable", "hg_profile_read",
     "hg_image_set", "hg_image_set_device",
     "hg_solve_affine", "hg_solve_projective", "hg_inverse_affine", "hg_transform_limits", "hg_solve_with_limits",
     "hg_warp_inverse_matrix", "hg_warp_inverse_points", "hg_warp_forward_matrix",
@@ -67,6 +68,8 @@ def load():
     L.hg_timer_start.argtypes = [vp]
     L.hg_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.hg_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.hg_profile_enable.argtypes = [vp, i]
+    L.hg_profile_read.argtypes = [vp, C.POINTER(d), C.POINTER(C.c_uint64)]
     L.hg_image_set.argtypes = [vp, vp, i, i]
     L.hg_image_set_device.argtypes = [vp, vp, i, i]
     L.hg_solve_affine.argtypes = [vp, vp, vp, vp]
@@ -147,6 +150,14 @@ class Context:
         n = C.c_uint64()
         self._ck(self.L.hg_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def profile_enable(self, on: bool = True):
+        self._ck(self.L.hg_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        ms, n = C.c_double(), C.c_uint64()
+        self._ck(self.L.hg_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def dev_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()

@@ -35,6 +35,10 @@ struct hg_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     uint64_t launches = 0;
+    // optional per-kernel timing of the pixel-loop kernels (roofline accounting in bench.py)
+    bool prof = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
+    size_t prof_used = 0;
 
     // image (this._image)
     const uint32_t *img = nullptr;
@@ -172,13 +176,37 @@ unsigned grid_for(hg_ctx *c, long long npix, int n_frames)
     return (unsigned)blocks;
 }
 
+// events bracketing one pixel-loop kernel (only when hg_profile_enable(ctx, 1))
+int prof_begin(hg_ctx *c)
+{
+    if (!c->prof) return HG_OK;
+    if (c->prof_used == c->prof_ev.size()) {
+        cudaEvent_t a, b;
+        CU(c, cudaEventCreate(&a));
+        CU(c, cudaEventCreate(&b));
+        c->prof_ev.emplace_back(a, b);
+    }
+    CU(c, cudaEventRecord(c->prof_ev[c->prof_used].first, c->stream));
+    return HG_OK;
+}
+
+int prof_end(hg_ctx *c)
+{
+    if (!c->prof) return HG_OK;
+    CU(c, cudaEventRecord(c->prof_ev[c->prof_used].second, c->stream));
+    c->prof_used++;
+    return HG_OK;
+}
+
 int launch_geo(hg_ctx *c, int kind, const GeoParams &P, long long max_npix, int n_frames)
 {
     dim3 grid(grid_for(c, max_npix, n_frames), (unsigned)n_frames);
+    TRY(prof_begin(c));
     if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, 256, 0, c->stream>>>(P);
     else warp_inverse_geo_kernel<1><<<grid, 256, 0, c->stream>>>(P);
     c->launches++;
     CU(c, cudaGetLastError());
+    TRY(prof_end(c));
     return HG_OK;
 }
 
@@ -275,6 +303,10 @@ int hg_ctx_destroy(hg_ctx *c)
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (auto &pr : c->prof_ev) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return HG_OK;
@@ -317,6 +349,31 @@ int hg_launch_count(hg_ctx *c, uint64_t *n)
 {
     if (!c || !n) return HG_ERR_INVALID;
     *n = c->launches;
+    return HG_OK;
+}
+
+int hg_profile_enable(hg_ctx *c, int on)
+{
+    if (!c) return HG_ERR_INVALID;
+    c->prof = on != 0;
+    c->prof_used = 0;
+    return HG_OK;
+}
+
+int hg_profile_read(hg_ctx *c, double *total_ms, uint64_t *n_kernels)
+{
+    BIND(c);
+    NEED(c, total_ms && n_kernels, "NULL argument");
+    CU(c, cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i < c->prof_used; ++i) {
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, c->prof_ev[i].first, c->prof_ev[i].second));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *n_kernels = c->prof_used;
+    c->prof_used = 0;
     return HG_OK;
 }
 
@@ -549,9 +606,8 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
     TRY(ensure(c, c->frames, sizeof(GeoFrame) * (size_t)n_frames));
     TRY(ensure(c, c->mats, mstride * (size_t)n_frames));
     CU(c, cudaMemcpyAsync(c->frames.p, gf.data(), sizeof(GeoFrame) * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
+    // pageable sources: cudaMemcpyAsync returns once they are staged, so gf may die at scope exit
     CU(c, cudaMemcpyAsync(c->mats.p, inv_matrices, mstride * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
-    // the staging vector must outlive the (pageable) async copy
-    CU(c, cudaStreamSynchronize(c->stream));
     const int chunk = 32768;
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
@@ -721,9 +777,11 @@ int hg_warp_piecewise_inverse(hg_ctx *c, const float *dst_pts, int x_off, int y_
     a.minSrcX = min_src_x;
     a.minSrcY = min_src_y;
     a.n_tris = c->n_tris;
+    TRY(prof_begin(c));
     pw_warp_inverse_kernel<<<grid_for(c, map_len, 1), 256, 0, c->stream>>>(a);
     c->launches++;
     CU(c, cudaGetLastError());
+    TRY(prof_end(c));
     return finish_out(c, dst, bytes, out_host);
 }
 

@@ -1,0 +1,66 @@
+"""Synthetic workloads of BASELINE.json's configs (shapes and point formulas from SURVEY.md §8d, which lifts
+them from the reference's test/benchmark.js and test/test.js) and the frame-sharding rule for multi-GPU runs."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def shard_range(n_units: int, rank: int, world: int):
+    """Block partition of independent frames over ranks: frames[r*N/G : (r+1)*N/G] (no data-path collective)."""
+    lo = (n_units * rank) // world
+    hi = (n_units * (rank + 1)) // world
+    return lo, hi
+
+
+def projective_1080p():
+    """Config 2: projective 4-point warp, 1920x1080 RGBA8; dst = [[w/10,0],[w/10,h],[w,h/4],[w,3h/4]]
+    (benchmark.js:282-283 shape) -> output window xOff=192, yOff=0, 1728x1080."""
+    w, h = 1920, 1080
+    src = np.array([0, 0, 0, h, w, 0, w, h], np.float64)
+    dst = np.array([w / 10, 0, w / 10, h, w, h / 4, w, 3 * h / 4], np.float64)
+    return dict(name="projective 4-point warp, 1920x1080 RGBA8 -> 1728x1080", kind=1, W=w, H=h, src=src, dst=dst,
+                x_off=192, y_off=0, o_w=1728, o_h=1080)
+
+
+def affine_256():
+    """Config 1: affine 3-point warp, 256x256 (benchmark.js:204-205 shape)."""
+    w = h = 256
+    src = np.array([0, 0, 0, h, w, 0], np.float64)
+    dst = np.array([0, h / 2, w / 2, h * 0.8, w / 2, 0], np.float64)
+    return dict(name="affine 3-point warp, 256x256 RGBA8", kind=0, W=w, H=h, src=src, dst=dst)
+
+
+def grid_mesh(nx: int, ny: int, w: float, h: float):
+    """Regular nx x ny point grid with the explicit triangle list of SURVEY §8d (cell (i,j): [p00,p10,p01],
+    [p10,p11,p01]) — a regular grid is Delaunay-degenerate, so the triangles are given, not derived."""
+    xs = np.arange(nx) * (w / (nx - 1))
+    ys = np.arange(ny) * (h / (ny - 1))
+    pts = np.array([[x, y] for y in ys for x in xs], np.float32)
+    tris = []
+    for j in range(ny - 1):
+        for i in range(nx - 1):
+            p00, p10, p01, p11 = j * nx + i, j * nx + i + 1, (j + 1) * nx + i, (j + 1) * nx + i + 1
+            tris += [[p00, p10, p01], [p10, p11, p01]]
+    return pts, np.array(tris, np.uint32)
+
+
+def piecewise_sinusoid(nx: int, ny: int, w: int, h: int, phase: float = 0.0, amplitude: float | None = None):
+    """Configs 3/4: dst = (x, A + y + A*sin(2*pi*2x/w + phase)), A = h/20 (test.js:133-144 shape)."""
+    A = h / 20.0 if amplitude is None else amplitude
+    src, tris = grid_mesh(nx, ny, w, h)
+    dst = src.copy()
+    dst[:, 1] = (A + src[:, 1].astype(np.float64)
+                 + A * np.sin(2 * math.pi * 2 * src[:, 0].astype(np.float64) / w + phase)).astype(np.float32)
+    return src, dst, tris
+
+
+def piecewise_extent(dst: np.ndarray):
+    """Piecewise output window (H.js:706-710): offsets = round(min), size = round(max) - round(min)."""
+    def r(v):
+        f = math.floor(v)
+        return f + 1 if v - f >= 0.5 else f
+    d = np.asarray(dst, np.float64).reshape(-1, 2)
+    x0, y0, x1, y1 = r(d[:, 0].min()), r(d[:, 1].min()), r(d[:, 0].max()), r(d[:, 1].max())
+    return int(x0), int(y0), int(x1 - x0), int(y1 - y0)

@@ -73,6 +73,10 @@ int hg_timer_start(hg_ctx *ctx);
 int hg_timer_stop(hg_ctx *ctx, float *elapsed_ms);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int hg_launch_count(hg_ctx *ctx, uint64_t *count);
+/* per-kernel device timing of the pixel-loop kernels: enable, run, then read the summed CUDA-event
+ * duration and the number of kernels it covers (resets the accumulation) */
+int hg_profile_enable(hg_ctx *ctx, int on);
+int hg_profile_read(hg_ctx *ctx, double *total_ms, uint64_t *n_kernels);
 
 /* ------------------------------------------------------------------ image (this._image, H.js:298) */
 int hg_image_set(hg_ctx *ctx, const uint8_t *rgba_host, int w, int h);      /* H2D copy, stays resident */
