@@ -90,6 +90,10 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def _inv_matrix(O, wl):
+    return O.calculate_transform_matrix("projective" if wl["kind"] else "affine", wl["dst"], wl["src"])
+
+
 def cpu_port_rate(wl, threads: int, budget_s: float, frames_per_round: int = 4, seed: int = 2):
     """The reference's loop (oracle port, C, -O2, unfused doubles) on the host cores: Mpix/s over a bounded sample."""
     from oracle import oracle as O
@@ -100,7 +104,7 @@ def cpu_port_rate(wl, threads: int, budget_s: float, frames_per_round: int = 4, 
     n = 0
     while True:
         for _ in range(frames_per_round):
-            inv = O.projective_from_squares(wl["dst"], wl["src"])  # per-frame solve, like _inverseGeometricWarp
+            inv = _inv_matrix(O, wl)  # per-frame solve, like _inverseGeometricWarp
             O.warp_inverse_geometric(img, wl["W"], wl["H"], inv, wl["x_off"], wl["y_off"], wl["o_w"], wl["o_h"], threads=threads)
             px += wl["o_w"] * wl["o_h"]
             n += 1
@@ -166,6 +170,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="projective", choices=["projective", "affine", "projective_generic"],
+                    help="projective = BASELINE config 2 (the headline); affine = same sizes through the affine kernel")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -200,7 +206,9 @@ def main():
         return float(t.item())
 
     ctx = hg.Context(local_rank)
-    wl = hg.workloads.projective_1080p()
+    wl = {"projective": hg.workloads.projective_1080p, "affine": hg.workloads.affine_1080p,
+          "projective_generic": hg.workloads.projective_1080p_generic}[args.workload]()
+    KIND = wl["kind"]
     W, H, oW, oH = wl["W"], wl["H"], wl["o_w"], wl["o_h"]
     F = args.frames
     npix_frame = oW * oH
@@ -211,14 +219,14 @@ def main():
     src_ring = torch.randint(0, 256, (F, H * W * 4), dtype=torch.uint8, device=dev, generator=g)
     out_ring = torch.zeros((F, npix_frame * 4), dtype=torch.uint8, device=dev)
     # inverse matrix: calculateTransformMatrix('projective', dst, src) on the device (K5)
-    inv = ctx.solve_projective(wl["dst"], wl["src"])
+    inv = ctx.solve_projective(wl["dst"], wl["src"]) if KIND == 1 else ctx.solve_affine(wl["dst"], wl["src"])
     mats = np.tile(inv, (F, 1))
     frames = [hg.HgFrame(src_ring[f].data_ptr(), out_ring[f].data_ptr(), W, H, wl["x_off"], wl["y_off"], oW, oH)
               for f in range(F)]
     torch.cuda.synchronize()
 
     def step():
-        ctx.warp_inverse_batch(hg._abi.HG_PROJECTIVE, mats, frames)
+        ctx.warp_inverse_batch(KIND, mats, frames)
 
     # ---- parity gate inside the run: frame 0 of the batch against the oracle (not timed)
     step()
@@ -227,7 +235,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
-        want = O.warp_inverse_geometric(src_ring[0].cpu().numpy(), W, H, O.projective_from_squares(wl["dst"], wl["src"]),
+        want = O.warp_inverse_geometric(src_ring[0].cpu().numpy(), W, H, O.calculate_transform_matrix("projective" if KIND else "affine", wl["dst"], wl["src"]),
                                         wl["x_off"], wl["y_off"], oW, oH, threads=os.cpu_count() or 1)
         parity = bool(np.array_equal(out_ring[0].cpu().numpy(), want))
         if not parity:
@@ -269,7 +277,7 @@ def main():
     def e2e_step():
         for f in range(Fe):
             ctx.image_set_host_ptr(h_src[f].data_ptr(), W, H)
-            ctx.warp_inverse_points(hg._abi.HG_PROJECTIVE, wl["dst"], wl["src"], wl["x_off"], wl["y_off"], oW, oH,
+            ctx.warp_inverse_points(KIND, wl["dst"], wl["src"], wl["x_off"], wl["y_off"], oW, oH,
                                     out_host_ptr=h_out[f].data_ptr())
 
     e2e_steps = args.steps
@@ -307,7 +315,7 @@ def main():
                              f"({(src_ring.numel() + out_ring.numel()) / 1e6:.0f} MB) > 126 MB L2",
                        "parity_gate": parity},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "warp_inverse_geo_kernel<projective>",
+                         "traffic": None, "kernel": "warp_inverse_geo_kernel<%s>" % ("projective" if KIND else "affine"),
                          "alg_bytes_per_launch": ALG_BYTES_PER_PIXEL * px_per_launch,
                          "avg_kernel_ms": avg_kernel_s * 1e3, "kernels_timed": kern_n, "peak_source": peak_src},
             "cpu_baseline": cpu,

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhgwarp.so")
+LIB_PATH = os.environ.get("HGWARP_LIB") or os.path.join(_HERE, "libhgwarp.so")  # env override: A/B builds
 
 HG_OK, HG_ERR_INVALID, HG_ERR_CUDA, HG_ERR_NOMEM, HG_ERR_UNSUPPORTED, HG_ERR_STATE = range(6)
 HG_AFFINE, HG_PROJECTIVE = 0, 1
@@ -26,6 +26,7 @@ SYMBOLS = [
     "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_build_index_map",
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
+    "hg_debug_rcp_max_error",
     "hg_dev_alloc", "hg_dev_free", "hg_host_alloc_pinned", "hg_host_free_pinned",
     "hg_memcpy_h2d", "hg_memcpy_d2h", "hg_output_device",
 ]
@@ -87,6 +88,7 @@ def load():
     L.hg_warp_piecewise_forward.argtypes = [vp, vp, i, i, i, i, i, i, i, i, i, vp, vp]
     L.hg_warp_inverse_batch.argtypes = [vp, i, vp, C.POINTER(HgFrame), i]
     L.hg_warp_piecewise_inverse_batch.argtypes = [vp, vp, C.POINTER(HgFrame), i, i, i]
+    L.hg_debug_rcp_max_error.argtypes = [vp, i, i, C.POINTER(d)]
     L.hg_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.hg_dev_free.argtypes = [vp, vp]
     L.hg_host_alloc_pinned.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -158,6 +160,11 @@ class Context:
         ms, n = C.c_double(), C.c_uint64()
         self._ck(self.L.hg_profile_read(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def debug_rcp_max_error(self, biased_exponent: int = 1023, negative: bool = False) -> float:
+        e = C.c_double()
+        self._ck(self.L.hg_debug_rcp_max_error(self.h, biased_exponent, int(negative), C.byref(e)))
+        return e.value
 
     def dev_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()

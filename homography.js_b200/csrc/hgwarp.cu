@@ -14,6 +14,7 @@
 #include "piecewise.cuh"
 #include "solve.cuh"
 #include "warp_geo.cuh"
+#include "diag.cuh"
 
 using namespace hg;
 
@@ -60,6 +61,10 @@ struct hg_ctx {
 };
 
 namespace {
+
+// scratch layout (bytes): [0,128) src pts, [128,256) dst pts, [256,320) matrix, [320,352) limits, [384,512) misc,
+// [512,528) zeros (the word out-of-window pixels read)
+constexpr size_t SC_SRC = 0, SC_DST = 128, SC_MAT = 256, SC_LIM = 320, SC_MISC = 384, SC_ZERO = 512;
 
 int fail(hg_ctx *c, int code, const char *fmt, ...)
 {
@@ -198,12 +203,24 @@ int prof_end(hg_ctx *c)
     return HG_OK;
 }
 
-int launch_geo(hg_ctx *c, int kind, const GeoParams &P, long long max_npix, int n_frames)
+// rows per CTA = 64 * niter: long-lived CTAs amortise their start-up and pipeline gathers against arithmetic,
+// but the grid must still fill the machine (>= ~6 CTAs per SM in total)
+int pick_niter(hg_ctx *c, int max_ow, int max_oh, int n_frames)
 {
-    dim3 grid(grid_for(c, max_npix, n_frames), (unsigned)n_frames);
+    int niter = 16;
+    while (niter > 1 &&
+           (long long)geo_tiles_x(max_ow) * geo_tiles_y(max_oh, niter) * n_frames < (long long)c->sm_count * 16)
+        niter >>= 1;
+    return niter;
+}
+
+int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_frames)
+{
+    P.niter = pick_niter(c, max_ow, max_oh, n_frames);
+    dim3 grid((unsigned)(geo_tiles_x(max_ow) * geo_tiles_y(max_oh, P.niter)), (unsigned)n_frames);
     TRY(prof_begin(c));
-    if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, 256, 0, c->stream>>>(P);
-    else warp_inverse_geo_kernel<1><<<grid, 256, 0, c->stream>>>(P);
+    if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, 0, c->stream>>>(P);
+    else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, 0, c->stream>>>(P);
     c->launches++;
     CU(c, cudaGetLastError());
     TRY(prof_end(c));
@@ -218,8 +235,6 @@ int launch_solve(hg_ctx *c, const SolveArgs &a)
     return HG_OK;
 }
 
-// scratch layout (bytes): [0,128) src pts, [128,256) dst pts, [256,320) matrix, [320,352) limits, [384,..) misc
-constexpr size_t SC_SRC = 0, SC_DST = 128, SC_MAT = 256, SC_LIM = 320, SC_MISC = 384;
 
 int upload_small(hg_ctx *c, size_t off, const void *host, size_t bytes)
 {
@@ -285,6 +300,7 @@ int hg_ctx_create(int device, hg_ctx **out)
     CUC(cudaEventCreate(&c->ev1));
     CUC(cudaMalloc(&c->scratch.p, 4096));
     c->scratch.cap = 4096;
+    CUC(cudaMemset(c->scratch.p, 0, 4096));
     CUC(cudaHostAlloc(&c->pinned, 4096, cudaHostAllocDefault));
 #undef CUC
     *out = c;
@@ -532,7 +548,7 @@ static int warp_inverse_common(hg_ctx *c, int kind, const void *inv_host, bool s
         else
             for (int k = 0; k < 8; ++k) P.mat_val[k] = ((const double *)inv_host)[k];
     }
-    TRY(launch_geo(c, kind, P, (long long)o_w * o_h, 1));
+    TRY(launch_geo(c, kind, P, o_w, o_h, 1));
     return finish_out(c, dst, bytes, out_host);
 }
 
@@ -577,7 +593,7 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
     NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
     NEED(c, n_frames >= 1, "n_frames must be >= 1");
     std::vector<GeoFrame> gf((size_t)n_frames);
-    long long max_npix = 0;
+    int max_ow = 1, max_oh = 1;
     for (int f = 0; f < n_frames; ++f) {
         const hg_frame &h = frames[f];
         TRY(check_window(c, h.x_off, h.y_off, h.o_w, h.o_h));
@@ -599,8 +615,8 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
         g.yOff = h.y_off;
         g.oW = h.o_w;
         g.oH = h.o_h;
-        const long long np = (long long)h.o_w * h.o_h;
-        if (np > max_npix) max_npix = np;
+        if (h.o_w > max_ow) max_ow = h.o_w;
+        if (h.o_h > max_oh) max_oh = h.o_h;
     }
     const size_t mstride = kind == HG_AFFINE ? 24 : 64;
     TRY(ensure(c, c->frames, sizeof(GeoFrame) * (size_t)n_frames));
@@ -614,7 +630,7 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
         GeoParams P{};
         P.many = (const GeoFrame *)c->frames.p + f0;
         P.mats_dev = (const char *)c->mats.p + mstride * (size_t)f0;
-        TRY(launch_geo(c, kind, P, max_npix, nf));
+        TRY(launch_geo(c, kind, P, max_ow, max_oh, nf));
     }
     return HG_OK;
 }
@@ -793,6 +809,24 @@ int hg_warp_piecewise_forward(hg_ctx *c, const float *, int, int, int, int, int,
 int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *, const hg_frame *, int, int, int)
 {
     return fail(c, HG_ERR_UNSUPPORTED, "batched piecewise warp is not built yet");
+}
+
+/* ------------------------------------------------------------------ diagnostics */
+int hg_debug_rcp_max_error(hg_ctx *c, int biased_exponent, int negative, double *max_rel_err)
+{
+    BIND(c);
+    NEED(c, max_rel_err, "NULL argument");
+    NEED(c, biased_exponent >= 1 && biased_exponent <= 2046, "biased_exponent must be a normal exponent");
+    unsigned long long *d = (unsigned long long *)((char *)c->scratch.p + SC_MISC);
+    CU(c, cudaMemsetAsync(d, 0, 8, c->stream));
+    rcp_error_kernel<<<(1 << 20) / 256, 256, 0, c->stream>>>(biased_exponent, negative, d);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    unsigned long long bits = 0;
+    CU(c, cudaMemcpyAsync(&bits, d, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    memcpy(max_rel_err, &bits, 8);
+    return HG_OK;
 }
 
 /* ------------------------------------------------------------------ memory helpers */

@@ -7,19 +7,33 @@
 //           out[x,y] = src_flat[round(sy)*W + round(sx)]   H.js:1005 (flat index, Math.round;
 //                                                 index past the end reads `undefined` -> 0)
 //
-// Layout: RGBA8 pixels are handled as one 32-bit word.  The output is addressed FLAT
-// (pixel p = yy*oW + xx); one thread produces 4 consecutive pixels and issues ONE 128-bit store,
-// so a warp writes 512 contiguous bytes regardless of oW.  Source reads are 32-bit read-only
-// gathers (adjacent output pixels map to adjacent source pixels, so a warp's 128 loads fall in a
-// handful of 128-byte lines and the image stays L2-resident across the frame).
+// Data layout.  RGBA8 pixels are 32-bit words; the output is dense (row pitch = oW pixels, the layout of
+// ImageData), so a row starts at flat pixel yy*oW whose 16-byte alignment is (yy*oW) mod 4.  The kernel
+// walks each row in FLAT-aligned quads: quad i of row yy covers x = 4i - a(yy) .. +3 with a(yy) = (yy*oW)&3,
+// so every interior quad is ONE aligned 128-bit store for any oW (the first/last quad of a row may be
+// partial and is stored pixel by pixel).  a(yy) repeats with period s = 4/gcd(oW mod 4, 4), so a thread
+// that owns rows yy, yy+s, yy+2s, ... sees the same x for all of them.
 //
-// Arithmetic: bit-exact with the reference's unfused doubles.
-//   affine      2 DFMA + 2 DADD + 2 DADD.RD per pixel (products float x int are exact, see jsnum.cuh)
-//   projective  numerators / denominator evaluated exactly as the reference does (DMUL + DADD);
-//               the two IEEE divides are replaced by ONE Newton reciprocal + 2 DMUL whose relative
-//               error is < 2^-48; every decision of the loop flips only at multiples of 0.5, so
-//               the quotient is trusted unless it lies within 2^-24 of such a multiple (probability
-//               ~2.4e-7 per coordinate), in which case the pixel is redone with __ddiv_rn.
+// Work decomposition.  CTA = 256 threads = 16 (x) x 16 (y); thread (tx,ty) owns one quad column and
+// R = 4 rows -> CTA tile = 64 pixels x 64 rows.  The terms that depend on x only (h0*x, h3*x, h6*x) are
+// computed once per thread and reused for its R rows, the terms that depend on y only once per row; a warp
+// (16 lanes x 2 rows) stores 2 x 256 contiguous bytes per row step and keeps 16 independent gathers in
+// flight per thread.
+//
+// Arithmetic (bit-exact with the reference's unfused doubles):
+//   affine      coefficient(float) * integer products are exact in double, so fma(m0,x,m2*y) equals the
+//               unfused sum; one round-down add of 1.5*2^20 then yields floor, bounds test and Math.round
+//               in integer registers (jsnum.cuh)                                  -> 6 FP64 ops / pixel
+//   projective  numerators / denominator evaluated exactly as the reference does (DMUL + DADD); the two
+//               IEEE divides are replaced by MUFU.RCP64H + ONE Newton step (relative error < 2^-36, checked
+//               exhaustively in tests/test_gpu_numerics.py) and one DFMA per coordinate that multiplies
+//               and adds the magic constant in a single rounding.  Every decision of the loop flips only at
+//               multiples of 0.5, so the quotient is trusted unless it lies within 2^-20 of such a multiple
+//               (probability ~4e-6 per coordinate); otherwise the pixel is redone with __ddiv_rn, i.e. the
+//               reference's own arithmetic.                                        -> ~11.5 FP64 ops / pixel
+//   mode        per-CTA uniform dispatch on the matrix: denominator == 1 everywhere (h6 = h7 = 0: exact, no
+//               reciprocal), denominator a function of x only (h7 = 0: one reciprocal per column), denominator
+//               provably in (0.25, 1.75) (no exponent guard), or general.
 #pragma once
 #include "jsnum.cuh"
 
@@ -33,49 +47,254 @@ struct GeoFrame {
 };
 
 struct GeoParams {
-    GeoFrame one;          // used when many == nullptr
-    const GeoFrame *many;  // device array, indexed by blockIdx.y
-    const void *mats_dev;  // device matrices (float[6] | double[8] per frame) or nullptr
-    double mat_val[8];     // matrix by value when mats_dev == nullptr (floats widened to double)
+    GeoFrame one;            // used when many == nullptr
+    const GeoFrame *many;    // device array, indexed by blockIdx.y
+    const void *mats_dev;    // device matrices (float[6] | double[8] per frame) or nullptr
+    int niter;               // row groups (of GEO_GROUP_ROWS rows) per CTA
+    double mat_val[8];       // matrix by value when mats_dev == nullptr (floats widened to double)
 };
 
-__device__ __forceinline__ uint32_t fetch_src(const uint32_t *__restrict__ src, int W, long long npx_src,
-                                              const FloorHalf &fx, const FloorHalf &fy)
+constexpr int GEO_TILE_QUADS = 16;  // quads per CTA row (64 pixels)
+constexpr int GEO_TY = 8;           // thread rows per CTA  -> 128 threads
+#ifndef HG_GEO_R
+#define HG_GEO_R 2
+#endif
+#ifndef HG_GEO_MINB
+#define HG_GEO_MINB 5
+#endif
+constexpr int GEO_ROWS_PER_THREAD = HG_GEO_R;
+constexpr int GEO_THREADS = GEO_TILE_QUADS * GEO_TY;
+constexpr int GEO_GROUP_ROWS = GEO_TY * GEO_ROWS_PER_THREAD;  // rows one CTA covers per iteration
+
+// host + device: CTAs needed for one frame.  Rows whose flat start is not 16-byte aligned begin with a partial
+// quad, so a row has at most (oW + 3 + 3) / 4 quads; when oW % 4 == 0 every row is aligned.
+__host__ __device__ inline int geo_tiles_x(int oW)
 {
-    // srcIdx = round(sy)*W + round(sx) in pixel units; >= W*H reads `undefined` -> 0 (H.js:1005-1007)
-    const long long flat = (long long)round_half_up(fy) * W + round_half_up(fx);
-    return (flat < npx_src) ? __ldg(src + flat) : 0u;
+    const int quads = (oW & 3) == 0 ? oW / 4 : (oW + 6) / 4;
+    return (quads + GEO_TILE_QUADS - 1) / GEO_TILE_QUADS;
+}
+__host__ __device__ inline int geo_tiles_y(int oH, int niter) { return (oH + GEO_GROUP_ROWS * niter - 1) / (GEO_GROUP_ROWS * niter); }
+
+// hi word of (v + 1.5*2^20) minus the hi word of (0 + 1.5*2^20): equals floor(v) for -2^19 <= v < 2^19 and is
+// >= 2^19 (as unsigned) for everything else incl. NaN / Inf, so `(unsigned)u < W` is the complete test
+// "v is finite and 0 <= v < W".
+#define HG_HI_ZERO 0x41380000
+
+#define HG_NEAR_DELTA 4096u  // 2^12 * 2^-32 = 2^-20 absolute
+
+// exact quotient path: t = RD(RN(n / d) + magic) — the reference's own arithmetic
+__device__ __noinline__ double exact_quotient_magic(double n, double d)
+{
+    return __dadd_rd(__ddiv_rn(n, d), HG_MAGIC);
 }
 
-// rcp.approx.ftz.f64 (MUFU.RCP64H, ~20 good bits) + two Newton steps: relative error < 2^-48 for
-// normal d.  NOT correctly rounded: callers must use the near-boundary filter.
-__device__ __forceinline__ double rcp_newton(double d)
+__device__ __forceinline__ double rcp_newton1(double d)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = __fma_rn(-d, r, 1.0);
-    r = __fma_rn(r, e, r);
-    e = __fma_rn(-d, r, 1.0);
-    r = __fma_rn(r, e, r);
-    return r;
+    const double e = __fma_rn(-d, r, 1.0);
+    return __fma_rn(r, e, r);
 }
 
-#define HG_NEAR_DELTA 256u  // 2^8 * 2^-32 = 2^-24 absolute
+__device__ __forceinline__ bool near_half_multiple(unsigned frac)
+{
+    // frac within DELTA of 0, 2^31 or 2^32  <=>  ((frac + DELTA) mod 2^31) < 2*DELTA
+    return ((frac + HG_NEAR_DELTA) << 1) < 4u * HG_NEAR_DELTA;
+}
+
+#define HG_OUTSIDE 0xFFFFFFFFu  // flat-index sentinel: the pixel reads nothing and becomes transparent
+
+// 32-bit gather that returns 0 without touching memory when idx is the OUTSIDE sentinel
+__device__ __forceinline__ uint32_t ldg_or_zero(const uint32_t *__restrict__ src, unsigned idx)
+{
+    uint32_t v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0xffffffff;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.b32 %0, [%1+0];\n\t}"
+        : "=r"(v)
+        : "l"(src + idx), "r"(idx));
+    return v;
+}
+
+// decode t = coordinate + magic into the flat source index (or HG_OUTSIDE); see Q1/Q2 in the header comment
+__device__ __forceinline__ unsigned decode_flat(double tx, double ty, unsigned W, unsigned H, unsigned npx_src)
+{
+    const unsigned ux = (unsigned)(__double2hiint(tx) - HG_HI_ZERO);
+    const unsigned uy = (unsigned)(__double2hiint(ty) - HG_HI_ZERO);
+    // Math.round = floor + (frac >= 0.5); the flat index may run past the row end (reads the next row, Q2)
+    const unsigned rx = ux + ((unsigned)__double2loint(tx) >> 31);
+    const unsigned ry = uy + ((unsigned)__double2loint(ty) >> 31);
+    const unsigned flat = ry * W + rx;
+    return ((ux < W) & (uy < H) & (flat < npx_src)) ? flat : HG_OUTSIDE;
+}
+
+// MODE (projective only): 0 general + denominator exponent guard, 1 general (denominator proven in
+// (0.25,1.75)), 2 denominator == 1 exactly, 3 denominator depends on x only (h7 == 0, e.g. keystone correction
+// along one axis): one reciprocal per column.
+//
+// Per thread: one quad column, GEO_ROWS_PER_THREAD rows per iteration, `niter` iterations (GEO_GROUP_ROWS rows
+// apart), run as a THREE-STAGE SOFTWARE PIPELINE so that no instruction ever waits on the stage before it:
+//   iteration i:   C  store the pixels gathered for group i-2          (their loads were issued one iteration ago)
+//                  B  fix up flagged pixels of group i-1 (rare), then issue its 32-bit gathers
+//                  A  arithmetic of group i: coordinates -> flat source index (+ "redo" bit)
+// Stage A is straight-line code over the thread's pixels, so the FP64 dependency chains of different pixels
+// interleave; its results are first consumed in the NEXT iteration, and memory latency is covered by a whole
+// iteration of arithmetic inside the same warp.
+template <int KIND, int MODE>
+__device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&m)[8], int base0, int niter, int s,
+                                              int x_first, unsigned mask)
+{
+    constexpr int R = GEO_ROWS_PER_THREAD;
+    const uint32_t *__restrict__ src = F.src;
+    const unsigned W = (unsigned)F.W, H = (unsigned)F.H;
+    const unsigned npx_src = W * H;  // < 2^31 (checked on the host)
+    const int oH = F.oH;
+
+    // x-only terms, shared by every row this thread touches
+    double xs[4], ax0[4], ax1[4], ax2[4], rcx[4];
+    unsigned col_bad = 0;  // MODE 3: columns whose denominator is outside the trusted exponent range
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        xs[k] = (double)(F.xOff + x_first + k);
+        if (KIND == 1) {
+            ax0[k] = __dmul_rn(m[0], xs[k]);
+            ax1[k] = __dmul_rn(m[3], xs[k]);
+            ax2[k] = (MODE == 2) ? 0.0 : __dmul_rn(m[6], xs[k]);
+            if (MODE == 3) {
+                // h7 == 0: h7*y is a signed zero, so the reference's denominator (h6*x + h7*y) + 1 equals
+                // (h6*x) + 1 bit for bit on every row -> one reciprocal per column instead of one per pixel
+                const double dn = __dadd_rn(ax2[k], 1.0);
+                rcx[k] = rcp_newton1(dn);
+                const unsigned de = ((unsigned)__double2hiint(dn) & 0x7FF00000u) - (523u << 20);
+                col_bad |= (de > (1000u << 20)) ? (0x11111111u << k) : 0u;
+            }
+        }
+    }
+
+    uint32_t px[R][4];       // stage C operands (gathers in flight)
+    unsigned idx[R][4];      // stage B operands (flat indices of the previous group)
+    unsigned redo_bits = 0;  // pixels of the previous group whose quotient must be resolved exactly
+    int base_px = -1, base_idx = -1;
+    const long long row_pitch = (long long)F.oW;
+
+#pragma unroll 1
+    for (int it = 0;; ++it) {
+        // ---- C: store group it-2
+        if (base_px >= 0) {
+            uint32_t *dst = F.out + ((long long)base_px * row_pitch + x_first);
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                if (base_px + s * j < oH) {
+                    if (mask == 0xFu) {
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(px[j][0], px[j][1], px[j][2], px[j][3]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (mask & (1u << k)) dst[k] = px[j][k];
+                    }
+                }
+                dst += (long long)s * row_pitch;
+            }
+            base_px = -1;
+        }
+        // ---- B: gathers of group it-1
+        if (base_idx >= 0) {
+            if (KIND == 1 && MODE != 2 && redo_bits) {
+                // k is static; every lane walks ITS flagged rows of column k, lanes side by side
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    unsigned rows = (redo_bits >> k) & 0x11111111u;
+                    while (rows) {
+                        const int j = (__ffs((int)rows) - 1) >> 2;
+                        rows &= rows - 1;
+                        const double y = (double)(F.yOff + base_idx + s * j);
+                        const double nx = __dadd_rn(__dadd_rn(ax0[k], __dmul_rn(m[1], y)), m[2]);
+                        const double ny = __dadd_rn(__dadd_rn(ax1[k], __dmul_rn(m[4], y)), m[5]);
+                        const double dn = __dadd_rn(__dadd_rn(ax2[k], __dmul_rn(m[7], y)), 1.0);
+                        const unsigned f = decode_flat(exact_quotient_magic(nx, dn), exact_quotient_magic(ny, dn), W, H,
+                                                       npx_src);
+#pragma unroll
+                        for (int jj = 0; jj < R; ++jj)
+                            if (jj == j) idx[jj][k] = f;  // select, no dynamic register indexing
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) px[j][k] = ldg_or_zero(src, idx[j][k]);
+            base_px = base_idx;
+            base_idx = -1;
+        }
+        // ---- A: arithmetic of group it
+        const int base = base0 + it * GEO_GROUP_ROWS;
+        if (it < niter && base < oH) {
+            redo_bits = (MODE == 3) ? col_bad : 0u;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const double y = (double)(F.yOff + base + s * j);
+                double r0, r1, r2 = 0.0;
+                if (KIND == 0) {
+                    r0 = __dmul_rn(m[2], y);
+                    r1 = __dmul_rn(m[3], y);
+                } else {
+                    r0 = __dmul_rn(m[1], y);
+                    r1 = __dmul_rn(m[4], y);
+                    if (MODE != 2) r2 = __dmul_rn(m[7], y);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double tx, ty;
+                    if (KIND == 0) {
+                        tx = __dadd_rd(affine_coord_exact(m[0], xs[k], r0, m[4]), HG_MAGIC);
+                        ty = __dadd_rd(affine_coord_exact(m[1], xs[k], r1, m[5]), HG_MAGIC);
+                    } else {
+                        const double nx = __dadd_rn(__dadd_rn(ax0[k], r0), m[2]);
+                        const double ny = __dadd_rn(__dadd_rn(ax1[k], r1), m[5]);
+                        if (MODE == 2) {
+                            // denominator is exactly 1: n / 1 = n, no approximation anywhere
+                            tx = __dadd_rd(nx, HG_MAGIC);
+                            ty = __dadd_rd(ny, HG_MAGIC);
+                        } else if (MODE == 3) {
+                            tx = __fma_rn(nx, rcx[k], HG_MAGIC);
+                            ty = __fma_rn(ny, rcx[k], HG_MAGIC);
+                            const bool again = near_half_multiple((unsigned)__double2loint(tx)) |
+                                               near_half_multiple((unsigned)__double2loint(ty));
+                            redo_bits |= again ? (1u << (4 * j + k)) : 0u;
+                        } else {
+                            const double dn = __dadd_rn(__dadd_rn(ax2[k], r2), 1.0);
+                            const double rc = rcp_newton1(dn);
+                            tx = __fma_rn(nx, rc, HG_MAGIC);
+                            ty = __fma_rn(ny, rc, HG_MAGIC);
+                            bool again = near_half_multiple((unsigned)__double2loint(tx)) |
+                                         near_half_multiple((unsigned)__double2loint(ty));
+                            if (MODE == 0) {
+                                // |dn| outside [2^-500, 2^500], or 0 / Inf / NaN: reciprocal not trusted
+                                const unsigned de = ((unsigned)__double2hiint(dn) & 0x7FF00000u) - (523u << 20);
+                                again |= de > (1000u << 20);
+                            }
+                            redo_bits |= again ? (1u << (4 * j + k)) : 0u;
+                        }
+                    }
+                    idx[j][k] = decode_flat(tx, ty, W, H, npx_src);
+                }
+            }
+            base_idx = base;
+        } else if (base_px < 0) {
+            break;  // nothing left in any stage
+        }
+    }
+}
 
 template <int KIND>
-__global__ void __launch_bounds__(256) warp_inverse_geo_kernel(const GeoParams P)
+__global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB) warp_inverse_geo_kernel(const GeoParams P)
 {
     const GeoFrame F = P.many ? P.many[blockIdx.y] : P.one;
-    const long long npix = (long long)F.oW * F.oH;
-    const long long nquad = (npix + 3) >> 2;
-    const long long npx_src = (long long)F.W * F.H;
-
     double m[8];
     if (P.mats_dev) {
         if (KIND == 0) {
             const float *mf = (const float *)P.mats_dev + 6 * (size_t)blockIdx.y;
 #pragma unroll
             for (int k = 0; k < 6; ++k) m[k] = (double)__ldg(mf + k);
+            m[6] = m[7] = 0.0;
         } else {
             const double *md = (const double *)P.mats_dev + 8 * (size_t)blockIdx.y;
 #pragma unroll
@@ -86,79 +305,38 @@ __global__ void __launch_bounds__(256) warp_inverse_geo_kernel(const GeoParams P
         for (int k = 0; k < 8; ++k) m[k] = P.mat_val[k];
     }
 
-    const uint32_t *__restrict__ src = F.src;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += stride) {
-        const long long p0 = q << 2;
-        int yy = (int)(p0 / F.oW);
-        int xx = (int)(p0 - (long long)yy * F.oW);
-        uint32_t px[4];
-        // row-constant terms (recomputed when the quad crosses a row end)
-        double y = (double)(F.yOff + yy);
-        double r0, r1, r2;
-        if (KIND == 0) {
-            r0 = __dmul_rn(m[2], y);
-            r1 = __dmul_rn(m[3], y);
-            r2 = 0.0;
-        } else {
-            r0 = __dmul_rn(m[1], y);
-            r1 = __dmul_rn(m[4], y);
-            r2 = __dmul_rn(m[7], y);
-        }
+    const int oW = F.oW, oH = F.oH;
+    const int tiles_x = geo_tiles_x(oW);
+    const int tile_y = blockIdx.x / tiles_x;
+    const int tile_x = blockIdx.x - tile_y * tiles_x;
+    const int row0 = tile_y * (GEO_GROUP_ROWS * P.niter);
+    if (row0 >= oH) return;  // grid is sized for the largest frame of the batch
+
+    // rows with equal flat alignment repeat with period s = 4 / gcd(oW mod 4, 4)
+    const int sl = (oW & 3) == 0 ? 0 : ((oW & 1) ? 2 : 1);  // log2(s)
+    const int s = 1 << sl;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int base = row0 + (ty >> sl) * (s * GEO_ROWS_PER_THREAD) + (ty & (s - 1));
+    if (base >= oH) return;
+    const int shift = (int)(((unsigned)base * (unsigned)oW) & 3u);
+    const int x_first = 4 * (tile_x * GEO_TILE_QUADS + tx) - shift;
+    if (x_first >= oW) return;
+    unsigned mask = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t v = 0u;
-            if (p0 + k < npix) {
-                const double x = (double)(F.xOff + xx);
-                if (KIND == 0) {
-                    const double sx = affine_coord_exact(m[0], x, r0, m[4]);
-                    const double sy = affine_coord_exact(m[1], x, r1, m[5]);
-                    const FloorHalf fx = floor_half_exact(sx);
-                    const FloorHalf fy = floor_half_exact(sy);
-                    if (fx.ok && fy.ok && (unsigned)fx.ipart < (unsigned)F.W && (unsigned)fy.ipart < (unsigned)F.H)
-                        v = fetch_src(src, F.W, npx_src, fx, fy);
-                } else {
-                    const double nx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), r0), m[2]);
-                    const double ny = __dadd_rn(__dadd_rn(__dmul_rn(m[3], x), r1), m[5]);
-                    const double dn = __dadd_rn(__dadd_rn(__dmul_rn(m[6], x), r2), 1.0);
-                    // fast quotients
-                    const double rc = rcp_newton(dn);
-                    bool nearx, neary;
-                    FloorHalf fx = floor_half_approx(__dmul_rn(nx, rc), HG_NEAR_DELTA, nearx);
-                    FloorHalf fy = floor_half_approx(__dmul_rn(ny, rc), HG_NEAR_DELTA, neary);
-                    // |dn| outside [2^-500, 2^500] (or 0 / Inf / NaN): the reciprocal is not trusted
-                    const unsigned de = ((unsigned)__double2hiint(dn) >> 20) & 0x7FFu;
-                    const bool d_bad = (de - 523u) > 1000u;
-                    if (d_bad || (fx.ok && nearx) || (fy.ok && neary)) {
-                        fx = floor_half_exact(__ddiv_rn(nx, dn));  // exact path == the reference
-                        fy = floor_half_exact(__ddiv_rn(ny, dn));
-                    }
-                    if (fx.ok && fy.ok && (unsigned)fx.ipart < (unsigned)F.W && (unsigned)fy.ipart < (unsigned)F.H)
-                        v = fetch_src(src, F.W, npx_src, fx, fy);
-                }
-                if (++xx == F.oW) {  // next pixel starts a new output row
-                    xx = 0;
-                    ++yy;
-                    y = (double)(F.yOff + yy);
-                    if (KIND == 0) {
-                        r0 = __dmul_rn(m[2], y);
-                        r1 = __dmul_rn(m[3], y);
-                    } else {
-                        r0 = __dmul_rn(m[1], y);
-                        r1 = __dmul_rn(m[4], y);
-                        r2 = __dmul_rn(m[7], y);
-                    }
-                }
-            }
-            px[k] = v;
-        }
-        if (p0 + 3 < npix) {
-            *reinterpret_cast<uint4 *>(F.out + p0) = make_uint4(px[0], px[1], px[2], px[3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (p0 + k < npix) F.out[p0 + k] = px[k];
-        }
+    for (int k = 0; k < 4; ++k)
+        if (x_first + k >= 0 && x_first + k < oW) mask |= 1u << k;
+
+    if (KIND == 0) {
+        geo_tile_body<0, 0>(F, m, base, P.niter, s, x_first, mask);
+    } else {
+        // CTA-uniform mode from the matrix and the frame window
+        const double ax = fmax(fabs((double)F.xOff), fabs((double)F.xOff + (double)oW));
+        const double ay = fmax(fabs((double)F.yOff), fabs((double)F.yOff + (double)oH));
+        const double spread = fabs(m[6]) * ax + fabs(m[7]) * ay;  // |h6 x + h7 y| <= spread (+ rounding)
+        if (m[6] == 0.0 && m[7] == 0.0) geo_tile_body<1, 2>(F, m, base, P.niter, s, x_first, mask);
+        else if (m[7] == 0.0) geo_tile_body<1, 3>(F, m, base, P.niter, s, x_first, mask);
+        else if (spread < 0.75) geo_tile_body<1, 1>(F, m, base, P.niter, s, x_first, mask);
+        else geo_tile_body<1, 0>(F, m, base, P.niter, s, x_first, mask);
     }
 }
 

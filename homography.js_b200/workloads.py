@@ -24,6 +24,25 @@ def projective_1080p():
                 x_off=192, y_off=0, o_w=1728, o_h=1080)
 
 
+def projective_1080p_generic():
+    """Diagnostic twin of config 2 with "un-nice" destination points (no coordinate lands exactly on a pixel
+    boundary, and the perspective has both an x and a y component)."""
+    wl = projective_1080p()
+    wl = dict(wl)
+    wl["dst"] = wl["dst"] + np.array([0.37, 0.11, -0.23, 0.41, 0.19, -0.31, -0.13, 0.29])
+    wl["name"] = "projective 4-point warp (generic points), 1920x1080 RGBA8 -> 1728x1080 window"
+    return wl
+
+
+def affine_1080p():
+    """Affine variant of config 2 (same frame and output window sizes): dst = [[w/10,0],[w/10,h],[w,0]]."""
+    w, h = 1920, 1080
+    src = np.array([0, 0, 0, h, w, 0], np.float64)
+    dst = np.array([w / 10, 0, w / 10, h, w, 0], np.float64)
+    return dict(name="affine 3-point warp, 1920x1080 RGBA8 -> 1728x1080", kind=0, W=w, H=h, src=src, dst=dst,
+                x_off=192, y_off=0, o_w=1728, o_h=1080)
+
+
 def affine_256():
     """Config 1: affine 3-point warp, 256x256 (benchmark.js:204-205 shape)."""
     w = h = 256

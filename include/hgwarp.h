@@ -142,6 +142,11 @@ int hg_warp_inverse_batch(hg_ctx *ctx, int kind, const void *inv_matrices, const
 int hg_warp_piecewise_inverse_batch(hg_ctx *ctx, const float *dst_pts, const hg_frame *frames, int n_frames,
                                     int min_src_x, int min_src_y);
 
+/* ------------------------------------------------------------------ diagnostics */
+/* max over all 2^20 high-mantissa patterns (x 6 low words) of |1 - d*r|, r = the reciprocal the projective
+ * fast path uses (MUFU.RCP64H + one Newton step), for doubles with the given biased exponent / sign */
+int hg_debug_rcp_max_error(hg_ctx *ctx, int biased_exponent, int negative, double *max_rel_err);
+
 /* ------------------------------------------------------------------ device memory helpers (benchmarks / bindings) */
 int hg_dev_alloc(hg_ctx *ctx, size_t bytes, void **dev_ptr);
 int hg_dev_free(hg_ctx *ctx, void *dev_ptr);

@@ -1,0 +1,75 @@
+"""Numerical guarantees the fast projective path relies on, measured on the device."""
+import numpy as np
+import pytest
+
+import homography_js_b200 as hg
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_newton_reciprocal_error_bound_exhaustive(ctx):
+    """warp_geo.cuh trusts quotients unless they are within 2^-20 of a multiple of 0.5; for coordinates below
+    2^16 that needs a reciprocal with relative error < 2^-36.  Exhaustive over the 2^20 mantissa patterns the
+    MUFU reads, for exponents across the guarded range [2^-500, 2^500] and both signs."""
+    worst = 0.0
+    for e in (1023, 1022, 1024, 1023 - 499, 1023 + 499, 900, 1100, 1, 2046 - 1):
+        for neg in (False, True):
+            if e in (1, 2045):
+                continue  # outside the guarded range: the kernel never uses the fast path there
+            err = ctx.debug_rcp_max_error(e, neg)
+            assert err == err, "NaN residual"
+            worst = max(worst, err)
+    print(f"max |1 - d*rcp| = {worst:.3e} = 2^{np.log2(worst):.1f}")
+    assert worst < 2.0 ** -38
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_projective_quotients_on_decision_boundaries(ctx, seed):
+    """Matrices built so that MANY quotients land exactly on k and k+0.5 with a non-trivial denominator
+    (denominator = 2^-j or 3/2^j on whole rows): every such pixel must take the exact-division path."""
+    rng = np.random.default_rng(900 + seed)
+    W, H = 96, 64
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    ctx.image_set(img, W, H)
+    d0 = [0.5, 0.25, 0.75, 1.5, 2.0, 0.375][seed]
+    # x' = (a x + c) / (g y + d0), y' = (b y + f) / (g y + d0) scaled so the "+1" of the reference form holds
+    g = [0.0, 1 / 64, -1 / 128, 1 / 32, 0.0, 1 / 16][seed]
+    h = np.array([0.5 / d0, 0, 1.0 / d0, 0, 0.25 / d0, 0.5 / d0, 0, g / d0], np.float64)
+    # reference form has denominator h6 x + h7 y + 1: divide everything by d0 already done above
+    got = ctx.warp_inverse_matrix(h, -4, -4, 220, 150)
+    want = O.warp_inverse_geometric(img, W, H, h, -4, -4, 220, 150)
+    assert np.array_equal(got, want)
+
+
+def test_many_random_projective_matrices_small(ctx):
+    """Differential test over 150 random homographies (incl. strong perspective) on a small image."""
+    rng = np.random.default_rng(77)
+    W, H = 53, 41
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    ctx.image_set(img, W, H)
+    for k in range(150):
+        s = np.array([0, 0, 0, H, W, 0, W, H], np.float64)
+        d = s + rng.uniform(-0.45, 0.45, 8) * max(W, H)
+        inv = O.projective_from_squares(d, s)
+        oW, oH = int(rng.integers(1, 90)), int(rng.integers(1, 70))
+        xo, yo = int(rng.integers(-20, 10)), int(rng.integers(-20, 10))
+        got = ctx.warp_inverse_matrix(inv, xo, yo, oW, oH)
+        want = O.warp_inverse_geometric(img, W, H, inv, xo, yo, oW, oH)
+        assert np.array_equal(got, want), k
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_projective_x_only_denominator_mode(ctx, seed):
+    """h7 == 0 (denominator a function of x only) takes the per-column reciprocal path; includes columns where
+    the denominator crosses zero (horizon inside the window) and -0.0 as h7."""
+    rng = np.random.default_rng(600 + seed)
+    W, H = 120, 90
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    ctx.image_set(img, W, H)
+    h6 = [1e-3, -2e-3, 1 / 64, -1 / 50, 3e-4][seed]
+    h = np.array([rng.uniform(0.5, 1.5), rng.uniform(-0.2, 0.2), rng.uniform(-10, 10),
+                  rng.uniform(-0.2, 0.2), rng.uniform(0.5, 1.5), rng.uniform(-10, 10), h6, -0.0 if seed % 2 else 0.0])
+    got = ctx.warp_inverse_matrix(h, -30, -20, 260, 170)
+    want = O.warp_inverse_geometric(img, W, H, h, -30, -20, 260, 170)
+    assert np.array_equal(got, want)
