@@ -26,6 +26,7 @@ SYMBOLS = [
     "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_build_index_map",
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
+    "hg_pipe_create", "hg_pipe_submit", "hg_pipe_wait", "hg_pipe_flush", "hg_pipe_destroy",
     "hg_debug_rcp_max_error",
     "hg_dev_alloc", "hg_dev_free", "hg_host_alloc_pinned", "hg_host_free_pinned",
     "hg_memcpy_h2d", "hg_memcpy_d2h", "hg_output_device",
@@ -88,6 +89,11 @@ def load():
     L.hg_warp_piecewise_forward.argtypes = [vp, vp, i, i, i, i, i, i, i, i, i, vp, vp]
     L.hg_warp_inverse_batch.argtypes = [vp, i, vp, C.POINTER(HgFrame), i]
     L.hg_warp_piecewise_inverse_batch.argtypes = [vp, vp, C.POINTER(HgFrame), i, i, i]
+    L.hg_pipe_create.argtypes = [vp, i, i, i, i, i, i, C.POINTER(vp)]
+    L.hg_pipe_submit.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, C.POINTER(C.c_uint64)]
+    L.hg_pipe_wait.argtypes = [vp, C.c_uint64]
+    L.hg_pipe_flush.argtypes = [vp]
+    L.hg_pipe_destroy.argtypes = [vp]
     L.hg_debug_rcp_max_error.argtypes = [vp, i, i, C.POINTER(d)]
     L.hg_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.hg_dev_free.argtypes = [vp, vp]
@@ -321,6 +327,43 @@ class Context:
         d = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(-1)
         arr = (HgFrame * len(frames))(*frames)
         self._ck(self.L.hg_warp_piecewise_inverse_batch(self.h, _ptr(d), arr, len(frames), min_src_x, min_src_y))
+
+
+class Pipe:
+    """hg_pipe: pipelined host-to-host stream of independent inverse warps (video use case)."""
+
+    def __init__(self, ctx: Context, kind: int, src_w: int, src_h: int, max_out_w: int, max_out_h: int, depth: int = 3):
+        self.ctx, self.L = ctx, ctx.L
+        h = C.c_void_p()
+        ctx._ck(self.L.hg_pipe_create(ctx.h, kind, src_w, src_h, max_out_w, max_out_h, depth, C.byref(h)))
+        self.h = h
+        self.npts = 6 if kind == HG_AFFINE else 8
+
+    def submit(self, rgba_host_ptr: int, dst_pts, src_pts, x_off, y_off, o_w, o_h, out_host_ptr: int) -> int:
+        d = np.ascontiguousarray(dst_pts, dtype=np.float64).reshape(-1)
+        s = np.ascontiguousarray(src_pts, dtype=np.float64).reshape(-1)
+        assert d.size == self.npts and s.size == self.npts
+        t = C.c_uint64()
+        self.ctx._ck(self.L.hg_pipe_submit(self.h, rgba_host_ptr, d.ctypes.data, s.ctypes.data, x_off, y_off, o_w, o_h,
+                                           out_host_ptr, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int):
+        self.ctx._ck(self.L.hg_pipe_wait(self.h, ticket))
+
+    def flush(self):
+        self.ctx._ck(self.L.hg_pipe_flush(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hg_pipe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def device_count() -> int:

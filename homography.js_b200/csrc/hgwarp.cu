@@ -811,6 +811,169 @@ int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *, const hg_frame *, 
     return fail(c, HG_ERR_UNSUPPORTED, "batched piecewise warp is not built yet");
 }
 
+
+/* ------------------------------------------------------------------ pipelined host-to-host stream */
+struct hg_pipe_slot {
+    void *d_src = nullptr, *d_out = nullptr;
+    char *d_small = nullptr;  // 256 B device scratch: [0,64) dst pts, [64,128) src pts, [128,192) matrix
+    char *h_small = nullptr;  // 128 B pinned staging for the points
+    cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+    bool busy = false;
+};
+
+struct hg_pipe {
+    hg_ctx *c = nullptr;
+    int kind = 0, W = 0, H = 0, max_ow = 0, max_oh = 0, depth = 0;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    std::vector<hg_pipe_slot> slots;
+    uint64_t next = 0;
+};
+
+int hg_pipe_create(hg_ctx *c, int kind, int src_w, int src_h, int max_out_w, int max_out_h, int depth, hg_pipe **out)
+{
+    BIND(c);
+    NEED(c, out, "out is NULL");
+    *out = nullptr;
+    NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
+    NEED(c, depth >= 1 && depth <= 16, "depth must be in [1,16]");
+    TRY(check_image_dims(c, src_w, src_h));
+    TRY(check_window(c, 0, 0, max_out_w, max_out_h));
+    hg_pipe *p = new hg_pipe();
+    p->c = c;
+    p->kind = kind;
+    p->W = src_w;
+    p->H = src_h;
+    p->max_ow = max_out_w;
+    p->max_oh = max_out_h;
+    p->depth = depth;
+    p->slots.resize((size_t)depth);
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; return r == cudaSuccess; };
+    ok(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&p->s_k, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    for (auto &sl : p->slots) {
+        ok(cudaMalloc(&sl.d_src, (size_t)src_w * src_h * 4));
+        ok(cudaMalloc(&sl.d_out, (size_t)max_out_w * max_out_h * 4));
+        ok(cudaMalloc((void **)&sl.d_small, 256));
+        ok(cudaHostAlloc((void **)&sl.h_small, 128, cudaHostAllocDefault));
+        ok(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
+        ok(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        hg_pipe_destroy(p);
+        return fail(c, e == cudaErrorMemoryAllocation ? HG_ERR_NOMEM : HG_ERR_CUDA, "hg_pipe_create: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return HG_OK;
+}
+
+int hg_pipe_destroy(hg_pipe *p)
+{
+    if (!p) return HG_ERR_INVALID;
+    cudaSetDevice(p->c->device);
+    if (p->s_in) cudaStreamSynchronize(p->s_in);
+    if (p->s_k) cudaStreamSynchronize(p->s_k);
+    if (p->s_out) cudaStreamSynchronize(p->s_out);
+    for (auto &sl : p->slots) {
+        if (sl.d_src) cudaFree(sl.d_src);
+        if (sl.d_out) cudaFree(sl.d_out);
+        if (sl.d_small) cudaFree(sl.d_small);
+        if (sl.h_small) cudaFreeHost(sl.h_small);
+        if (sl.in_done) cudaEventDestroy(sl.in_done);
+        if (sl.k_done) cudaEventDestroy(sl.k_done);
+        if (sl.out_done) cudaEventDestroy(sl.out_done);
+    }
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_k) cudaStreamDestroy(p->s_k);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
+    delete p;
+    return HG_OK;
+}
+
+int hg_pipe_submit(hg_pipe *p, const uint8_t *rgba_host, const double *dst_pts, const double *src_pts, int x_off,
+                   int y_off, int o_w, int o_h, uint8_t *out_host, uint64_t *ticket)
+{
+    if (!p) return HG_ERR_INVALID;
+    hg_ctx *c = p->c;
+    BIND(c);
+    NEED(c, rgba_host && dst_pts && src_pts && out_host, "NULL argument");
+    TRY(check_window(c, x_off, y_off, o_w, o_h));
+    if (o_w > p->max_ow || o_h > p->max_oh || (long long)o_w * o_h > (long long)p->max_ow * p->max_oh)
+        return fail(c, HG_ERR_INVALID, "output %dx%d exceeds the pipe's maximum %dx%d", o_w, o_h, p->max_ow, p->max_oh);
+    hg_pipe_slot &sl = p->slots[(size_t)(p->next % (uint64_t)p->depth)];
+    if (sl.busy) CU(c, cudaEventSynchronize(sl.out_done));  // the slot's previous frame has left the device
+    const size_t pb = p->kind == HG_AFFINE ? 48 : 64;
+    memcpy(sl.h_small, dst_pts, pb);       // inverse matrix = calculateTransformMatrix(kind, dst, src) (H.js:994)
+    memcpy(sl.h_small + 64, src_pts, pb);
+    // copy-in stream: image + points
+    CU(c, cudaMemcpyAsync(sl.d_src, rgba_host, (size_t)p->W * p->H * 4, cudaMemcpyHostToDevice, p->s_in));
+    CU(c, cudaMemcpyAsync(sl.d_small, sl.h_small, 128, cudaMemcpyHostToDevice, p->s_in));
+    CU(c, cudaEventRecord(sl.in_done, p->s_in));
+    // compute stream: solve + pixel loop
+    CU(c, cudaStreamWaitEvent(p->s_k, sl.in_done, 0));
+    SolveArgs a{};
+    a.src = (const double *)sl.d_small;
+    a.dst = (const double *)(sl.d_small + 64);
+    a.out_f = (float *)(sl.d_small + 128);
+    a.out_d = (double *)(sl.d_small + 128);
+    a.n = 1;
+    a.op = p->kind == HG_AFFINE ? 0 : 1;
+    solve_kernel<<<1, 64, 0, p->s_k>>>(a);
+    GeoParams P{};
+    P.one.src = (const uint32_t *)sl.d_src;
+    P.one.out = (uint32_t *)sl.d_out;
+    P.one.W = p->W;
+    P.one.H = p->H;
+    P.one.xOff = x_off;
+    P.one.yOff = y_off;
+    P.one.oW = o_w;
+    P.one.oH = o_h;
+    P.many = nullptr;
+    P.mats_dev = sl.d_small + 128;
+    P.niter = pick_niter(c, o_w, o_h, 1);
+    dim3 grid((unsigned)(geo_tiles_x(o_w) * geo_tiles_y(o_h, P.niter)), 1);
+    if (p->kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, 0, p->s_k>>>(P);
+    else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, 0, p->s_k>>>(P);
+    c->launches += 2;
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(sl.k_done, p->s_k));
+    // copy-out stream
+    CU(c, cudaStreamWaitEvent(p->s_out, sl.k_done, 0));
+    CU(c, cudaMemcpyAsync(out_host, sl.d_out, (size_t)o_w * o_h * 4, cudaMemcpyDeviceToHost, p->s_out));
+    CU(c, cudaEventRecord(sl.out_done, p->s_out));
+    sl.busy = true;
+    if (ticket) *ticket = p->next;
+    p->next++;
+    return HG_OK;
+}
+
+int hg_pipe_wait(hg_pipe *p, uint64_t ticket)
+{
+    if (!p) return HG_ERR_INVALID;
+    hg_ctx *c = p->c;
+    BIND(c);
+    NEED(c, ticket < p->next, "unknown ticket");
+    if (ticket + (uint64_t)p->depth < p->next) return HG_OK;  // its slot was already recycled, i.e. completed
+    hg_pipe_slot &sl = p->slots[(size_t)(ticket % (uint64_t)p->depth)];
+    if (sl.busy) CU(c, cudaEventSynchronize(sl.out_done));
+    return HG_OK;
+}
+
+int hg_pipe_flush(hg_pipe *p)
+{
+    if (!p) return HG_ERR_INVALID;
+    hg_ctx *c = p->c;
+    BIND(c);
+    CU(c, cudaStreamSynchronize(p->s_out));
+    CU(c, cudaStreamSynchronize(p->s_k));
+    CU(c, cudaStreamSynchronize(p->s_in));
+    for (auto &sl : p->slots) sl.busy = false;
+    return HG_OK;
+}
+
 /* ------------------------------------------------------------------ diagnostics */
 int hg_debug_rcp_max_error(hg_ctx *c, int biased_exponent, int negative, double *max_rel_err)
 {

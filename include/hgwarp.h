@@ -142,6 +142,18 @@ int hg_warp_inverse_batch(hg_ctx *ctx, int kind, const void *inv_matrices, const
 int hg_warp_piecewise_inverse_batch(hg_ctx *ctx, const float *dst_pts, const hg_frame *frames, int n_frames,
                                     int min_src_x, int min_src_y);
 
+/* ------------------------------------------------------------------ pipelined host-to-host stream (video) */
+/* Independent frames arriving in HOST memory (pinned for full overlap) and leaving to HOST memory: up to `depth`
+ * frames in flight, H2D of frame i+1, solve+warp of frame i and D2H of frame i-1 overlap on three CUDA streams.
+ * Each submit is _inverseGeometricWarp (H.js:987) for its own image and its own point sets. */
+typedef struct hg_pipe hg_pipe;
+int hg_pipe_create(hg_ctx *ctx, int kind, int src_w, int src_h, int max_out_w, int max_out_h, int depth, hg_pipe **out);
+int hg_pipe_submit(hg_pipe *pipe, const uint8_t *rgba_host, const double *dst_pts, const double *src_pts, int x_off,
+                   int y_off, int o_w, int o_h, uint8_t *out_host, uint64_t *ticket);
+int hg_pipe_wait(hg_pipe *pipe, uint64_t ticket); /* returns once that frame's out_host is complete */
+int hg_pipe_flush(hg_pipe *pipe);                 /* returns once every submitted frame is complete */
+int hg_pipe_destroy(hg_pipe *pipe);
+
 /* ------------------------------------------------------------------ diagnostics */
 /* max over all 2^20 high-mantissa patterns (x 6 low words) of |1 - d*r|, r = the reciprocal the projective
  * fast path uses (MUFU.RCP64H + one Newton step), for doubles with the given biased exponent / sign */

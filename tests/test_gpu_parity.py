@@ -344,3 +344,26 @@ def test_unsupported_and_state_errors(ctx):
     with pytest.raises(hg.HgError):
         c2.warp_inverse_matrix(np.array([1, 0, 0, 1, 0, 0], np.float32), 0, 0, 0, 4)
     c2.close()
+
+
+def test_pipelined_host_stream_matches_oracle(ctx):
+    """hg_pipe_*: independent frames, each with its own image and its own points, more frames than slots."""
+    rng = np.random.default_rng(71)
+    W, H = 200, 150
+    pipe = hg.Pipe(ctx, hg._abi.HG_PROJECTIVE, W, H, 400, 300, depth=3)
+    n = 8
+    imgs = [_rand_img(80 + k, W, H) for k in range(n)]
+    outs, wants = [], []
+    for k in range(n):
+        s = np.array([0, 0, 0, H, W, 0, W, H], np.float64)
+        d = s + rng.uniform(-0.15, 0.15, 8) * W
+        xo, yo, oW, oH = [int(v) for v in O.transform_limits(O.projective_from_squares(s, d), W, H)]
+        oW, oH = min(oW, 400), min(oH, 300)
+        out = np.zeros(oW * oH * 4, np.uint8)
+        outs.append(out)
+        pipe.submit(imgs[k].ctypes.data, d, s, xo, yo, oW, oH, out.ctypes.data)
+        wants.append(O.warp_inverse_geometric(imgs[k], W, H, O.projective_from_squares(d, s), xo, yo, oW, oH))
+    pipe.flush()
+    for k in range(n):
+        assert _diff(outs[k], wants[k]) == 0, k
+    pipe.close()
