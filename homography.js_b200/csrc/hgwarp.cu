@@ -15,6 +15,7 @@
 #include "solve.cuh"
 #include "warp_geo.cuh"
 #include "diag.cuh"
+#include "forward.cuh"
 
 using namespace hg;
 
@@ -55,7 +56,7 @@ struct hg_ctx {
     void *pinned = nullptr;  // 4 KiB pinned host mirror
 
     // mesh
-    DevBuf src_pts, dst_pts, tris, rec, map32, map16, frames, mats;
+    DevBuf src_pts, dst_pts, tris, rec, map32, map16, frames, mats, winner;
     int n_pts = 0, n_tris = 0;
     long long map_len = 0;  // length of the map currently in map32 (for the aliasing forward read)
 };
@@ -313,7 +314,7 @@ int hg_ctx_destroy(hg_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->img_own, &c->out, &c->scratch, &c->src_pts, &c->dst_pts, &c->tris,
-                      &c->rec, &c->map32, &c->map16, &c->frames, &c->mats};
+                      &c->rec, &c->map32, &c->map16, &c->frames, &c->mats, &c->winner};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -581,9 +582,52 @@ int hg_warp_inverse_points(hg_ctx *c, int kind, const double *dst_pts, const dou
     return warp_inverse_common(c, kind, nullptr, true, x_off, y_off, o_w, o_h, out_host, out_dev);
 }
 
-int hg_warp_forward_matrix(hg_ctx *c, int, const void *, int, int, int, int, uint8_t *, void *)
+static int run_forward(hg_ctx *c, FwdArgs &a, bool piecewise, uint32_t *dst, size_t bytes, uint8_t *out_host)
 {
-    return fail(c, HG_ERR_UNSUPPORTED, "forward scatter (_geometricWarp) is not built yet");
+    const long long npix = (long long)a.oW * a.oH;
+    TRY(ensure(c, c->winner, sizeof(int) * (size_t)npix));
+    CU(c, cudaMemsetAsync(c->winner.p, 0xFF, sizeof(int) * (size_t)npix, c->stream));
+    a.winner = (int *)c->winner.p;
+    a.out = dst;
+    const long long n = (long long)a.domW * a.domH;
+    if (n > 0) {
+        long long blocks = (n + 255) / 256;
+        if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
+        if (piecewise) forward_scatter_kernel<true><<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+        else forward_scatter_kernel<false><<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    TRY(prof_begin(c));
+    forward_gather_kernel<<<grid_for(c, npix, 1), 256, 0, c->stream>>>(a);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    TRY(prof_end(c));
+    return finish_out(c, dst, bytes, out_host);
+}
+
+int hg_warp_forward_matrix(hg_ctx *c, int kind, const void *fwd_matrix, int x_off, int y_off, int o_w, int o_h,
+                           uint8_t *out_host, void *out_dev)
+{
+    BIND(c);
+    NEED(c, fwd_matrix, "fwd_matrix is NULL");
+    NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
+    if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
+    TRY(check_window(c, x_off, y_off, o_w, o_h));
+    const size_t bytes = (size_t)o_w * o_h * 4;
+    uint32_t *dst = nullptr;
+    TRY(pick_out(c, out_dev, bytes, &dst));
+    FwdArgs a{};
+    a.src = c->img;
+    a.kind = kind;
+    if (kind == HG_AFFINE)
+        for (int k = 0; k < 6; ++k) a.mat[k] = (double)((const float *)fwd_matrix)[k];
+    else
+        for (int k = 0; k < 8; ++k) a.mat[k] = ((const double *)fwd_matrix)[k];
+    a.W = c->W; a.H = c->H;
+    a.xOff = x_off; a.yOff = y_off; a.oW = o_w; a.oH = o_h;
+    a.minX = 0; a.minY = 0; a.domW = c->W; a.domH = c->H;  // for (y < H) for (x < W), H.js:919-920
+    return run_forward(c, a, false, dst, bytes, out_host);
 }
 
 int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const hg_frame *frames, int n_frames)
@@ -801,9 +845,42 @@ int hg_warp_piecewise_inverse(hg_ctx *c, const float *dst_pts, int x_off, int y_
     return finish_out(c, dst, bytes, out_host);
 }
 
-int hg_warp_piecewise_forward(hg_ctx *c, const float *, int, int, int, int, int, int, int, int, int, uint8_t *, void *)
+int hg_warp_piecewise_forward(hg_ctx *c, const float *dst_pts, int x_off, int y_off, int o_w, int o_h, int min_src_x,
+                              int min_src_y, int max_src_x, int max_src_y, int use_inverse_map, uint8_t *out_host,
+                              void *out_dev)
 {
-    return fail(c, HG_ERR_UNSUPPORTED, "forward scatter (_piecewiseAffineWarp) is not built yet");
+    BIND(c);
+    NEED(c, dst_pts, "dst_pts is NULL");
+    if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
+    if (c->n_pts == 0) return fail(c, HG_ERR_STATE, "no mesh set (hg_piecewise_set_mesh)");
+    TRY(check_window(c, x_off, y_off, o_w, o_h));
+    const long long dom_w = (long long)max_src_x - min_src_x, dom_h = (long long)max_src_y - min_src_y;
+    if (min_src_x > (1 << 18) || min_src_x < -(1 << 18) || min_src_y > (1 << 18) || min_src_y < -(1 << 18) ||
+        dom_w > 65536 || dom_h > 65536 || dom_w * dom_h >= (1LL << 31))
+        return fail(c, HG_ERR_UNSUPPORTED, "source-point bounding box outside the supported range");
+    TRY(check_points(c, dst_pts, c->n_pts, "dst_pts"));
+    const size_t bytes = (size_t)o_w * o_h * 4;
+    uint32_t *dst = nullptr;
+    TRY(pick_out(c, out_dev, bytes, &dst));
+    TRY(upload_dst_points(c, dst_pts, 1));
+    // forward matrices from (src, dst); edge equations of the SOURCE triangles for the forward map (H.js:817-832)
+    TRY(launch_setup(c, (const float *)c->dst_pts.p, (const float *)c->src_pts.p, nullptr, nullptr));
+    if (!use_inverse_map) {
+        const long long len = dom_w > 0 && dom_h > 0 ? dom_w * dom_h : 0;
+        TRY(launch_fill(c, (double)dom_w, (double)min_src_y, len));
+    }  // else: the map left in place by the last inverse warp / hg_build_index_map is read as is (H.js:957 aliasing)
+    FwdArgs a{};
+    a.src = c->img;
+    a.map32 = (const int *)c->map32.p;
+    a.map_len = c->map_len;
+    a.rec = (const TriRec *)c->rec.p;
+    a.n_tris = c->n_tris;
+    a.W = c->W; a.H = c->H;
+    a.xOff = x_off; a.yOff = y_off; a.oW = o_w; a.oH = o_h;
+    a.minX = min_src_x; a.minY = min_src_y;
+    a.domW = dom_w > 0 ? (int)dom_w : 0;
+    a.domH = dom_h > 0 ? (int)dom_h : 0;
+    return run_forward(c, a, true, dst, bytes, out_host);
 }
 
 int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *, const hg_frame *, int, int, int)

@@ -318,7 +318,7 @@ def test_config3_full_size_piecewise_4k(ctx):
 
 
 # ------------------------------------------------------------------ the class surface over CUDA
-@pytest.mark.parametrize("flow", flows.INVERSE_ONLY, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("flow", flows.ALL, ids=lambda f: f.__name__)
 def test_reference_test_page_flows_over_cuda(ctx, flow, golden):
     ref_res, ref = flow(lambda *a: RefHomography(*a), RefImageData(golden["src"].reshape(-1).copy(), 400, 400))
     got_res, got = flow(lambda *a: hg.Homography(*a, context=ctx), hg.ImageData(golden["src"].reshape(-1).copy(), 400, 400))
@@ -367,3 +367,58 @@ def test_pipelined_host_stream_matches_oracle(ctx):
     for k in range(n):
         assert _diff(outs[k], wants[k]) == 0, k
     pipe.close()
+
+
+# ------------------------------------------------------------------ forward scatter (A3 / A4)
+@pytest.mark.parametrize("seed", range(8))
+def test_forward_geometric_bit_exact(ctx, seed):
+    """_geometricWarp: last-writer-wins collisions (minification), wrapped / dropped writes (Q3)."""
+    rng = np.random.default_rng(500 + seed)
+    W, H = int(rng.integers(8, 200)), int(rng.integers(8, 200))
+    img = _rand_img(seed, W, H)
+    ctx.image_set(img, W, H)
+    ang = rng.uniform(0, 2 * math.pi)
+    sc = [1.0, 0.6, 1.7, 0.35, 1.0, 2.5, 0.9, 1.2][seed]
+    if seed in (0, 4):
+        fwd = np.array([1, 0, 0, 1, rng.integers(-30, 30), rng.integers(-30, 30)], np.float32)   # pure translation
+    else:
+        fwd = np.array([math.cos(ang) * sc, math.sin(ang) * sc, -math.sin(ang) * sc, math.cos(ang) * sc,
+                        rng.uniform(-40, 40), rng.uniform(-40, 40)], np.float32)
+    xo, yo = int(rng.integers(-20, 20)), int(rng.integers(-20, 20))
+    oW, oH = int(rng.integers(4, 260)), int(rng.integers(4, 260))
+    got = ctx.warp_forward_matrix(fwd, xo, yo, oW, oH)
+    want = O.warp_forward_geometric(img, W, H, fwd, xo, yo, oW, oH)
+    assert _diff(got, want) == 0
+
+
+def test_forward_geometric_projective_and_degenerate(ctx):
+    img = _rand_img(9, 60, 40)
+    ctx.image_set(img, 60, 40)
+    for fwd in (np.array([1.1, 0.05, 2.0, -0.03, 0.95, 1.0, 1e-3, -5e-4], np.float64),
+                np.full(6, np.nan, np.float32), np.array([1e9, 0, 0, 1, 0, 0], np.float32),
+                np.array([1, 0, 0, 1, 1e12, 0], np.float32)):
+        got = ctx.warp_forward_matrix(fwd, -5, -5, 90, 70)
+        want = O.warp_forward_geometric(img, 60, 40, fwd, -5, -5, 90, 70)
+        assert _diff(got, want) == 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_forward_piecewise_bit_exact(ctx, seed):
+    rng = np.random.default_rng(550 + seed)
+    W, H = 240, 180
+    img = _rand_img(70 + seed, W, H)
+    src, tris = _grid_mesh(6, 5, W, H)
+    if seed % 2:
+        src = (src + rng.uniform(-6, 6, src.shape)).astype(np.float32)   # bbox leaves the image: OOB source reads
+    dst = (src * rng.uniform(0.85, 1.0) + rng.uniform(-8, 8, src.shape) + 10).astype(np.float32)
+    mm = O.minmax_xy(dst)
+    xo, yo, oW, oH = int(mm[0]), int(mm[1]), int(mm[2] - mm[0]), int(mm[3] - mm[1])
+    smm = [int(v) for v in O.minmax_xy(src)]
+    ctx.image_set(img, W, H)
+    ctx.piecewise_set_mesh(src, tris)
+    got = ctx.warp_piecewise_forward(dst, xo, yo, oW, oH, smm[0], smm[1], smm[2], smm[3])
+    fwd = O.piecewise_matrices(src, dst, tris)
+    mw = smm[2] - smm[0]
+    fmap = O.build_index_map(src, tris, mw, smm[1], mw * (smm[3] - smm[1]))
+    want = O.warp_forward_piecewise(img, W, H, fmap, fwd, xo, yo, oW, oH, smm[0], smm[1], smm[2], smm[3])
+    assert _diff(got, want) == 0
