@@ -16,6 +16,7 @@
 #include "warp_geo.cuh"
 #include "diag.cuh"
 #include "forward.cuh"
+#include "piecewise_fused.cuh"
 
 using namespace hg;
 
@@ -57,6 +58,13 @@ struct hg_ctx {
 
     // mesh
     DevBuf src_pts, dst_pts, tris, rec, map32, map16, frames, mats, winner;
+    DevBuf invd, bin_cnt, bin_ent, fstatus, fframes;  // fused piecewise path
+    // parameters of the last inverse index map (rebuilt on demand for the aliasing forward read, Q8)
+    std::vector<float> last_inv_pts;
+    double last_inv_mw = 0, last_inv_yoff = 0;
+    long long last_inv_len = -1;
+    bool map32_current = false;
+    int force_general = 0;  // diagnostics: 1 = always use the map-based general path
     int n_pts = 0, n_tris = 0;
     long long map_len = 0;  // length of the map currently in map32 (for the aliasing forward read)
 };
@@ -314,7 +322,8 @@ int hg_ctx_destroy(hg_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->img_own, &c->out, &c->scratch, &c->src_pts, &c->dst_pts, &c->tris,
-                      &c->rec, &c->map32, &c->map16, &c->frames, &c->mats, &c->winner};
+                      &c->rec, &c->map32, &c->map16, &c->frames, &c->mats, &c->winner,
+                      &c->invd, &c->bin_cnt, &c->bin_ent, &c->fstatus, &c->fframes};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -793,6 +802,11 @@ int hg_build_index_map(hg_ctx *c, const float *pts, double map_width, double y_o
     TRY(upload_dst_points(c, pts, 1));
     TRY(launch_setup(c, nullptr, (const float *)c->dst_pts.p, nullptr, nullptr));
     TRY(launch_fill(c, map_width, y_offset, map_len));
+    c->last_inv_pts.assign(pts, pts + 2 * (size_t)c->n_pts);
+    c->last_inv_mw = map_width;
+    c->last_inv_yoff = y_offset;
+    c->last_inv_len = map_len;
+    c->map32_current = true;
     if (map_out_host && map_len > 0) {
         TRY(ensure(c, c->map16, sizeof(short) * (size_t)map_len));
         map32_to_int16_kernel<<<(unsigned)((map_len + 255) / 256), 256, 0, c->stream>>>((const int *)c->map32.p,
@@ -803,6 +817,104 @@ int hg_build_index_map(hg_ctx *c, const float *pts, double map_width, double y_o
     }
     CU(c, cudaStreamSynchronize(c->stream));
     return HG_OK;
+}
+
+struct PwFrameHost {
+    const uint32_t *src;
+    uint32_t *out;
+    int W, H, xOff, yOff, oW, oH;
+};
+
+// general (map-based) inverse piecewise warp of ONE frame whose destiny points are already on the device
+static int pw_inverse_general_frame(hg_ctx *c, const float *dst_dev, const PwFrameHost &f, int min_src_x, int min_src_y)
+{
+    TRY(launch_setup(c, dst_dev, dst_dev, nullptr, nullptr));
+    const long long map_len = (long long)f.oW * f.oH;
+    TRY(launch_fill(c, (double)f.oW, (double)f.yOff, map_len));
+    PwWarpArgs a{};
+    a.src = f.src;
+    a.out = f.out;
+    a.map32 = (const int *)c->map32.p;
+    a.rec = (const TriRec *)c->rec.p;
+    a.W = f.W; a.H = f.H;
+    a.xOff = f.xOff; a.yOff = f.yOff; a.oW = f.oW; a.oH = f.oH;
+    a.minSrcX = min_src_x; a.minSrcY = min_src_y;
+    a.n_tris = c->n_tris;
+    TRY(prof_begin(c));
+    pw_warp_inverse_kernel<<<grid_for(c, map_len, 1), 256, 0, c->stream>>>(a);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    TRY(prof_end(c));
+    return HG_OK;
+}
+
+// fused (map-free) inverse piecewise warp of nF frames in four launches; status_dev[f] != 0 afterwards means
+// frame f could not be represented and must be redone with pw_inverse_general_frame
+static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrameHost *fr, int nF, int min_src_x,
+                                  int min_src_y)
+{
+    const size_t T = (size_t)c->n_tris;
+    std::vector<FusedFrame> ff((size_t)nF);
+    size_t total_bins = 0;
+    int max_tiles = 1;
+    for (int f = 0; f < nF; ++f) {
+        const int bx = pwf_tiles_x(fr[f].oW);
+        total_bins += (size_t)bx * fr[f].oH;
+        const int nt = bx * pwf_tiles_y(fr[f].oH);
+        if (nt > max_tiles) max_tiles = nt;
+    }
+    TRY(ensure(c, c->rec, sizeof(TriRec) * T * nF));
+    TRY(ensure(c, c->invd, sizeof(double) * 6 * T * nF));
+    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * total_bins));
+    TRY(ensure(c, c->bin_ent, sizeof(unsigned) * total_bins * PW_BIN_CAP));
+    TRY(ensure(c, c->fstatus, sizeof(int) * (size_t)nF));
+    TRY(ensure(c, c->fframes, sizeof(FusedFrame) * (size_t)nF));
+    size_t bin0 = 0;
+    for (int f = 0; f < nF; ++f) {
+        FusedFrame &F = ff[(size_t)f];
+        F.src = fr[f].src; F.out = fr[f].out;
+        F.rec = (const TriRec *)c->rec.p + T * f;
+        F.inv = (const double *)c->invd.p + 6 * T * f;
+        F.bin_cnt = (unsigned *)c->bin_cnt.p + bin0;
+        F.bin_ent = (unsigned *)c->bin_ent.p + bin0 * PW_BIN_CAP;
+        F.status = (int *)c->fstatus.p + f;
+        F.W = fr[f].W; F.H = fr[f].H;
+        F.xOff = fr[f].xOff; F.yOff = fr[f].yOff; F.oW = fr[f].oW; F.oH = fr[f].oH;
+        F.minSrcX = min_src_x; F.minSrcY = min_src_y;
+        F.n_tris = c->n_tris;
+        F.bins_x = pwf_tiles_x(fr[f].oW);
+        bin0 += (size_t)F.bins_x * fr[f].oH;
+    }
+    CU(c, cudaMemcpyAsync(c->fframes.p, ff.data(), sizeof(FusedFrame) * (size_t)nF, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * total_bins, c->stream));
+    CU(c, cudaMemsetAsync(c->fstatus.p, 0, sizeof(int) * (size_t)nF, c->stream));
+    if (T > 0) {
+        PwSetupArgs a{};
+        a.src_pts = (const float *)c->src_pts.p;
+        a.dst_pts = dst_dev;
+        a.map_pts = dst_dev;
+        a.tris = (const uint32_t *)c->tris.p;
+        a.rec = (TriRec *)c->rec.p;
+        a.invd_out = (double *)c->invd.p;
+        a.n_tris = c->n_tris;
+        a.dst_stride = 2 * (size_t)c->n_pts;
+        a.rec_stride = T;
+        pw_setup_kernel<<<dim3((unsigned)((T + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>(a);
+        pw_span_bin_kernel<<<dim3((unsigned)((T + 3) / 4), (unsigned)nF), 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
+        c->launches += 2;
+        CU(c, cudaGetLastError());
+    }
+    TRY(prof_begin(c));
+    pw_warp_fused_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    TRY(prof_end(c));
+    return HG_OK;
+}
+
+static bool pw_fused_possible(hg_ctx *c, const PwFrameHost &f)
+{
+    return !c->force_general && c->n_tris < PW_MAX_TRIS && f.oW <= 65536;
 }
 
 int hg_warp_piecewise_inverse(hg_ctx *c, const float *dst_pts, int x_off, int y_off, int o_w, int o_h,
@@ -820,28 +932,25 @@ int hg_warp_piecewise_inverse(hg_ctx *c, const float *dst_pts, int x_off, int y_
     uint32_t *dst = nullptr;
     TRY(pick_out(c, out_dev, bytes, &dst));
     TRY(upload_dst_points(c, dst_pts, 1));
-    TRY(launch_setup(c, (const float *)c->dst_pts.p, (const float *)c->dst_pts.p, nullptr, nullptr));
-    const long long map_len = (long long)o_w * o_h;
-    TRY(launch_fill(c, (double)o_w, (double)y_off, map_len));
-    PwWarpArgs a{};
-    a.src = c->img;
-    a.out = dst;
-    a.map32 = (const int *)c->map32.p;
-    a.rec = (const TriRec *)c->rec.p;
-    a.W = c->W;
-    a.H = c->H;
-    a.xOff = x_off;
-    a.yOff = y_off;
-    a.oW = o_w;
-    a.oH = o_h;
-    a.minSrcX = min_src_x;
-    a.minSrcY = min_src_y;
-    a.n_tris = c->n_tris;
-    TRY(prof_begin(c));
-    pw_warp_inverse_kernel<<<grid_for(c, map_len, 1), 256, 0, c->stream>>>(a);
-    c->launches++;
-    CU(c, cudaGetLastError());
-    TRY(prof_end(c));
+    // remember what the reference's shared map field would now hold (inverse map of these points), Q8
+    c->last_inv_pts.assign(dst_pts, dst_pts + 2 * (size_t)c->n_pts);
+    c->last_inv_mw = (double)o_w;
+    c->last_inv_yoff = (double)y_off;
+    c->last_inv_len = (long long)o_w * o_h;
+    c->map32_current = false;
+    PwFrameHost f{c->img, dst, c->W, c->H, x_off, y_off, o_w, o_h};
+    bool general = !pw_fused_possible(c, f);
+    if (!general) {
+        TRY(pw_inverse_fused_chunk(c, (const float *)c->dst_pts.p, &f, 1, min_src_x, min_src_y));
+        int *st = (int *)c->pinned;
+        CU(c, cudaMemcpyAsync(st, c->fstatus.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        general = (*st != 0);
+    }
+    if (general) {
+        TRY(pw_inverse_general_frame(c, (const float *)c->dst_pts.p, f, min_src_x, min_src_y));
+        c->map32_current = true;
+    }
     return finish_out(c, dst, bytes, out_host);
 }
 
@@ -868,7 +977,18 @@ int hg_warp_piecewise_forward(hg_ctx *c, const float *dst_pts, int x_off, int y_
     if (!use_inverse_map) {
         const long long len = dom_w > 0 && dom_h > 0 ? dom_w * dom_h : 0;
         TRY(launch_fill(c, (double)dom_w, (double)min_src_y, len));
-    }  // else: the map left in place by the last inverse warp / hg_build_index_map is read as is (H.js:957 aliasing)
+        c->map32_current = false;
+    } else if (!c->map32_current) {
+        // the map the reference would still hold (inverse map of the last inverse warp) was never materialised by
+        // the fused path: rebuild it now from the remembered points (H.js:957 aliasing, Q8)
+        if (c->last_inv_len < 0) return fail(c, HG_ERR_STATE, "use_inverse_map without a previous inverse warp");
+        TRY(upload_dst_points(c, c->last_inv_pts.data(), 1));
+        TRY(launch_setup(c, nullptr, (const float *)c->dst_pts.p, nullptr, nullptr));
+        TRY(launch_fill(c, c->last_inv_mw, c->last_inv_yoff, c->last_inv_len));
+        c->map32_current = true;
+        TRY(upload_dst_points(c, dst_pts, 1));
+        TRY(launch_setup(c, (const float *)c->dst_pts.p, (const float *)c->src_pts.p, nullptr, nullptr));
+    }
     FwdArgs a{};
     a.src = c->img;
     a.map32 = (const int *)c->map32.p;
@@ -883,11 +1003,78 @@ int hg_warp_piecewise_forward(hg_ctx *c, const float *dst_pts, int x_off, int y_
     return run_forward(c, a, true, dst, bytes, out_host);
 }
 
-int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *, const hg_frame *, int, int, int)
+int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *dst_pts, const hg_frame *frames, int n_frames,
+                                    int min_src_x, int min_src_y)
 {
-    return fail(c, HG_ERR_UNSUPPORTED, "batched piecewise warp is not built yet");
+    BIND(c);
+    NEED(c, dst_pts && frames, "NULL argument");
+    NEED(c, n_frames >= 1, "n_frames must be >= 1");
+    if (c->n_pts == 0) return fail(c, HG_ERR_STATE, "no mesh set (hg_piecewise_set_mesh)");
+    if (min_src_x > (1 << 18) || min_src_x < -(1 << 18) || min_src_y > (1 << 18) || min_src_y < -(1 << 18))
+        return fail(c, HG_ERR_UNSUPPORTED, "min_src (%d,%d) outside the supported range", min_src_x, min_src_y);
+    std::vector<PwFrameHost> fr((size_t)n_frames);
+    for (int f = 0; f < n_frames; ++f) {
+        const hg_frame &h = frames[f];
+        TRY(check_window(c, h.x_off, h.y_off, h.o_w, h.o_h));
+        NEED(c, h.out_dev && ((uintptr_t)h.out_dev & 15) == 0, "frame out_dev must be a 16-byte aligned device pointer");
+        PwFrameHost &g = fr[(size_t)f];
+        if (h.src_dev) {
+            TRY(check_image_dims(c, h.src_w, h.src_h));
+            g.src = (const uint32_t *)h.src_dev; g.W = h.src_w; g.H = h.src_h;
+        } else {
+            if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
+            g.src = c->img; g.W = c->W; g.H = c->H;
+        }
+        g.out = (uint32_t *)h.out_dev;
+        g.xOff = h.x_off; g.yOff = h.y_off; g.oW = h.o_w; g.oH = h.o_h;
+    }
+    const size_t pts_per_frame = 2 * (size_t)c->n_pts;
+    for (size_t i = 0; i < pts_per_frame * (size_t)n_frames; ++i) {
+        const float v = dst_pts[i];
+        if (!(v >= -1048576.f && v <= 1048576.f))
+            return fail(c, HG_ERR_UNSUPPORTED, "dst_pts[%zu] = %g: piecewise points must be finite and |v| <= 2^20", i, (double)v);
+    }
+    TRY(upload_dst_points(c, dst_pts, (size_t)n_frames));
+    c->map32_current = false;
+    c->last_inv_len = -1;
+    // chunk so that the per-frame scratch (triangle records, inverse matrices, bins) stays below ~1.5 GB
+    size_t per_frame = (sizeof(TriRec) + 48) * (size_t)c->n_tris;
+    for (int f = 0; f < n_frames; ++f) {
+        const size_t b = (size_t)pwf_tiles_x(fr[(size_t)f].oW) * fr[(size_t)f].oH * (4 + 4 * PW_BIN_CAP);
+        if (b + (sizeof(TriRec) + 48) * (size_t)c->n_tris > per_frame) per_frame = b + (sizeof(TriRec) + 48) * (size_t)c->n_tris;
+    }
+    int chunk = (int)((1500ull << 20) / (per_frame ? per_frame : 1));
+    if (chunk < 1) chunk = 1;
+    if (chunk > 1024) chunk = 1024;
+    std::vector<int> status((size_t)n_frames, 0);
+    const bool fused = pw_fused_possible(c, fr[0]);
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        const float *dd = (const float *)c->dst_pts.p + pts_per_frame * (size_t)f0;
+        if (fused) {
+            TRY(pw_inverse_fused_chunk(c, dd, fr.data() + f0, nf, min_src_x, min_src_y));
+            // the scratch is reused by the next chunk: collect this chunk's status first (stream-ordered copy)
+            CU(c, cudaMemcpyAsync(status.data() + f0, c->fstatus.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            for (int f = 0; f < nf; ++f) status[(size_t)(f0 + f)] = 1;
+        }
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int f = 0; f < n_frames; ++f) {
+        if (status[(size_t)f]) {  // not representable by the bins: the general, map-based path (exact for everything)
+            TRY(pw_inverse_general_frame(c, (const float *)c->dst_pts.p + pts_per_frame * (size_t)f, fr[(size_t)f],
+                                         min_src_x, min_src_y));
+        }
+    }
+    return HG_OK;
 }
 
+int hg_debug_force_general(hg_ctx *c, int on)
+{
+    if (!c) return HG_ERR_INVALID;
+    c->force_general = on != 0;
+    return HG_OK;
+}
 
 /* ------------------------------------------------------------------ pipelined host-to-host stream */
 struct hg_pipe_slot {

@@ -37,6 +37,7 @@ struct PwSetupArgs {
     TriRec *rec;
     float *fwd_out;         // optional dense copies (T*6)
     float *inv_out;
+    double *invd_out;       // optional: inverse matrices widened to double (T*6 per frame), for the fused kernel
     int n_tris;
     size_t dst_stride;      // frame stride (floats) for batched calls, indexed by blockIdx.y
     size_t rec_stride;
@@ -98,6 +99,10 @@ __global__ void pw_setup_kernel(PwSetupArgs a)
     if (a.inv_out) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) a.inv_out[(f * a.n_tris + t) * 6 + k] = r.inv[k];
+    }
+    if (a.invd_out) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.invd_out[(f * a.n_tris + t) * 6 + k] = (double)r.inv[k];
     }
 }
 

@@ -158,6 +158,8 @@ int hg_pipe_destroy(hg_pipe *pipe);
 /* max over all 2^20 high-mantissa patterns (x 6 low words) of |1 - d*r|, r = the reciprocal the projective
  * fast path uses (MUFU.RCP64H + one Newton step), for doubles with the given biased exponent / sign */
 int hg_debug_rcp_max_error(hg_ctx *ctx, int biased_exponent, int negative, double *max_rel_err);
+/* on != 0: inverse piecewise warps always take the general map-based path (tests compare it with the fused one) */
+int hg_debug_force_general(hg_ctx *ctx, int on);
 
 /* ------------------------------------------------------------------ device memory helpers (benchmarks / bindings) */
 int hg_dev_alloc(hg_ctx *ctx, size_t bytes, void **dev_ptr);

@@ -422,3 +422,102 @@ def test_forward_piecewise_bit_exact(ctx, seed):
     fmap = O.build_index_map(src, tris, mw, smm[1], mw * (smm[3] - smm[1]))
     want = O.warp_forward_piecewise(img, W, H, fmap, fwd, xo, yo, oW, oH, smm[0], smm[1], smm[2], smm[3])
     assert _diff(got, want) == 0
+
+
+# ------------------------------------------------------------------ fused (map-free) piecewise path
+def _pw_case(ctx, img, src, dst, tris, force_general=False):
+    H, W = img.shape[:2]
+    mm = O.minmax_xy(dst)
+    xo, yo, oW, oH = int(mm[0]), int(mm[1]), int(mm[2] - mm[0]), int(mm[3] - mm[1])
+    if oW < 1 or oH < 1:
+        return
+    smm = O.minmax_xy(src)
+    ctx.image_set(img, W, H)
+    ctx.piecewise_set_mesh(src, tris)
+    ctx.debug_force_general(force_general)
+    try:
+        got = ctx.warp_piecewise_inverse(dst, xo, yo, oW, oH, int(smm[0]), int(smm[1]))
+    finally:
+        ctx.debug_force_general(False)
+    fwd = O.piecewise_matrices(src, dst, tris)
+    imap = O.build_index_map(dst, tris, oW, yo, oW * oH)
+    want = O.warp_inverse_piecewise(img, W, H, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, int(smm[0]), int(smm[1]), threads=4)
+    assert _diff(got, want) == 0, f"{_diff(got, want)} of {oW * oH} pixels differ (force_general={force_general})"
+
+
+@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("force_general", [False, True])
+def test_piecewise_irregular_frames_fused_and_general(ctx, seed, force_general):
+    """Offsets != 0 (Q4: spans spill over row ends), ~~minY < round(minY) (Q5: fills wrap to the END of the map),
+    negative coordinates, non-multiple-of-4 widths, folded meshes with many overlaps (bin overflow -> fallback)."""
+    rng = np.random.default_rng(700 + seed)
+    W, H = 300, 220
+    img = _rand_img(90 + seed, W, H)
+    src, tris = _grid_mesh(8, 6, W, H)
+    dst = src.astype(np.float64)
+    kind = seed % 5
+    if kind == 0:      # positive offset: xOff > 0 -> every span is shifted and spills
+        dst = dst * 1.3 + [37.6, 21.7]
+    elif kind == 1:    # negative offset (video-style jitter around the frame)
+        dst = dst + rng.uniform(-0.03, 0.03, dst.shape) * [W, H] - [11.3, 7.8]
+    elif kind == 2:    # strong fold: triangles overlap heavily
+        dst = dst + rng.uniform(-60, 60, dst.shape) + 30
+    elif kind == 3:    # fractional minima with frac >= .5 (Q5) and odd output width
+        dst = dst * [1.117, 0.93] + [0.6, 0.7]
+    else:              # minification far below 1/1.2
+        dst = dst * 0.31 + [3.3, 2.2]
+    _pw_case(ctx, img, src, dst.astype(np.float32), tris, force_general)
+
+
+def test_piecewise_random_triangle_soup(ctx):
+    """Arbitrary (non-mesh) triangles incl. degenerate and repeated ones."""
+    rng = np.random.default_rng(808)
+    W, H = 160, 120
+    img = _rand_img(12, W, H)
+    src = rng.uniform(0, [W, H], (14, 2)).astype(np.float32)
+    dst = (src + rng.uniform(-25, 25, src.shape) + 12).astype(np.float32)
+    tris = rng.integers(0, 14, (20, 3)).astype(np.uint32)
+    for fg in (False, True):
+        _pw_case(ctx, img, src, dst, tris, fg)
+
+
+def test_config4_mesh_one_frame_4k(ctx):
+    """Config 4 mesh (64x64 points, 7,938 triangles) on a 3840x2160 frame, one frame, all pixels."""
+    import homography_js_b200 as hgm
+    w, h = 3840, 2160
+    img = _rand_img(4, w, h)
+    src, dst, tris = hgm.workloads.piecewise_sinusoid(64, 64, w, h, phase=0.7)
+    _pw_case(ctx, img, src, dst, tris)
+
+
+def test_piecewise_batch_matches_oracle(ctx):
+    import homography_js_b200 as hgm
+    w, h = 480, 270
+    n = 5
+    imgs = [_rand_img(30 + k, w, h) for k in range(2)]
+    dev_src = [ctx.dev_alloc(w * h * 4) for _ in imgs]
+    for p, im in zip(dev_src, imgs):
+        ctx.memcpy_h2d(p, im.ctypes.data, im.nbytes)
+    src, _, tris = hgm.workloads.piecewise_sinusoid(12, 9, w, h)
+    ctx.piecewise_set_mesh(src, tris)
+    dsts, frames, outs, shapes = [], [], [], []
+    for f in range(n):
+        _, dst, _ = hgm.workloads.piecewise_sinusoid(12, 9, w, h, phase=2 * math.pi * f / n)
+        if f == 3:
+            dst = (dst + np.float32(13.4)).astype(np.float32)   # an irregular frame inside the batch
+        xo, yo, oW, oH = hgm.workloads.piecewise_extent(dst)
+        p = ctx.dev_alloc(oW * oH * 4)
+        dsts.append(dst); outs.append(p); shapes.append((xo, yo, oW, oH))
+        frames.append(hg.HgFrame(dev_src[f % 2], p, w, h, xo, yo, oW, oH))
+    ctx.warp_piecewise_inverse_batch(np.stack(dsts), frames, 0, 0)
+    for f in range(n):
+        xo, yo, oW, oH = shapes[f]
+        got = np.empty(oW * oH * 4, np.uint8)
+        ctx.memcpy_d2h(got.ctypes.data, outs[f], got.nbytes)
+        ctx.synchronize()
+        fwd = O.piecewise_matrices(src, dsts[f], tris)
+        imap = O.build_index_map(dsts[f], tris, oW, yo, oW * oH)
+        want = O.warp_inverse_piecewise(imgs[f % 2], w, h, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, 0, 0, threads=4)
+        assert _diff(got, want) == 0, f
+    for p in dev_src + outs:
+        ctx.dev_free(p)
