@@ -159,6 +159,68 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_piecewise(args, which):
+    """Secondary bench lines (not the headline): BASELINE configs 3 / 4 through hg_warp_piecewise_inverse_batch."""
+    import torch
+    import homography_js_b200 as hg
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = hg.Context(0)
+    w, h = 3840, 2160
+    nx = ny = 10 if which == "piecewise3" else 64
+    F = args.frames if args.frames != 64 else 16
+    src, _, tris = hg.workloads.piecewise_sinusoid(nx, ny, w, h)
+    ctx.piecewise_set_mesh(src, tris)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    src_ring = torch.randint(0, 256, (F, h * w * 4), dtype=torch.uint8, device=dev, generator=g)
+    dsts, frames, outs, npix = [], [], [], 0
+    for f in range(F):
+        _, dst, _ = hg.workloads.piecewise_sinusoid(nx, ny, w, h, phase=2 * np.pi * f / max(F, 1))
+        xo, yo, oW, oH = hg.workloads.piecewise_extent(dst)
+        o = torch.zeros(oW * oH * 4, dtype=torch.uint8, device=dev)
+        outs.append(o)
+        dsts.append(dst)
+        frames.append(hg.HgFrame(src_ring[f].data_ptr(), o.data_ptr(), w, h, xo, yo, oW, oH))
+        npix += oW * oH
+    dst_all = np.stack(dsts)
+    torch.cuda.synchronize()
+    res = {}
+    for mode in ("fused", "general"):
+        ctx.debug_force_general(mode == "general")
+        for _ in range(args.warmup):
+            ctx.warp_piecewise_inverse_batch(dst_all, frames, 0, 0)
+        ctx.synchronize()
+        l0 = ctx.launch_count()
+        ctx.profile_enable(True)
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            ctx.warp_piecewise_inverse_batch(dst_all, frames, 0, 0)
+        ms = ctx.timer_stop()
+        wall = (time.perf_counter() - t0) * 1e3
+        kms, kn = ctx.profile_read()
+        ctx.profile_enable(False)
+        res[mode] = {"Mpix/s": npix * args.steps / (max(ms, wall) * 1e-3) / 1e6, "ms_per_step": max(ms, wall) / args.steps,
+                     "pixel_kernel_ms_per_step": kms / args.steps, "pixel_kernels": kn, "launches": ctx.launch_count() - l0}
+    ctx.debug_force_general(False)
+    # parity of frame 0 against the oracle
+    from oracle import oracle as O
+    xo, yo, oW, oH = frames[0].x_off, frames[0].y_off, frames[0].o_w, frames[0].o_h
+    fwd = O.piecewise_matrices(src, dsts[0], tris)
+    imap = O.build_index_map(dsts[0], tris, oW, yo, oW * oH)
+    want = O.warp_inverse_piecewise(src_ring[0].cpu().numpy(), w, h, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, 0, 0,
+                                    threads=os.cpu_count() or 1)
+    parity = bool(np.array_equal(outs[0].cpu().numpy(), want))
+    peak, _ = measured_peak_gbs()
+    fr = res["fused"]
+    print(json.dumps({"metric": "Mpix/s warped", "workload": f"piecewiseaffine {nx}x{ny} grid ({len(tris)} tris), 3840x2160, {F} frames/step",
+                      "value": fr["Mpix/s"], "unit": "Mpix/s", "parity_gate": parity, "fused": fr, "general": res["general"],
+                      "roofline_frac_pixel_kernel": ALG_BYTES_PER_PIXEL * npix / (fr["pixel_kernel_ms_per_step"] * 1e-3) / 1e9 / peak,
+                      "roofline_frac_whole_step": ALG_BYTES_PER_PIXEL * npix / (fr["ms_per_step"] * 1e-3) / 1e9 / peak}), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,7 +232,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="projective", choices=["projective", "affine", "projective_generic"],
+    ap.add_argument("--workload", default="projective", choices=["projective", "affine", "projective_generic", "piecewise3", "piecewise4"],
                     help="projective = BASELINE config 2 (the headline); affine = same sizes through the affine kernel")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -178,6 +240,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload.startswith("piecewise"):
+        run_piecewise(args, args.workload)
         return
 
     rank = int(os.environ.get("RANK", "0"))

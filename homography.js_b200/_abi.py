@@ -329,7 +329,7 @@ class Context:
 
     def warp_piecewise_inverse_batch(self, dst_pts, frames, min_src_x, min_src_y):
         d = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(-1)
-        arr = (HgFrame * len(frames))(*frames)
+        arr = frames if isinstance(frames, C.Array) else (HgFrame * len(frames))(*frames)
         self._ck(self.L.hg_warp_piecewise_inverse_batch(self.h, _ptr(d), arr, len(frames), min_src_x, min_src_y))
 
 

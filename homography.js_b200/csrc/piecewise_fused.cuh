@@ -111,6 +111,10 @@ __global__ void __launch_bounds__(PWF_THREADS, 4) pw_warp_fused_kernel(const Fus
     for (int k = 0; k < 4; ++k) xs[k] = (double)(F.xOff + xx0 + k);
 
     long long flat[PWF_ROWS][4];
+    // the inverse matrix of the triangle the thread is currently inside: neighbouring pixels and rows mostly share
+    // it, so it is (re)loaded only when the triangle id changes (3 x 16 B from L1/L2 instead of 48 B per pixel)
+    int cur_t = -1;
+    double m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;
 #pragma unroll
     for (int j = 0; j < PWF_ROWS; ++j) {
         const int yy = yy0 + j;
@@ -133,10 +137,14 @@ __global__ void __launch_bounds__(PWF_THREADS, 4) pw_warp_fused_kernel(const Fus
             // Int16Array semantics of the map: the stored id is t mod 2^16 as int16; negative = no triangle
             const int t = (best[k] < 0) ? -1 : (int)(short)(unsigned short)(best[k] & 0xFFFF);
             if (t >= 0 && t < F.n_tris) {
-                const double2 *m = reinterpret_cast<const double2 *>(F.inv + 6 * (size_t)t);
-                const double2 m01 = __ldg(m), m23 = __ldg(m + 1), m45 = __ldg(m + 2);
-                const double sx = affine_coord_exact(m01.x, xs[k], __dmul_rn(m23.x, y), m45.x);
-                const double sy = affine_coord_exact(m01.y, xs[k], __dmul_rn(m23.y, y), m45.y);
+                if (t != cur_t) {
+                    const double2 *m = reinterpret_cast<const double2 *>(F.inv + 6 * (size_t)t);
+                    const double2 m01 = __ldg(m), m23 = __ldg(m + 1), m45 = __ldg(m + 2);
+                    m0 = m01.x; m1 = m01.y; m2 = m23.x; m3 = m23.y; m4 = m45.x; m5 = m45.y;
+                    cur_t = t;
+                }
+                const double sx = affine_coord_exact(m0, xs[k], __dmul_rn(m2, y), m4);
+                const double sy = affine_coord_exact(m1, xs[k], __dmul_rn(m3, y), m5);
                 const double tx2 = __dadd_rd(sx, HG_MAGIC), ty2 = __dadd_rd(sy, HG_MAGIC);
                 const int ix = __double2hiint(tx2) - HG_HI_ZERO, iy = __double2hiint(ty2) - HG_HI_ZERO;
                 // minSrcX <= sx < W + minSrcX and minSrcY <= sy < H + minSrcY  (H.js:1047)

@@ -1,0 +1,246 @@
+/* hgwarp_napi.c — thin Node-API addon over the C ABI of include/hgwarp.h.
+ *
+ * Every exported function is a 1:1 marshalling stub: JS typed arrays are passed as borrowed pointers into their
+ * ArrayBuffers (no copies on the JS side), results are written into a Uint8ClampedArray allocated here, and a
+ * non-zero hg_status becomes a thrown JS Error carrying hg_last_error().  js/Homography.mjs holds the state machine.
+ *
+ * Build (with a Node toolchain):
+ *   cc -O2 -fPIC -shared -DHG_USE_SYSTEM_NAPI -I$(node -p "process.execPath+'/../../include/node'") \
+ *      -I../../include hgwarp_napi.c -L.. -lhgwarp -Wl,-rpath,'$ORIGIN/..' -o hgwarp.node
+ * In this image (no Node) it is only compile-checked against js/napi_min.h (tests/test_js_binding_sources.py).
+ */
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/hgwarp.h"
+#include "napi_min.h"
+
+#define MAXARG 12
+#define ARGS(n)                                                         \
+    size_t argc = (n);                                                  \
+    napi_value argv[MAXARG];                                            \
+    if (napi_get_cb_info(env, info, &argc, argv, NULL, NULL) != napi_ok || argc < (n)) \
+        return throw_text(env, "hgwarp: wrong number of arguments")
+
+static napi_value throw_text(napi_env env, const char *msg)
+{
+    napi_throw_error(env, "HGWARP", msg);
+    return NULL;
+}
+
+static napi_value check(napi_env env, hg_ctx *ctx, int status)
+{
+    if (status == HG_OK) {
+        napi_value u;
+        napi_get_undefined(env, &u);
+        return u;
+    }
+    char buf[600];
+    snprintf(buf, sizeof buf, "hgwarp status %d: %s", status, hg_last_error(ctx));
+    return throw_text(env, buf);
+}
+
+static hg_ctx *ctx_of(napi_env env, napi_value v)
+{
+    void *p = NULL;
+    return napi_get_value_external(env, v, &p) == napi_ok ? (hg_ctx *)p : NULL;
+}
+
+static void *typed(napi_env env, napi_value v, napi_typedarray_type want, size_t min_len)
+{
+    napi_typedarray_type t;
+    size_t n = 0;
+    void *data = NULL;
+    if (napi_get_typedarray_info(env, v, &t, &n, &data, NULL, NULL) != napi_ok) return NULL;
+    if (t != want && !(want == napi_uint8_array && t == napi_uint8_clamped_array)) return NULL;
+    return n >= min_len ? data : NULL;
+}
+
+static int i32(napi_env env, napi_value v)
+{
+    int32_t x = 0;
+    napi_get_value_int32(env, v, &x);
+    return x;
+}
+
+static void ctx_finalize(napi_env env, void *data, void *hint)
+{
+    (void)env; (void)hint;
+    hg_ctx_destroy((hg_ctx *)data);
+}
+
+/* createContext(device) -> external */
+static napi_value CreateContext(napi_env env, napi_callback_info info)
+{
+    ARGS(1);
+    hg_ctx *ctx = NULL;
+    int st = hg_ctx_create(i32(env, argv[0]), &ctx);
+    if (st != HG_OK) return check(env, NULL, st);
+    napi_value ext;
+    napi_create_external(env, ctx, ctx_finalize, NULL, &ext);
+    return ext;
+}
+
+/* setImage(ctx, Uint8ClampedArray rgba, w, h)           <- this._image = image.data, H.js:298 */
+static napi_value SetImage(napi_env env, napi_callback_info info)
+{
+    ARGS(4);
+    hg_ctx *ctx = ctx_of(env, argv[0]);
+    int w = i32(env, argv[2]), h = i32(env, argv[3]);
+    const uint8_t *px = (const uint8_t *)typed(env, argv[1], napi_uint8_array, (size_t)w * h * 4);
+    if (!ctx || !px) return throw_text(env, "setImage(ctx, Uint8ClampedArray, w, h)");
+    return check(env, ctx, hg_image_set(ctx, px, w, h));
+}
+
+/* solveWithLimits(ctx, kind, Float64Array src, Float64Array dst, w, h) -> {matrix, limits}
+ *                                                        <- calculateTransformMatrix + calculateTransformLimits */
+static napi_value SolveWithLimits(napi_env env, napi_callback_info info)
+{
+    ARGS(6);
+    hg_ctx *ctx = ctx_of(env, argv[0]);
+    int kind = i32(env, argv[1]);
+    size_t np = kind == HG_AFFINE ? 6 : 8;
+    const double *src = (const double *)typed(env, argv[2], napi_float64_array, np);
+    const double *dst = (const double *)typed(env, argv[3], napi_float64_array, np);
+    double w = 0, h = 0;
+    napi_get_value_double(env, argv[4], &w);
+    napi_get_value_double(env, argv[5], &h);
+    if (!ctx || !src || !dst) return throw_text(env, "solveWithLimits(ctx, kind, Float64Array, Float64Array, w, h)");
+    napi_value ab, m, lab, lim, out;
+    void *mp = NULL, *lp = NULL;
+    napi_create_arraybuffer(env, kind == HG_AFFINE ? 24 : 64, &mp, &ab);
+    napi_create_typedarray(env, kind == HG_AFFINE ? napi_float32_array : napi_float64_array, np, ab, 0, &m);
+    napi_create_arraybuffer(env, 32, &lp, &lab);
+    napi_create_typedarray(env, napi_float64_array, 4, lab, 0, &lim);
+    int st = hg_solve_with_limits(ctx, kind, src, dst, w, h, mp, (double *)lp);
+    if (st != HG_OK) return check(env, ctx, st);
+    napi_create_object(env, &out);
+    napi_set_named_property(env, out, "matrix", m);
+    napi_set_named_property(env, out, "limits", lim);
+    return out;
+}
+
+static napi_value new_output(napi_env env, int ow, int oh, uint8_t **data)
+{
+    napi_value ab, arr;
+    void *p = NULL;
+    napi_create_arraybuffer(env, (size_t)ow * oh * 4, &p, &ab);
+    napi_create_typedarray(env, napi_uint8_clamped_array, (size_t)ow * oh * 4, ab, 0, &arr);
+    *data = (uint8_t *)p;
+    return arr;
+}
+
+/* warpInversePoints(ctx, kind, Float64Array dst, Float64Array src, xOff, yOff, oW, oH) -> Uint8ClampedArray
+ *                                                        <- _inverseGeometricWarp, H.js:987 */
+static napi_value WarpInversePoints(napi_env env, napi_callback_info info)
+{
+    ARGS(8);
+    hg_ctx *ctx = ctx_of(env, argv[0]);
+    int kind = i32(env, argv[1]);
+    size_t np = kind == HG_AFFINE ? 6 : 8;
+    const double *dst = (const double *)typed(env, argv[2], napi_float64_array, np);
+    const double *src = (const double *)typed(env, argv[3], napi_float64_array, np);
+    if (!ctx || !dst || !src) return throw_text(env, "warpInversePoints(ctx, kind, Float64Array, Float64Array, ...)");
+    int ow = i32(env, argv[6]), oh = i32(env, argv[7]);
+    uint8_t *out = NULL;
+    napi_value arr = new_output(env, ow, oh, &out);
+    int st = hg_warp_inverse_points(ctx, kind, dst, src, i32(env, argv[4]), i32(env, argv[5]), ow, oh, out, NULL);
+    return st == HG_OK ? arr : check(env, ctx, st);
+}
+
+/* warpForwardMatrix(ctx, kind, matrix, xOff, yOff, oW, oH) -> Uint8ClampedArray     <- _geometricWarp, H.js:911 */
+static napi_value WarpForwardMatrix(napi_env env, napi_callback_info info)
+{
+    ARGS(7);
+    hg_ctx *ctx = ctx_of(env, argv[0]);
+    int kind = i32(env, argv[1]);
+    const void *m = kind == HG_AFFINE ? typed(env, argv[2], napi_float32_array, 6) : typed(env, argv[2], napi_float64_array, 8);
+    if (!ctx || !m) return throw_text(env, "warpForwardMatrix(ctx, kind, matrix, ...)");
+    int ow = i32(env, argv[5]), oh = i32(env, argv[6]);
+    uint8_t *out = NULL;
+    napi_value arr = new_output(env, ow, oh, &out);
+    int st = hg_warp_forward_matrix(ctx, kind, m, i32(env, argv[3]), i32(env, argv[4]), ow, oh, out, NULL);
+    return st == HG_OK ? arr : check(env, ctx, st);
+}
+
+/* setMesh(ctx, Float32Array srcPts, Uint32Array triangles)      <- this._srcPoints / this._triangles */
+static napi_value SetMesh(napi_env env, napi_callback_info info)
+{
+    ARGS(3);
+    hg_ctx *ctx = ctx_of(env, argv[0]);
+    napi_typedarray_type t;
+    size_t npts2 = 0, ntri3 = 0;
+    void *pts = NULL, *tris = NULL;
+    if (!ctx || napi_get_typedarray_info(env, argv[1], &t, &npts2, &pts, NULL, NULL) != napi_ok || t != napi_float32_array ||
+        napi_get_typedarray_info(env, argv[2], &t, &ntri3, &tris, NULL, NULL) != napi_ok || t != napi_uint32_array)
+        return throw_text(env, "setMesh(ctx, Float32Array, Uint32Array)");
+    return check(env, ctx, hg_piecewise_set_mesh(ctx, (const float *)pts, (int)(npts2 / 2), (const uint32_t *)tris, (int)(ntri3 / 3)));
+}
+
+/* piecewiseMatrices(ctx, Float32Array dstPts, nTris) -> Float32Array(6*nTris)
+ *                                                        <- _calculatePiecewiseAffineTransformMatrices, H.js:785 */
+static napi_value PiecewiseMatrices(napi_env env, napi_callback_info info)
+{
+    ARGS(3);
+    hg_ctx *ctx = ctx_of(env, argv[0]);
+    const float *dst = (const float *)typed(env, argv[1], napi_float32_array, 6);
+    int nt = i32(env, argv[2]);
+    if (!ctx || !dst || nt < 0) return throw_text(env, "piecewiseMatrices(ctx, Float32Array, nTris)");
+    napi_value ab, arr;
+    void *p = NULL;
+    napi_create_arraybuffer(env, (size_t)nt * 24, &p, &ab);
+    napi_create_typedarray(env, napi_float32_array, (size_t)nt * 6, ab, 0, &arr);
+    int st = hg_piecewise_matrices(ctx, dst, (float *)p, NULL);
+    return st == HG_OK ? arr : check(env, ctx, st);
+}
+
+/* warpPiecewiseInverse(ctx, Float32Array dst, xOff, yOff, oW, oH, minSrcX, minSrcY) -> Uint8ClampedArray
+ *                                                        <- _inversePiecewiseAffineWarp, H.js:1029 */
+static napi_value WarpPiecewiseInverse(napi_env env, napi_callback_info info)
+{
+    ARGS(8);
+    hg_ctx *ctx = ctx_of(env, argv[0]);
+    const float *dst = (const float *)typed(env, argv[1], napi_float32_array, 6);
+    if (!ctx || !dst) return throw_text(env, "warpPiecewiseInverse(ctx, Float32Array, ...)");
+    int ow = i32(env, argv[4]), oh = i32(env, argv[5]);
+    uint8_t *out = NULL;
+    napi_value arr = new_output(env, ow, oh, &out);
+    int st = hg_warp_piecewise_inverse(ctx, dst, i32(env, argv[2]), i32(env, argv[3]), ow, oh, i32(env, argv[6]),
+                                       i32(env, argv[7]), out, NULL);
+    return st == HG_OK ? arr : check(env, ctx, st);
+}
+
+/* warpPiecewiseForward(ctx, Float32Array dst, xOff, yOff, oW, oH, minSrcX, minSrcY, maxSrcX, maxSrcY, useInverseMap)
+ *                                                        <- _piecewiseAffineWarp, H.js:948 */
+static napi_value WarpPiecewiseForward(napi_env env, napi_callback_info info)
+{
+    ARGS(11);
+    hg_ctx *ctx = ctx_of(env, argv[0]);
+    const float *dst = (const float *)typed(env, argv[1], napi_float32_array, 6);
+    if (!ctx || !dst) return throw_text(env, "warpPiecewiseForward(ctx, Float32Array, ...)");
+    int ow = i32(env, argv[4]), oh = i32(env, argv[5]);
+    uint8_t *out = NULL;
+    napi_value arr = new_output(env, ow, oh, &out);
+    int st = hg_warp_piecewise_forward(ctx, dst, i32(env, argv[2]), i32(env, argv[3]), ow, oh, i32(env, argv[6]),
+                                       i32(env, argv[7]), i32(env, argv[8]), i32(env, argv[9]), i32(env, argv[10]), out, NULL);
+    return st == HG_OK ? arr : check(env, ctx, st);
+}
+
+static napi_value Init(napi_env env, napi_value exports)
+{
+    const napi_property_descriptor d[] = {
+        {"createContext", 0, CreateContext, 0, 0, 0, napi_default, 0},
+        {"setImage", 0, SetImage, 0, 0, 0, napi_default, 0},
+        {"solveWithLimits", 0, SolveWithLimits, 0, 0, 0, napi_default, 0},
+        {"warpInversePoints", 0, WarpInversePoints, 0, 0, 0, napi_default, 0},
+        {"warpForwardMatrix", 0, WarpForwardMatrix, 0, 0, 0, napi_default, 0},
+        {"setMesh", 0, SetMesh, 0, 0, 0, napi_default, 0},
+        {"piecewiseMatrices", 0, PiecewiseMatrices, 0, 0, 0, napi_default, 0},
+        {"warpPiecewiseInverse", 0, WarpPiecewiseInverse, 0, 0, 0, napi_default, 0},
+        {"warpPiecewiseForward", 0, WarpPiecewiseForward, 0, 0, 0, napi_default, 0},
+    };
+    napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
+    return exports;
+}
+
+NAPI_MODULE(hgwarp, Init)
