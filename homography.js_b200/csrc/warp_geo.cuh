@@ -32,8 +32,7 @@
 //               (probability ~4e-6 per coordinate); otherwise the pixel is redone with __ddiv_rn, i.e. the
 //               reference's own arithmetic.                                        -> ~11.5 FP64 ops / pixel
 //   mode        per-CTA uniform dispatch on the matrix: denominator == 1 everywhere (h6 = h7 = 0: exact, no
-//               reciprocal), denominator a function of x only (h7 = 0: one reciprocal per column), denominator
-//               provably in (0.25, 1.75) (no exponent guard), or general.
+//               reciprocal), denominator provably in (0.25, 1.75) (no exponent guard), or general.
 #pragma once
 #include "jsnum.cuh"
 
@@ -60,11 +59,12 @@ constexpr int GEO_TY = 8;           // thread rows per CTA  -> 128 threads
 #define HG_GEO_R 2
 #endif
 #ifndef HG_GEO_MINB
-#define HG_GEO_MINB 5
+#define HG_GEO_MINB 6
 #endif
 constexpr int GEO_ROWS_PER_THREAD = HG_GEO_R;
 constexpr int GEO_THREADS = GEO_TILE_QUADS * GEO_TY;
 constexpr int GEO_GROUP_ROWS = GEO_TY * GEO_ROWS_PER_THREAD;  // rows one CTA covers per iteration
+constexpr int GEO_QCAP = 96;  // queued (thread, row group) entries per warp awaiting exact resolution
 
 // host + device: CTAs needed for one frame.  Rows whose flat start is not 16-byte aligned begin with a partial
 // quad, so a row has at most (oW + 3 + 3) / 4 quads; when oW % 4 == 0 every row is aligned.
@@ -127,8 +127,8 @@ __device__ __forceinline__ unsigned decode_flat(double tx, double ty, unsigned W
 }
 
 // MODE (projective only): 0 general + denominator exponent guard, 1 general (denominator proven in
-// (0.25,1.75)), 2 denominator == 1 exactly, 3 denominator depends on x only (h7 == 0, e.g. keystone correction
-// along one axis): one reciprocal per column.
+// (0.25,1.75)), 2 denominator == 1 exactly.  (A fourth mode — one reciprocal per column when h7 == 0 — was built and
+// measured: its extra live registers cost more occupancy than the 5 FP64 ops per pixel it saved, so it was dropped.)
 //
 // Per thread: one quad column, GEO_ROWS_PER_THREAD rows per iteration, `niter` iterations (GEO_GROUP_ROWS rows
 // apart), run as a THREE-STAGE SOFTWARE PIPELINE so that no instruction ever waits on the stage before it:
@@ -140,8 +140,9 @@ __device__ __forceinline__ unsigned decode_flat(double tx, double ty, unsigned W
 // iteration of arithmetic inside the same warp.
 template <int KIND, int MODE>
 __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&m)[8], int base0, int niter, int s,
-                                              int x_first, unsigned mask)
+                                              int x_first, unsigned mask, uint2 *q, int *qn)
 {
+    static_assert(4 * GEO_ROWS_PER_THREAD + 17 <= 32, "queue entry packs the redo bits above a 17-bit row");
     constexpr int R = GEO_ROWS_PER_THREAD;
     const uint32_t *__restrict__ src = F.src;
     const unsigned W = (unsigned)F.W, H = (unsigned)F.H;
@@ -149,8 +150,7 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
     const int oH = F.oH;
 
     // x-only terms, shared by every row this thread touches
-    double xs[4], ax0[4], ax1[4], ax2[4], rcx[4];
-    unsigned col_bad = 0;  // MODE 3: columns whose denominator is outside the trusted exponent range
+    double xs[4], ax0[4], ax1[4], ax2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         xs[k] = (double)(F.xOff + x_first + k);
@@ -158,20 +158,13 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
             ax0[k] = __dmul_rn(m[0], xs[k]);
             ax1[k] = __dmul_rn(m[3], xs[k]);
             ax2[k] = (MODE == 2) ? 0.0 : __dmul_rn(m[6], xs[k]);
-            if (MODE == 3) {
-                // h7 == 0: h7*y is a signed zero, so the reference's denominator (h6*x + h7*y) + 1 equals
-                // (h6*x) + 1 bit for bit on every row -> one reciprocal per column instead of one per pixel
-                const double dn = __dadd_rn(ax2[k], 1.0);
-                rcx[k] = rcp_newton1(dn);
-                const unsigned de = ((unsigned)__double2hiint(dn) & 0x7FF00000u) - (523u << 20);
-                col_bad |= (de > (1000u << 20)) ? (0x11111111u << k) : 0u;
-            }
         }
     }
 
     uint32_t px[R][4];       // stage C operands (gathers in flight)
     unsigned idx[R][4];      // stage B operands (flat indices of the previous group)
     unsigned redo_bits = 0;  // pixels of the previous group whose quotient must be resolved exactly
+    int qpos = 0;            // queue slot reserved for them
     int base_px = -1, base_idx = -1;
     const long long row_pitch = (long long)F.oW;
 
@@ -198,22 +191,30 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
         // ---- B: gathers of group it-1
         if (base_idx >= 0) {
             if (KIND == 1 && MODE != 2 && redo_bits) {
-                // k is static; every lane walks ITS flagged rows of column k, lanes side by side
+                // Flagged pixels (quotient within 2^-20 of a decision boundary) are NOT resolved here, where one
+                // lane would run the IEEE divide while 31 wait.  The thread appends ONE entry (quad column, row
+                // group, flag bits) to its warp's queue — the slot was reserved one iteration ago, so the atomic's
+                // latency is hidden — and the queue is resolved after the loop (geo_flush_queue), overwriting the
+                // provisional pixels stored below.  Only when the queue is full is a thread resolved in place.
+                if (qpos < GEO_QCAP) {
+                    q[qpos] = make_uint2((unsigned)(x_first + 4), (redo_bits << 17) | (unsigned)base_idx);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    unsigned rows = (redo_bits >> k) & 0x11111111u;
-                    while (rows) {
-                        const int j = (__ffs((int)rows) - 1) >> 2;
-                        rows &= rows - 1;
-                        const double y = (double)(F.yOff + base_idx + s * j);
-                        const double nx = __dadd_rn(__dadd_rn(ax0[k], __dmul_rn(m[1], y)), m[2]);
-                        const double ny = __dadd_rn(__dadd_rn(ax1[k], __dmul_rn(m[4], y)), m[5]);
-                        const double dn = __dadd_rn(__dadd_rn(ax2[k], __dmul_rn(m[7], y)), 1.0);
-                        const unsigned f = decode_flat(exact_quotient_magic(nx, dn), exact_quotient_magic(ny, dn), W, H,
-                                                       npx_src);
+                    for (int k = 0; k < 4; ++k) {
+                        unsigned rows = (redo_bits >> k) & 0x11111111u;
+                        while (rows) {
+                            const int j = (__ffs((int)rows) - 1) >> 2;
+                            rows &= rows - 1;
+                            const double y = (double)(F.yOff + base_idx + s * j);
+                            const double nx = __dadd_rn(__dadd_rn(ax0[k], __dmul_rn(m[1], y)), m[2]);
+                            const double ny = __dadd_rn(__dadd_rn(ax1[k], __dmul_rn(m[4], y)), m[5]);
+                            const double dn = __dadd_rn(__dadd_rn(ax2[k], __dmul_rn(m[7], y)), 1.0);
+                            const unsigned f = decode_flat(exact_quotient_magic(nx, dn), exact_quotient_magic(ny, dn), W,
+                                                           H, npx_src);
 #pragma unroll
-                        for (int jj = 0; jj < R; ++jj)
-                            if (jj == j) idx[jj][k] = f;  // select, no dynamic register indexing
+                            for (int jj = 0; jj < R; ++jj)
+                                if (jj == j) idx[jj][k] = f;  // select, no dynamic register indexing
+                        }
                     }
                 }
             }
@@ -227,7 +228,7 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
         // ---- A: arithmetic of group it
         const int base = base0 + it * GEO_GROUP_ROWS;
         if (it < niter && base < oH) {
-            redo_bits = (MODE == 3) ? col_bad : 0u;
+            redo_bits = 0u;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const double y = (double)(F.yOff + base + s * j);
@@ -253,12 +254,6 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
                             // denominator is exactly 1: n / 1 = n, no approximation anywhere
                             tx = __dadd_rd(nx, HG_MAGIC);
                             ty = __dadd_rd(ny, HG_MAGIC);
-                        } else if (MODE == 3) {
-                            tx = __fma_rn(nx, rcx[k], HG_MAGIC);
-                            ty = __fma_rn(ny, rcx[k], HG_MAGIC);
-                            const bool again = near_half_multiple((unsigned)__double2loint(tx)) |
-                                               near_half_multiple((unsigned)__double2loint(ty));
-                            redo_bits |= again ? (1u << (4 * j + k)) : 0u;
                         } else {
                             const double dn = __dadd_rn(__dadd_rn(ax2[k], r2), 1.0);
                             const double rc = rcp_newton1(dn);
@@ -277,6 +272,7 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
                     idx[j][k] = decode_flat(tx, ty, W, H, npx_src);
                 }
             }
+            if (KIND == 1 && MODE != 2 && redo_bits) qpos = atomicAdd(qn, 1);  // consumed in the next iteration
             base_idx = base;
         } else if (base_px < 0) {
             break;  // nothing left in any stage
@@ -284,9 +280,42 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
     }
 }
 
+// Resolve the queued pixels of one warp with the reference's own arithmetic (H.js:1401-1404 followed by the bounds
+// test, Math.round and the flat read of H.js:1001-1007), one pixel per lane, and overwrite them in the output.
+__device__ __forceinline__ void geo_flush_queue(const GeoFrame &F, const double (&m)[8], const uint2 *q, int n, int s,
+                                                int lane)
+{
+    const unsigned W = (unsigned)F.W, H = (unsigned)F.H;
+    const unsigned npx_src = W * H;
+    for (int e = lane; e < n; e += 32) {
+        const uint2 ent = q[e];
+        const int x_first = (int)ent.x - 4, base = (int)(ent.y & 0x1FFFFu);
+        unsigned bits = ent.y >> 17;
+        while (bits) {
+            const int b = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            const int xx = x_first + (b & 3), yy = base + s * (b >> 2);
+            if (xx < 0 || xx >= F.oW || yy >= F.oH) continue;  // not a pixel of the image
+            const double x = (double)(F.xOff + xx), y = (double)(F.yOff + yy);
+            const double nx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), m[2]);
+            const double ny = __dadd_rn(__dadd_rn(__dmul_rn(m[3], x), __dmul_rn(m[4], y)), m[5]);
+            const double dn = __dadd_rn(__dadd_rn(__dmul_rn(m[6], x), __dmul_rn(m[7], y)), 1.0);
+            const unsigned f = decode_flat(exact_quotient_magic(nx, dn), exact_quotient_magic(ny, dn), W, H, npx_src);
+            F.out[(long long)yy * F.oW + xx] = ldg_or_zero(F.src, f);
+        }
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB) warp_inverse_geo_kernel(const GeoParams P)
 {
+    // per-warp queue of pixels whose quotient must be resolved exactly (projective only)
+    __shared__ uint2 s_q[KIND == 1 ? GEO_THREADS / 32 : 1][KIND == 1 ? GEO_QCAP : 1];
+    __shared__ int s_qn[GEO_THREADS / 32];
+    const int warp_id = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
+    if (lane_id == 0) s_qn[warp_id] = 0;
+    __syncwarp();
+
     const GeoFrame F = P.many ? P.many[blockIdx.y] : P.one;
     double m[8];
     if (P.mats_dev) {
@@ -317,26 +346,35 @@ __global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB) warp_inverse_geo_ker
     const int s = 1 << sl;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int base = row0 + (ty >> sl) * (s * GEO_ROWS_PER_THREAD) + (ty & (s - 1));
-    if (base >= oH) return;
     const int shift = (int)(((unsigned)base * (unsigned)oW) & 3u);
     const int x_first = 4 * (tile_x * GEO_TILE_QUADS + tx) - shift;
-    if (x_first >= oW) return;
+    const bool active = (base < oH) && (x_first < oW);
     unsigned mask = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (x_first + k >= 0 && x_first + k < oW) mask |= 1u << k;
+    uint2 *q = s_q[KIND == 1 ? warp_id : 0];
+    int *qn = &s_qn[warp_id];
 
-    if (KIND == 0) {
-        geo_tile_body<0, 0>(F, m, base, P.niter, s, x_first, mask);
-    } else {
-        // CTA-uniform mode from the matrix and the frame window
-        const double ax = fmax(fabs((double)F.xOff), fabs((double)F.xOff + (double)oW));
-        const double ay = fmax(fabs((double)F.yOff), fabs((double)F.yOff + (double)oH));
-        const double spread = fabs(m[6]) * ax + fabs(m[7]) * ay;  // |h6 x + h7 y| <= spread (+ rounding)
-        if (m[6] == 0.0 && m[7] == 0.0) geo_tile_body<1, 2>(F, m, base, P.niter, s, x_first, mask);
-        else if (m[7] == 0.0) geo_tile_body<1, 3>(F, m, base, P.niter, s, x_first, mask);
-        else if (spread < 0.75) geo_tile_body<1, 1>(F, m, base, P.niter, s, x_first, mask);
-        else geo_tile_body<1, 0>(F, m, base, P.niter, s, x_first, mask);
+    if (active) {
+        if (KIND == 0) {
+            geo_tile_body<0, 0>(F, m, base, P.niter, s, x_first, mask, q, qn);
+        } else {
+            // CTA-uniform mode from the matrix and the frame window
+            const double ax = fmax(fabs((double)F.xOff), fabs((double)F.xOff + (double)oW));
+            const double ay = fmax(fabs((double)F.yOff), fabs((double)F.yOff + (double)oH));
+            const double spread = fabs(m[6]) * ax + fabs(m[7]) * ay;  // |h6 x + h7 y| <= spread (+ rounding)
+            if (m[6] == 0.0 && m[7] == 0.0) geo_tile_body<1, 2>(F, m, base, P.niter, s, x_first, mask, q, qn);
+            else if (spread < 0.75) geo_tile_body<1, 1>(F, m, base, P.niter, s, x_first, mask, q, qn);
+            else geo_tile_body<1, 0>(F, m, base, P.niter, s, x_first, mask, q, qn);
+        }
+    }
+    if (KIND == 1) {
+        // every lane of the warp gets here; the barrier also orders the provisional stores above before the
+        // corrected ones below
+        __syncwarp();
+        const int n = min(*qn, GEO_QCAP);
+        if (n > 0) geo_flush_queue(F, m, q, n, s, lane_id);
     }
 }
 
