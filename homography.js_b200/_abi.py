@@ -27,7 +27,7 @@ SYMBOLS = [
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
     "hg_pipe_create", "hg_pipe_submit", "hg_pipe_wait", "hg_pipe_flush", "hg_pipe_destroy",
-    "hg_debug_rcp_max_error", "hg_debug_force_general",
+    "hg_debug_rcp_max_error", "hg_debug_force_general", "hg_debug_piecewise_stats",
     "hg_dev_alloc", "hg_dev_free", "hg_host_alloc_pinned", "hg_host_free_pinned",
     "hg_memcpy_h2d", "hg_memcpy_d2h", "hg_output_device",
 ]
@@ -95,6 +95,7 @@ def load():
     L.hg_pipe_flush.argtypes = [vp]
     L.hg_pipe_destroy.argtypes = [vp]
     L.hg_debug_force_general.argtypes = [vp, i]
+    L.hg_debug_piecewise_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.hg_debug_rcp_max_error.argtypes = [vp, i, i, C.POINTER(d)]
     L.hg_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.hg_dev_free.argtypes = [vp, vp]
@@ -172,6 +173,11 @@ class Context:
         e = C.c_double()
         self._ck(self.L.hg_debug_rcp_max_error(self.h, biased_exponent, int(negative), C.byref(e)))
         return e.value
+
+    def debug_piecewise_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.hg_debug_piecewise_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def debug_force_general(self, on: bool):
         self._ck(self.L.hg_debug_force_general(self.h, int(on)))

@@ -65,6 +65,7 @@ struct hg_ctx {
     long long last_inv_len = -1;
     bool map32_current = false;
     int force_general = 0;  // diagnostics: 1 = always use the map-based general path
+    uint64_t n_fused = 0, n_general = 0;  // inverse piecewise frames finished by each path
     int n_pts = 0, n_tris = 0;
     long long map_len = 0;  // length of the map currently in map32 (for the aliasing forward read)
 };
@@ -860,9 +861,16 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
     for (int f = 0; f < nF; ++f) {
         const int bx = pwf_tiles_x(fr[f].oW);
         total_bins += (size_t)bx * fr[f].oH;
-        const int nt = bx * pwf_tiles_y(fr[f].oH);
-        if (nt > max_tiles) max_tiles = nt;
     }
+    // rows per CTA = 16 * niter: long-lived CTAs amortise their start-up and keep the software pipeline full
+    int max_ow = 1, max_oh = 1;
+    for (int f = 0; f < nF; ++f) {
+        if (fr[f].oW > max_ow) max_ow = fr[f].oW;
+        if (fr[f].oH > max_oh) max_oh = fr[f].oH;
+    }
+    int niter = 16;
+    while (niter > 1 && (long long)pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter) * nF < (long long)c->sm_count * 16) niter >>= 1;
+    max_tiles = pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter);
     TRY(ensure(c, c->rec, sizeof(TriRec) * T * nF));
     TRY(ensure(c, c->invd, sizeof(double) * 6 * T * nF));
     TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * total_bins));
@@ -905,7 +913,7 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         CU(c, cudaGetLastError());
     }
     TRY(prof_begin(c));
-    pw_warp_fused_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
+    pw_warp_fused_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p, niter);
     c->launches++;
     CU(c, cudaGetLastError());
     TRY(prof_end(c));
@@ -950,6 +958,9 @@ int hg_warp_piecewise_inverse(hg_ctx *c, const float *dst_pts, int x_off, int y_
     if (general) {
         TRY(pw_inverse_general_frame(c, (const float *)c->dst_pts.p, f, min_src_x, min_src_y));
         c->map32_current = true;
+        c->n_general++;
+    } else {
+        c->n_fused++;
     }
     return finish_out(c, dst, bytes, out_host);
 }
@@ -1064,8 +1075,19 @@ int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *dst_pts, const hg_fr
         if (status[(size_t)f]) {  // not representable by the bins: the general, map-based path (exact for everything)
             TRY(pw_inverse_general_frame(c, (const float *)c->dst_pts.p + pts_per_frame * (size_t)f, fr[(size_t)f],
                                          min_src_x, min_src_y));
+            c->n_general++;
+        } else {
+            c->n_fused++;
         }
     }
+    return HG_OK;
+}
+
+int hg_debug_piecewise_stats(hg_ctx *c, uint64_t *frames_fused, uint64_t *frames_general)
+{
+    if (!c || !frames_fused || !frames_general) return HG_ERR_INVALID;
+    *frames_fused = c->n_fused;
+    *frames_general = c->n_general;
     return HG_OK;
 }
 

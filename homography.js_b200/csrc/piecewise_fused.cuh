@@ -79,101 +79,199 @@ __global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *fram
     }
 }
 
-constexpr int PWF_ROWS = 4;                    // rows per thread
-constexpr int PWF_TY = 8;                      // thread rows per CTA
-constexpr int PWF_THREADS = 16 * PWF_TY;       // 16 quads (= one 64-column bin) x 8
-constexpr int PWF_TILE_ROWS = PWF_TY * PWF_ROWS;
+#ifndef HG_PWF_MINB
+#define HG_PWF_MINB 5
+#endif
+constexpr int PWF_R = 2;                        // rows per thread per row group
+constexpr int PWF_TY = 8;                       // thread rows per CTA
+constexpr int PWF_THREADS = 16 * PWF_TY;        // 16 quads (= one 64-column bin) x 8
+constexpr int PWF_GROUP_ROWS = PWF_TY * PWF_R;  // rows one CTA covers per iteration
 
 __host__ __device__ inline int pwf_tiles_x(int oW) { return (oW + PW_BIN_W - 1) / PW_BIN_W; }
-__host__ __device__ inline int pwf_tiles_y(int oH) { return (oH + PWF_TILE_ROWS - 1) / PWF_TILE_ROWS; }
+__host__ __device__ inline int pwf_tiles_y(int oH, int niter) { return (oH + PWF_GROUP_ROWS * niter - 1) / (PWF_GROUP_ROWS * niter); }
 
-// CTA = one 64-column bin x 32 rows; thread = one quad x 4 consecutive rows (16 pixels, 16 gathers in flight)
-__global__ void __launch_bounds__(PWF_THREADS, 4) pw_warp_fused_kernel(const FusedFrame *frames)
+__device__ __forceinline__ void pwf_load_matrix(const double *inv, int t, double (&m)[6])
+{
+    const double2 *p = reinterpret_cast<const double2 *>(inv + 6 * (size_t)t);
+    const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    m[0] = a.x; m[1] = a.y; m[2] = b.x; m[3] = b.y; m[4] = c.x; m[5] = c.y;
+}
+
+// coordinates -> flat source index or HG_OUTSIDE: window test [minSrc, W+minSrc) x [minSrc, H+minSrc) on the unrounded
+// coordinate (H.js:1047), Math.round, flat index, reads outside the image give nothing (H.js:1048-1052)
+__device__ __forceinline__ unsigned pwf_decode(double sx, double sy, const FusedFrame &F, long long npx_src)
+{
+    const double tx2 = __dadd_rd(sx, HG_MAGIC), ty2 = __dadd_rd(sy, HG_MAGIC);
+    const int ix = __double2hiint(tx2) - HG_HI_ZERO, iy = __double2hiint(ty2) - HG_HI_ZERO;
+    const int rx = ix + (int)((unsigned)__double2loint(tx2) >> 31);
+    const int ry = iy + (int)((unsigned)__double2loint(ty2) >> 31);
+    const long long fl = (long long)ry * F.W + rx;
+    const bool ok = ((unsigned)(ix - F.minSrcX) < (unsigned)F.W) & ((unsigned)(iy - F.minSrcY) < (unsigned)F.H) &
+                    (fl >= 0) & (fl < npx_src);
+    return ok ? (unsigned)fl : HG_OUTSIDE;
+}
+
+// CTA = one 64-column bin column x (16 * niter) rows; thread = one quad x PWF_R rows per row group.
+// FIVE-STAGE SOFTWARE PIPELINE inside each warp — every stage consumes what an earlier iteration produced, so the
+// three dependent memory round trips of the path (bins -> triangle matrix -> source pixel) overlap with arithmetic:
+//   iteration i:  S4 store group i-4 | S3 issue gathers of group i-3 | S2 coordinates of group i-2 (H.js:1046-1048)
+//                 S1 resolve triangle ids of group i-1 from its bins, issue the matrix loads | S0 issue bin loads of i
+// The thread keeps the inverse matrices of two triangles in registers (those of the first and last pixel of its
+// block); a pixel in a third triangle fetches its matrix on the spot (rare: the block is 4 x 2 pixels).
+__global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel(const FusedFrame *frames, int niter)
 {
     const FusedFrame F = frames[blockIdx.y];
     const int tiles_x = pwf_tiles_x(F.oW);
     const int tile_y = blockIdx.x / tiles_x;
     const int tile_x = blockIdx.x - tile_y * tiles_x;
-    if (tile_y * PWF_TILE_ROWS >= F.oH) return;
+    const int row0 = tile_y * PWF_GROUP_ROWS * niter;
+    if (row0 >= F.oH) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int c_rel = tx * 4;                       // first column of the quad inside the bin
     const int xx0 = tile_x * PW_BIN_W + c_rel;      // output column
     if (xx0 >= F.oW) return;
-    const int yy0 = tile_y * PWF_TILE_ROWS + ty * PWF_ROWS;
-    if (yy0 >= F.oH) return;
+    const int base0 = row0 + ty * PWF_R;
+    if (base0 >= F.oH) return;
+    const int ngroups = min(niter, (F.oH - base0 + PWF_GROUP_ROWS - 1) / PWF_GROUP_ROWS);
     const uint32_t *__restrict__ src = F.src;
     const long long npx_src = (long long)F.W * F.H;
-    const bool vec = ((F.oW & 3) == 0);             // dense rows are 16-byte aligned only then
+    const bool vec = ((F.oW & 3) == 0) && (F.oW - xx0 >= 4);  // dense rows are 16-byte aligned only when oW % 4 == 0
     const int nvalid = min(4, F.oW - xx0);
 
     double xs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) xs[k] = (double)(F.xOff + xx0 + k);
 
-    long long flat[PWF_ROWS][4];
-    // the inverse matrix of the triangle the thread is currently inside: neighbouring pixels and rows mostly share
-    // it, so it is (re)loaded only when the triangle id changes (3 x 16 B from L1/L2 instead of 48 B per pixel)
-    int cur_t = -1;
-    double m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;
+    unsigned bcnt[PWF_R];
+    uint4 be0[PWF_R], be1[PWF_R];
+    int tri[PWF_R][4];
+    int tA = -1, tB = -1;
+    unsigned rowuni = 0;  // bit j: the four pixels of row j share one triangle id
+    double mA[6] = {0, 0, 0, 0, 0, 0}, mB[6] = {0, 0, 0, 0, 0, 0};
+    unsigned idx[PWF_R][4];
+    uint32_t px[PWF_R][4];
+
+#pragma unroll 1
+    for (int it = 0; it < ngroups + 4; ++it) {
+        // ---- S4: store group it-4
+        if (it >= 4) {
+            const int yb = base0 + (it - 4) * PWF_GROUP_ROWS;
+            uint32_t *dst = F.out + ((long long)yb * F.oW + xx0);
 #pragma unroll
-    for (int j = 0; j < PWF_ROWS; ++j) {
-        const int yy = yy0 + j;
-        int best[4] = {-1, -1, -1, -1};
-        if (yy < F.oH) {
-            const size_t bin = (size_t)yy * F.bins_x + tile_x;
-            const unsigned cnt = min(__ldg(F.bin_cnt + bin), (unsigned)PW_BIN_CAP);
-            for (unsigned e = 0; e < cnt; ++e) {
-                const unsigned ent = __ldg(F.bin_ent + bin * PW_BIN_CAP + e);
-                const int lo = (int)(ent & 127u), hi = (int)((ent >> 7) & 127u), t = (int)(ent >> 14);
+            for (int j = 0; j < PWF_R; ++j) {
+                if (yb + j < F.oH) {
+                    if (vec) {
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(px[j][0], px[j][1], px[j][2], px[j][3]);
+                    } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if ((unsigned)(c_rel + k - lo) < (unsigned)(hi - lo)) best[k] = max(best[k], t);
+                        for (int k = 0; k < 4; ++k)
+                            if (k < nvalid) dst[k] = px[j][k];
+                    }
+                }
+                dst += F.oW;
             }
         }
-        const double y = (double)(F.yOff + yy);
+        // ---- S3: gathers of group it-3
+        if (it >= 3 && it - 3 < ngroups) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            long long f = -1;
-            // Int16Array semantics of the map: the stored id is t mod 2^16 as int16; negative = no triangle
-            const int t = (best[k] < 0) ? -1 : (int)(short)(unsigned short)(best[k] & 0xFFFF);
-            if (t >= 0 && t < F.n_tris) {
-                if (t != cur_t) {
-                    const double2 *m = reinterpret_cast<const double2 *>(F.inv + 6 * (size_t)t);
-                    const double2 m01 = __ldg(m), m23 = __ldg(m + 1), m45 = __ldg(m + 2);
-                    m0 = m01.x; m1 = m01.y; m2 = m23.x; m3 = m23.y; m4 = m45.x; m5 = m45.y;
-                    cur_t = t;
-                }
-                const double sx = affine_coord_exact(m0, xs[k], __dmul_rn(m2, y), m4);
-                const double sy = affine_coord_exact(m1, xs[k], __dmul_rn(m3, y), m5);
-                const double tx2 = __dadd_rd(sx, HG_MAGIC), ty2 = __dadd_rd(sy, HG_MAGIC);
-                const int ix = __double2hiint(tx2) - HG_HI_ZERO, iy = __double2hiint(ty2) - HG_HI_ZERO;
-                // minSrcX <= sx < W + minSrcX and minSrcY <= sy < H + minSrcY  (H.js:1047)
-                if ((unsigned)(ix - F.minSrcX) < (unsigned)F.W && (unsigned)(iy - F.minSrcY) < (unsigned)F.H) {
-                    const int rx = ix + (int)((unsigned)__double2loint(tx2) >> 31);
-                    const int ry = iy + (int)((unsigned)__double2loint(ty2) >> 31);
-                    const long long fl = (long long)ry * F.W + rx;
-                    if (fl >= 0 && fl < npx_src) f = fl;
+            for (int j = 0; j < PWF_R; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) px[j][k] = ldg_or_zero(src, idx[j][k]);
+        }
+        // ---- S2: coordinates of group it-2
+        if (it >= 2 && it - 2 < ngroups) {
+            const int yb = base0 + (it - 2) * PWF_GROUP_ROWS;
+#pragma unroll
+            for (int j = 0; j < PWF_R; ++j) {
+                const double y = (double)(F.yOff + yb + j);
+                const int t0 = tri[j][0];
+                if (((rowuni >> j) & 1u) && t0 == tA) {
+                    // common case: the four pixels of this row lie in the triangle whose matrix is in mA
+                    if (t0 >= 0) {
+                        const double r0 = __dmul_rn(mA[2], y), r1 = __dmul_rn(mA[3], y);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            idx[j][k] = pwf_decode(affine_coord_exact(mA[0], xs[k], r0, mA[4]),
+                                                   affine_coord_exact(mA[1], xs[k], r1, mA[5]), F, npx_src);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) idx[j][k] = HG_OUTSIDE;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int t = tri[j][k];
+                        unsigned f = HG_OUTSIDE;
+                        if (t >= 0) {
+                            double m[6];
+                            if (t != tA && t != tB) {
+                                pwf_load_matrix(F.inv, t, m);  // third triangle inside a 4x2 block: rare
+                            } else {
+                                const bool useA = (t == tA);
+#pragma unroll
+                                for (int q = 0; q < 6; ++q) m[q] = useA ? mA[q] : mB[q];
+                            }
+                            f = pwf_decode(affine_coord_exact(m[0], xs[k], __dmul_rn(m[2], y), m[4]),
+                                           affine_coord_exact(m[1], xs[k], __dmul_rn(m[3], y), m[5]), F, npx_src);
+                        }
+                        idx[j][k] = f;
+                    }
                 }
             }
-            flat[j][k] = f;
         }
-    }
-    uint32_t px[PWF_ROWS][4];
+        // ---- S1: triangle ids of group it-1 from its bins; fetch the matrices S2 will need next iteration
+        if (it >= 1 && it - 1 < ngroups) {
+            const int yb = base0 + (it - 1) * PWF_GROUP_ROWS;
+            rowuni = 0;
 #pragma unroll
-    for (int j = 0; j < PWF_ROWS; ++j)
+            for (int j = 0; j < PWF_R; ++j) {
+                int tfull = -1;                      // highest id among entries covering the WHOLE quad
+                int best[4] = {-1, -1, -1, -1};      // per pixel, only for entries that cut through the quad
+                bool mixed = false;
+                if (yb + j < F.oH) {
+                    const unsigned ent[8] = {be0[j].x, be0[j].y, be0[j].z, be0[j].w, be1[j].x, be1[j].y, be1[j].z, be1[j].w};
+                    const unsigned cnt = min(bcnt[j], (unsigned)PW_BIN_CAP);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) px[j][k] = (flat[j][k] >= 0) ? __ldg(src + flat[j][k]) : 0u;
+                    for (int e = 0; e < PW_BIN_CAP; ++e) {
+                        if ((unsigned)e >= cnt) break;
+                        const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u), t = (int)(ent[e] >> 14);
+                        if (lo <= c_rel && c_rel + 4 <= hi) {
+                            tfull = max(tfull, t);
+                        } else if (lo < c_rel + 4 && c_rel < hi) {
+                            mixed = true;
 #pragma unroll
-    for (int j = 0; j < PWF_ROWS; ++j) {
-        const int yy = yy0 + j;
-        if (yy < F.oH) {
-            uint32_t *dst = F.out + ((long long)yy * F.oW + xx0);
-            if (vec && nvalid == 4) {
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(px[j][0], px[j][1], px[j][2], px[j][3]);
-            } else {
+                            for (int k = 0; k < 4; ++k)
+                                if ((unsigned)(c_rel + k - lo) < (unsigned)(hi - lo)) best[k] = max(best[k], t);
+                        }
+                    }
+                }
+                bool uni = true;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (k < nvalid) dst[k] = px[j][k];
+                for (int k = 0; k < 4; ++k) {
+                    const int raw = mixed ? max(tfull, best[k]) : tfull;
+                    // Int16Array semantics of the map: the stored id is t mod 2^16 as int16; negative = no triangle
+                    const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);
+                    tri[j][k] = (t >= 0 && t < F.n_tris) ? t : -1;
+                    uni = uni && (tri[j][k] == tri[j][0]);
+                }
+                rowuni |= uni ? (1u << j) : 0u;
+            }
+            tA = tri[0][0];
+            tB = tri[PWF_R - 1][3];
+            if (tA >= 0) pwf_load_matrix(F.inv, tA, mA);
+            if (tB >= 0 && tB != tA) pwf_load_matrix(F.inv, tB, mB);
+        }
+        // ---- S0: bin loads of group it
+        if (it < ngroups) {
+            const int yb = base0 + it * PWF_GROUP_ROWS;
+#pragma unroll
+            for (int j = 0; j < PWF_R; ++j) {
+                const int yy = min(yb + j, F.oH - 1);
+                const size_t bin = (size_t)yy * F.bins_x + tile_x;
+                bcnt[j] = __ldg(F.bin_cnt + bin);
+                const uint4 *e = reinterpret_cast<const uint4 *>(F.bin_ent + bin * PW_BIN_CAP);
+                be0[j] = __ldg(e);
+                be1[j] = __ldg(e + 1);
             }
         }
     }

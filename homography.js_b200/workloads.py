@@ -83,3 +83,20 @@ def piecewise_extent(dst: np.ndarray):
     d = np.asarray(dst, np.float64).reshape(-1, 2)
     x0, y0, x1, y1 = r(d[:, 0].min()), r(d[:, 1].min()), r(d[:, 0].max()), r(d[:, 1].max())
     return int(x0), int(y0), int(x1 - x0), int(y1 - y0)
+
+
+def video_stream(n_frames: int, w: int = 1920, h: int = 1080, seed: int = 5):
+    """Config 5: 30 points (6x5 grid, interior points jittered +-2 % by rng seed 5), a fixed triangulation, and per-frame
+    destiny points dst_f = src + 0.03*(w,h)*(sin(w1 f + th_i), cos(w2 f + th_i)); the output window changes every frame."""
+    rng = np.random.default_rng(seed)
+    src, tris = grid_mesh(6, 5, w, h)
+    src = src.astype(np.float64)
+    interior = (src[:, 0] > 0) & (src[:, 0] < w) & (src[:, 1] > 0) & (src[:, 1] < h)
+    src[interior] += rng.uniform(-0.02, 0.02, (int(interior.sum()), 2)) * [w, h]
+    src = src.astype(np.float32)
+    theta = rng.uniform(0, 2 * math.pi, len(src))
+    f = np.arange(n_frames)[:, None]
+    dx = 0.03 * w * np.sin(0.11 * f + theta[None, :])
+    dy = 0.03 * h * np.cos(0.07 * f + theta[None, :])
+    dst = (src[None, :, :].astype(np.float64) + np.stack([dx, dy], axis=2)).astype(np.float32)
+    return src, dst, tris

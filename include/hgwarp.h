@@ -160,6 +160,8 @@ int hg_pipe_destroy(hg_pipe *pipe);
 int hg_debug_rcp_max_error(hg_ctx *ctx, int biased_exponent, int negative, double *max_rel_err);
 /* on != 0: inverse piecewise warps always take the general map-based path (tests compare it with the fused one) */
 int hg_debug_force_general(hg_ctx *ctx, int on);
+/* how many inverse piecewise frames were finished by the fused (map-free) path / by the general map-based path */
+int hg_debug_piecewise_stats(hg_ctx *ctx, uint64_t *frames_fused, uint64_t *frames_general);
 
 /* ------------------------------------------------------------------ device memory helpers (benchmarks / bindings) */
 int hg_dev_alloc(hg_ctx *ctx, size_t bytes, void **dev_ptr);

@@ -521,3 +521,52 @@ def test_piecewise_batch_matches_oracle(ctx):
         assert _diff(got, want) == 0, f
     for p in dev_src + outs:
         ctx.dev_free(p)
+
+
+def test_config5_video_stream_variable_windows(ctx):
+    """Config 5 shape (scaled down 4x): 30-point mesh, per-frame destiny points, a different output window per
+    frame (negative offsets -> Q4 spill on every frame); all frames through one batch call, bit-exact, and the
+    fused path must take them (no silent fallback to the map)."""
+    import homography_js_b200 as hgm
+    w, h, n = 480, 270, 12
+    img = _rand_img(5, w, h)
+    src, dst, tris = hgm.workloads.video_stream(n, w, h)
+    smm = [int(v) for v in O.minmax_xy(src)]
+    ctx.image_set(img, w, h)
+    ctx.piecewise_set_mesh(src, tris)
+    frames, outs, shapes = [], [], []
+    for f in range(n):
+        xo, yo, oW, oH = hgm.workloads.piecewise_extent(dst[f])
+        p = ctx.dev_alloc(oW * oH * 4)
+        outs.append(p); shapes.append((xo, yo, oW, oH))
+        frames.append(hg.HgFrame(None, p, 0, 0, xo, yo, oW, oH))
+    assert len(set(shapes)) > 1
+    f0, g0 = ctx.debug_piecewise_stats()
+    ctx.warp_piecewise_inverse_batch(dst, frames, smm[0], smm[1])
+    f1, g1 = ctx.debug_piecewise_stats()
+    assert (f1 - f0, g1 - g0) == (n, 0), "frames fell back to the general path"
+    for f in range(n):
+        xo, yo, oW, oH = shapes[f]
+        got = np.empty(oW * oH * 4, np.uint8)
+        ctx.memcpy_d2h(got.ctypes.data, outs[f], got.nbytes)
+        ctx.synchronize()
+        fwd = O.piecewise_matrices(src, dst[f], tris)
+        imap = O.build_index_map(dst[f], tris, oW, yo, oW * oH)
+        want = O.warp_inverse_piecewise(img, w, h, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, smm[0], smm[1], threads=4)
+        assert _diff(got, want) == 0, f
+    for p in outs:
+        ctx.dev_free(p)
+
+
+def test_folded_mesh_overflows_bins_and_falls_back(ctx):
+    """More than 8 overlapping spans in one 64-pixel block: the fused path must refuse and the general path answer."""
+    rng = np.random.default_rng(99)
+    W, H = 128, 96
+    img = _rand_img(13, W, H)
+    src = rng.uniform(0, [W, H], (40, 2)).astype(np.float32)
+    dst = (rng.uniform(0, [W, H], (40, 2)) * 0.9 + 3).astype(np.float32)   # unrelated to src: everything overlaps
+    tris = rng.integers(0, 40, (60, 3)).astype(np.uint32)
+    f0, g0 = ctx.debug_piecewise_stats()
+    _pw_case(ctx, img, src, dst, tris)
+    f1, g1 = ctx.debug_piecewise_stats()
+    assert g1 - g0 == 1 and f1 == f0
