@@ -28,6 +28,14 @@ if ROOT not in sys.path:
 ALG_BYTES_PER_PIXEL = 8  # 4 B RGBA8 read + 4 B RGBA8 write per output pixel (SURVEY §8d / north_star)
 
 
+def measured_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -403,7 +411,8 @@ def main():
                              f"({(src_ring.numel() + out_ring.numel()) / 1e6:.0f} MB) > 126 MB L2",
                        "parity_gate": parity},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "warp_inverse_geo_kernel<%s>" % ("projective" if KIND else "affine"),
+                         "traffic": measured_traffic("warp_inverse_geo_kernel<%s>" % ("projective" if KIND else "affine")) if F == 64 else None,
+                         "kernel": "warp_inverse_geo_kernel<%s>" % ("projective" if KIND else "affine"),
                          "alg_bytes_per_launch": ALG_BYTES_PER_PIXEL * px_per_launch,
                          "avg_kernel_ms": avg_kernel_s * 1e3, "kernels_timed": kern_n, "peak_source": peak_src},
             "cpu_baseline": cpu,
