@@ -229,6 +229,98 @@ def run_piecewise(args, which):
     ctx.close()
 
 
+def run_video5(args):
+    """Secondary line: BASELINE config 5 — video stream, 1920x1080, 30-point piecewise mesh, per-frame destiny points
+    (a different output window every frame), ONE source image shared by all GPUs: rank 0 owns it and it is broadcast
+    once over NCCL (NVLink) before the timed region; frames are block-partitioned over ranks, no other collective."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    import homography_js_b200 as hg
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = hg.Context(local_rank)
+    w, h = 1920, 1080
+    n_total = args.frames * world if args.frames != 64 else 256 * world   # frames per step, whole job
+    src_pts, dst_all, tris = hg.workloads.video_stream(n_total, w, h)
+    lo, hi = hg.workloads.shard_range(n_total, rank, world)
+    image = torch.zeros(h * w * 4, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        image = torch.randint(0, 256, (h * w * 4,), dtype=torch.uint8, device=dev, generator=g)
+    bcast_ms = None
+    if world > 1:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dist.broadcast(image, src=0)          # the one collective of the design: W*H*4 bytes, once
+        torch.cuda.synchronize()
+        bcast_ms = (time.perf_counter() - t0) * 1e3
+    ctx.image_set_device(image.data_ptr(), w, h)
+    ctx.piecewise_set_mesh(src_pts, tris)
+    smm = [int(np.floor(v + 0.5)) for v in (src_pts[:, 0].min(), src_pts[:, 1].min())]
+    frames, outs, npix = [], [], 0
+    for f in range(lo, hi):
+        xo, yo, oW, oH = hg.workloads.piecewise_extent(dst_all[f])
+        o = torch.empty(oW * oH * 4, dtype=torch.uint8, device=dev)
+        outs.append(o)
+        frames.append(hg.HgFrame(None, o.data_ptr(), 0, 0, xo, yo, oW, oH))
+        npix += oW * oH
+    arr = (hg.HgFrame * len(frames))(*frames)
+    mine = np.ascontiguousarray(dst_all[lo:hi])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        ctx.warp_piecewise_inverse_batch(mine, arr, smm[0], smm[1])
+    f0, g0 = ctx.debug_piecewise_stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.warp_piecewise_inverse_batch(mine, arr, smm[0], smm[1])   # ends with a stream sync (status read-back)
+    ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    f1, g1 = ctx.debug_piecewise_stats()
+    tot = torch.tensor([float(npix), ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        px_all = tot[:1].clone()
+        dist.all_reduce(px_all, op=dist.ReduceOp.SUM)
+        ms_max = tot[1:].clone()
+        dist.all_reduce(ms_max, op=dist.ReduceOp.MAX)
+        npix_all, ms = float(px_all.item()), float(ms_max.item())
+    else:
+        npix_all = float(npix)
+    parity = None
+    if rank == 0:
+        from oracle import oracle as O
+        O.build()
+        xo, yo, oW, oH = frames[0].x_off, frames[0].y_off, frames[0].o_w, frames[0].o_h
+        fwd = O.piecewise_matrices(src_pts, dst_all[lo], tris)
+        imap = O.build_index_map(dst_all[lo], tris, oW, yo, oW * oH)
+        want = O.warp_inverse_piecewise(image.cpu().numpy(), w, h, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, smm[0], smm[1],
+                                        threads=os.cpu_count() or 1)
+        parity = bool(np.array_equal(outs[0].cpu().numpy(), want))
+        peak, _ = measured_peak_gbs()
+        val = npix_all * args.steps / (ms * 1e-3) / 1e6
+        print(json.dumps({"metric": "Mpix/s warped", "value": val, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+                          "ms_per_step": ms / args.steps, "scaling": "weak", "parity_gate": parity,
+                          "workload": f"video: 1920x1080, 30-pt piecewise ({len(tris)} tris), per-frame dstPoints, {n_total} frames/step sharded over {world} GPU(s)",
+                          "frames_fused_vs_general": [int(f1 - f0), int(g1 - g0)],
+                          "nccl_broadcast_ms": bcast_ms, "roofline_frac_whole_step": ALG_BYTES_PER_PIXEL * val * 1e6 / 1e9 / (peak * world)}),
+              flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -240,7 +332,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="projective", choices=["projective", "affine", "projective_generic", "piecewise3", "piecewise4"],
+    ap.add_argument("--workload", default="projective", choices=["projective", "affine", "projective_generic", "affine_rot90", "piecewise3", "piecewise4", "video5"],
                     help="projective = BASELINE config 2 (the headline); affine = same sizes through the affine kernel")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -248,6 +340,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "video5":
+        run_video5(args)
         return
     if args.workload.startswith("piecewise"):
         run_piecewise(args, args.workload)
@@ -280,7 +375,8 @@ def main():
 
     ctx = hg.Context(local_rank)
     wl = {"projective": hg.workloads.projective_1080p, "affine": hg.workloads.affine_1080p,
-          "projective_generic": hg.workloads.projective_1080p_generic}[args.workload]()
+          "projective_generic": hg.workloads.projective_1080p_generic,
+          "affine_rot90": hg.workloads.affine_1080p_rot90}[args.workload]()
     KIND = wl["kind"]
     W, H, oW, oH = wl["W"], wl["H"], wl["o_w"], wl["o_h"]
     F = args.frames

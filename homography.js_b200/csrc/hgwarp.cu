@@ -873,8 +873,10 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
     max_tiles = pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter);
     TRY(ensure(c, c->rec, sizeof(TriRec) * T * nF));
     TRY(ensure(c, c->invd, sizeof(double) * 6 * T * nF));
-    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * total_bins));
-    TRY(ensure(c, c->bin_ent, sizeof(unsigned) * total_bins * PW_BIN_CAP));
+    // + one row group of slack: the pixel kernel's bin pointers may step (and read, but never use) past the last row
+    const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
+    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * (total_bins + slack)));
+    TRY(ensure(c, c->bin_ent, sizeof(unsigned) * (total_bins + slack) * PW_BIN_CAP));
     TRY(ensure(c, c->fstatus, sizeof(int) * (size_t)nF));
     TRY(ensure(c, c->fframes, sizeof(FusedFrame) * (size_t)nF));
     size_t bin0 = 0;

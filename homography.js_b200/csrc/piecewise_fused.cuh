@@ -98,17 +98,29 @@ __device__ __forceinline__ void pwf_load_matrix(const double *inv, int t, double
 }
 
 // coordinates -> flat source index or HG_OUTSIDE: window test [minSrc, W+minSrc) x [minSrc, H+minSrc) on the unrounded
-// coordinate (H.js:1047), Math.round, flat index, reads outside the image give nothing (H.js:1048-1052)
-__device__ __forceinline__ unsigned pwf_decode(double sx, double sy, const FusedFrame &F, long long npx_src)
+// coordinate (H.js:1047), Math.round, flat index, reads outside the image give nothing (H.js:1048-1052).
+// ZERO_OFF: minSrcX == minSrcY == 0 (source points start at the image origin — the usual case): everything fits
+// unsigned 32-bit arithmetic exactly like the affine / projective kernels.
+template <bool ZERO_OFF>
+__device__ __forceinline__ unsigned pwf_decode(double sx, double sy, const FusedFrame &F, unsigned npx_src)
 {
     const double tx2 = __dadd_rd(sx, HG_MAGIC), ty2 = __dadd_rd(sy, HG_MAGIC);
+    if (ZERO_OFF) return decode_flat(tx2, ty2, (unsigned)F.W, (unsigned)F.H, npx_src);
     const int ix = __double2hiint(tx2) - HG_HI_ZERO, iy = __double2hiint(ty2) - HG_HI_ZERO;
     const int rx = ix + (int)((unsigned)__double2loint(tx2) >> 31);
     const int ry = iy + (int)((unsigned)__double2loint(ty2) >> 31);
     const long long fl = (long long)ry * F.W + rx;
     const bool ok = ((unsigned)(ix - F.minSrcX) < (unsigned)F.W) & ((unsigned)(iy - F.minSrcY) < (unsigned)F.H) &
-                    (fl >= 0) & (fl < npx_src);
+                    (fl >= 0) & (fl < (long long)npx_src);
     return ok ? (unsigned)fl : HG_OUTSIDE;
+}
+
+// Int16Array semantics of the map (H.js:848): the stored id is t mod 2^16 as int16, negative = no triangle; ids that
+// would index past the matrix list never occur for maps built from the same mesh
+__device__ __forceinline__ int pwf_map_id(int raw, int n_tris)
+{
+    const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);
+    return (t >= 0 && t < n_tris) ? t : -1;
 }
 
 // CTA = one 64-column bin column x (16 * niter) rows; thread = one quad x PWF_R rows per row group.
@@ -118,14 +130,9 @@ __device__ __forceinline__ unsigned pwf_decode(double sx, double sy, const Fused
 //                 S1 resolve triangle ids of group i-1 from its bins, issue the matrix loads | S0 issue bin loads of i
 // The thread keeps the inverse matrices of two triangles in registers (those of the first and last pixel of its
 // block); a pixel in a third triangle fetches its matrix on the spot (rare: the block is 4 x 2 pixels).
-__global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel(const FusedFrame *frames, int niter)
+template <bool ZERO_OFF>
+__device__ __forceinline__ void pwf_body(const FusedFrame &F, int niter, int tile_x, int row0)
 {
-    const FusedFrame F = frames[blockIdx.y];
-    const int tiles_x = pwf_tiles_x(F.oW);
-    const int tile_y = blockIdx.x / tiles_x;
-    const int tile_x = blockIdx.x - tile_y * tiles_x;
-    const int row0 = tile_y * PWF_GROUP_ROWS * niter;
-    if (row0 >= F.oH) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int c_rel = tx * 4;                       // first column of the quad inside the bin
     const int xx0 = tile_x * PW_BIN_W + c_rel;      // output column
@@ -134,13 +141,22 @@ __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel
     if (base0 >= F.oH) return;
     const int ngroups = min(niter, (F.oH - base0 + PWF_GROUP_ROWS - 1) / PWF_GROUP_ROWS);
     const uint32_t *__restrict__ src = F.src;
-    const long long npx_src = (long long)F.W * F.H;
+    const unsigned npx_src = (unsigned)F.W * (unsigned)F.H;
     const bool vec = ((F.oW & 3) == 0) && (F.oW - xx0 >= 4);  // dense rows are 16-byte aligned only when oW % 4 == 0
     const int nvalid = min(4, F.oW - xx0);
+    const int oH = F.oH, n_tris = F.n_tris;
 
     double xs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) xs[k] = (double)(F.xOff + xx0 + k);
+
+    // S0 walks the bins of its rows with two pointers that advance by one row group per iteration (the bin arrays
+    // are allocated with one row group of slack, so the last partial group may read, and ignore, past its frame)
+    const unsigned *p_cnt = F.bin_cnt + ((size_t)base0 * F.bins_x + tile_x);
+    const uint4 *p_ent = reinterpret_cast<const uint4 *>(F.bin_ent) + 2 * ((size_t)base0 * F.bins_x + tile_x);
+    const size_t cnt_step = (size_t)PWF_GROUP_ROWS * F.bins_x, row_step = (size_t)F.bins_x;
+    uint32_t *p_out = F.out + ((long long)base0 * F.oW + xx0);
+    const long long out_step = (long long)PWF_GROUP_ROWS * F.oW;
 
     unsigned bcnt[PWF_R];
     uint4 be0[PWF_R], be1[PWF_R];
@@ -156,10 +172,10 @@ __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel
         // ---- S4: store group it-4
         if (it >= 4) {
             const int yb = base0 + (it - 4) * PWF_GROUP_ROWS;
-            uint32_t *dst = F.out + ((long long)yb * F.oW + xx0);
+            uint32_t *dst = p_out;
 #pragma unroll
             for (int j = 0; j < PWF_R; ++j) {
-                if (yb + j < F.oH) {
+                if (yb + j < oH) {
                     if (vec) {
                         *reinterpret_cast<uint4 *>(dst) = make_uint4(px[j][0], px[j][1], px[j][2], px[j][3]);
                     } else {
@@ -170,6 +186,7 @@ __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel
                 }
                 dst += F.oW;
             }
+            p_out += out_step;
         }
         // ---- S3: gathers of group it-3
         if (it >= 3 && it - 3 < ngroups) {
@@ -191,8 +208,8 @@ __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel
                         const double r0 = __dmul_rn(mA[2], y), r1 = __dmul_rn(mA[3], y);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            idx[j][k] = pwf_decode(affine_coord_exact(mA[0], xs[k], r0, mA[4]),
-                                                   affine_coord_exact(mA[1], xs[k], r1, mA[5]), F, npx_src);
+                            idx[j][k] = pwf_decode<ZERO_OFF>(affine_coord_exact(mA[0], xs[k], r0, mA[4]),
+                                                             affine_coord_exact(mA[1], xs[k], r1, mA[5]), F, npx_src);
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) idx[j][k] = HG_OUTSIDE;
@@ -211,8 +228,8 @@ __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel
 #pragma unroll
                                 for (int q = 0; q < 6; ++q) m[q] = useA ? mA[q] : mB[q];
                             }
-                            f = pwf_decode(affine_coord_exact(m[0], xs[k], __dmul_rn(m[2], y), m[4]),
-                                           affine_coord_exact(m[1], xs[k], __dmul_rn(m[3], y), m[5]), F, npx_src);
+                            f = pwf_decode<ZERO_OFF>(affine_coord_exact(m[0], xs[k], __dmul_rn(m[2], y), m[4]),
+                                                     affine_coord_exact(m[1], xs[k], __dmul_rn(m[3], y), m[5]), F, npx_src);
                         }
                         idx[j][k] = f;
                     }
@@ -228,33 +245,35 @@ __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel
                 int tfull = -1;                      // highest id among entries covering the WHOLE quad
                 int best[4] = {-1, -1, -1, -1};      // per pixel, only for entries that cut through the quad
                 bool mixed = false;
-                if (yb + j < F.oH) {
-                    const unsigned ent[8] = {be0[j].x, be0[j].y, be0[j].z, be0[j].w, be1[j].x, be1[j].y, be1[j].z, be1[j].w};
-                    const unsigned cnt = min(bcnt[j], (unsigned)PW_BIN_CAP);
+                const unsigned cnt = (yb + j < oH) ? min(bcnt[j], (unsigned)PW_BIN_CAP) : 0u;
+                const unsigned ent[8] = {be0[j].x, be0[j].y, be0[j].z, be0[j].w, be1[j].x, be1[j].y, be1[j].z, be1[j].w};
 #pragma unroll
-                    for (int e = 0; e < PW_BIN_CAP; ++e) {
-                        if ((unsigned)e >= cnt) break;
-                        const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u), t = (int)(ent[e] >> 14);
-                        if (lo <= c_rel && c_rel + 4 <= hi) {
-                            tfull = max(tfull, t);
-                        } else if (lo < c_rel + 4 && c_rel < hi) {
-                            mixed = true;
+                for (int e = 0; e < PW_BIN_CAP; ++e) {
+                    if ((unsigned)e >= cnt) break;
+                    const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u), t = (int)(ent[e] >> 14);
+                    if (lo <= c_rel && c_rel + 4 <= hi) {
+                        tfull = max(tfull, t);
+                    } else if (lo < c_rel + 4 && c_rel < hi) {
+                        mixed = true;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if ((unsigned)(c_rel + k - lo) < (unsigned)(hi - lo)) best[k] = max(best[k], t);
-                        }
+                        for (int k = 0; k < 4; ++k)
+                            if ((unsigned)(c_rel + k - lo) < (unsigned)(hi - lo)) best[k] = max(best[k], t);
                     }
                 }
-                bool uni = true;
+                if (!mixed) {
+                    const int t = pwf_map_id(tfull, n_tris);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int raw = mixed ? max(tfull, best[k]) : tfull;
-                    // Int16Array semantics of the map: the stored id is t mod 2^16 as int16; negative = no triangle
-                    const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);
-                    tri[j][k] = (t >= 0 && t < F.n_tris) ? t : -1;
-                    uni = uni && (tri[j][k] == tri[j][0]);
+                    for (int k = 0; k < 4; ++k) tri[j][k] = t;
+                    rowuni |= 1u << j;
+                } else {
+                    bool uni = true;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tri[j][k] = pwf_map_id(max(tfull, best[k]), n_tris);
+                        uni = uni && (tri[j][k] == tri[j][0]);
+                    }
+                    rowuni |= uni ? (1u << j) : 0u;
                 }
-                rowuni |= uni ? (1u << j) : 0u;
             }
             tA = tri[0][0];
             tB = tri[PWF_R - 1][3];
@@ -263,18 +282,28 @@ __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel
         }
         // ---- S0: bin loads of group it
         if (it < ngroups) {
-            const int yb = base0 + it * PWF_GROUP_ROWS;
 #pragma unroll
             for (int j = 0; j < PWF_R; ++j) {
-                const int yy = min(yb + j, F.oH - 1);
-                const size_t bin = (size_t)yy * F.bins_x + tile_x;
-                bcnt[j] = __ldg(F.bin_cnt + bin);
-                const uint4 *e = reinterpret_cast<const uint4 *>(F.bin_ent + bin * PW_BIN_CAP);
-                be0[j] = __ldg(e);
-                be1[j] = __ldg(e + 1);
+                bcnt[j] = __ldg(p_cnt + j * row_step);
+                be0[j] = __ldg(p_ent + 2 * j * row_step);
+                be1[j] = __ldg(p_ent + 2 * j * row_step + 1);
             }
+            p_cnt += cnt_step;
+            p_ent += 2 * cnt_step;
         }
     }
+}
+
+__global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel(const FusedFrame *frames, int niter)
+{
+    const FusedFrame F = frames[blockIdx.y];
+    const int tiles_x = pwf_tiles_x(F.oW);
+    const int tile_y = blockIdx.x / tiles_x;
+    const int tile_x = blockIdx.x - tile_y * tiles_x;
+    const int row0 = tile_y * PWF_GROUP_ROWS * niter;
+    if (row0 >= F.oH) return;
+    if (F.minSrcX == 0 && F.minSrcY == 0) pwf_body<true>(F, niter, tile_x, row0);
+    else pwf_body<false>(F, niter, tile_x, row0);
 }
 
 }  // namespace hg

@@ -68,30 +68,36 @@ __device__ __forceinline__ void projective_from_squares(const double *s, const d
         A[2 * p + 1][3] = sx; A[2 * p + 1][4] = sy; A[2 * p + 1][5] = 1.0;
         A[2 * p + 1][6] = __dmul_rn(ndy, sx); A[2 * p + 1][7] = __dmul_rn(ndy, sy);
     }
+    // Every loop below runs a FIXED 0..7 trip count with an `if` on compile-time indices, so full unrolling is
+    // guaranteed and, after it, every array subscript is a literal: A, P and x stay in registers.
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         int Pk = k;
         double mx = fabs(A[k][k]);
 #pragma unroll
-        for (int j = k + 1; j < 8; ++j) {
-            const double a = fabs(A[j][k]);
-            if (mx < a) { mx = a; Pk = j; }
+        for (int j = 0; j < 8; ++j) {
+            if (j > k) {
+                const double a = fabs(A[j][k]);
+                if (mx < a) { mx = a; Pk = j; }
+            }
         }
         P[k] = Pk;
 #pragma unroll
-        for (int j = k + 1; j < 8; ++j) {
-            if (Pk == j) {
+        for (int j = 0; j < 8; ++j) {
+            if (j > k && Pk == j) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) { const double t = A[k][c]; A[k][c] = A[j][c]; A[j][c] = t; }
             }
         }
         const double Akk = A[k][k];
 #pragma unroll
-        for (int i = k + 1; i < 8; ++i) A[i][k] = __ddiv_rn(A[i][k], Akk);
+        for (int i = 0; i < 8; ++i)
+            if (i > k) A[i][k] = __ddiv_rn(A[i][k], Akk);
 #pragma unroll
-        for (int i = k + 1; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i) {
 #pragma unroll
-            for (int j = k + 1; j < 8; ++j) A[i][j] = __dsub_rn(A[i][j], __dmul_rn(A[i][k], A[k][j]));
+            for (int j = 0; j < 8; ++j)
+                if (i > k && j > k) A[i][j] = __dsub_rn(A[i][j], __dmul_rn(A[i][k], A[k][j]));
         }
     }
     double x[8];
@@ -100,16 +106,19 @@ __device__ __forceinline__ void projective_from_squares(const double *s, const d
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
-        for (int j = i + 1; j < 8; ++j) {
-            if (P[i] == j) { const double t = x[i]; x[i] = x[j]; x[j] = t; }
+        for (int j = 0; j < 8; ++j) {
+            if (j > i && P[i] == j) { const double t = x[i]; x[i] = x[j]; x[j] = t; }
         }
 #pragma unroll
-        for (int j = 0; j < i; ++j) x[i] = __dsub_rn(x[i], __dmul_rn(x[j], A[i][j]));
+        for (int j = 0; j < 8; ++j)
+            if (j < i) x[i] = __dsub_rn(x[i], __dmul_rn(x[j], A[i][j]));
     }
 #pragma unroll
-    for (int i = 7; i >= 0; --i) {
+    for (int ii = 0; ii < 8; ++ii) {
+        const int i = 7 - ii;
 #pragma unroll
-        for (int j = i + 1; j < 8; ++j) x[i] = __dsub_rn(x[i], __dmul_rn(x[j], A[i][j]));
+        for (int j = 0; j < 8; ++j)
+            if (j > i) x[i] = __dsub_rn(x[i], __dmul_rn(x[j], A[i][j]));
         x[i] = __ddiv_rn(x[i], A[i][i]);
     }
 #pragma unroll

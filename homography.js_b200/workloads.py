@@ -43,6 +43,16 @@ def affine_1080p():
                 x_off=192, y_off=0, o_w=1728, o_h=1080)
 
 
+def affine_1080p_rot90():
+    """Diagnostic: 90-degree rotation (x' = h - y, y' = x) with a 10 % shrink so the inverse loop is dispatched; every
+    warp's gathers walk DOWN a source column (worst case for coalescing, the case TMA-staged source tiles would fix)."""
+    w, h = 1920, 1080
+    src = np.array([0, 0, 0, h, w, 0], np.float64)
+    dst = np.array([0.9 * h, 0, 0, 0, 0.9 * h, 0.9 * w], np.float64)
+    return dict(name="affine 90-degree rotation x0.9, 1920x1080 RGBA8 -> 972x1728", kind=0, W=w, H=h, src=src, dst=dst,
+                x_off=0, y_off=0, o_w=972, o_h=1728)
+
+
 def affine_256():
     """Config 1: affine 3-point warp, 256x256 (benchmark.js:204-205 shape)."""
     w = h = 256
