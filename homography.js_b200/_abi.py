@@ -23,7 +23,7 @@ SYMBOLS = [
     "hg_image_set", "hg_image_set_device",
     "hg_solve_affine", "hg_solve_projective", "hg_inverse_affine", "hg_transform_limits", "hg_solve_with_limits",
     "hg_warp_inverse_matrix", "hg_warp_inverse_points", "hg_warp_forward_matrix",
-    "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_build_index_map",
+    "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_piecewise_extents", "hg_build_index_map",
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
     "hg_pipe_create", "hg_pipe_submit", "hg_pipe_wait", "hg_pipe_flush", "hg_pipe_destroy",
@@ -84,6 +84,7 @@ def load():
     L.hg_warp_forward_matrix.argtypes = [vp, i, vp, i, i, i, i, vp, vp]
     L.hg_piecewise_set_mesh.argtypes = [vp, vp, i, vp, i]
     L.hg_piecewise_matrices.argtypes = [vp, vp, vp, vp]
+    L.hg_piecewise_extents.argtypes = [vp, vp, i, i, vp]
     L.hg_build_index_map.argtypes = [vp, vp, d, d, C.c_int64, vp]
     L.hg_warp_piecewise_inverse.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp]
     L.hg_warp_piecewise_forward.argtypes = [vp, vp, i, i, i, i, i, i, i, i, i, vp, vp]
@@ -310,6 +311,15 @@ class Context:
         inv = np.empty((self._n_tris, 6), np.float32) if want_inverse else None
         self._ck(self.L.hg_piecewise_matrices(self.h, _ptr(d), _ptr(fwd), _ptr(inv)))
         return (fwd, inv) if want_inverse else fwd
+
+    def piecewise_extents(self, dst_pts) -> np.ndarray:
+        """dst_pts: (n_frames, n_pts, 2) float32 -> (n_frames, 4) [xOff, yOff, oW, oH] (H.js:706-710)."""
+        d = np.ascontiguousarray(dst_pts, dtype=np.float32)
+        if d.ndim == 2:
+            d = d[None]
+        out = np.empty((d.shape[0], 4), np.float64)
+        self._ck(self.L.hg_piecewise_extents(self.h, _ptr(d), d.shape[1], d.shape[0], _ptr(out)))
+        return out
 
     def build_index_map(self, pts, map_width, y_offset, map_len) -> np.ndarray:
         p = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1)

@@ -792,6 +792,24 @@ int hg_piecewise_matrices(hg_ctx *c, const float *dst_pts, float *fwd_out, float
     return HG_OK;
 }
 
+int hg_piecewise_extents(hg_ctx *c, const float *dst_pts, int n_pts, int n_frames, double *out)
+{
+    BIND(c);
+    NEED(c, dst_pts && out, "NULL argument");
+    NEED(c, n_pts >= 1 && n_frames >= 1, "n_pts and n_frames must be >= 1");
+    const size_t in_bytes = sizeof(float) * 2 * (size_t)n_pts * n_frames, out_bytes = sizeof(double) * 4 * (size_t)n_frames;
+    TRY(ensure(c, c->dst_pts, in_bytes));
+    TRY(ensure(c, c->mats, out_bytes));
+    CU(c, cudaMemcpyAsync(c->dst_pts.p, dst_pts, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    pw_extent_kernel<<<(unsigned)((n_frames + 3) / 4), 128, 0, c->stream>>>((const float *)c->dst_pts.p, n_pts, n_frames,
+                                                                          (double *)c->mats.p);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(out, c->mats.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
 int hg_build_index_map(hg_ctx *c, const float *pts, double map_width, double y_offset, int64_t map_len,
                        int16_t *map_out_host)
 {

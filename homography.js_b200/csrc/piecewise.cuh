@@ -165,6 +165,40 @@ __global__ void map32_to_int16_kernel(const int *map32, short *out, long long n)
     }
 }
 
+// A9 for piecewise frames (H.js:706-710): xOff = round(min x), yOff = round(min y), oW = round(max x) - xOff,
+// oH = round(max y) - yOff — the difference of ROUNDED extrema (Q13).  One warp per frame; `>`/`<` skip NaN exactly
+// like minmaxXYofArray (H.js:1558).  out[f] = {xOff, yOff, oW, oH} as doubles (JS Numbers: may be +-Inf).
+__global__ void __launch_bounds__(128) pw_extent_kernel(const float *dst_pts, int n_pts, int n_frames, double *out)
+{
+    const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (f >= n_frames) return;
+    const int lane = threadIdx.x & 31;
+    const float *p = dst_pts + (size_t)f * 2 * n_pts;
+    const float inf = __int_as_float(0x7f800000);
+    float mnx = inf, mny = inf, mxx = -inf, mxy = -inf;
+    for (int i = lane; i < n_pts; i += 32) {
+        const float x = p[2 * i], y = p[2 * i + 1];
+        if (x > mxx) mxx = x;
+        if (x < mnx) mnx = x;
+        if (y > mxy) mxy = y;
+        if (y < mny) mny = y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if (lane == 0) {
+        const double x0 = js_round((double)mnx), y0 = js_round((double)mny);
+        out[4 * f + 0] = x0;
+        out[4 * f + 1] = y0;
+        out[4 * f + 2] = __dsub_rn(js_round((double)mxx), x0);
+        out[4 * f + 3] = __dsub_rn(js_round((double)mxy), y0);
+    }
+}
+
 struct PwWarpArgs {
     const uint32_t *src;
     uint32_t *out;

@@ -328,10 +328,15 @@ class Homography:
                 self._transformMatrix = self._solve(self._srcPoints, self._dstPoints)
             self._set_limits(self._ctx.transform_limits(self._transformMatrix, self._width, self._height))
         elif not self._dstPointsAreNormalized:
-            mnx, mny, mxx, mxy = _minmax_xy(self._dstPoints)
-            self._xOutputOffset, self._yOutputOffset = _js_round(mnx), _js_round(mny)
-            self._objectiveWidth = _js_round(mxx) - self._xOutputOffset      # difference of ROUNDED extrema
-            self._objectiveHeight = _js_round(mxy) - self._yOutputOffset
+            if self._dstPoints.dtype == np.float32 and hasattr(self._ctx, "piecewise_extents"):
+                # difference of ROUNDED extrema (H.js:707-710), on the device
+                lim = self._ctx.piecewise_extents(self._dstPoints.reshape(1, -1, 2))[0]
+                self._set_limits(lim)
+            else:  # Float64Array points (kept as given, H.js:220): same arithmetic on the host
+                mnx, mny, mxx, mxy = _minmax_xy(self._dstPoints)
+                self._xOutputOffset, self._yOutputOffset = _js_round(mnx), _js_round(mny)
+                self._objectiveWidth = _js_round(mxx) - self._xOutputOffset
+                self._objectiveHeight = _js_round(mxy) - self._yOutputOffset
         elif _positive(self._width) and _positive(self._height):
             mnx, mny, mxx, mxy = _minmax_xy(self._dstPoints)
             self._xOutputOffset, self._yOutputOffset = _js_round(mnx), _js_round(mny)

@@ -116,6 +116,9 @@ int hg_piecewise_set_mesh(hg_ctx *ctx, const float *src_pts, int n_pts, const ui
 /* _calculatePiecewiseAffineTransformMatrices, H.js:785: T forward 2x3 float matrices; optionally
  * also their inverses (inverseAffineMatrix, H.js:1036-1038).  Either output may be NULL. */
 int hg_piecewise_matrices(hg_ctx *ctx, const float *dst_pts, float *fwd_out, float *inv_out);
+/* output window of piecewise frames with pixel-range destiny points (_induceBestObjectiveWidthAndHeight, H.js:706-710 +
+ * minmaxXYofArray, H.js:1558): out[4*f..] = {xOff, yOff, oW, oH} as JS Numbers; dst_pts = n_frames x n_pts x 2 floats */
+int hg_piecewise_extents(hg_ctx *ctx, const float *dst_pts, int n_pts, int n_frames, double *out);
 /* _build(Inverse)TrianglesCorrespondencesMatrix + fillTriangle, H.js:817/845/1111: Int16 map of
  * map_len entries built from `pts` (n_pts of the mesh) with row stride map_width and row origin
  * y_offset; copied to map_out_host */

@@ -64,6 +64,14 @@ class OracleContext:
         fwd = O.piecewise_matrices(self.src_pts, dst_pts, self.tris)
         return (fwd, O.inverse_matrices(fwd)) if want_inverse else fwd
 
+    def piecewise_extents(self, dst_pts):
+        d = np.asarray(dst_pts, dtype=np.float32)
+        out = np.empty((d.shape[0], 4), np.float64)
+        for f in range(d.shape[0]):
+            mm = O.minmax_xy(d[f])
+            out[f] = [mm[0], mm[1], mm[2] - mm[0], mm[3] - mm[1]]
+        return out
+
     def build_index_map(self, pts, map_width, y_offset, map_len):
         self.last_map = O.build_index_map(pts, self.tris, map_width, y_offset, map_len)
         return self.last_map

@@ -570,3 +570,20 @@ def test_folded_mesh_overflows_bins_and_falls_back(ctx):
     _pw_case(ctx, img, src, dst, tris)
     f1, g1 = ctx.debug_piecewise_stats()
     assert g1 - g0 == 1 and f1 == f0
+
+
+def test_piecewise_extents_on_device(ctx):
+    """A9 for piecewise frames: difference of ROUNDED extrema (Q13), incl. .5 ties and negative values."""
+    import homography_js_b200 as hgm
+    rng = np.random.default_rng(61)
+    d = rng.uniform(-50, 2000, (17, 33, 2)).astype(np.float32)
+    d[0, 0] = [-2.5, 7.5]      # Math.round ties toward +inf
+    d[1, :, 0] = 12.5
+    got = ctx.piecewise_extents(d)
+    for f in range(d.shape[0]):
+        mm = O.minmax_xy(d[f])
+        assert list(got[f]) == [mm[0], mm[1], mm[2] - mm[0], mm[3] - mm[1]], f
+    _, dst, _ = hgm.workloads.video_stream(5, 480, 270)
+    got = ctx.piecewise_extents(dst)
+    for f in range(5):
+        assert tuple(int(v) for v in got[f]) == hgm.workloads.piecewise_extent(dst[f])
