@@ -82,10 +82,10 @@ __global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *fram
 #ifndef HG_PWF_MINB
 #define HG_PWF_MINB 5
 #endif
-constexpr int PWF_R = 2;                        // rows per thread per row group
-constexpr int PWF_TY = 8;                       // thread rows per CTA
-constexpr int PWF_THREADS = 16 * PWF_TY;        // 16 quads (= one 64-column bin) x 8
-constexpr int PWF_GROUP_ROWS = PWF_TY * PWF_R;  // rows one CTA covers per iteration
+constexpr int PWF_TX = 8;                       // threads across one 64-column bin: each owns quads tx and tx+8
+constexpr int PWF_TY = 16;                      // thread rows per CTA
+constexpr int PWF_THREADS = PWF_TX * PWF_TY;    // 128
+constexpr int PWF_GROUP_ROWS = PWF_TY;          // rows one CTA covers per iteration (one row per thread)
 
 __host__ __device__ inline int pwf_tiles_x(int oW) { return (oW + PW_BIN_W - 1) / PW_BIN_W; }
 __host__ __device__ inline int pwf_tiles_y(int oH, int niter) { return (oH + PWF_GROUP_ROWS * niter - 1) / (PWF_GROUP_ROWS * niter); }
@@ -123,171 +123,168 @@ __device__ __forceinline__ int pwf_map_id(int raw, int n_tris)
     return (t >= 0 && t < n_tris) ? t : -1;
 }
 
-// CTA = one 64-column bin column x (16 * niter) rows; thread = one quad x PWF_R rows per row group.
+// CTA = one 64-column bin column x (16 * niter) rows.  Thread (tx,ty) owns ONE row per row group and TWO quads of
+// it: columns 4tx..4tx+3 and 32+4tx..32+4tx+3 — both inside the same bin, so the bin's entries are decoded once per
+// 8 pixels, and a warp (8 lanes x 4 rows) stores 2 x 128 contiguous bytes per row.
 // FIVE-STAGE SOFTWARE PIPELINE inside each warp — every stage consumes what an earlier iteration produced, so the
 // three dependent memory round trips of the path (bins -> triangle matrix -> source pixel) overlap with arithmetic:
-//   iteration i:  S4 store group i-4 | S3 issue gathers of group i-3 | S2 coordinates of group i-2 (H.js:1046-1048)
-//                 S1 resolve triangle ids of group i-1 from its bins, issue the matrix loads | S0 issue bin loads of i
-// The thread keeps the inverse matrices of two triangles in registers (those of the first and last pixel of its
-// block); a pixel in a third triangle fetches its matrix on the spot (rare: the block is 4 x 2 pixels).
+//   iteration i:  S4 store row group i-4 | S3 issue gathers of group i-3 | S2 coordinates of group i-2 (H.js:1046-1048)
+//                 S1 resolve triangle ids of group i-1 from its bin, issue the matrix loads | S0 issue bin loads of i
+// Each quad keeps the inverse matrix of its first pixel's triangle in registers; a quad that a span boundary cuts
+// through resolves its pixels one by one (and fetches a second matrix on the spot).
 template <bool ZERO_OFF>
 __device__ __forceinline__ void pwf_body(const FusedFrame &F, int niter, int tile_x, int row0)
 {
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int c_rel = tx * 4;                       // first column of the quad inside the bin
-    const int xx0 = tile_x * PW_BIN_W + c_rel;      // output column
-    if (xx0 >= F.oW) return;
-    const int base0 = row0 + ty * PWF_R;
+    const int tx = threadIdx.x & (PWF_TX - 1), ty = threadIdx.x / PWF_TX;
+    const int base0 = row0 + ty;
     if (base0 >= F.oH) return;
+    const int c_rel[2] = {tx * 4, 32 + tx * 4};                          // first column of each quad inside the bin
+    const int xx0[2] = {tile_x * PW_BIN_W + c_rel[0], tile_x * PW_BIN_W + c_rel[1]};  // output columns
+    if (xx0[0] >= F.oW) return;
     const int ngroups = min(niter, (F.oH - base0 + PWF_GROUP_ROWS - 1) / PWF_GROUP_ROWS);
     const uint32_t *__restrict__ src = F.src;
     const unsigned npx_src = (unsigned)F.W * (unsigned)F.H;
-    const bool vec = ((F.oW & 3) == 0) && (F.oW - xx0 >= 4);  // dense rows are 16-byte aligned only when oW % 4 == 0
-    const int nvalid = min(4, F.oW - xx0);
-    const int oH = F.oH, n_tris = F.n_tris;
+    const bool aligned = (F.oW & 3) == 0;  // dense rows are 16-byte aligned only when oW % 4 == 0
+    int nvalid[2];
+    nvalid[0] = min(4, F.oW - xx0[0]);
+    nvalid[1] = max(0, min(4, F.oW - xx0[1]));
+    const int n_tris = F.n_tris;
 
-    double xs[4];
+    double xs[2][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) xs[k] = (double)(F.xOff + xx0 + k);
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xs[q][k] = (double)(F.xOff + xx0[q] + k);
 
-    // S0 walks the bins of its rows with two pointers that advance by one row group per iteration (the bin arrays
-    // are allocated with one row group of slack, so the last partial group may read, and ignore, past its frame)
     const unsigned *p_cnt = F.bin_cnt + ((size_t)base0 * F.bins_x + tile_x);
     const uint4 *p_ent = reinterpret_cast<const uint4 *>(F.bin_ent) + 2 * ((size_t)base0 * F.bins_x + tile_x);
-    const size_t cnt_step = (size_t)PWF_GROUP_ROWS * F.bins_x, row_step = (size_t)F.bins_x;
-    uint32_t *p_out = F.out + ((long long)base0 * F.oW + xx0);
+    const size_t cnt_step = (size_t)PWF_GROUP_ROWS * F.bins_x;
+    uint32_t *p_out = F.out + ((long long)base0 * F.oW + xx0[0]);
     const long long out_step = (long long)PWF_GROUP_ROWS * F.oW;
 
-    unsigned bcnt[PWF_R];
-    uint4 be0[PWF_R], be1[PWF_R];
-    int tri[PWF_R][4];
-    int tA = -1, tB = -1;
-    unsigned rowuni = 0;  // bit j: the four pixels of row j share one triangle id
-    double mA[6] = {0, 0, 0, 0, 0, 0}, mB[6] = {0, 0, 0, 0, 0, 0};
-    unsigned idx[PWF_R][4];
-    uint32_t px[PWF_R][4];
+    unsigned bcnt = 0;
+    uint4 be0 = make_uint4(0, 0, 0, 0), be1 = be0;
+    int tri[2][4];
+    unsigned uni = 0;      // bit q: the four pixels of quad q share one triangle id
+    double mq[2][6];       // inverse matrix of the first pixel's triangle of each quad
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) mq[q][k] = 0.0;
+    unsigned idx[2][4];
+    uint32_t px[2][4];
 
 #pragma unroll 1
     for (int it = 0; it < ngroups + 4; ++it) {
-        // ---- S4: store group it-4
+        // ---- S4: store row group it-4
         if (it >= 4) {
-            const int yb = base0 + (it - 4) * PWF_GROUP_ROWS;
-            uint32_t *dst = p_out;
 #pragma unroll
-            for (int j = 0; j < PWF_R; ++j) {
-                if (yb + j < oH) {
-                    if (vec) {
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(px[j][0], px[j][1], px[j][2], px[j][3]);
-                    } else {
+            for (int q = 0; q < 2; ++q) {
+                uint32_t *dst = p_out + 32 * q;
+                if (aligned && nvalid[q] == 4) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(px[q][0], px[q][1], px[q][2], px[q][3]);
+                } else {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k < nvalid) dst[k] = px[j][k];
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        if (k < nvalid[q]) dst[k] = px[q][k];
                 }
-                dst += F.oW;
             }
             p_out += out_step;
         }
         // ---- S3: gathers of group it-3
         if (it >= 3 && it - 3 < ngroups) {
 #pragma unroll
-            for (int j = 0; j < PWF_R; ++j)
+            for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) px[j][k] = ldg_or_zero(src, idx[j][k]);
+                for (int k = 0; k < 4; ++k) px[q][k] = ldg_or_zero(src, idx[q][k]);
         }
         // ---- S2: coordinates of group it-2
         if (it >= 2 && it - 2 < ngroups) {
-            const int yb = base0 + (it - 2) * PWF_GROUP_ROWS;
+            const double y = (double)(F.yOff + base0 + (it - 2) * PWF_GROUP_ROWS);
 #pragma unroll
-            for (int j = 0; j < PWF_R; ++j) {
-                const double y = (double)(F.yOff + yb + j);
-                const int t0 = tri[j][0];
-                if (((rowuni >> j) & 1u) && t0 == tA) {
-                    // common case: the four pixels of this row lie in the triangle whose matrix is in mA
+            for (int q = 0; q < 2; ++q) {
+                const int t0 = tri[q][0];
+                if ((uni >> q) & 1u) {
+                    // common case: the four pixels of the quad lie in one triangle, whose matrix is in mq[q]
                     if (t0 >= 0) {
-                        const double r0 = __dmul_rn(mA[2], y), r1 = __dmul_rn(mA[3], y);
+                        const double r0 = __dmul_rn(mq[q][2], y), r1 = __dmul_rn(mq[q][3], y);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            idx[j][k] = pwf_decode<ZERO_OFF>(affine_coord_exact(mA[0], xs[k], r0, mA[4]),
-                                                             affine_coord_exact(mA[1], xs[k], r1, mA[5]), F, npx_src);
+                            idx[q][k] = pwf_decode<ZERO_OFF>(affine_coord_exact(mq[q][0], xs[q][k], r0, mq[q][4]),
+                                                             affine_coord_exact(mq[q][1], xs[q][k], r1, mq[q][5]), F, npx_src);
                     } else {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) idx[j][k] = HG_OUTSIDE;
+                        for (int k = 0; k < 4; ++k) idx[q][k] = HG_OUTSIDE;
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const int t = tri[j][k];
+                        const int t = tri[q][k];
                         unsigned f = HG_OUTSIDE;
                         if (t >= 0) {
                             double m[6];
-                            if (t != tA && t != tB) {
-                                pwf_load_matrix(F.inv, t, m);  // third triangle inside a 4x2 block: rare
+                            if (t != t0) {
+                                pwf_load_matrix(F.inv, t, m);  // a span boundary cuts through the quad
                             } else {
-                                const bool useA = (t == tA);
 #pragma unroll
-                                for (int q = 0; q < 6; ++q) m[q] = useA ? mA[q] : mB[q];
+                                for (int c = 0; c < 6; ++c) m[c] = mq[q][c];
                             }
-                            f = pwf_decode<ZERO_OFF>(affine_coord_exact(m[0], xs[k], __dmul_rn(m[2], y), m[4]),
-                                                     affine_coord_exact(m[1], xs[k], __dmul_rn(m[3], y), m[5]), F, npx_src);
+                            f = pwf_decode<ZERO_OFF>(affine_coord_exact(m[0], xs[q][k], __dmul_rn(m[2], y), m[4]),
+                                                     affine_coord_exact(m[1], xs[q][k], __dmul_rn(m[3], y), m[5]), F, npx_src);
                         }
-                        idx[j][k] = f;
+                        idx[q][k] = f;
                     }
                 }
             }
         }
-        // ---- S1: triangle ids of group it-1 from its bins; fetch the matrices S2 will need next iteration
+        // ---- S1: triangle ids of group it-1 from its bin; fetch the matrices S2 will need next iteration
         if (it >= 1 && it - 1 < ngroups) {
-            const int yb = base0 + (it - 1) * PWF_GROUP_ROWS;
-            rowuni = 0;
+            int tfull[2] = {-1, -1};                                   // highest id among entries covering a WHOLE quad
+            int best[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};     // per pixel, for entries cutting through a quad
+            unsigned mixed = 0;
+            const unsigned cnt = min(bcnt, (unsigned)PW_BIN_CAP);
+            const unsigned ent[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
 #pragma unroll
-            for (int j = 0; j < PWF_R; ++j) {
-                int tfull = -1;                      // highest id among entries covering the WHOLE quad
-                int best[4] = {-1, -1, -1, -1};      // per pixel, only for entries that cut through the quad
-                bool mixed = false;
-                const unsigned cnt = (yb + j < oH) ? min(bcnt[j], (unsigned)PW_BIN_CAP) : 0u;
-                const unsigned ent[8] = {be0[j].x, be0[j].y, be0[j].z, be0[j].w, be1[j].x, be1[j].y, be1[j].z, be1[j].w};
+            for (int e = 0; e < PW_BIN_CAP; ++e) {
+                if ((unsigned)e >= cnt) break;
+                const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u), t = (int)(ent[e] >> 14);
 #pragma unroll
-                for (int e = 0; e < PW_BIN_CAP; ++e) {
-                    if ((unsigned)e >= cnt) break;
-                    const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u), t = (int)(ent[e] >> 14);
-                    if (lo <= c_rel && c_rel + 4 <= hi) {
-                        tfull = max(tfull, t);
-                    } else if (lo < c_rel + 4 && c_rel < hi) {
-                        mixed = true;
+                for (int q = 0; q < 2; ++q) {
+                    if (lo <= c_rel[q] && c_rel[q] + 4 <= hi) {
+                        tfull[q] = max(tfull[q], t);
+                    } else if (lo < c_rel[q] + 4 && c_rel[q] < hi) {
+                        mixed |= 1u << q;
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if ((unsigned)(c_rel + k - lo) < (unsigned)(hi - lo)) best[k] = max(best[k], t);
+                            if ((unsigned)(c_rel[q] + k - lo) < (unsigned)(hi - lo)) best[q][k] = max(best[q][k], t);
                     }
-                }
-                if (!mixed) {
-                    const int t = pwf_map_id(tfull, n_tris);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) tri[j][k] = t;
-                    rowuni |= 1u << j;
-                } else {
-                    bool uni = true;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        tri[j][k] = pwf_map_id(max(tfull, best[k]), n_tris);
-                        uni = uni && (tri[j][k] == tri[j][0]);
-                    }
-                    rowuni |= uni ? (1u << j) : 0u;
                 }
             }
-            tA = tri[0][0];
-            tB = tri[PWF_R - 1][3];
-            if (tA >= 0) pwf_load_matrix(F.inv, tA, mA);
-            if (tB >= 0 && tB != tA) pwf_load_matrix(F.inv, tB, mB);
+            uni = 0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!((mixed >> q) & 1u)) {
+                    const int t = pwf_map_id(tfull[q], n_tris);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tri[q][k] = t;
+                    uni |= 1u << q;
+                } else {
+                    bool u = true;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tri[q][k] = pwf_map_id(max(tfull[q], best[q][k]), n_tris);
+                        u = u && (tri[q][k] == tri[q][0]);
+                    }
+                    uni |= u ? (1u << q) : 0u;
+                }
+                if (tri[q][0] >= 0) pwf_load_matrix(F.inv, tri[q][0], mq[q]);
+            }
         }
         // ---- S0: bin loads of group it
         if (it < ngroups) {
-#pragma unroll
-            for (int j = 0; j < PWF_R; ++j) {
-                bcnt[j] = __ldg(p_cnt + j * row_step);
-                be0[j] = __ldg(p_ent + 2 * j * row_step);
-                be1[j] = __ldg(p_ent + 2 * j * row_step + 1);
-            }
+            bcnt = __ldg(p_cnt);
+            be0 = __ldg(p_ent);
+            be1 = __ldg(p_ent + 1);
             p_cnt += cnt_step;
             p_ent += 2 * cnt_step;
         }
