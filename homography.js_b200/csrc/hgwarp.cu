@@ -3,6 +3,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared -Xcompiler -fPIC
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -928,7 +929,12 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         a.dst_stride = 2 * (size_t)c->n_pts;
         a.rec_stride = T;
         pw_setup_kernel<<<dim3((unsigned)((T + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>(a);
-        pw_span_bin_kernel<<<dim3((unsigned)((T + 3) / 4), (unsigned)nF), 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
+        // warps per triangle: a mesh of T triangles over oH rows has triangles ~ oH / sqrt(T/2) rows tall
+        int split = (int)((double)max_oh / (32.0 * sqrt((double)T / 2.0 + 1.0)) + 0.5);
+        if (split < 1) split = 1;
+        if (split > 16) split = 16;
+        pw_span_bin_kernel<<<dim3((unsigned)((T * split + 3) / 4), (unsigned)nF), 128, 0, c->stream>>>(
+            (const FusedFrame *)c->fframes.p, split);
         c->launches += 2;
         CU(c, cudaGetLastError());
     }

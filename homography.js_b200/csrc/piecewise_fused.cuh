@@ -41,17 +41,20 @@ struct FusedFrame {
     int W, H, xOff, yOff, oW, oH, minSrcX, minSrcY, n_tris, bins_x;
 };
 
-// one warp per triangle, lanes stride over its rows
-__global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *frames)
+// `split` warps per triangle (tall triangles of small meshes would otherwise leave the machine empty); the lanes of
+// those warps stride over the triangle's rows
+__global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *frames, int split)
 {
     const FusedFrame &F = frames[blockIdx.y];
-    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int t = gw / split;
     if (t >= F.n_tris) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = (threadIdx.x & 31) + 32 * (gw - t * split);
+    const int stride = 32 * split;
     const TriRec &r = F.rec[t];
     const long long len = (long long)F.oW * F.oH;
     const double mw = (double)F.oW, yoff = (double)F.yOff;
-    for (long long i = lane;; i += 32) {
+    for (long long i = lane;; i += stride) {
         const double y = (double)r.y0 + (double)i;
         if (!(y < r.maxY)) break;  // also ends on NaN
         double xo, xd;
