@@ -14,11 +14,12 @@ LIB_PATH = os.environ.get("HGWARP_LIB") or os.path.join(_HERE, "libhgwarp.so")  
 
 HG_OK, HG_ERR_INVALID, HG_ERR_CUDA, HG_ERR_NOMEM, HG_ERR_UNSUPPORTED, HG_ERR_STATE = range(6)
 HG_AFFINE, HG_PROJECTIVE = 0, 1
+HG_NEAREST, HG_BILINEAR = 0, 1
 
 # every symbol include/hgwarp.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "hg_abi_version", "hg_device_count", "hg_ctx_create", "hg_ctx_destroy", "hg_last_error",
-    "hg_ctx_synchronize", "hg_ctx_stream", "hg_timer_start", "hg_timer_stop", "hg_launch_count",
+    "hg_ctx_synchronize", "hg_ctx_stream", "hg_timer_start", "hg_timer_stop", "hg_ctx_set_sampling", "hg_launch_count",
     "hg_profile_enable", "hg_profile_read",
     "hg_image_set", "hg_image_set_device",
     "hg_solve_affine", "hg_solve_projective", "hg_inverse_affine", "hg_transform_limits", "hg_solve_with_limits",
@@ -69,6 +70,7 @@ def load():
     L.hg_ctx_stream.argtypes = [vp, C.POINTER(vp)]
     L.hg_timer_start.argtypes = [vp]
     L.hg_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.hg_ctx_set_sampling.argtypes = [vp, i]
     L.hg_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.hg_profile_enable.argtypes = [vp, i]
     L.hg_profile_read.argtypes = [vp, C.POINTER(d), C.POINTER(C.c_uint64)]
@@ -156,6 +158,10 @@ class Context:
         ms = C.c_float()
         self._ck(self.L.hg_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def set_sampling(self, sampling: int):
+        """HG_NEAREST (the reference's Math.round sampling) or HG_BILINEAR (extension, <= 1 LSB vs its oracle)."""
+        self._ck(self.L.hg_ctx_set_sampling(self.h, sampling))
 
     def launch_count(self) -> int:
         n = C.c_uint64()

@@ -16,6 +16,7 @@
 #include "solve.cuh"
 #include "warp_geo.cuh"
 #include "diag.cuh"
+#include "bilinear.cuh"
 #include "forward.cuh"
 #include "piecewise_fused.cuh"
 
@@ -65,6 +66,7 @@ struct hg_ctx {
     double last_inv_mw = 0, last_inv_yoff = 0;
     long long last_inv_len = -1;
     bool map32_current = false;
+    int sampling = 0;       // HG_NEAREST (the reference) | HG_BILINEAR (extension; inverse affine / projective only)
     int force_general = 0;  // diagnostics: 1 = always use the map-based general path
     uint64_t n_fused = 0, n_general = 0;  // inverse piecewise frames finished by each path
     int n_pts = 0, n_tris = 0;
@@ -229,6 +231,19 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
 {
     P.niter = pick_niter(c, max_ow, max_oh, n_frames);
     dim3 grid((unsigned)(geo_tiles_x(max_ow) * geo_tiles_y(max_oh, P.niter)), (unsigned)n_frames);
+    if (c->sampling == HG_BILINEAR) {
+        const long long nq = ((long long)max_ow * max_oh + 3) / 4;
+        long long blocks = (nq + 255) / 256;
+        if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
+        dim3 g2((unsigned)blocks, (unsigned)n_frames);
+        TRY(prof_begin(c));
+        if (kind == HG_AFFINE) warp_inverse_geo_bilinear_kernel<0><<<g2, 256, 0, c->stream>>>(P);
+        else warp_inverse_geo_bilinear_kernel<1><<<g2, 256, 0, c->stream>>>(P);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        TRY(prof_end(c));
+        return HG_OK;
+    }
     TRY(prof_begin(c));
     if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, 0, c->stream>>>(P);
     else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, 0, c->stream>>>(P);
@@ -370,6 +385,14 @@ int hg_timer_stop(hg_ctx *c, float *ms)
     CU(c, cudaEventRecord(c->ev1, c->stream));
     CU(c, cudaEventSynchronize(c->ev1));
     CU(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return HG_OK;
+}
+
+int hg_ctx_set_sampling(hg_ctx *c, int sampling)
+{
+    if (!c) return HG_ERR_INVALID;
+    NEED(c, sampling == HG_NEAREST || sampling == HG_BILINEAR, "sampling must be HG_NEAREST or HG_BILINEAR");
+    c->sampling = sampling;
     return HG_OK;
 }
 

@@ -52,6 +52,11 @@ typedef enum {
 
 typedef enum { HG_AFFINE = 0, HG_PROJECTIVE = 1 } hg_kind;
 
+/* HG_NEAREST is the reference's sampling (Math.round, H.js:1005).  HG_BILINEAR is an EXTENSION the reference does not
+ * have (north_star asks for it): it applies to hg_warp_inverse_matrix / _points / _batch only, is defined by the oracle
+ * (oracle/hg_oracle.c) and is accurate to <= 1 LSB per channel, not bit-exact. */
+typedef enum { HG_NEAREST = 0, HG_BILINEAR = 1 } hg_sampling;
+
 /* one frame of a batched warp: where it reads, where it writes, its output window */
 typedef struct {
     const void *src_dev;  /* RGBA8 source image on the device (NULL = the context image) */
@@ -71,6 +76,7 @@ int hg_ctx_stream(hg_ctx *ctx, void **cuda_stream); /* the cudaStream_t all work
 /* CUDA-event stopwatch on the context stream (device time, not wall clock) */
 int hg_timer_start(hg_ctx *ctx);
 int hg_timer_stop(hg_ctx *ctx, float *elapsed_ms);
+int hg_ctx_set_sampling(hg_ctx *ctx, int sampling); /* HG_NEAREST (default) | HG_BILINEAR */
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int hg_launch_count(hg_ctx *ctx, uint64_t *count);
 /* per-kernel device timing of the pixel-loop kernels: enable, run, then read the summed CUDA-event

@@ -396,6 +396,51 @@ ORC_API void orc_warp_inverse_geometric(int kind, const uint8_t *img, int32_t W,
     }
 }
 
+/* EXTENSION (not in the reference, which only has Math.round sampling — SURVEY Q12): bilinear sampling for the inverse
+ * affine / projective loop.  Definition used as the oracle ("parity unpinned": the reference has nothing to pin it to):
+ * same window test as H.js:1001 on the unrounded (sx,sy); x0 = floor(sx), fx = sx - x0, x1 = min(x0+1, W-1) (edge
+ * replicate), likewise y; channel = p00(1-fx)(1-fy) + p10 fx(1-fy) + p01(1-fx)fy + p11 fx fy in double; stored like a
+ * Uint8ClampedArray store (round half to even, clamp). */
+ORC_API void orc_warp_inverse_geometric_bilinear(int kind, const uint8_t *img, int32_t W, int32_t H, const void *inv,
+                                                 int32_t xOff, int32_t yOff, int32_t oW, int32_t oH, uint8_t *out,
+                                                 int threads)
+{
+    const int64_t out_len = (int64_t)oW * oH * 4;
+    if (out_len <= 0) return;
+    memset(out, 0, (size_t)out_len);
+    const float *ma = (const float *)inv;
+    const double *mp = (const double *)inv;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads > 1 ? threads : 1) if (threads > 1)
+#endif
+    for (int32_t yy = 0; yy < oH; ++yy) {
+        const double y = (double)yOff + (double)yy;
+        for (int32_t xx = 0; xx < oW; ++xx) {
+            const double x = (double)xOff + (double)xx;
+            double sx, sy;
+            if (kind == 0) apply_affine(ma, x, y, &sx, &sy);
+            else apply_projective(mp, x, y, &sx, &sy);
+            if (sx >= 0 && sx < (double)W && sy >= 0 && sy < (double)H) {
+                const double fx0 = floor(sx), fy0 = floor(sy);
+                const double fx = sx - fx0, fy = sy - fy0;
+                const int64_t x0 = (int64_t)fx0, y0 = (int64_t)fy0;
+                const int64_t x1 = x0 + 1 < W ? x0 + 1 : W - 1, y1 = y0 + 1 < H ? y0 + 1 : H - 1;
+                const uint8_t *p00 = img + 4 * (y0 * W + x0), *p10 = img + 4 * (y0 * W + x1);
+                const uint8_t *p01 = img + 4 * (y1 * W + x0), *p11 = img + 4 * (y1 * W + x1);
+                uint8_t *o = out + 4 * ((int64_t)yy * oW + xx);
+                for (int c = 0; c < 4; ++c) {
+                    const double v = p00[c] * (1 - fx) * (1 - fy) + p10[c] * fx * (1 - fy) + p01[c] * (1 - fx) * fy +
+                                     p11[c] * fx * fy;
+                    double r = nearbyint(v); /* round half to even (default rounding mode) */
+                    if (r < 0) r = 0;
+                    if (r > 255) r = 255;
+                    o[c] = (uint8_t)r;
+                }
+            }
+        }
+    }
+}
+
 /* _geometricWarp, H.js:911-932 (forward scatter; source raster order, last writer wins). */
 ORC_API void orc_warp_forward_geometric(int kind, const uint8_t *img, int32_t W, int32_t H, const void *fwd,
                                         int32_t xOff, int32_t yOff, int32_t oW, int32_t oH, uint8_t *out)

@@ -52,6 +52,7 @@ def lib():
         L.orc_build_index_map.argtypes = [_f32p, _u32p, C.c_int32, C.c_double, C.c_double, _i16p, C.c_int64]
         L.orc_piecewise_matrices.argtypes = [_f32p, _f32p, _u32p, C.c_int32, _f32p]
         L.orc_warp_inverse_geometric.argtypes = [C.c_int, _u8p, C.c_int32, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [_u8p, C.c_int]
+        L.orc_warp_inverse_geometric_bilinear.argtypes = [C.c_int, _u8p, C.c_int32, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [_u8p, C.c_int]
         L.orc_warp_forward_geometric.argtypes = [C.c_int, _u8p, C.c_int32, C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [_u8p]
         L.orc_warp_inverse_piecewise.argtypes = [_u8p, C.c_int32, C.c_int32, _i16p, C.c_int64, _f32p, C.c_int32] + [C.c_int32] * 6 + [_u8p, C.c_int]
         L.orc_warp_forward_piecewise.argtypes = [_u8p, C.c_int32, C.c_int32, _i16p, C.c_int64, _f32p, C.c_int32] + [C.c_int32] * 8 + [_u8p]
@@ -175,6 +176,18 @@ def warp_inverse_geometric(image, W, H, inv, xOff, yOff, oW, oH, threads=1) -> n
     out = np.zeros(max(oW, 0) * max(oH, 0) * 4, np.uint8)
     lib().orc_warp_inverse_geometric(kind, _p(img, _u8p), W, H, inv.ctypes.data, xOff, yOff, oW, oH,
                                      _p(out, _u8p), threads)
+    return out
+
+
+def warp_inverse_geometric_bilinear(image, W, H, inv, xOff, yOff, oW, oH, threads=1) -> np.ndarray:
+    """EXTENSION (no counterpart in the reference): bilinear sampling, see hg_oracle.c."""
+    img = _img(image)
+    inv = np.ascontiguousarray(inv)
+    kind = 0 if inv.size == 6 else 1
+    inv = inv.astype(np.float32 if kind == 0 else np.float64)
+    out = np.zeros(max(oW, 0) * max(oH, 0) * 4, np.uint8)
+    lib().orc_warp_inverse_geometric_bilinear(kind, _p(img, _u8p), W, H, inv.ctypes.data, xOff, yOff, oW, oH,
+                                              _p(out, _u8p), threads)
     return out
 
 

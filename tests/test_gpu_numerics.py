@@ -73,3 +73,33 @@ def test_projective_x_only_denominator_mode(ctx, seed):
     got = ctx.warp_inverse_matrix(h, -30, -20, 260, 170)
     want = O.warp_inverse_geometric(img, W, H, h, -30, -20, 260, 170)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("kind", ["affine", "projective"])
+def test_bilinear_extension_within_one_lsb(ctx, kind):
+    """EXTENSION (not in the reference): bilinear sampling, <= 1 LSB per channel against the oracle's definition,
+    and exactly the nearest-neighbour result when every coordinate is an integer."""
+    rng = np.random.default_rng(321)
+    W, H = 180, 130
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    ctx.image_set(img, W, H)
+    ctx.set_sampling(hg._abi.HG_BILINEAR)
+    try:
+        for trial in range(6):
+            if kind == "affine":
+                inv = np.array([rng.uniform(0.4, 2.2), rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), rng.uniform(0.4, 2.2),
+                                rng.uniform(-20, 20), rng.uniform(-20, 20)], np.float32)
+            else:
+                s = np.array([0, 0, 0, H, W, 0, W, H], np.float64)
+                inv = O.projective_from_squares(s + rng.uniform(-0.2, 0.2, 8) * W, s)
+            got = ctx.warp_inverse_matrix(inv, -10, -10, 230, 170).astype(np.int16)
+            want = O.warp_inverse_geometric_bilinear(img, W, H, inv, -10, -10, 230, 170).astype(np.int16)
+            diff = np.abs(got - want)
+            assert diff.max() <= 1, diff.max()
+            assert (diff > 0).mean() < 0.02   # differences only at rounding ties
+        ident = np.array([1, 0, 0, 1, 3, 2], np.float32) if kind == "affine" else np.array([1, 0, 3, 0, 1, 2, 0, 0.0])
+        got = ctx.warp_inverse_matrix(ident, 0, 0, 100, 90)
+        ctx.set_sampling(hg._abi.HG_NEAREST)
+        assert np.array_equal(got, ctx.warp_inverse_matrix(ident, 0, 0, 100, 90))
+    finally:
+        ctx.set_sampling(hg._abi.HG_NEAREST)
