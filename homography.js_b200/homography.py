@@ -130,8 +130,14 @@ def default_triangulation(points: np.ndarray) -> np.ndarray:
 class Homography:
     _KIND = {"affine": _abi.HG_AFFINE, "projective": _abi.HG_PROJECTIVE}
 
-    def __init__(self, transform: str = "auto", width=None, height=None, device: int = 0, context=None):
+    def __init__(self, transform: str = "auto", width=None, height=None, device: int = 0, context=None,
+                 sampling: str = "nearest"):
+        """`sampling="bilinear"` is an EXTENSION (the reference only has Math.round sampling): it applies to the
+        inverse affine / projective loop and is accurate to <= 1 LSB per channel (see csrc/bilinear.cuh)."""
         self._ctx = context if context is not None else _abi.Context(device)
+        if sampling not in ("nearest", "bilinear"):
+            raise HomographyError(f'sampling "{sampling}" is unknown')
+        self._sampling = _abi.HG_BILINEAR if sampling == "bilinear" else _abi.HG_NEAREST
         self._width = None if width is None else _js_round(width)
         self._height = None if height is None else _js_round(height)
         self._objectiveWidth = None
@@ -407,7 +413,13 @@ class Homography:
         if empty:
             return None
         xo, yo, oW, oH = self._window()
-        return self._ctx.warp_inverse_points(self._KIND[self.transform], self._dstPoints, self._srcPoints, xo, yo, oW, oH)
+        if self._sampling != _abi.HG_NEAREST:
+            self._ctx.set_sampling(self._sampling)
+        try:
+            return self._ctx.warp_inverse_points(self._KIND[self.transform], self._dstPoints, self._srcPoints, xo, yo, oW, oH)
+        finally:
+            if self._sampling != _abi.HG_NEAREST:
+                self._ctx.set_sampling(_abi.HG_NEAREST)
 
     def _geometricWarp(self, empty):
         """H.js:911."""
