@@ -75,9 +75,8 @@ struct hg_ctx {
 
 namespace {
 
-// scratch layout (bytes): [0,128) src pts, [128,256) dst pts, [256,320) matrix, [320,352) limits, [384,512) misc,
-// [512,528) zeros (the word out-of-window pixels read)
-constexpr size_t SC_SRC = 0, SC_DST = 128, SC_MAT = 256, SC_LIM = 320, SC_MISC = 384, SC_ZERO = 512;
+// scratch layout (bytes): [0,128) src pts, [128,256) dst pts, [256,320) matrix, [320,352) limits, [384,512) misc
+constexpr size_t SC_SRC = 0, SC_DST = 128, SC_MAT = 256, SC_LIM = 320, SC_MISC = 384;
 
 int fail(hg_ctx *c, int code, const char *fmt, ...)
 {

@@ -4,7 +4,7 @@
 // multiply-add, rounds with Math.round (ties toward +inf) and indexes typed arrays with the
 // result.  Everything here is written with explicit round-to-nearest intrinsics (__dmul_rn,
 // __dadd_rn, __ddiv_rn never contract), and FMA appears only where it is provably identical
-// (one of the two products is exact, see apply_affine_exact()).
+// (both products are exact, see affine_coord_exact()).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -34,22 +34,6 @@ __device__ __forceinline__ FloorHalf floor_half_exact(double v)
     r.frac = (unsigned)__double2loint(t);
     r.ok = (hi >> 20) == HG_MAGIC_EXP;
     r.ipart = (hi & 0xFFFFF) - (1 << 19);
-    return r;
-}
-
-// Same decomposition for an APPROXIMATE v (round-to-nearest add).  `near` is set when v is within
-// delta * 2^-32 of a multiple of 0.5 — every decision the warp loops take (v >= lo, v < hi with
-// integer lo/hi, Math.round(v)) flips only at multiples of 0.5, so a caller whose error bound is
-// below delta may trust ipart/frac whenever !near and must recompute exactly otherwise.
-__device__ __forceinline__ FloorHalf floor_half_approx(double v, unsigned delta, bool &near)
-{
-    const double t = __dadd_rn(v, HG_MAGIC);
-    const int hi = __double2hiint(t);
-    FloorHalf r;
-    r.frac = (unsigned)__double2loint(t);
-    r.ok = (hi >> 20) == HG_MAGIC_EXP;
-    r.ipart = (hi & 0xFFFFF) - (1 << 19);
-    near = ((r.frac + delta) & 0x7FFFFFFFu) < 2u * delta;
     return r;
 }
 

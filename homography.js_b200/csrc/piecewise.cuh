@@ -12,9 +12,10 @@
 //   pw_warp_inverse_kernel   pixel loop of _inversePiecewiseAffineWarp (H.js:1042-1056)
 //   map32_to_int16_kernel    Int16Array store semantics of the map (H.js:820/848: ids wrap mod 2^16)
 //
-// The tile-binned fused kernel that avoids the map round trip for regular meshes lives in
-// piecewise_fused.cuh; this file is the reference-exact fallback for everything else (spans that spill
-// over row ends because fillTriangle ignores the x offset, negative relative fill indices, ...).
+// The fused, map-free path lives in piecewise_fused.cuh and reuses pw_setup_kernel / predict_x_limits from here.
+// The map-based kernels below are (a) the fallback for frames the bins of the fused path cannot represent (more
+// than 8 overlapping spans in one 64-pixel block, >= 2^17 triangles), (b) the forward map of _piecewiseAffineWarp
+// and (c) hg_build_index_map, i.e. the Int16 map itself for callers / tests that want it.
 #pragma once
 #include "solve.cuh"
 
