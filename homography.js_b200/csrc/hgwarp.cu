@@ -1240,22 +1240,16 @@ int hg_pipe_submit(hg_pipe *p, const uint8_t *rgba_host, const double *dst_pts, 
     hg_pipe_slot &sl = p->slots[(size_t)(p->next % (uint64_t)p->depth)];
     if (sl.busy) CU(c, cudaEventSynchronize(sl.out_done));  // the slot's previous frame has left the device
     const size_t pb = p->kind == HG_AFFINE ? 48 : 64;
-    memcpy(sl.h_small, dst_pts, pb);       // inverse matrix = calculateTransformMatrix(kind, dst, src) (H.js:994)
-    memcpy(sl.h_small + 64, src_pts, pb);
-    // copy-in stream: image + points
+    SolvePoints sp{};
+    memcpy(sp.src, dst_pts, pb);  // inverse matrix = calculateTransformMatrix(kind, dst, src) (H.js:994)
+    memcpy(sp.dst, src_pts, pb);
+    // copy-in stream: the image
     CU(c, cudaMemcpyAsync(sl.d_src, rgba_host, (size_t)p->W * p->H * 4, cudaMemcpyHostToDevice, p->s_in));
-    CU(c, cudaMemcpyAsync(sl.d_small, sl.h_small, 128, cudaMemcpyHostToDevice, p->s_in));
     CU(c, cudaEventRecord(sl.in_done, p->s_in));
-    // compute stream: solve + pixel loop
+    // compute stream: solve (points travel as kernel parameters) + pixel loop
     CU(c, cudaStreamWaitEvent(p->s_k, sl.in_done, 0));
-    SolveArgs a{};
-    a.src = (const double *)sl.d_small;
-    a.dst = (const double *)(sl.d_small + 64);
-    a.out_f = (float *)(sl.d_small + 128);
-    a.out_d = (double *)(sl.d_small + 128);
-    a.n = 1;
-    a.op = p->kind == HG_AFFINE ? 0 : 1;
-    solve_kernel<<<1, 64, 0, p->s_k>>>(a);
+    solve_points_kernel<<<1, 32, 0, p->s_k>>>(sp, p->kind == HG_AFFINE ? 0 : 1, (float *)(sl.d_small + 128),
+                                              (double *)(sl.d_small + 128));
     GeoParams P{};
     P.one.src = (const uint32_t *)sl.d_src;
     P.one.out = (uint32_t *)sl.d_out;

@@ -209,6 +209,27 @@ __global__ void solve_kernel(SolveArgs a)
     }
 }
 
+// one system whose points travel as kernel parameters (no host->device copy of 128 bytes in front of the solve):
+// used by the pipelined stream, where a tiny copy between two 8 MB image copies would stall the copy engine
+struct SolvePoints {
+    double src[8], dst[8];
+};
+__global__ void solve_points_kernel(const SolvePoints p, int op, float *out_f, double *out_d)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (op == 0) {
+        float o[6];
+        affine_from_triangles(p.src, p.dst, o);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out_f[k] = o[k];
+    } else {
+        double o[8];
+        projective_from_squares(p.src, p.dst, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out_d[k] = o[k];
+    }
+}
+
 // limits of one matrix already on the device
 __global__ void limits_kernel(int kind, const void *matrix, double w, double h, double *out)
 {
