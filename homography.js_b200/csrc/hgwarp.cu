@@ -5,9 +5,12 @@
 #include <cstdio>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/hgwarp.h"
@@ -71,6 +74,17 @@ struct hg_ctx {
     uint64_t n_fused = 0, n_general = 0;  // inverse piecewise frames finished by each path
     int n_pts = 0, n_tris = 0;
     long long map_len = 0;  // length of the map currently in map32 (for the aliasing forward read)
+
+    // TMA staging of source tiles (warp_geo.cuh): cuTensorMapEncodeTiled from the driver, the tensor maps of the
+    // context image (passed to single-frame launches by value) and a device-side cache for batch frames
+    void *tm_encode = nullptr;
+    int geo_box_bytes = 32 * 1024;  // dynamic shared memory per CTA for the staged tile (HG_GEO_SMEM_KB)
+    int geo_niter_staged = 2;       // row groups per CTA when staging is possible (HG_GEO_NITER)
+    CUtensorMap img_tm[GEO_NBOX];
+    bool img_tm_ok = false;
+    DevBuf tm_dev;                   // TM_CACHE_SLOTS x GEO_NBOX tensor maps
+    std::unordered_map<uint64_t, std::vector<std::pair<uint64_t, int>>> tm_index;  // hash -> [(ptr ^ dims, slot)]
+    int tm_used = 0;
 };
 
 namespace {
@@ -215,6 +229,63 @@ int prof_end(hg_ctx *c)
     return HG_OK;
 }
 
+constexpr int TM_CACHE_SLOTS = 4096;
+
+typedef CUresult (*tm_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// GEO_NBOX tensor maps over a device image seen as a [H][W] tensor of 32-bit pixels, one per box width
+// (box = geo_box_w(i) pixels x GEO_BOX_ROWS rows, out-of-image elements read as zero).  False when the image
+// cannot be described (row pitch or base not 16-byte aligned) — the kernels then gather directly.
+bool encode_tmaps(hg_ctx *c, const void *img, int W, int H, CUtensorMap *out)
+{
+    if (!c->tm_encode || !img || (W & 3) != 0 || ((uintptr_t)img & 15) != 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t strides[1] = {(cuuint64_t)W * 4};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < GEO_NBOX; ++i) {
+        const cuuint32_t box[2] = {(cuuint32_t)geo_box_w(i), (cuuint32_t)GEO_BOX_ROWS};
+        const CUresult r = ((tm_encode_fn)c->tm_encode)(&out[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(img),
+                                                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    return true;
+}
+
+// device copy of the tensor maps of a borrowed image (batch frames), cached by (pointer, size); nullptr = no staging
+int tmaps_device(hg_ctx *c, const void *img, int W, int H, const CUtensorMap **out)
+{
+    *out = nullptr;
+    if (!c->tm_encode || (W & 3) != 0 || ((uintptr_t)img & 15) != 0) return HG_OK;
+    const uint64_t key = (uint64_t)(uintptr_t)img, dims = ((uint64_t)(uint32_t)W << 32) | (uint32_t)H;
+    auto &bucket = c->tm_index[key];
+    for (auto &e : bucket)
+        if (e.first == dims) {
+            *out = (const CUtensorMap *)c->tm_dev.p + (size_t)e.second * GEO_NBOX;
+            return HG_OK;
+        }
+    CUtensorMap tm[GEO_NBOX];
+    if (!encode_tmaps(c, img, W, H, tm)) return HG_OK;
+    if (!c->tm_dev.p) TRY(ensure(c, c->tm_dev, sizeof(CUtensorMap) * GEO_NBOX * (size_t)TM_CACHE_SLOTS));
+    if (c->tm_used == TM_CACHE_SLOTS) {
+        // cache full: drop everything once no kernel can still be reading it
+        CU(c, cudaDeviceSynchronize());
+        c->tm_index.clear();
+        c->tm_used = 0;
+        return tmaps_device(c, img, W, H, out);
+    }
+    const int slot = c->tm_used++;
+    CUtensorMap *dst = (CUtensorMap *)c->tm_dev.p + (size_t)slot * GEO_NBOX;
+    // pageable source: staged before the call returns, ordered on the context stream before any launch that uses it
+    CU(c, cudaMemcpyAsync(dst, tm, sizeof tm, cudaMemcpyHostToDevice, c->stream));
+    bucket.emplace_back(dims, slot);
+    *out = dst;
+    return HG_OK;
+}
+
 // rows per CTA = 64 * niter: long-lived CTAs amortise their start-up and pipeline gathers against arithmetic,
 // but the grid must still fill the machine (>= ~6 CTAs per SM in total)
 int pick_niter(hg_ctx *c, int max_ow, int max_oh, int n_frames)
@@ -226,9 +297,12 @@ int pick_niter(hg_ctx *c, int max_ow, int max_oh, int n_frames)
     return niter;
 }
 
-int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_frames)
+// `staged`: the frames carry tensor maps (P.has_tm / GeoFrame::tm), so CTAs cover few rows and stage their source
+// footprint in shared memory; otherwise long-lived CTAs gather directly
+int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_frames, bool staged, cudaStream_t stream)
 {
-    P.niter = pick_niter(c, max_ow, max_oh, n_frames);
+    P.niter = staged ? c->geo_niter_staged : pick_niter(c, max_ow, max_oh, n_frames);
+    P.box_bytes = staged ? c->geo_box_bytes : 0;
     dim3 grid((unsigned)(geo_tiles_x(max_ow) * geo_tiles_y(max_oh, P.niter)), (unsigned)n_frames);
     if (c->sampling == HG_BILINEAR) {
         const long long nq = ((long long)max_ow * max_oh + 3) / 4;
@@ -236,19 +310,20 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
         if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
         dim3 g2((unsigned)blocks, (unsigned)n_frames);
         TRY(prof_begin(c));
-        if (kind == HG_AFFINE) warp_inverse_geo_bilinear_kernel<0><<<g2, 256, 0, c->stream>>>(P);
-        else warp_inverse_geo_bilinear_kernel<1><<<g2, 256, 0, c->stream>>>(P);
+        if (kind == HG_AFFINE) warp_inverse_geo_bilinear_kernel<0><<<g2, 256, 0, stream>>>(P);
+        else warp_inverse_geo_bilinear_kernel<1><<<g2, 256, 0, stream>>>(P);
         c->launches++;
         CU(c, cudaGetLastError());
         TRY(prof_end(c));
         return HG_OK;
     }
-    TRY(prof_begin(c));
-    if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, 0, c->stream>>>(P);
-    else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, 0, c->stream>>>(P);
+    const bool timed = stream == c->stream;  // the per-kernel events live on the context stream
+    if (timed) TRY(prof_begin(c));
+    if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, (size_t)P.box_bytes, stream>>>(P);
+    else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, (size_t)P.box_bytes, stream>>>(P);
     c->launches++;
     CU(c, cudaGetLastError());
-    TRY(prof_end(c));
+    if (timed) TRY(prof_end(c));
     return HG_OK;
 }
 
@@ -327,6 +402,28 @@ int hg_ctx_create(int device, hg_ctx **out)
     c->scratch.cap = 4096;
     CUC(cudaMemset(c->scratch.p, 0, 4096));
     CUC(cudaHostAlloc(&c->pinned, 4096, cudaHostAllocDefault));
+    {
+        // TMA staging: the tensor-map encoder lives in the driver; without it (or with HG_GEO_TMA=0) every tile
+        // gathers directly
+        const char *off = getenv("HG_GEO_TMA");
+        cudaDriverEntryPointQueryResult qres;
+        void *fn = nullptr;
+        if (!(off && off[0] == '0') &&
+            cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            c->tm_encode = fn;
+        cudaGetLastError();
+        if (const char *v = getenv("HG_GEO_SMEM_KB")) {
+            const int kb = atoi(v);
+            if (kb >= 8 && kb <= 200) c->geo_box_bytes = kb * 1024;
+        }
+        if (const char *v = getenv("HG_GEO_NITER")) {
+            const int n = atoi(v);
+            if (n >= 1 && n <= 16) c->geo_niter_staged = n;
+        }
+        CUC(cudaFuncSetAttribute(warp_inverse_geo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->geo_box_bytes));
+        CUC(cudaFuncSetAttribute(warp_inverse_geo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->geo_box_bytes));
+    }
 #undef CUC
     *out = c;
     return HG_OK;
@@ -439,6 +536,7 @@ int hg_image_set(hg_ctx *c, const uint8_t *rgba, int w, int h)
     c->img = (const uint32_t *)c->img_own.p;
     c->W = w;
     c->H = h;
+    c->img_tm_ok = encode_tmaps(c, c->img, w, h, c->img_tm);
     return HG_OK;
 }
 
@@ -451,6 +549,7 @@ int hg_image_set_device(hg_ctx *c, const void *rgba_dev, int w, int h)
     c->img = (const uint32_t *)rgba_dev;
     c->W = w;
     c->H = h;
+    c->img_tm_ok = encode_tmaps(c, c->img, w, h, c->img_tm);
     return HG_OK;
 }
 
@@ -582,7 +681,9 @@ static int warp_inverse_common(hg_ctx *c, int kind, const void *inv_host, bool s
         else
             for (int k = 0; k < 8; ++k) P.mat_val[k] = ((const double *)inv_host)[k];
     }
-    TRY(launch_geo(c, kind, P, o_w, o_h, 1));
+    P.has_tm = c->img_tm_ok ? 1 : 0;
+    if (c->img_tm_ok) memcpy(P.tm_val, c->img_tm, sizeof c->img_tm);
+    TRY(launch_geo(c, kind, P, o_w, o_h, 1, c->img_tm_ok, c->stream));
     return finish_out(c, dst, bytes, out_host);
 }
 
@@ -671,6 +772,7 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
     NEED(c, n_frames >= 1, "n_frames must be >= 1");
     std::vector<GeoFrame> gf((size_t)n_frames);
     int max_ow = 1, max_oh = 1;
+    bool staged = false;
     for (int f = 0; f < n_frames; ++f) {
         const hg_frame &h = frames[f];
         TRY(check_window(c, h.x_off, h.y_off, h.o_w, h.o_h));
@@ -687,6 +789,8 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
             g.W = c->W;
             g.H = c->H;
         }
+        TRY(tmaps_device(c, g.src, g.W, g.H, &g.tm));
+        staged = staged || g.tm != nullptr;
         g.out = (uint32_t *)h.out_dev;
         g.xOff = h.x_off;
         g.yOff = h.y_off;
@@ -707,7 +811,7 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
         GeoParams P{};
         P.many = (const GeoFrame *)c->frames.p + f0;
         P.mats_dev = (const char *)c->mats.p + mstride * (size_t)f0;
-        TRY(launch_geo(c, kind, P, max_ow, max_oh, nf));
+        TRY(launch_geo(c, kind, P, max_ow, max_oh, nf, staged, c->stream));
     }
     return HG_OK;
 }
@@ -1153,6 +1257,8 @@ struct hg_pipe_slot {
     char *h_small = nullptr;  // 128 B pinned staging for the points
     cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
     bool busy = false;
+    CUtensorMap tm[GEO_NBOX];  // over d_src
+    bool tm_ok = false;
 };
 
 struct hg_pipe {
@@ -1194,6 +1300,7 @@ int hg_pipe_create(hg_ctx *c, int kind, int src_w, int src_h, int max_out_w, int
         ok(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
         ok(cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
         ok(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+        sl.tm_ok = sl.d_src && encode_tmaps(c, sl.d_src, src_w, src_h, sl.tm);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -1261,12 +1368,15 @@ int hg_pipe_submit(hg_pipe *p, const uint8_t *rgba_host, const double *dst_pts, 
     P.one.oH = o_h;
     P.many = nullptr;
     P.mats_dev = sl.d_small + 128;
-    P.niter = pick_niter(c, o_w, o_h, 1);
-    dim3 grid((unsigned)(geo_tiles_x(o_w) * geo_tiles_y(o_h, P.niter)), 1);
-    if (p->kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, 0, p->s_k>>>(P);
-    else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, 0, p->s_k>>>(P);
-    c->launches += 2;
+    P.has_tm = sl.tm_ok ? 1 : 0;
+    if (sl.tm_ok) memcpy(P.tm_val, sl.tm, sizeof sl.tm);
+    c->launches++;
     CU(c, cudaGetLastError());
+    const int sampling = c->sampling;
+    c->sampling = HG_NEAREST;  // the pipe is the reference's nearest-neighbour path
+    const int lr = launch_geo(c, p->kind, P, o_w, o_h, 1, sl.tm_ok, p->s_k);
+    c->sampling = sampling;
+    TRY(lr);
     CU(c, cudaEventRecord(sl.k_done, p->s_k));
     // copy-out stream
     CU(c, cudaStreamWaitEvent(p->s_out, sl.k_done, 0));

@@ -36,14 +36,26 @@
 //               reciprocal), denominator provably in (0.25, 1.75) (no exponent guard), or general.
 #pragma once
 #include "jsnum.cuh"
+#include "tma.cuh"
 
 namespace hg {
+
+// Source-tile staging (TMA).  One tensor map per box width: a CTA stages the source footprint of its output
+// tile as `nstrips` boxes of GEO_BOX_ROWS rows x GEO_BOX_W[sel] pixels, stacked in shared memory with row pitch
+// GEO_BOX_W[sel], so a staged pixel is addressed as (ry - by0) * pitch + (rx - bx0).
+constexpr int GEO_NBOX = 8;
+constexpr int GEO_BOX_ROWS = 8;
+__host__ __device__ inline int geo_box_w(int i)
+{
+    return i == 0 ? 72 : i == 1 ? 80 : i == 2 ? 96 : i == 3 ? 112 : i == 4 ? 128 : i == 5 ? 160 : i == 6 ? 192 : 256;
+}
 
 struct GeoFrame {
     const uint32_t *src;
     uint32_t *out;
     int W, H;
     int xOff, yOff, oW, oH;
+    const CUtensorMap *tm;   // device array of GEO_NBOX tensor maps over src, or nullptr (no staging)
 };
 
 struct GeoParams {
@@ -51,7 +63,10 @@ struct GeoParams {
     const GeoFrame *many;    // device array, indexed by blockIdx.y
     const void *mats_dev;    // device matrices (float[6] | double[8] per frame) or nullptr
     int niter;               // row groups (of GEO_GROUP_ROWS rows) per CTA
+    int has_tm;              // tm_val holds the tensor maps of one.src (single-frame launches)
+    int box_bytes;           // dynamic shared memory available for the staged source tile
     double mat_val[8];       // matrix by value when mats_dev == nullptr (floats widened to double)
+    CUtensorMap tm_val[GEO_NBOX];
 };
 
 constexpr int GEO_TILE_QUADS = 16;  // quads per CTA row (64 pixels)
@@ -307,17 +322,282 @@ __device__ __forceinline__ void geo_flush_queue(const GeoFrame &F, const double 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Source-tile staging through TMA
+//
+// An output tile (64 pixels x 16*niter rows) of an affine or projective map reads a convex source footprint: the
+// image of the tile rectangle is the quadrilateral of its four mapped corners (for the projective map as long as
+// the denominator keeps one sign over the tile).  Thread 0 of the CTA maps the corners, takes the bounding box
+// (rounded outwards) and sorts the tile into one of four classes:
+//   ZERO     the footprint lies entirely outside the image: the tile is transparent, nothing is read;
+//   STAGED   footprint inside [0, W-1) x [0, H-1): every pixel is in range and reads a real pixel — the pixel loop
+//            needs no bounds test, no flat-index test and no Math.round fix-up (see geo_smem_body);
+//   STAGED_CHECK  footprint crosses the image border but stays left of column W-1: out-of-image elements of the
+//            box are zero-filled by the TMA unit (= the reference's "index past the end reads undefined -> 0" for
+//            row H, Q2); the un-rounded bounds test of H.js:1001 is done per pixel;
+//   DIRECT   everything else: footprint reaches column W (where the reference's flat index wraps into the next row,
+//            Q2 — a 2-D box cannot express that), box larger than the shared-memory budget (strong minification),
+//            no tensor maps (W % 4 != 0 or unaligned source), denominator changing sign or far from 1, huge
+//            coordinates.  These tiles run the direct-gather pipeline above (geo_tile_body).
+// For the staged classes thread 0 immediately issues the box loads (cp.async.bulk.tensor.2d -> UTMALDG) against one
+// mbarrier; the other threads meanwhile set up their per-column terms and wait on the barrier.  Several CTAs are
+// resident per SM, so one CTA's load latency is covered by its neighbours' pixel loops — memory-level parallelism
+// no longer costs registers, which is what bounded the direct-gather kernel (ncu: long_scoreboard, 24 warps/SM).
+enum { GEO_CLS_DIRECT = 0, GEO_CLS_ZERO = 1, GEO_CLS_STAGED = 2, GEO_CLS_STAGED_CHECK = 3 };
+
+struct GeoTileClass {
+    int cls, bx0, by0, pitch, sel, nstrips;
+};
+
+// half-width of the zone around a rounding / bounds decision inside which an approximate quotient is not trusted,
+// in units of 2^-32 pixel (2^12 -> 2^-20 pixel); the staged projective path folds it into the magic constant
+#define HG_NEAR_DELTA_PX (4096.0 / 4294967296.0)
+
 template <int KIND>
-__global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB) warp_inverse_geo_kernel(const GeoParams P)
+__device__ __noinline__ GeoTileClass geo_classify(const GeoFrame &F, const double *mp, int tile_x, int row0, int rows,
+                                                  bool has_tm, int box_bytes)
 {
+    GeoTileClass r;
+    r.cls = GEO_CLS_DIRECT;
+    r.bx0 = r.by0 = r.pitch = r.sel = r.nstrips = 0;
+    double m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = mp[k];
+    // the NOMINAL tile (partial quads and rows past the image included), so every thread's coordinates lie in the box
+    const double X0 = (double)(F.xOff + 4 * GEO_TILE_QUADS * tile_x - 3), X1 = (double)(F.xOff + 4 * GEO_TILE_QUADS * tile_x + 4 * GEO_TILE_QUADS - 1);
+    const double Y0 = (double)(F.yOff + row0), Y1 = (double)(F.yOff + row0 + rows - 1);
+    double minx = 1e300, maxx = -1e300, miny = 1e300, maxy = -1e300, dmin = 1e300, dmax = 0.0;
+    bool finite = true, pos = true, neg = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double X = (c & 1) ? X1 : X0, Y = (c & 2) ? Y1 : Y0;
+        double sx, sy;
+        if (KIND == 0) {
+            sx = m[0] * X + m[2] * Y + m[4];
+            sy = m[1] * X + m[3] * Y + m[5];
+        } else {
+            const double dn = m[6] * X + m[7] * Y + 1.0;
+            sx = (m[0] * X + m[1] * Y + m[2]) / dn;
+            sy = (m[3] * X + m[4] * Y + m[5]) / dn;
+            pos = pos && (dn > 0.0);
+            neg = neg && (dn < 0.0);
+            const double ad = fabs(dn);
+            finite = finite && (ad < 1e300);
+            dmin = fmin(dmin, ad);
+            dmax = fmax(dmax, ad);
+        }
+        finite = finite && (fabs(sx) < 131072.0) && (fabs(sy) < 131072.0);  // false for NaN / Inf
+        minx = fmin(minx, sx);
+        maxx = fmax(maxx, sx);
+        miny = fmin(miny, sy);
+        maxy = fmax(maxy, sy);
+    }
+    if (!finite) return r;
+    if (KIND == 1) {
+        // one sign and a moderate range: the tile's image is the convex hull of its corners, the reciprocal needs no
+        // exponent guard and the error bound below holds
+        if (!(pos || neg) || !(dmin >= 0.015625) || !(dmax <= 64.0)) return r;
+    }
+    const double W = (double)F.W, H = (double)F.H;
+    if (maxx < -0.01 || minx > W + 0.01 || maxy < -0.01 || miny > H + 0.01) {
+        r.cls = GEO_CLS_ZERO;
+        return r;
+    }
+    if (!has_tm) return r;
+    if (!(maxx <= W - 1.51)) return r;  // Math.round(sx) could reach column W (flat-index wrap, Q2)
+    if (KIND == 1) {
+        if (m[6] == 0.0 && m[7] == 0.0) return r;  // denominator == 1: the direct path is exact without a reciprocal
+        // error of the staged path's quotient against the reference's RN(n / d): the numerators / denominator are
+        // formed with a different association (<= 3 ulp of the largest term each) and the reciprocal is good to
+        // 2^-39.9 relative; with |q| < 2^17 the bounds below keep the total under 2^-22 pixel << HG_NEAR_DELTA_PX
+        const double Xm = fmax(fabs(X0), fabs(X1)), Ym = fmax(fabs(Y0), fabs(Y1));
+        const double big = 33554432.0;  // 2^25
+        if (!(fabs(m[0]) * Xm + fabs(m[1]) * Ym + fabs(m[2]) < dmin * big)) return r;
+        if (!(fabs(m[3]) * Xm + fabs(m[4]) * Ym + fabs(m[5]) < dmin * big)) return r;
+        if (!(fabs(m[6]) * Xm + fabs(m[7]) * Ym + 1.0 < dmin * 256.0)) return r;
+    }
+    // Math.round of every coordinate in [min, max] (+- the 2^-20 the approximate quotient may be off, +- the rounding
+    // of this corner arithmetic) lies in [floor(min + 0.49), floor(max + 0.51)].  The TMA unit needs the first
+    // column of a box 16-byte aligned in global memory: bx0 is rounded down to a multiple of 4 pixels.
+    const int bx0 = ((int)floor(minx + 0.49)) & ~3, bx1 = (int)floor(maxx + 0.51);
+    const int by0 = (int)floor(miny + 0.49), by1 = (int)floor(maxy + 0.51);
+    const int fw = bx1 - bx0 + 1, fh = by1 - by0 + 1;
+    int sel = -1;
+#pragma unroll
+    for (int i = GEO_NBOX - 1; i >= 0; --i)
+        if (geo_box_w(i) >= fw) sel = i;
+    if (sel < 0) return r;
+    const int pitch = geo_box_w(sel);
+    const int nstrips = (fh + GEO_BOX_ROWS - 1) / GEO_BOX_ROWS;
+    if (nstrips * GEO_BOX_ROWS * pitch * 4 > box_bytes) return r;
+    const bool interior = (minx >= 0.01) && (miny >= 0.01) && (maxy <= H - 1.51);
+    r.cls = interior ? GEO_CLS_STAGED : GEO_CLS_STAGED_CHECK;
+    r.bx0 = bx0;
+    r.by0 = by0;
+    r.pitch = pitch;
+    r.sel = sel;
+    r.nstrips = nstrips;
+    return r;
+}
+
+// Pixel loop over a staged source tile.  `box` is the shared-memory copy of source rows by0.. / columns bx0.. with
+// row pitch `pitch` (out-of-image elements are zero).
+//
+// Math.round without a fix-up: t = v + (1.5*2^20 + 0.5) puts floor(v + 0.5) = Math.round(v) in the high word.
+//   affine      v is formed exactly as the reference does and the magic add rounds DOWN: integers are on the 2^-32
+//               grid, so the high word is exact for every v (ties included: v = k + 0.5 gives k + 1, as Math.round).
+//   projective  q ~ n * (1/d) with |q - RN(n/d)| < 2^-22; the magic constant also carries +HG_NEAR_DELTA_PX, so the low
+//               word of t is frac(q + 0.5) + delta and "q within delta of a rounding boundary" is simply
+//               low word < 2*delta.  Two coordinates are tested with ONE multiply: umulhi(lo_x, lo_y) < 2*delta
+//               holds whenever either factor is < 2*delta (false positives need both within 2^-9.5 of a boundary;
+//               they only cost a trip through the exact path).  Flagged pixels go to the warp queue and are redone
+//               by geo_flush_queue with the reference's own arithmetic, reading global memory.
+//   CHECK       tiles crossing the image border also need the reference's test on the UNROUNDED coordinate
+//               (H.js:1001): floor(v) = round(v) - 1 + (frac(v + 0.5) >= 0.5), then 0 <= floor < W; for the
+//               projective map the near zone is widened to every multiple of 0.5 (low word shifted left by one).
+template <int KIND, bool CHECK>
+__device__ __forceinline__ void geo_smem_body(const GeoFrame &F, const double (&m)[8], int base0, int niter, int s,
+                                              int x_first, unsigned mask, uint2 *q, int *qn,
+                                              const uint32_t *__restrict__ box, int bx0, int by0, int pitch)
+{
+    constexpr int R = GEO_ROWS_PER_THREAD;
+    const unsigned W = (unsigned)F.W, H = (unsigned)F.H;
+    const int oH = F.oH;
+    const long long row_pitch = (long long)F.oW;
+    const double MG = (KIND == 0) ? (HG_MAGIC + 0.5) : (HG_MAGIC + 0.5 + HG_NEAR_DELTA_PX);
+    const int cx = HG_HI_ZERO + bx0, cy = HG_HI_ZERO + by0;
+    double xs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xs[k] = (double)(F.xOff + x_first + k);
+
+#pragma unroll 1
+    for (int it = 0; it < niter; ++it) {
+        const int base = base0 + it * GEO_GROUP_ROWS;
+        if (base >= oH) break;
+        uint32_t px[R][4];
+        unsigned redo_bits = 0u;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const double y = (double)(F.yOff + base + s * j);
+            double r0, r1, r2 = 0.0;
+            if (KIND == 0) {
+                r0 = __dmul_rn(m[2], y);
+                r1 = __dmul_rn(m[3], y);
+            } else {
+                r0 = __fma_rn(m[1], y, m[2]);
+                r1 = __fma_rn(m[4], y, m[5]);
+                r2 = __fma_rn(m[7], y, 1.0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double tx, ty;
+                if (KIND == 0) {
+                    tx = __dadd_rd(affine_coord_exact(m[0], xs[k], r0, m[4]), MG);
+                    ty = __dadd_rd(affine_coord_exact(m[1], xs[k], r1, m[5]), MG);
+                } else {
+                    const double rc = rcp_newton1(__fma_rn(m[6], xs[k], r2));
+                    tx = __fma_rn(__fma_rn(m[0], xs[k], r0), rc, MG);
+                    ty = __fma_rn(__fma_rn(m[3], xs[k], r1), rc, MG);
+                    const unsigned lx = (unsigned)__double2loint(tx), ly = (unsigned)__double2loint(ty);
+                    const bool again = CHECK ? (__umulhi(lx << 1, ly << 1) < 4u * HG_NEAR_DELTA)
+                                             : (__umulhi(lx, ly) < 2u * HG_NEAR_DELTA);
+                    redo_bits |= again ? (1u << (4 * j + k)) : 0u;
+                }
+                const int rxr = __double2hiint(tx) - cx, ryr = __double2hiint(ty) - cy;
+                uint32_t v = box[ryr * pitch + rxr];
+                if (CHECK) {
+                    const unsigned ux = (unsigned)(rxr + bx0 - 1) + ((unsigned)__double2loint(tx) >> 31);
+                    const unsigned uy = (unsigned)(ryr + by0 - 1) + ((unsigned)__double2loint(ty) >> 31);
+                    v = ((ux < W) & (uy < H)) ? v : 0u;
+                }
+                px[j][k] = v;
+            }
+        }
+        if (KIND == 1 && redo_bits) {
+            const int qpos = atomicAdd(qn, 1);
+            if (qpos < GEO_QCAP) {
+                q[qpos] = make_uint2((unsigned)(x_first + 4), (redo_bits << 17) | (unsigned)base);
+            } else {
+                // queue full: resolve this thread's flagged pixels in place with the reference's arithmetic
+                const unsigned npx_src = W * H;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const double y = (double)(F.yOff + base + s * j);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (redo_bits & (1u << (4 * j + k))) {
+                            const double nx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], xs[k]), __dmul_rn(m[1], y)), m[2]);
+                            const double ny = __dadd_rn(__dadd_rn(__dmul_rn(m[3], xs[k]), __dmul_rn(m[4], y)), m[5]);
+                            const double dn = __dadd_rn(__dadd_rn(__dmul_rn(m[6], xs[k]), __dmul_rn(m[7], y)), 1.0);
+                            px[j][k] = ldg_or_zero(F.src, decode_flat(exact_quotient_magic(nx, dn),
+                                                                      exact_quotient_magic(ny, dn), W, H, npx_src));
+                        }
+                    }
+                }
+            }
+        }
+        uint32_t *dst = F.out + ((long long)base * row_pitch + x_first);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (base + s * j < oH) {
+                if (mask == 0xFu) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(px[j][0], px[j][1], px[j][2], px[j][3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (mask & (1u << k)) dst[k] = px[j][k];
+                }
+            }
+            dst += (long long)s * row_pitch;
+        }
+    }
+}
+
+// a tile whose footprint misses the image: transparent
+__device__ __forceinline__ void geo_zero_body(const GeoFrame &F, int base0, int niter, int s, int x_first, unsigned mask)
+{
+    const long long row_pitch = (long long)F.oW;
+    for (int it = 0; it < niter; ++it) {
+        const int base = base0 + it * GEO_GROUP_ROWS;
+        if (base >= F.oH) break;
+        uint32_t *dst = F.out + ((long long)base * row_pitch + x_first);
+#pragma unroll
+        for (int j = 0; j < GEO_ROWS_PER_THREAD; ++j) {
+            if (base + s * j < F.oH) {
+                if (mask == 0xFu) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (mask & (1u << k)) dst[k] = 0u;
+                }
+            }
+            dst += (long long)s * row_pitch;
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB) warp_inverse_geo_kernel(const __grid_constant__ GeoParams P)
+{
+    extern __shared__ __align__(128) unsigned char s_box[];  // staged source tile (P.box_bytes)
     // per-warp queue of pixels whose quotient must be resolved exactly (projective only)
     __shared__ uint2 s_q[KIND == 1 ? GEO_THREADS / 32 : 1][KIND == 1 ? GEO_QCAP : 1];
     __shared__ int s_qn[GEO_THREADS / 32];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_cls[4];  // class, bx0, by0, pitch
     const int warp_id = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
     if (lane_id == 0) s_qn[warp_id] = 0;
     __syncwarp();
 
     const GeoFrame F = P.many ? P.many[blockIdx.y] : P.one;
+    const int oW = F.oW, oH = F.oH;
+    const int tiles_x = geo_tiles_x(oW);
+    const int tile_y = blockIdx.x / tiles_x;
+    const int tile_x = blockIdx.x - tile_y * tiles_x;
+    const int row0 = tile_y * (GEO_GROUP_ROWS * P.niter);
+    if (row0 >= oH) return;  // grid is sized for the largest frame of the batch (CTA-uniform exit)
+
     double m[8];
     if (P.mats_dev) {
         if (KIND == 0) {
@@ -335,12 +615,27 @@ __global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB) warp_inverse_geo_ker
         for (int k = 0; k < 8; ++k) m[k] = P.mat_val[k];
     }
 
-    const int oW = F.oW, oH = F.oH;
-    const int tiles_x = geo_tiles_x(oW);
-    const int tile_y = blockIdx.x / tiles_x;
-    const int tile_x = blockIdx.x - tile_y * tiles_x;
-    const int row0 = tile_y * (GEO_GROUP_ROWS * P.niter);
-    if (row0 >= oH) return;  // grid is sized for the largest frame of the batch
+    if (threadIdx.x == 0) {
+        const CUtensorMap *tm = P.many ? F.tm : (P.has_tm ? P.tm_val : nullptr);
+        double mc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mc[k] = m[k];
+        const GeoTileClass tc = geo_classify<KIND>(F, mc, tile_x, row0, GEO_GROUP_ROWS * P.niter, tm != nullptr, P.box_bytes);
+        if (tc.cls >= GEO_CLS_STAGED) {
+            const uint32_t bar = smem_u32(&s_bar);
+            mbar_init(bar, 1);
+            fence_barrier_init();
+            const unsigned strip_bytes = (unsigned)(GEO_BOX_ROWS * tc.pitch * 4);
+            mbar_arrive_expect_tx(bar, strip_bytes * (unsigned)tc.nstrips);
+            const uint32_t dst0 = smem_u32(s_box);
+            for (int i = 0; i < tc.nstrips; ++i)
+                tma_load_2d(dst0 + (unsigned)i * strip_bytes, tm + tc.sel, tc.bx0, tc.by0 + GEO_BOX_ROWS * i, bar);
+        }
+        s_cls[0] = tc.cls;
+        s_cls[1] = tc.bx0;
+        s_cls[2] = tc.by0;
+        s_cls[3] = tc.pitch;
+    }
 
     // rows with equal flat alignment repeat with period s = 4 / gcd(oW mod 4, 4)
     const int sl = (oW & 3) == 0 ? 0 : ((oW & 1) ? 2 : 1);  // log2(s)
@@ -357,7 +652,20 @@ __global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB) warp_inverse_geo_ker
     uint2 *q = s_q[KIND == 1 ? warp_id : 0];
     int *qn = &s_qn[warp_id];
 
-    if (active) {
+    __syncthreads();  // tile class + barrier initialisation published by thread 0
+    const int cls = s_cls[0];
+
+    if (cls >= GEO_CLS_STAGED) {
+        // every thread waits (also the ones without pixels: the CTA must not retire under an in-flight copy)
+        mbar_wait(smem_u32(&s_bar), 0);
+        if (active) {
+            const uint32_t *box = reinterpret_cast<const uint32_t *>(s_box);
+            if (cls == GEO_CLS_STAGED) geo_smem_body<KIND, false>(F, m, base, P.niter, s, x_first, mask, q, qn, box, s_cls[1], s_cls[2], s_cls[3]);
+            else geo_smem_body<KIND, true>(F, m, base, P.niter, s, x_first, mask, q, qn, box, s_cls[1], s_cls[2], s_cls[3]);
+        }
+    } else if (cls == GEO_CLS_ZERO) {
+        if (active) geo_zero_body(F, base, P.niter, s, x_first, mask);
+    } else if (active) {
         if (KIND == 0) {
             geo_tile_body<0, 0>(F, m, base, P.niter, s, x_first, mask, q, qn);
         } else {
