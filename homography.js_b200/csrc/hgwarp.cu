@@ -78,8 +78,10 @@ struct hg_ctx {
     // TMA staging of source tiles (warp_geo.cuh): cuTensorMapEncodeTiled from the driver, the tensor maps of the
     // context image (passed to single-frame launches by value) and a device-side cache for batch frames
     void *tm_encode = nullptr;
-    int geo_box_bytes = 32 * 1024;  // dynamic shared memory per CTA for the staged tile (HG_GEO_SMEM_KB)
-    int geo_niter_staged = 2;       // row groups per CTA when staging is possible (HG_GEO_NITER)
+    int geo_box_bytes = 13824;      // shared memory for one staged source box (HG_GEO_BOX_BYTES): 72 x 48 pixels
+    int geo_niter_staged = 2;       // row groups (16 rows) per tile of the staged kernel (HG_GEO_NITER)
+    int geo_stages = 3;             // ring depth per CTA (HG_GEO_STAGES)
+    int geo_ctas_per_sm = 5;        // persistent CTAs per SM (HG_GEO_CTAS; bounded by registers / shared memory)
     CUtensorMap img_tm[GEO_NBOX];
     bool img_tm_ok = false;
     DevBuf tm_dev;                   // TM_CACHE_SLOTS x GEO_NBOX tensor maps
@@ -236,7 +238,7 @@ typedef CUresult (*tm_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // GEO_NBOX tensor maps over a device image seen as a [H][W] tensor of 32-bit pixels, one per box width
-// (box = geo_box_w(i) pixels x GEO_BOX_ROWS rows, out-of-image elements read as zero).  False when the image
+// and height (geo_box_w(i % 8) pixels x 8 or 32 rows, out-of-image elements read as zero).  False when the image
 // cannot be described (row pitch or base not 16-byte aligned) — the kernels then gather directly.
 bool encode_tmaps(hg_ctx *c, const void *img, int W, int H, CUtensorMap *out)
 {
@@ -245,7 +247,8 @@ bool encode_tmaps(hg_ctx *c, const void *img, int W, int H, CUtensorMap *out)
     const cuuint64_t strides[1] = {(cuuint64_t)W * 4};
     const cuuint32_t estr[2] = {1, 1};
     for (int i = 0; i < GEO_NBOX; ++i) {
-        const cuuint32_t box[2] = {(cuuint32_t)geo_box_w(i), (cuuint32_t)GEO_BOX_ROWS};
+        const cuuint32_t box[2] = {(cuuint32_t)geo_box_w(i % GEO_NBOX_W),
+                                   (cuuint32_t)(i < GEO_NBOX_W ? GEO_BOX_ROWS : GEO_BOX_ROWS_TALL)};
         const CUresult r = ((tm_encode_fn)c->tm_encode)(&out[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(img),
                                                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -302,7 +305,9 @@ int pick_niter(hg_ctx *c, int max_ow, int max_oh, int n_frames)
 int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_frames, bool staged, cudaStream_t stream)
 {
     P.niter = staged ? c->geo_niter_staged : pick_niter(c, max_ow, max_oh, n_frames);
+    if (staged && 32 * P.niter > GEO_QCAP) P.niter = GEO_QCAP / 32;  // per-tile exact queue: one entry per thread and row group
     P.box_bytes = staged ? c->geo_box_bytes : 0;
+    P.stages = 0;
     dim3 grid((unsigned)(geo_tiles_x(max_ow) * geo_tiles_y(max_oh, P.niter)), (unsigned)n_frames);
     if (c->sampling == HG_BILINEAR) {
         const long long nq = ((long long)max_ow * max_oh + 3) / 4;
@@ -319,8 +324,22 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
     }
     const bool timed = stream == c->stream;  // the per-kernel events live on the context stream
     if (timed) TRY(prof_begin(c));
-    if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, (size_t)P.box_bytes, stream>>>(P);
-    else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, (size_t)P.box_bytes, stream>>>(P);
+    if (staged) {
+        P.stages = c->geo_stages;
+        P.tiles_x = geo_tiles_x(max_ow);
+        P.tiles_y = geo_tiles_y(max_oh, P.niter);
+        P.n_frames = n_frames;
+        P.debug = getenv("HG_GEO_DEBUG") ? atoi(getenv("HG_GEO_DEBUG")) : 0;  // 1: trace ring entries, 2: no 32-row boxes
+        const long long total = (long long)P.tiles_x * P.tiles_y * n_frames;
+        long long ctas = (long long)c->sm_count * c->geo_ctas_per_sm;
+        if (ctas > total) ctas = total;
+        const size_t smem = (size_t)P.stages * (size_t)(GEO_HDR_BYTES + P.box_bytes);
+        if (kind == HG_AFFINE) warp_inverse_geo_staged_kernel<0><<<(unsigned)ctas, GEO_STAGED_THREADS, smem, stream>>>(P);
+        else warp_inverse_geo_staged_kernel<1><<<(unsigned)ctas, GEO_STAGED_THREADS, smem, stream>>>(P);
+    } else {
+        if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, 0, stream>>>(P);
+        else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, 0, stream>>>(P);
+    }
     c->launches++;
     CU(c, cudaGetLastError());
     if (timed) TRY(prof_end(c));
@@ -413,16 +432,35 @@ int hg_ctx_create(int device, hg_ctx **out)
             qres == cudaDriverEntryPointSuccess)
             c->tm_encode = fn;
         cudaGetLastError();
-        if (const char *v = getenv("HG_GEO_SMEM_KB")) {
-            const int kb = atoi(v);
-            if (kb >= 8 && kb <= 200) c->geo_box_bytes = kb * 1024;
-        }
-        if (const char *v = getenv("HG_GEO_NITER")) {
-            const int n = atoi(v);
-            if (n >= 1 && n <= 16) c->geo_niter_staged = n;
-        }
-        CUC(cudaFuncSetAttribute(warp_inverse_geo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->geo_box_bytes));
-        CUC(cudaFuncSetAttribute(warp_inverse_geo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->geo_box_bytes));
+        auto env_int = [](const char *name, int lo, int hi, int &dst) {
+            if (const char *v = getenv(name)) {
+                const int n = atoi(v);
+                if (n >= lo && n <= hi) dst = n;
+            }
+        };
+        env_int("HG_GEO_BOX_BYTES", 4096, 100 * 1024, c->geo_box_bytes);
+        c->geo_box_bytes &= ~127;
+        env_int("HG_GEO_NITER", 1, 16, c->geo_niter_staged);
+        env_int("HG_GEO_STAGES", 2, GEO_MAX_STAGES, c->geo_stages);
+        env_int("HG_GEO_CTAS", 1, 8, c->geo_ctas_per_sm);
+        // the ring must fit a CTA's shared memory: shrink the depth (the CTA count follows from the occupancy below)
+        const size_t cta_max = prop.sharedMemPerBlockOptin;
+        auto ring = [&]() { return (size_t)c->geo_stages * (size_t)(GEO_HDR_BYTES + c->geo_box_bytes); };
+        while (c->geo_stages > 2 && ring() + 4096 > cta_max) c->geo_stages--;
+        if (ring() + 4096 > cta_max) c->tm_encode = nullptr;  // box does not fit at all: direct kernel only
+        CUC(cudaFuncSetAttribute(warp_inverse_geo_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring()));
+        CUC(cudaFuncSetAttribute(warp_inverse_geo_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring()));
+        // persistent grid: never more CTAs per SM than can be resident (registers / shared memory)
+        int occ0 = 0, occ1 = 0;
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, warp_inverse_geo_staged_kernel<0>, GEO_STAGED_THREADS, ring()));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, warp_inverse_geo_staged_kernel<1>, GEO_STAGED_THREADS, ring()));
+        const int occ = occ0 < occ1 ? occ0 : occ1;
+        if (occ < 1) c->tm_encode = nullptr;
+        else if (c->geo_ctas_per_sm > occ) c->geo_ctas_per_sm = occ;
+        if (getenv("HG_GEO_VERBOSE"))
+            fprintf(stderr, "hgwarp: staged kernel: box %d B, %d stages, niter %d, %d CTAs/SM (occupancy %d/%d), tma %s\n",
+                    c->geo_box_bytes, c->geo_stages, c->geo_niter_staged, c->geo_ctas_per_sm, occ0, occ1,
+                    c->tm_encode ? "on" : "off");
     }
 #undef CUC
     *out = c;
@@ -805,7 +843,13 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
     CU(c, cudaMemcpyAsync(c->frames.p, gf.data(), sizeof(GeoFrame) * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
     // pageable sources: cudaMemcpyAsync returns once they are staged, so gf may die at scope exit
     CU(c, cudaMemcpyAsync(c->mats.p, inv_matrices, mstride * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
-    const int chunk = 32768;
+    // blockIdx.y of the direct kernel and the 32-bit tile index of the staged kernel bound the frames per launch
+    int chunk = 32768;
+    if (staged) {
+        const long long tpf = (long long)geo_tiles_x(max_ow) * geo_tiles_y(max_oh, 1);
+        const long long fit = (1LL << 30) / tpf;
+        if (fit < chunk) chunk = fit < 1 ? 1 : (int)fit;
+    }
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         GeoParams P{};

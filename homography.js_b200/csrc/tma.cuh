@@ -6,12 +6,20 @@
 // TMA unit, which is exactly what an out-of-image nearest-neighbour read must produce (transparent black).
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace hg {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count)
 {
@@ -30,6 +38,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, unsigned byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, unsigned parity)
 {
     uint32_t ok;
@@ -46,10 +59,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, unsigned parity)
 }
 
 // blocks until the phase with the given parity has completed; the waiting thread then sees the bytes the
-// async proxy wrote
-__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity)
+// async proxy wrote.  A wait that lasts seconds is a protocol bug, never load: it traps (the launch then fails with
+// an error the host reports) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity, int site = 0)
 {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+            printf("hgwarp: mbarrier wait timed out (site %d, block %d, thread %d, parity %u)\n", site, (int)blockIdx.x,
+                   (int)threadIdx.x, parity);
+            __trap();
+        }
     }
 }
 
