@@ -422,12 +422,13 @@ int hg_ctx_create(int device, hg_ctx **out)
     CUC(cudaMemset(c->scratch.p, 0, 4096));
     CUC(cudaHostAlloc(&c->pinned, 4096, cudaHostAllocDefault));
     {
-        // TMA staging: the tensor-map encoder lives in the driver; without it (or with HG_GEO_TMA=0) every tile
-        // gathers directly
-        const char *off = getenv("HG_GEO_TMA");
+        // TMA staging (warp_inverse_geo_staged_kernel) is opt-in, HG_GEO_STAGED=1: measured on B200 it is slower than
+        // the direct-gather kernel for these nearest-neighbour maps; the tensor-map encoder lives in
+        // the driver
+        const char *on = getenv("HG_GEO_STAGED");
         cudaDriverEntryPointQueryResult qres;
         void *fn = nullptr;
-        if (!(off && off[0] == '0') &&
+        if ((on && on[0] == '1') &&
             cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
             c->tm_encode = fn;

@@ -306,6 +306,204 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// geo_fast_body — the pixel loop on DOUBLED coordinates (affine always; projective when the denominator keeps one
+// sign and a moderate range over the frame window, see geo_fast_mode).
+//
+// With T = 2*v + 1 (+ delta) + 1.5*2^20 in the 2^-32 fixed-point layout of jsnum.cuh, n = hi(T) - HG_HI_ZERO is
+// floor(2v + 1), so
+//     Math.round(v) = floor(v + 1/2) = n >> 1            floor(v) = (n - 1) >> 1
+//     0 <= v < W  (H.js:1001, on the unrounded v)   <=>   1 <= n <= 2W   <=>   (unsigned)(n - 1) < 2W
+// and every decision of the loop (bounds at integers, rounding at half-integers) sits at an INTEGER of 2v: "the
+// quotient is within delta of a decision boundary" is "frac(2v + 1 + delta) < 2 delta", one zone instead of two.
+//   affine      v is formed exactly as the reference does (jsnum.cuh) and T = fma_rd(v, 2, magic) is one more exact
+//               step (the add rounds down onto a grid that holds every integer): no near test at all.
+//   projective  the numerators use doubled coefficients (an exact scaling) and ONE fma each with a per-row constant —
+//               a different association than the reference's, off by <= 3 ulp of the largest term, which
+//               geo_fast_mode bounds below 2^-25 pixel — and the reciprocal of the denominator (MUFU.RCP64H + one
+//               Newton step, 2^-39.9 relative).  Total error of 2v < 2^-20.9 < delta = 2^-19.  Both coordinates are
+//               tested with one multiply: umulhi(lo_x, lo_y) < 2 delta holds whenever either factor is < 2 delta
+//               (false positives, both within 2^-9 of a boundary, only cost a trip through the exact path).  Flagged
+//               pixels go to the warp queue and are redone by geo_flush_queue with the reference's own arithmetic.
+// Two-stage software pipeline, unrolled by two row groups: a group's gathers are issued right after its
+// arithmetic and stored one group later, so the loads of 8 pixels per thread stay in flight across a full group of
+// arithmetic of the same warp; the bounds predicate guards the load directly (no sentinel round trip).
+#define HG_NEAR_DELTA2 8192u  // 2^13 * 2^-32 = 2^-19 in units of 2v
+
+struct GeoGroup {
+    uint32_t px[GEO_ROWS_PER_THREAD][4];
+    int base;        // first row of the group (-1: empty)
+    unsigned redo;   // pixels whose quotient must be resolved exactly
+    int qpos;        // queue slot reserved for them
+};
+
+template <int KIND>
+struct GeoFastCtx {
+    const uint32_t *src;
+    unsigned W, H, W2, H2, npx;
+    unsigned kflat;          // flat = (hy >> 1) * W + (hx >> 1) - kflat
+    double xs[4];
+    double c0, c1, c2, c3, c4, c5, c6, c7;  // affine: m0..m5; projective: 2h0, 2h1, 2h2, 2h3, 2h4, 2h5, h6, h7
+    int xOff, yOff, s;
+};
+
+// arithmetic + gathers of one row group
+template <int KIND>
+__device__ __forceinline__ void geo_fast_issue(const GeoFastCtx<KIND> &C, GeoGroup &g, int base, int *qn)
+{
+    constexpr int R = GEO_ROWS_PER_THREAD;
+    const double MG = (KIND == 0) ? (HG_MAGIC + 1.0) : (HG_MAGIC + 1.0 + (double)HG_NEAR_DELTA2 / 4294967296.0);
+    g.base = base;
+    g.redo = 0u;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const double y = (double)(C.yOff + base + C.s * j);
+        double r0, r1, r2 = 0.0;
+        if (KIND == 0) {
+            r0 = __dmul_rn(C.c2, y);
+            r1 = __dmul_rn(C.c3, y);
+        } else {
+            r0 = __fma_rn(C.c1, y, C.c2);
+            r1 = __fma_rn(C.c4, y, C.c5);
+            r2 = __fma_rn(C.c7, y, 1.0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double tx, ty;
+            if (KIND == 0) {
+                tx = __fma_rd(affine_coord_exact(C.c0, C.xs[k], r0, C.c4), 2.0, MG);
+                ty = __fma_rd(affine_coord_exact(C.c1, C.xs[k], r1, C.c5), 2.0, MG);
+            } else {
+                const double rc = rcp_newton1(__fma_rn(C.c6, C.xs[k], r2));
+                tx = __fma_rn(__fma_rn(C.c0, C.xs[k], r0), rc, MG);
+                ty = __fma_rn(__fma_rn(C.c3, C.xs[k], r1), rc, MG);
+                const bool again = __umulhi((unsigned)__double2loint(tx), (unsigned)__double2loint(ty)) < 2u * HG_NEAR_DELTA2;
+                g.redo |= again ? (1u << (4 * j + k)) : 0u;
+            }
+            const unsigned hx = (unsigned)__double2hiint(tx), hy = (unsigned)__double2hiint(ty);
+            const unsigned flat = (hy >> 1) * C.W + (hx >> 1) - C.kflat;
+            // 0 <= v < W on the unrounded coordinate, and the flat index inside the image (Q2: past the end reads 0)
+            const bool in = ((hx - (unsigned)(HG_HI_ZERO + 1)) < C.W2) & ((hy - (unsigned)(HG_HI_ZERO + 1)) < C.H2) & (flat < C.npx);
+            uint32_t v = 0u;
+            if (in) v = __ldg(C.src + flat);
+            g.px[j][k] = v;
+        }
+    }
+    g.qpos = 0;
+    if (KIND == 1 && g.redo) g.qpos = atomicAdd(qn, 1);  // consumed when the group retires
+}
+
+// queue entry (or in-place exact resolution when the queue is full), then the stores of one row group
+template <int KIND>
+__device__ __forceinline__ void geo_fast_retire(const GeoFrame &F, const double (&m)[8], const GeoFastCtx<KIND> &C, GeoGroup &g,
+                                                int x_first, unsigned mask, uint2 *q)
+{
+    constexpr int R = GEO_ROWS_PER_THREAD;
+    if (g.base < 0) return;
+    if (KIND == 1 && g.redo) {
+        if (g.qpos < GEO_QCAP) {
+            q[g.qpos] = make_uint2((unsigned)(x_first + 4), (g.redo << 17) | (unsigned)g.base);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned rows = (g.redo >> k) & 0x11111111u;
+                while (rows) {
+                    const int j = (__ffs((int)rows) - 1) >> 2;
+                    rows &= rows - 1;
+                    const double x = C.xs[k], y = (double)(C.yOff + g.base + C.s * j);
+                    const double nx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), m[2]);
+                    const double ny = __dadd_rn(__dadd_rn(__dmul_rn(m[3], x), __dmul_rn(m[4], y)), m[5]);
+                    const double dn = __dadd_rn(__dadd_rn(__dmul_rn(m[6], x), __dmul_rn(m[7], y)), 1.0);
+                    const uint32_t v = ldg_or_zero(C.src, decode_flat(exact_quotient_magic(nx, dn), exact_quotient_magic(ny, dn),
+                                                                      C.W, C.H, C.npx));
+#pragma unroll
+                    for (int jj = 0; jj < R; ++jj)
+                        if (jj == j) g.px[jj][k] = v;  // select, no dynamic register indexing
+                }
+            }
+        }
+    }
+    uint32_t *dst = F.out + ((long long)g.base * (long long)F.oW + x_first);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        if (g.base + C.s * j < F.oH) {
+            if (mask == 0xFu) {
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(g.px[j][0], g.px[j][1], g.px[j][2], g.px[j][3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (mask & (1u << k)) dst[k] = g.px[j][k];
+            }
+        }
+        dst += (long long)C.s * (long long)F.oW;
+    }
+    g.base = -1;
+}
+
+template <int KIND>
+__device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&m)[8], int base0, int niter, int s,
+                                              int x_first, unsigned mask, uint2 *q, int *qn)
+{
+    GeoFastCtx<KIND> C;
+    C.src = F.src;
+    C.W = (unsigned)F.W;
+    C.H = (unsigned)F.H;
+    C.W2 = 2u * C.W;
+    C.H2 = 2u * C.H;
+    C.npx = C.W * C.H;
+    C.kflat = (unsigned)(HG_HI_ZERO >> 1) * (C.W + 1u);
+    C.xOff = F.xOff;
+    C.yOff = F.yOff;
+    C.s = s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) C.xs[k] = (double)(F.xOff + x_first + k);
+    if (KIND == 0) {
+        C.c0 = m[0]; C.c1 = m[1]; C.c2 = m[2]; C.c3 = m[3]; C.c4 = m[4]; C.c5 = m[5]; C.c6 = 0.0; C.c7 = 0.0;
+    } else {
+        C.c0 = 2.0 * m[0]; C.c1 = 2.0 * m[1]; C.c2 = 2.0 * m[2]; C.c3 = 2.0 * m[3]; C.c4 = 2.0 * m[4]; C.c5 = 2.0 * m[5];
+        C.c6 = m[6]; C.c7 = m[7];
+    }
+    GeoGroup ga, gb;
+    ga.base = gb.base = -1;
+    const int oH = F.oH;
+#pragma unroll 1
+    for (int it = 0; it < niter; it += 2) {
+        const int b0 = base0 + it * GEO_GROUP_ROWS, b1 = b0 + GEO_GROUP_ROWS;
+        if (b0 >= oH) break;
+        geo_fast_issue<KIND>(C, ga, b0, qn);
+        geo_fast_retire<KIND>(F, m, C, gb, x_first, mask, q);
+        if (it + 1 < niter && b1 < oH) {
+            geo_fast_issue<KIND>(C, gb, b1, qn);
+            geo_fast_retire<KIND>(F, m, C, ga, x_first, mask, q);
+        }
+    }
+    geo_fast_retire<KIND>(F, m, C, ga, x_first, mask, q);
+    geo_fast_retire<KIND>(F, m, C, gb, x_first, mask, q);
+}
+
+// CTA-uniform: may the projective frame run geo_fast_body?  The denominator h6 x + h7 y + 1 is affine in (x, y), so
+// its range over the frame window is spanned by the four corners.
+__device__ __forceinline__ bool geo_fast_mode(const GeoFrame &F, const double (&m)[8])
+{
+    if (m[6] == 0.0 && m[7] == 0.0) return false;  // denominator == 1: geo_tile_body<1,2> is exact without a reciprocal
+    const double X0 = (double)(F.xOff - 3), X1 = (double)(F.xOff + F.oW + 3);
+    const double Y0 = (double)F.yOff, Y1 = (double)(F.yOff + F.oH + 15);
+    double dmin = 1e300, dmax = 0.0;
+    bool pos = true, neg = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double dn = m[6] * ((c & 1) ? X1 : X0) + m[7] * ((c & 2) ? Y1 : Y0) + 1.0;
+        pos = pos && (dn > 0.0);
+        neg = neg && (dn < 0.0);
+        dmin = fmin(dmin, fabs(dn));
+        dmax = fmax(dmax, fabs(dn));
+    }
+    if (!(pos || neg) || !(dmin >= 0.015625) || !(dmax <= 64.0)) return false;  // also false for NaN
+    const double Xm = fmax(fabs(X0), fabs(X1)), Ym = fmax(fabs(Y0), fabs(Y1)), big = 33554432.0 * dmin;  // 2^25 dmin
+    return (fabs(m[0]) * Xm + fabs(m[1]) * Ym + fabs(m[2]) < big) && (fabs(m[3]) * Xm + fabs(m[4]) * Ym + fabs(m[5]) < big) &&
+           (fabs(m[6]) * Xm + fabs(m[7]) * Ym + 1.0 < 256.0 * dmin);
+}
+
 // Resolve the queued pixels of one warp with the reference's own arithmetic (H.js:1401-1404 followed by the bounds
 // test, Math.round and the flat read of H.js:1001-1007), one pixel per lane, and overwrite them in the output.
 __device__ __forceinline__ void geo_flush_queue(const GeoFrame &F, const double (&m)[8], const uint2 *q, int n, int s,
@@ -633,14 +831,11 @@ __global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB) warp_inverse_geo_ker
 
     if (active) {
         if (KIND == 0) {
-            geo_tile_body<0, 0>(F, m, base, P.niter, s, x_first, mask, q, qn);
+            geo_fast_body<0>(F, m, base, P.niter, s, x_first, mask, q, qn);
         } else {
             // CTA-uniform mode from the matrix and the frame window
-            const double ax = fmax(fabs((double)F.xOff), fabs((double)F.xOff + (double)oW));
-            const double ay = fmax(fabs((double)F.yOff), fabs((double)F.yOff + (double)oH));
-            const double spread = fabs(m[6]) * ax + fabs(m[7]) * ay;  // |h6 x + h7 y| <= spread (+ rounding)
             if (m[6] == 0.0 && m[7] == 0.0) geo_tile_body<1, 2>(F, m, base, P.niter, s, x_first, mask, q, qn);
-            else if (spread < 0.75) geo_tile_body<1, 1>(F, m, base, P.niter, s, x_first, mask, q, qn);
+            else if (geo_fast_mode(F, m)) geo_fast_body<1>(F, m, base, P.niter, s, x_first, mask, q, qn);
             else geo_tile_body<1, 0>(F, m, base, P.niter, s, x_first, mask, q, qn);
         }
     }
