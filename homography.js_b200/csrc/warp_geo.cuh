@@ -82,7 +82,10 @@ constexpr int GEO_TY = 8;           // thread rows per CTA  -> 128 threads
 #define HG_GEO_R 2
 #endif
 #ifndef HG_GEO_MINB
-#define HG_GEO_MINB 6
+#define HG_GEO_MINB 6  // CTAs per SM the affine kernel is compiled for (80 registers)
+#endif
+#ifndef HG_GEO_MINB_PROJ
+#define HG_GEO_MINB_PROJ 5  // projective: 96 registers measured 3 % faster than 80 (no spills, freer scheduling)
 #endif
 #ifndef HG_GEO_STAGED_MINB
 #define HG_GEO_STAGED_MINB 5
@@ -319,8 +322,8 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
 //   affine      v is formed exactly as the reference does (jsnum.cuh) and T = fma_rd(v, 2, magic) is one more exact
 //               step (the add rounds down onto a grid that holds every integer): no near test at all.
 //   projective  the numerators use doubled coefficients (an exact scaling) and ONE fma each with a per-row constant —
-//               a different association than the reference's, off by <= 3 ulp of the largest term, which
-//               geo_fast_mode bounds below 2^-25 pixel — and the reciprocal of the denominator (MUFU.RCP64H + one
+//               a different association than the reference's (and one add per pixel along the quad), off by <= 8 ulp of the
+//               largest term, which geo_fast_mode bounds below 2^-25 pixel — and the reciprocal of the denominator (MUFU.RCP64H + one
 //               Newton step, 2^-39.9 relative).  Total error of 2v < 2^-20.9 < delta = 2^-19.  Both coordinates are
 //               tested with one multiply: umulhi(lo_x, lo_y) < 2 delta holds whenever either factor is < 2 delta
 //               (false positives, both within 2^-9 of a boundary, only cost a trip through the exact path).  Flagged
@@ -341,7 +344,9 @@ template <int KIND>
 struct GeoFastCtx {
     const uint32_t *src;
     unsigned W, H, W2, H2, npx;
+    unsigned Wi, Hi;         // 2W - 3, 2H - 3 (0 for a 1-pixel dimension): the strictly-inside range of the end-pixel test
     unsigned kflat;          // flat = (hy >> 1) * W + (hx >> 1) - kflat
+    unsigned last[GEO_ROWS_PER_THREAD];  // flat index of the row's first pixel in the previous group (L2 prefetch stride)
     double xs[4];
     double c0, c1, c2, c3, c4, c5, c6, c7;  // affine: m0..m5; projective: 2h0, 2h1, 2h2, 2h3, 2h4, 2h5, h6, h7
     int xOff, yOff, s;
@@ -349,7 +354,7 @@ struct GeoFastCtx {
 
 // arithmetic + gathers of one row group
 template <int KIND>
-__device__ __forceinline__ void geo_fast_issue(const GeoFastCtx<KIND> &C, GeoGroup &g, int base, int *qn)
+__device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g, int base, int *qn)
 {
     constexpr int R = GEO_ROWS_PER_THREAD;
     const double MG = (KIND == 0) ? (HG_MAGIC + 1.0) : (HG_MAGIC + 1.0 + (double)HG_NEAR_DELTA2 / 4294967296.0);
@@ -367,6 +372,14 @@ __device__ __forceinline__ void geo_fast_issue(const GeoFastCtx<KIND> &C, GeoGro
             r1 = __fma_rn(C.c4, y, C.c5);
             r2 = __fma_rn(C.c7, y, 1.0);
         }
+        // projective: numerators / denominator of the quad's first pixel, then one add per pixel (x advances by 1)
+        double nx = 0.0, ny = 0.0, dn = 0.0;
+        if (KIND == 1) {
+            nx = __fma_rn(C.c0, C.xs[0], r0);
+            ny = __fma_rn(C.c3, C.xs[0], r1);
+            dn = __fma_rn(C.c6, C.xs[0], r2);
+        }
+        unsigned hx[4], hy[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             double tx, ty;
@@ -374,19 +387,55 @@ __device__ __forceinline__ void geo_fast_issue(const GeoFastCtx<KIND> &C, GeoGro
                 tx = __fma_rd(affine_coord_exact(C.c0, C.xs[k], r0, C.c4), 2.0, MG);
                 ty = __fma_rd(affine_coord_exact(C.c1, C.xs[k], r1, C.c5), 2.0, MG);
             } else {
-                const double rc = rcp_newton1(__fma_rn(C.c6, C.xs[k], r2));
-                tx = __fma_rn(__fma_rn(C.c0, C.xs[k], r0), rc, MG);
-                ty = __fma_rn(__fma_rn(C.c3, C.xs[k], r1), rc, MG);
+                const double rc = rcp_newton1(dn);
+                tx = __fma_rn(nx, rc, MG);
+                ty = __fma_rn(ny, rc, MG);
+                if (k < 3) {
+                    nx = __dadd_rn(nx, C.c0);
+                    ny = __dadd_rn(ny, C.c3);
+                    dn = __dadd_rn(dn, C.c6);
+                }
                 const bool again = __umulhi((unsigned)__double2loint(tx), (unsigned)__double2loint(ty)) < 2u * HG_NEAR_DELTA2;
                 g.redo |= again ? (1u << (4 * j + k)) : 0u;
             }
-            const unsigned hx = (unsigned)__double2hiint(tx), hy = (unsigned)__double2hiint(ty);
-            const unsigned flat = (hy >> 1) * C.W + (hx >> 1) - C.kflat;
-            // 0 <= v < W on the unrounded coordinate, and the flat index inside the image (Q2: past the end reads 0)
-            const bool in = ((hx - (unsigned)(HG_HI_ZERO + 1)) < C.W2) & ((hy - (unsigned)(HG_HI_ZERO + 1)) < C.H2) & (flat < C.npx);
-            uint32_t v = 0u;
-            if (in) v = __ldg(C.src + flat);
-            g.px[j][k] = v;
+            hx[k] = (unsigned)__double2hiint(tx);
+            hy[k] = (unsigned)__double2hiint(ty);
+        }
+        // Along an output row both source coordinates are monotone in x (the denominator keeps its sign), so when the
+        // quad's two END pixels lie at least one half-pixel step inside the image (2 <= n <= 2W - 2, same for y) the
+        // two middle ones lie inside too — also after the <= 1 step an approximate, flagged quotient may be off —
+        // and their flat index is a real pixel: no per-pixel test, no predicate on the load.
+#ifndef HG_GEO_NO_PREFETCH
+        {
+            // L2 prefetch one group ahead: the row's first pixel moves by an almost constant flat stride from group to
+            // group, so "this group's index + the stride since the last group" names the cache line the next group
+            // will gather from.  A hint only: a wrong guess costs one useless line, never a wrong pixel.
+            const unsigned f0 = (hy[0] >> 1) * C.W + (hx[0] >> 1) - C.kflat;
+            const unsigned pf = f0 + (f0 - C.last[j]);
+            C.last[j] = f0;
+            // only when the quad reads along one source row (a rotated map walks down a column: one line per pixel,
+            // where a single hint per quad is noise)
+            if ((pf < C.npx) & ((hy[0] ^ hy[3]) < 2u)) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.src + pf));
+        }
+#endif
+        const unsigned cz = (unsigned)(HG_HI_ZERO + 2);
+        const bool ends_inside = ((hx[0] - cz) < C.Wi) & ((hy[0] - cz) < C.Hi) & ((hx[3] - cz) < C.Wi) & ((hy[3] - cz) < C.Hi);
+        // decided per warp (the lanes that run the body stay together), so it is a real branch, not predication of
+        // both variants
+        if (__all_sync(__activemask(), ends_inside)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) g.px[j][k] = __ldg(C.src + ((hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned flat = (hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat;
+                // 0 <= v < W on the unrounded coordinate, and the flat index inside the image (Q2: past the end reads 0)
+                const bool in = ((hx[k] - (unsigned)(HG_HI_ZERO + 1)) < C.W2) & ((hy[k] - (unsigned)(HG_HI_ZERO + 1)) < C.H2) &
+                                (flat < C.npx);
+                uint32_t v = 0u;
+                if (in) v = __ldg(C.src + flat);
+                g.px[j][k] = v;
+            }
         }
     }
     g.qpos = 0;
@@ -410,7 +459,7 @@ __device__ __forceinline__ void geo_fast_retire(const GeoFrame &F, const double 
                 while (rows) {
                     const int j = (__ffs((int)rows) - 1) >> 2;
                     rows &= rows - 1;
-                    const double x = C.xs[k], y = (double)(C.yOff + g.base + C.s * j);
+                    const double x = (double)(C.xOff + x_first + k), y = (double)(C.yOff + g.base + C.s * j);
                     const double nx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), m[2]);
                     const double ny = __dadd_rn(__dadd_rn(__dmul_rn(m[3], x), __dmul_rn(m[4], y)), m[5]);
                     const double dn = __dadd_rn(__dadd_rn(__dmul_rn(m[6], x), __dmul_rn(m[7], y)), 1.0);
@@ -450,18 +499,25 @@ __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&
     C.H = (unsigned)F.H;
     C.W2 = 2u * C.W;
     C.H2 = 2u * C.H;
+    C.Wi = C.W2 >= 3u ? C.W2 - 3u : 0u;
+    C.Hi = C.H2 >= 3u ? C.H2 - 3u : 0u;
     C.npx = C.W * C.H;
     C.kflat = (unsigned)(HG_HI_ZERO >> 1) * (C.W + 1u);
     C.xOff = F.xOff;
     C.yOff = F.yOff;
     C.s = s;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) C.xs[k] = (double)(F.xOff + x_first + k);
+    for (int j = 0; j < GEO_ROWS_PER_THREAD; ++j) C.last[j] = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) C.xs[k] = (double)(F.xOff + x_first + (KIND == 0 ? k : 0));  // projective: xs[0] only
     if (KIND == 0) {
         C.c0 = m[0]; C.c1 = m[1]; C.c2 = m[2]; C.c3 = m[3]; C.c4 = m[4]; C.c5 = m[5]; C.c6 = 0.0; C.c7 = 0.0;
     } else {
         C.c0 = 2.0 * m[0]; C.c1 = 2.0 * m[1]; C.c2 = 2.0 * m[2]; C.c3 = 2.0 * m[3]; C.c4 = 2.0 * m[4]; C.c5 = 2.0 * m[5];
         C.c6 = m[6]; C.c7 = m[7];
+        // keep the doubled coefficients in registers (the compiler would otherwise re-derive them from the kernel
+        // parameters inside the loop)
+        asm volatile("" : "+d"(C.c0), "+d"(C.c1), "+d"(C.c2), "+d"(C.c3), "+d"(C.c4), "+d"(C.c5));
     }
     GeoGroup ga, gb;
     ga.base = gb.base = -1;
@@ -499,7 +555,7 @@ __device__ __forceinline__ bool geo_fast_mode(const GeoFrame &F, const double (&
         dmax = fmax(dmax, fabs(dn));
     }
     if (!(pos || neg) || !(dmin >= 0.015625) || !(dmax <= 64.0)) return false;  // also false for NaN
-    const double Xm = fmax(fabs(X0), fabs(X1)), Ym = fmax(fabs(Y0), fabs(Y1)), big = 33554432.0 * dmin;  // 2^25 dmin
+    const double Xm = fmax(fabs(X0), fabs(X1)), Ym = fmax(fabs(Y0), fabs(Y1)), big = 16777216.0 * dmin;  // 2^24 dmin
     return (fabs(m[0]) * Xm + fabs(m[1]) * Ym + fabs(m[2]) < big) && (fabs(m[3]) * Xm + fabs(m[4]) * Ym + fabs(m[5]) < big) &&
            (fabs(m[6]) * Xm + fabs(m[7]) * Ym + 1.0 < 256.0 * dmin);
 }
@@ -780,7 +836,7 @@ __device__ __forceinline__ void geo_zero_body(const GeoFrame &F, int base0, int 
 // Direct-gather kernel: one CTA per (tile, frame), every tile through geo_tile_body.  Used when the source cannot be
 // described by a tensor map (row pitch or base not 16-byte aligned) and as the A/B baseline (HG_GEO_TMA=0).
 template <int KIND>
-__global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB) warp_inverse_geo_kernel(const GeoParams P)
+__global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG_GEO_MINB) warp_inverse_geo_kernel(const GeoParams P)
 {
     // per-warp queue of pixels whose quotient must be resolved exactly (projective only)
     __shared__ uint2 s_q[KIND == 1 ? GEO_THREADS / 32 : 1][KIND == 1 ? GEO_QCAP : 1];
