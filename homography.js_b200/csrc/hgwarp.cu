@@ -63,7 +63,7 @@ struct hg_ctx {
 
     // mesh
     DevBuf src_pts, dst_pts, tris, rec, map32, map16, frames, mats, winner;
-    DevBuf invd, bin_cnt, bin_ent, fstatus, fframes;  // fused piecewise path
+    DevBuf invd, bin_cnt, bin_ent, bin_run, fstatus, fframes;  // fused piecewise path
     // parameters of the last inverse index map (rebuilt on demand for the aliasing forward read, Q8)
     std::vector<float> last_inv_pts;
     double last_inv_mw = 0, last_inv_yoff = 0;
@@ -475,7 +475,7 @@ int hg_ctx_destroy(hg_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->img_own, &c->out, &c->scratch, &c->src_pts, &c->dst_pts, &c->tris,
                       &c->rec, &c->map32, &c->map16, &c->frames, &c->mats, &c->winner,
-                      &c->invd, &c->bin_cnt, &c->bin_ent, &c->fstatus, &c->fframes};
+                      &c->invd, &c->bin_cnt, &c->bin_ent, &c->bin_run, &c->fstatus, &c->fframes, &c->tm_dev};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -1067,6 +1067,7 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
     const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
     TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * (total_bins + slack)));
     TRY(ensure(c, c->bin_ent, sizeof(unsigned) * (total_bins + slack) * PW_BIN_CAP));
+    TRY(ensure(c, c->bin_run, sizeof(uint4) * 2 * (total_bins + slack)));
     TRY(ensure(c, c->fstatus, sizeof(int) * (size_t)nF));
     TRY(ensure(c, c->fframes, sizeof(FusedFrame) * (size_t)nF));
     size_t bin0 = 0;
@@ -1077,6 +1078,7 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         F.inv = (const double *)c->invd.p + 6 * T * f;
         F.bin_cnt = (unsigned *)c->bin_cnt.p + bin0;
         F.bin_ent = (unsigned *)c->bin_ent.p + bin0 * PW_BIN_CAP;
+        F.bin_run = (uint4 *)c->bin_run.p + 2 * bin0;
         F.status = (int *)c->fstatus.p + f;
         F.W = fr[f].W; F.H = fr[f].H;
         F.xOff = fr[f].xOff; F.yOff = fr[f].yOff; F.oW = fr[f].oW; F.oH = fr[f].oH;
@@ -1107,6 +1109,16 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         pw_span_bin_kernel<<<dim3((unsigned)((T * split + 3) / 4), (unsigned)nF), 128, 0, c->stream>>>(
             (const FusedFrame *)c->fframes.p, split);
         c->launches += 2;
+        CU(c, cudaGetLastError());
+    }
+    {
+        size_t max_bins = 1;
+        for (int f = 0; f < nF; ++f) {
+            const size_t nb = (size_t)pwf_tiles_x(fr[f].oW) * fr[f].oH;
+            if (nb > max_bins) max_bins = nb;
+        }
+        pw_bin_runs_kernel<<<dim3((unsigned)((max_bins + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
+        c->launches++;
         CU(c, cudaGetLastError());
     }
     TRY(prof_begin(c));

@@ -10,14 +10,15 @@
 //   bin (row R, 64-column block B)  ->  up to PW_BIN_CAP entries  (t, c0, c1)   "triangle t covers columns
 //                                                                               [c0,c1) of this block in row R"
 //
-// (~1/64 of the map's size; a few entries per bin for any non-folded mesh).  The warp kernel resolves
-// t = max over the matching entries of its pixel's bin, then does what H.js:1046-1052 does: inverse 2x3 of the
-// triangle, window test, Math.round, flat gather, 128-bit store.
+// (~1/64 of the map's size; a few entries per bin for any non-folded mesh).  A second pass (pw_bin_runs_kernel, one
+// thread per bin) resolves the overlaps — highest id wins — and run-length encodes each bin as a 64-bit start mask +
+// up to 8 int16 ids.  The warp kernel finds t with two popcounts, then does what H.js:1046-1052 does: inverse 2x3 of
+// the triangle, window test, Math.round, flat gather, 128-bit store.
 //
 // Exactness: every quirk of the reference's map (no x offset -> spans spilling into the next row, negative
 // relative fill indices landing at the END of the map, last-writer-wins overlaps, int16 wrap of ids) is inherited
 // from the exact interval computation.  A frame that cannot be represented (a bin with more than PW_BIN_CAP
-// entries, an interval crossing more than PW_MAX_PIECES rows, >= 2^17 triangles) raises a status flag and is redone
+// entries or runs, an interval crossing more than PW_MAX_PIECES rows, >= 2^17 triangles) raises a status flag and is redone
 // by the general map-based path — never approximated.
 #pragma once
 #include "piecewise.cuh"
@@ -37,6 +38,7 @@ struct FusedFrame {
     const double *inv;     // n_tris * 6 doubles: the f32-rounded inverse matrices, widened
     unsigned *bin_cnt;     // oH * bins_x counters (zeroed before the span kernel)
     unsigned *bin_ent;     // oH * bins_x * PW_BIN_CAP packed entries  (t << 14 | c1 << 7 | c0)
+    uint4 *bin_run;        // oH * bins_x run records (pw_bin_runs_kernel): what the pixel kernel reads
     int *status;           // bit 0: not representable -> redo with the general path
     int W, H, xOff, yOff, oW, oH, minSrcX, minSrcY, n_tris, bins_x;
 };
@@ -82,6 +84,87 @@ __global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *fram
     }
 }
 
+
+// Int16Array semantics of the map (H.js:848): the stored id is t mod 2^16 as int16, negative = no triangle; ids that
+// would index past the matrix list never occur for maps built from the same mesh
+__device__ __forceinline__ int pwf_map_id(int raw, int n_tris)
+{
+    const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);
+    return (t >= 0 && t < n_tris) ? t : -1;
+}
+
+// Second binning pass, one thread per bin: resolve the overlaps ONCE (highest triangle id wins, then the Int16 wrap)
+// and run-length encode the 64 columns of the bin:
+//     record = { start mask (bit c: a run begins at column c), up to PW_RUN_CAP ids as int16, in column order }
+// so the pixel kernel finds a pixel's triangle with two popcounts instead of scanning the entries: run index =
+// popc(mask & bits[0..c]) - 1.  Adjacent runs with the same final id are merged; more than PW_RUN_CAP runs in one bin
+// flags the frame for the general path.
+constexpr int PW_RUN_CAP = 8;
+
+__global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *frames)
+{
+    const FusedFrame &F = frames[blockIdx.y];
+    const size_t nbins = (size_t)F.bins_x * F.oH;
+    const size_t bin = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (bin >= nbins) return;
+    const unsigned cnt = min(F.bin_cnt[bin], (unsigned)PW_BIN_CAP);
+    unsigned ent[PW_BIN_CAP];
+    {
+        const uint4 *pe = reinterpret_cast<const uint4 *>(F.bin_ent) + 2 * bin;
+        const uint4 a = cnt > 0 ? pe[0] : make_uint4(0, 0, 0, 0), b = cnt > 4 ? pe[1] : make_uint4(0, 0, 0, 0);
+        ent[0] = a.x; ent[1] = a.y; ent[2] = a.z; ent[3] = a.w; ent[4] = b.x; ent[5] = b.y; ent[6] = b.z; ent[7] = b.w;
+    }
+    // candidate run starts: column 0 and every interval end point inside the bin
+    unsigned long long cand = 1ull;
+#pragma unroll
+    for (int e = 0; e < PW_BIN_CAP; ++e) {
+        if ((unsigned)e < cnt) {
+            const unsigned lo = ent[e] & 127u, hi = (ent[e] >> 7) & 127u;
+            cand |= 1ull << lo;          // lo <= 63
+            if (hi < 64u) cand |= 1ull << hi;
+        }
+    }
+    unsigned long long mask = 0ull;
+    unsigned ids[PW_RUN_CAP / 2] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // int16 pairs, -1 = no triangle
+    int runs = 0, prev = -2;
+    while (cand) {
+        const int c = __ffsll((long long)cand) - 1;
+        cand &= cand - 1;
+        int raw = -1;
+#pragma unroll
+        for (int e = 0; e < PW_BIN_CAP; ++e) {
+            if ((unsigned)e < cnt) {
+                const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u);
+                if (lo <= c && c < hi) raw = max(raw, (int)(ent[e] >> 14));
+            }
+        }
+        const int id = pwf_map_id(raw, F.n_tris);
+        if (id != prev) {
+            if (runs == PW_RUN_CAP) {
+                atomicOr(F.status, 1);
+                break;
+            }
+            const unsigned h = (unsigned)id & 0xFFFFu;
+#pragma unroll
+            for (int w = 0; w < PW_RUN_CAP / 2; ++w)
+                if (w == (runs >> 1)) ids[w] = (runs & 1) ? ((ids[w] & 0x0000FFFFu) | (h << 16)) : ((ids[w] & 0xFFFF0000u) | h);
+            mask |= 1ull << c;
+            prev = id;
+            ++runs;
+        }
+    }
+    F.bin_run[2 * bin] = make_uint4((unsigned)mask, (unsigned)(mask >> 32), 0u, 0u);
+    F.bin_run[2 * bin + 1] = make_uint4(ids[0], ids[1], ids[2], ids[3]);
+}
+
+// id of run r (0..7) from the packed int16 ids
+__device__ __forceinline__ int pwf_run_id(const uint4 &ids, unsigned r)
+{
+    const unsigned lo = (r & 2u) ? ids.y : ids.x, hi = (r & 2u) ? ids.w : ids.z;
+    const unsigned w = (r & 4u) ? hi : lo;
+    return (int)(short)(unsigned short)((r & 1u) ? (w >> 16) : w);
+}
+
 #ifndef HG_PWF_MINB
 #define HG_PWF_MINB 5
 #endif
@@ -107,8 +190,17 @@ __device__ __forceinline__ void pwf_load_matrix(const double *inv, int t, double
 template <bool ZERO_OFF>
 __device__ __forceinline__ unsigned pwf_decode(double sx, double sy, const FusedFrame &F, unsigned npx_src)
 {
+    if (ZERO_OFF) {
+        // doubled coordinates (see geo_fast_body): n = hi(2v + 1 + magic) - HG_HI_ZERO = floor(2v + 1), exact for every v;
+        // 0 <= v < W  <=>  (unsigned)(n - 1) < 2W,  Math.round(v) = n >> 1
+        const unsigned hx = (unsigned)__double2hiint(__fma_rd(sx, 2.0, HG_MAGIC + 1.0));
+        const unsigned hy = (unsigned)__double2hiint(__fma_rd(sy, 2.0, HG_MAGIC + 1.0));
+        const unsigned flat = (hy >> 1) * (unsigned)F.W + (hx >> 1) - (unsigned)(HG_HI_ZERO >> 1) * ((unsigned)F.W + 1u);
+        const bool in = ((hx - (unsigned)(HG_HI_ZERO + 1)) < 2u * (unsigned)F.W) & ((hy - (unsigned)(HG_HI_ZERO + 1)) < 2u * (unsigned)F.H) &
+                        (flat < npx_src);
+        return in ? flat : HG_OUTSIDE;
+    }
     const double tx2 = __dadd_rd(sx, HG_MAGIC), ty2 = __dadd_rd(sy, HG_MAGIC);
-    if (ZERO_OFF) return decode_flat(tx2, ty2, (unsigned)F.W, (unsigned)F.H, npx_src);
     const int ix = __double2hiint(tx2) - HG_HI_ZERO, iy = __double2hiint(ty2) - HG_HI_ZERO;
     const int rx = ix + (int)((unsigned)__double2loint(tx2) >> 31);
     const int ry = iy + (int)((unsigned)__double2loint(ty2) >> 31);
@@ -116,14 +208,6 @@ __device__ __forceinline__ unsigned pwf_decode(double sx, double sy, const Fused
     const bool ok = ((unsigned)(ix - F.minSrcX) < (unsigned)F.W) & ((unsigned)(iy - F.minSrcY) < (unsigned)F.H) &
                     (fl >= 0) & (fl < (long long)npx_src);
     return ok ? (unsigned)fl : HG_OUTSIDE;
-}
-
-// Int16Array semantics of the map (H.js:848): the stored id is t mod 2^16 as int16, negative = no triangle; ids that
-// would index past the matrix list never occur for maps built from the same mesh
-__device__ __forceinline__ int pwf_map_id(int raw, int n_tris)
-{
-    const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);
-    return (t >= 0 && t < n_tris) ? t : -1;
 }
 
 // CTA = one 64-column bin column x (16 * niter) rows.  Thread (tx,ty) owns ONE row per row group and TWO quads of
@@ -159,14 +243,12 @@ __device__ __forceinline__ void pwf_body(const FusedFrame &F, int niter, int til
 #pragma unroll
         for (int k = 0; k < 4; ++k) xs[q][k] = (double)(F.xOff + xx0[q] + k);
 
-    const unsigned *p_cnt = F.bin_cnt + ((size_t)base0 * F.bins_x + tile_x);
-    const uint4 *p_ent = reinterpret_cast<const uint4 *>(F.bin_ent) + 2 * ((size_t)base0 * F.bins_x + tile_x);
+    const uint4 *p_run = F.bin_run + 2 * ((size_t)base0 * F.bins_x + tile_x);
     const size_t cnt_step = (size_t)PWF_GROUP_ROWS * F.bins_x;
     uint32_t *p_out = F.out + ((long long)base0 * F.oW + xx0[0]);
     const long long out_step = (long long)PWF_GROUP_ROWS * F.oW;
 
-    unsigned bcnt = 0;
-    uint4 be0 = make_uint4(0, 0, 0, 0), be1 = be0;
+    uint4 be0 = make_uint4(0, 0, 0, 0), be1 = be0;  // run record of the row's bin: start mask, packed ids
     int tri[2][4];
     unsigned uni = 0;      // bit q: the four pixels of quad q share one triangle id
     double mq[2][6];       // inverse matrix of the first pixel's triangle of each quad
@@ -242,54 +324,37 @@ __device__ __forceinline__ void pwf_body(const FusedFrame &F, int niter, int til
         }
         // ---- S1: triangle ids of group it-1 from its bin; fetch the matrices S2 will need next iteration
         if (it >= 1 && it - 1 < ngroups) {
-            int tfull[2] = {-1, -1};                                   // highest id among entries covering a WHOLE quad
-            int best[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};     // per pixel, for entries cutting through a quad
-            unsigned mixed = 0;
-            const unsigned cnt = min(bcnt, (unsigned)PW_BIN_CAP);
-            const unsigned ent[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
-#pragma unroll
-            for (int e = 0; e < PW_BIN_CAP; ++e) {
-                if ((unsigned)e >= cnt) break;
-                const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u), t = (int)(ent[e] >> 14);
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    if (lo <= c_rel[q] && c_rel[q] + 4 <= hi) {
-                        tfull[q] = max(tfull[q], t);
-                    } else if (lo < c_rel[q] + 4 && c_rel[q] < hi) {
-                        mixed |= 1u << q;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if ((unsigned)(c_rel[q] + k - lo) < (unsigned)(hi - lo)) best[q][k] = max(best[q][k], t);
-                    }
-                }
-            }
+            // quad 0 lives in the low word of the start mask (columns 0..31), quad 1 in the high word
+            const unsigned below1 = __popc(be0.x);
             uni = 0;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                if (!((mixed >> q) & 1u)) {
-                    const int t = pwf_map_id(tfull[q], n_tris);
+                const unsigned word = q ? be0.y : be0.x, cb = 4u * (unsigned)tx;
+                const unsigned r = (q ? below1 : 0u) + __popc(word & ((2u << cb) - 1u)) - 1u;  // run of the quad's first column
+                const unsigned inner = (word >> (cb + 1u)) & 7u;                               // runs starting inside the quad
+                const int t0 = pwf_run_id(be1, r);
+                tri[q][0] = t0;
+                if (inner == 0u) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tri[q][k] = t;
+                    for (int k = 1; k < 4; ++k) tri[q][k] = t0;
                     uni |= 1u << q;
                 } else {
                     bool u = true;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        tri[q][k] = pwf_map_id(max(tfull[q], best[q][k]), n_tris);
-                        u = u && (tri[q][k] == tri[q][0]);
+                    for (int k = 1; k < 4; ++k) {
+                        tri[q][k] = pwf_run_id(be1, r + __popc(inner & ((1u << k) - 1u)));
+                        u = u && (tri[q][k] == t0);
                     }
                     uni |= u ? (1u << q) : 0u;
                 }
-                if (tri[q][0] >= 0) pwf_load_matrix(F.inv, tri[q][0], mq[q]);
+                if (t0 >= 0) pwf_load_matrix(F.inv, t0, mq[q]);
             }
         }
-        // ---- S0: bin loads of group it
+        // ---- S0: run record of group it
         if (it < ngroups) {
-            bcnt = __ldg(p_cnt);
-            be0 = __ldg(p_ent);
-            be1 = __ldg(p_ent + 1);
-            p_cnt += cnt_step;
-            p_ent += 2 * cnt_step;
+            be0 = __ldg(p_run);
+            be1 = __ldg(p_run + 1);
+            p_run += 2 * cnt_step;
         }
     }
 }
