@@ -71,13 +71,25 @@ __global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *fram
             const long long row_end = (row + 1) * F.oW;
             const long long e = k1 < row_end ? k1 : row_end;
             const int c0 = (int)(k0 - row * F.oW), c1 = (int)(e - row * F.oW);
-            for (int b = c0 / PW_BIN_W; b <= (c1 - 1) / PW_BIN_W; ++b) {
-                const int lo = max(c0, b * PW_BIN_W) - b * PW_BIN_W;
-                const int hi = min(c1, (b + 1) * PW_BIN_W) - b * PW_BIN_W;
-                const size_t bin = (size_t)row * F.bins_x + b;
-                const unsigned slot = atomicAdd(F.bin_cnt + bin, 1u);
-                if (slot < PW_BIN_CAP) F.bin_ent[bin * PW_BIN_CAP + slot] = ((unsigned)t << 14) | ((unsigned)hi << 7) | (unsigned)lo;
-                else atomicOr(F.status, 1);
+            // eight bins at a time: the slot reservations (independent atomics) go out back to back, the entry
+            // stores that depend on them follow
+            const int b_last = (c1 - 1) / PW_BIN_W;
+            for (int b0 = c0 / PW_BIN_W; b0 <= b_last; b0 += 8) {
+                unsigned slot[8];
+                const size_t bin0 = (size_t)row * F.bins_x + b0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (b0 + i <= b_last) slot[i] = atomicAdd(F.bin_cnt + bin0 + i, 1u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (b0 + i <= b_last) {
+                        const int b = b0 + i;
+                        const int lo = max(c0, b * PW_BIN_W) - b * PW_BIN_W;
+                        const int hi = min(c1, (b + 1) * PW_BIN_W) - b * PW_BIN_W;
+                        if (slot[i] < PW_BIN_CAP) F.bin_ent[(bin0 + i) * PW_BIN_CAP + slot[i]] = ((unsigned)t << 14) | ((unsigned)hi << 7) | (unsigned)lo;
+                        else atomicOr(F.status, 1);
+                    }
+                }
             }
             k0 = e;
         }
@@ -114,15 +126,15 @@ __global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *fram
         const uint4 a = cnt > 0 ? pe[0] : make_uint4(0, 0, 0, 0), b = cnt > 4 ? pe[1] : make_uint4(0, 0, 0, 0);
         ent[0] = a.x; ent[1] = a.y; ent[2] = a.z; ent[3] = a.w; ent[4] = b.x; ent[5] = b.y; ent[6] = b.z; ent[7] = b.w;
     }
-    // candidate run starts: column 0 and every interval end point inside the bin
+    // candidate run starts: column 0 and every interval end point inside the bin.  Typical bins hold 1-3 entries: the
+    // loops stop at cnt instead of running predicated over all PW_BIN_CAP slots
     unsigned long long cand = 1ull;
 #pragma unroll
     for (int e = 0; e < PW_BIN_CAP; ++e) {
-        if ((unsigned)e < cnt) {
-            const unsigned lo = ent[e] & 127u, hi = (ent[e] >> 7) & 127u;
-            cand |= 1ull << lo;          // lo <= 63
-            if (hi < 64u) cand |= 1ull << hi;
-        }
+        if ((unsigned)e >= cnt) break;
+        const unsigned lo = ent[e] & 127u, hi = (ent[e] >> 7) & 127u;
+        cand |= 1ull << lo;          // lo <= 63
+        if (hi < 64u) cand |= 1ull << hi;
     }
     unsigned long long mask = 0ull;
     unsigned ids[PW_RUN_CAP / 2] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // int16 pairs, -1 = no triangle
@@ -133,10 +145,10 @@ __global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *fram
         int raw = -1;
 #pragma unroll
         for (int e = 0; e < PW_BIN_CAP; ++e) {
-            if ((unsigned)e < cnt) {
-                const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u);
-                if (lo <= c && c < hi) raw = max(raw, (int)(ent[e] >> 14));
-            }
+            if ((unsigned)e >= cnt) break;
+            // lo <= c < hi  <=>  (unsigned)(c - lo) < (unsigned)(hi - lo)
+            const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u);
+            if ((unsigned)(c - lo) < (unsigned)(hi - lo)) raw = max(raw, (int)(ent[e] >> 14));
         }
         const int id = pwf_map_id(raw, F.n_tris);
         if (id != prev) {
