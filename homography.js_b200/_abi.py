@@ -24,6 +24,7 @@ SYMBOLS = [
     "hg_image_set", "hg_image_set_device",
     "hg_solve_affine", "hg_solve_projective", "hg_inverse_affine", "hg_transform_limits", "hg_solve_with_limits",
     "hg_warp_inverse_matrix", "hg_warp_inverse_points", "hg_warp_forward_matrix",
+    "hg_delaunay",
     "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_piecewise_extents", "hg_build_index_map",
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
@@ -107,6 +108,7 @@ def load():
     L.hg_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
     L.hg_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     L.hg_output_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.hg_delaunay.argtypes = [vp, i, vp, i, C.POINTER(i)]
     _lib = L
     return L
 
@@ -390,6 +392,19 @@ class Pipe:
             self.close()
         except Exception:
             pass
+
+
+def delaunay(points) -> np.ndarray:
+    """hg_delaunay: `new Delaunator(points).triangles` (H.js:1216) — host only, needs no GPU.  points: (n, 2) or flat
+    [x0, y0, ...]; returns a flat uint32 array, three vertex ids per triangle."""
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1))
+    n = pts.size // 2
+    out = np.zeros(3 * max(2 * n - 5, 0), np.uint32)
+    cnt = C.c_int()
+    st = load().hg_delaunay(_ptr(pts), n, _ptr(out) if out.size else None, out.size // 3, C.byref(cnt))
+    if st:
+        raise HgError(st, "hg_delaunay failed")
+    return out[:3 * cnt.value].copy()
 
 
 def device_count() -> int:

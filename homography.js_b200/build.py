@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # JS never fuses a*b+c; FMA is used only through explicit __fma_rn where it is exact
-    "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off",  # host math (Delaunay) is JS-Number arithmetic too
 ]
 
 

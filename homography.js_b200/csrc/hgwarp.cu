@@ -22,6 +22,7 @@
 #include "bilinear.cuh"
 #include "forward.cuh"
 #include "piecewise_fused.cuh"
+#include "delaunay_host.cuh"
 
 using namespace hg;
 
@@ -858,6 +859,20 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
         P.mats_dev = (const char *)c->mats.p + mstride * (size_t)f0;
         TRY(launch_geo(c, kind, P, max_ow, max_oh, nf, staged, c->stream));
     }
+    return HG_OK;
+}
+
+/* ------------------------------------------------------------------ triangulation */
+int hg_delaunay(const double *points, int n_points, uint32_t *triangles_out, int capacity_triangles, int *n_triangles)
+{
+    if (!points || !n_triangles || n_points < 0 || capacity_triangles < 0 || (capacity_triangles > 0 && !triangles_out))
+        return HG_ERR_INVALID;
+    *n_triangles = 0;
+    const std::vector<uint32_t> t = hg_delaunay_detail::triangulate(points, (size_t)n_points);
+    const size_t nt = t.size() / 3;
+    if (nt > (size_t)capacity_triangles) return HG_ERR_INVALID;
+    if (nt) memcpy(triangles_out, t.data(), t.size() * sizeof(uint32_t));
+    *n_triangles = (int)nt;
     return HG_OK;
 }
 

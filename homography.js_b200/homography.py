@@ -119,12 +119,11 @@ def _select_transform(first: str, points: np.ndarray) -> str:
 
 
 def default_triangulation(points: np.ndarray) -> np.ndarray:
-    """Stand-in for `new Delaunator(points).triangles` (H.js:1216).  delaunator 5.0.0 is a third-party
-    dependency that is not part of the reference tree; any valid Delaunay triangulation gives the
-    same picture up to shared-edge pixels, but triangle ORDER is not guaranteed identical — pass the
-    triangles explicitly with setTriangles() when bit-exact parity with a given mesh is needed."""
-    from scipy.spatial import Delaunay
-    return Delaunay(np.asarray(points, dtype=np.float64).reshape(-1, 2)).simplices.astype(np.uint32).reshape(-1)
+    """`new Delaunator(points).triangles` (H.js:1216): the library's host-side restatement of delaunator 5.0.0
+    (hg_delaunay, csrc/delaunay_host.cuh).  The package is third-party and absent from the reference tree, so the
+    triangle order is by construction, not pinned by any reference fixture; pass triangles explicitly with
+    setTriangles() (the reference's own hook, H.js:517) to reproduce a given mesh."""
+    return _abi.delaunay(points)
 
 
 class Homography:

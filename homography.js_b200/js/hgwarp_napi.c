@@ -10,6 +10,7 @@
  * In this image (no Node) it is only compile-checked against js/napi_min.h (tests/test_js_binding_sources.py).
  */
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/hgwarp.h"
@@ -177,6 +178,34 @@ static napi_value SetMesh(napi_env env, napi_callback_info info)
     return check(env, ctx, hg_piecewise_set_mesh(ctx, (const float *)pts, (int)(npts2 / 2), (const uint32_t *)tris, (int)(ntri3 / 3)));
 }
 
+/* delaunay(Float32Array | Float64Array points) -> Uint32Array     <- Delaunay(points), H.js:1216 (delaunator@5.0.0) */
+static napi_value Delaunay(napi_env env, napi_callback_info info)
+{
+    ARGS(1);
+    napi_typedarray_type t;
+    size_t n2 = 0;
+    void *data = NULL;
+    if (napi_get_typedarray_info(env, argv[0], &t, &n2, &data, NULL, NULL) != napi_ok ||
+        (t != napi_float32_array && t != napi_float64_array))
+        return throw_text(env, "delaunay(Float32Array | Float64Array)");
+    const int n = (int)(n2 / 2);
+    /* the package reads coords[i] as JS Numbers: widen a Float32Array exactly */
+    double *pts = (double *)malloc(sizeof(double) * (n2 ? n2 : 1));
+    if (!pts) return throw_text(env, "out of memory");
+    for (size_t i = 0; i < n2; ++i) pts[i] = t == napi_float32_array ? (double)((const float *)data)[i] : ((const double *)data)[i];
+    const int cap = 2 * n > 5 ? 2 * n - 5 : 0;
+    napi_value ab, arr;
+    void *p = NULL;
+    napi_create_arraybuffer(env, (size_t)cap * 12, &p, &ab);
+    int nt = 0;
+    const int st = hg_delaunay(pts, n, (uint32_t *)p, cap, &nt);
+    free(pts);
+    if (st != HG_OK) return throw_text(env, "hg_delaunay failed");
+    /* a view of the first nt triangles, like the package's `triangles` subarray */
+    napi_create_typedarray(env, napi_uint32_array, (size_t)nt * 3, ab, 0, &arr);
+    return arr;
+}
+
 /* piecewiseMatrices(ctx, Float32Array dstPts, nTris) -> Float32Array(6*nTris)
  *                                                        <- _calculatePiecewiseAffineTransformMatrices, H.js:785 */
 static napi_value PiecewiseMatrices(napi_env env, napi_callback_info info)
@@ -235,6 +264,7 @@ static napi_value Init(napi_env env, napi_value exports)
         {"warpInversePoints", 0, WarpInversePoints, 0, 0, 0, napi_default, 0},
         {"warpForwardMatrix", 0, WarpForwardMatrix, 0, 0, 0, napi_default, 0},
         {"setMesh", 0, SetMesh, 0, 0, 0, napi_default, 0},
+        {"delaunay", 0, Delaunay, 0, 0, 0, napi_default, 0},
         {"piecewiseMatrices", 0, PiecewiseMatrices, 0, 0, 0, napi_default, 0},
         {"warpPiecewiseInverse", 0, WarpPiecewiseInverse, 0, 0, 0, napi_default, 0},
         {"warpPiecewiseForward", 0, WarpPiecewiseForward, 0, 0, 0, napi_default, 0},

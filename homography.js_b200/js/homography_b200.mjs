@@ -64,8 +64,9 @@ const f32 = (a) => (a instanceof Float32Array ? a : Float32Array.from(a));
 class Homography {
   constructor(transform = 'auto', width = null, height = null, { device = 0, triangulate = null } = {}) {
     this._ctx = native.createContext(device);
-    // `triangulate(points) -> Uint32Array`: the reference calls delaunator@5.0.0 here (H.js:1216); pass
-    // `(p) => new Delaunator(p).triangles` to get its exact triangle order, or call setTriangles().
+    // `triangulate(points) -> Uint32Array` (optional): the reference calls delaunator@5.0.0 here (H.js:1216).  Without
+    // it the addon's own restatement of that package runs (hg_delaunay); pass `(p) => new Delaunator(p).triangles`
+    // to use the real package, or call setTriangles().
     this._triangulate = triangulate;
     this._width = width === null ? null : Math.round(width);
     this._height = height === null ? null : Math.round(height);
@@ -182,8 +183,9 @@ class Homography {
   _denormalizeSrc() { scaleInPlace(this._srcPoints, this._width, this._height, false); this._srcPointsAreNormalized = false; this._meshOnDevice = false; }
   _denormalizeDst() { scaleInPlace(this._dstPoints, this._width, this._height, false); this._dstPointsAreNormalized = false; }
   _delaunay(points) {
-    if (!this._triangulate) throw ('No triangulation available: pass {triangulate} to the constructor or call setTriangles()');
-    return this._triangulate(points);
+    // H.js:1216: new Delaunator(points).triangles.  Default: the library's restatement of delaunator 5.0.0
+    // (hg_delaunay); {triangulate} overrides it, e.g. with the real package.
+    return this._triangulate ? this._triangulate(points) : native.delaunay(points);
   }
 
   _setSrcWidthHeight(width, height) {

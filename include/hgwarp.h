@@ -116,6 +116,16 @@ int hg_warp_inverse_points(hg_ctx *ctx, int kind, const double *dst_pts, const d
 int hg_warp_forward_matrix(hg_ctx *ctx, int kind, const void *fwd_matrix, int x_off, int y_off, int o_w, int o_h,
                            uint8_t *out_host, void *out_dev);
 
+/* ------------------------------------------------------------------ triangulation (host only, no context, no GPU) */
+/* Delaunay(points) = new Delaunator(points).triangles, H.js:1216-1218.  The package (delaunator@5.0.0, imported at
+ * H.js:27, pinned by package.json:10-12 / package-lock.json:17-24) is third-party and absent from the reference tree;
+ * csrc/delaunay_host.cuh restates its published algorithm so that triangle order and vertex order follow it ("parity
+ * unpinned": no reference fixture holds a triangulation).  points: n_points (x, y) pairs, read as the JS Numbers a
+ * Float32Array / Float64Array element converts to.  triangles_out receives 3 vertex ids per triangle, at most
+ * max(2 n - 5, 0) triangles; *n_triangles is the count (0 for fewer than 3 points or collinear input).  Returns
+ * HG_ERR_INVALID when capacity_triangles is too small (nothing is written). */
+int hg_delaunay(const double *points, int n_points, uint32_t *triangles_out, int capacity_triangles, int *n_triangles);
+
 /* ------------------------------------------------------------------ piecewise affine */
 /* mesh = this._srcPoints (pixel range) + this._triangles (H.js:1216 / setTriangles H.js:517) */
 int hg_piecewise_set_mesh(hg_ctx *ctx, const float *src_pts, int n_pts, const uint32_t *tris, int n_tris);

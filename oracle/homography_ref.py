@@ -5,10 +5,10 @@ reference statement by statement (line numbers cite /root/reference/Homography.j
 every arithmetic loop to the C oracle, so that `tests/` can compare the product's CUDA-backed
 `Homography` with the reference's behaviour at the class surface.
 
-Not restated: the DOM branches (hidden canvas, HTMLImageElement in/out, CSS export) and the
-third-party `delaunator` triangulation (pass triangles through setTriangles, H.js:517; when none
-are given a scipy Delaunay stands in, which is a valid triangulation but NOT order-identical to
-delaunator 5.0.0 — parity unpinned at that boundary).
+Not restated here: the DOM branches (hidden canvas, HTMLImageElement in/out, CSS export).  The
+third-party `delaunator` triangulation (H.js:27, 1216) is restated in oracle/delaunator_ref.py from
+the package's published algorithm — no reference fixture pins it (parity unpinned at that boundary);
+pass triangles through setTriangles (H.js:517) to fix a mesh.
 """
 from __future__ import annotations
 
@@ -86,10 +86,10 @@ def check_and_select_transform(transform, points):  # H.js:1444
 
 
 def stand_in_delaunay(points):
-    """Stand-in for `new Delaunator(points).triangles` (H.js:1216) — see module docstring."""
-    from scipy.spatial import Delaunay as _D
-    pts = np.asarray(points, dtype=np.float64).reshape(-1, 2)
-    return _D(pts).simplices.astype(np.uint32).reshape(-1)
+    """`new Delaunator(points).triangles` (H.js:1216): the oracle's own restatement of delaunator 5.0.0
+    (oracle/delaunator_ref.py; the package is third-party and absent from the reference tree — parity unpinned)."""
+    from oracle import delaunator_ref
+    return np.asarray(delaunator_ref.triangles(np.asarray(points, dtype=np.float64).reshape(-1)), dtype=np.uint32)
 
 
 class RefHomography:

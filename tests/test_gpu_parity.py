@@ -587,3 +587,72 @@ def test_piecewise_extents_on_device(ctx):
     got = ctx.piecewise_extents(dst)
     for f in range(5):
         assert tuple(int(v) for v in got[f]) == hgm.workloads.piecewise_extent(dst[f])
+
+
+# ------------------------------------------------------------------ doubled-coordinate pixel loop (geo_fast_body) edge cases
+def test_fast_body_tiny_images_and_wrap_column(ctx):
+    """1- and 2-pixel dimensions (the end-pixel interior test must never apply), and maps whose rounded coordinate
+    reaches column W / row H (flat-index wrap and past-the-end reads, Q2) for affine and projective."""
+    for W, H in ((1, 1), (1, 7), (9, 1), (2, 2), (3, 2)):
+        img = _rand_img(40 + W + H, W, H)
+        for inv in (np.array([1, 0, 0, 1, 0, 0], np.float32), np.array([0.25, 0, 0, 0.25, -0.3, -0.2], np.float32),
+                    np.array([0.3, 0.1, -0.1, 0.3, 0.49, 0.51], np.float32)):
+            _geo_case(ctx, img, inv, -5, -5, 37, 29)
+            h8 = np.array([inv[0], inv[2], inv[4], inv[1], inv[3], inv[5], 1e-3, -2e-3], np.float64)
+            _geo_case(ctx, img, h8, -5, -5, 37, 29)
+    img = _rand_img(50, 40, 30)
+    # sx in [W - 0.5, W) and sy in [H - 0.5, H) on whole rows / columns
+    _geo_case(ctx, img, np.array([1, 0, 0, 1, 0.75, 0.75], np.float32), -4, -4, 60, 50)
+    _geo_case(ctx, img, np.array([1, 0, 0.75, 0, 1, 0.75, 1e-4, 1e-4], np.float64), -4, -4, 60, 50)
+
+
+def test_fast_body_far_offsets_and_large_coordinates(ctx):
+    """Windows far from the origin (|offset| up to 2^18) and steep scales: coordinates beyond the +-2^18 range of the
+    doubled fixed-point layout must read as outside, never alias into the image."""
+    img = _rand_img(51, 64, 48)
+    for xo, yo in ((-(1 << 18), -(1 << 18)), ((1 << 18) - 300, (1 << 18) - 200), (-(1 << 18), 100)):
+        for inv in (np.array([1, 0, 0, 1, -xo, -yo], np.float32), np.array([3.5, 0.25, -0.5, 2.75, 7, 9], np.float32)):
+            _geo_case(ctx, img, inv, xo, yo, 300, 200)
+        h8 = np.array([1, 0, -xo, 0, 1, -yo, 1e-7, -1e-7], np.float64)
+        _geo_case(ctx, img, h8, xo, yo, 300, 200)
+    # a quad row whose end pixels are inside while the map is steep: 40x minification
+    _geo_case(ctx, img, np.array([40, 0, 0, 40, 0, 0], np.float32), -2, -2, 20, 20)
+    _geo_case(ctx, img, np.array([0.01, 0, 0, 0.01, 10, 10], np.float32), 0, 0, 500, 300)
+
+
+def test_fast_body_denominator_range_switches_mode(ctx):
+    """Projective frames on both sides of geo_fast_mode's conditions (denominator range / sign over the window) give
+    the oracle's bytes: strong perspective, denominators near 1/64 and 64, negative denominators."""
+    img = _rand_img(52, 160, 120)
+    for h6, h7 in ((2e-3, 1e-3), (-3e-3, 0.0), (0.0, 4e-3), (0.2, 0.0), (-0.0035, -0.0035), (1e-2, -1e-2)):
+        inv = np.array([1.1, 0.05, 3.0, -0.04, 0.9, 2.0, h6, h7], np.float64)
+        _geo_case(ctx, img, inv, -10, -10, 260, 200)
+    # every denominator negative over the window (sign flips both numerators' roles)
+    _geo_case(ctx, img, np.array([-1.0, 0, -5.0, 0, -1.0, -4.0, -1e-3, -1e-3], np.float64) * 1.0, 2000, 2000, 200, 150)
+
+
+def test_staged_tma_kernel_parity():
+    """The opt-in TMA-staged kernel (HG_GEO_STAGED=1: tensor maps, producer warp, shared-memory ring) gives the same
+    bytes as the oracle on maps that exercise every tile class: interior, image border, wrap column, rotation,
+    minification beyond the box budget, horizon."""
+    import os
+    os.environ["HG_GEO_STAGED"] = "1"
+    try:
+        c = hg.Context(0)
+    finally:
+        del os.environ["HG_GEO_STAGED"]
+    try:
+        for W, H in ((256, 192), (120, 90), (644, 100)):
+            img = _rand_img(60 + W, W, H)
+            cases = [np.array([1, 0, 0, 1, 3, 2], np.float32), np.array([0.9, 0.2, -0.2, 0.9, 10, -5], np.float32),
+                     np.array([0, 1, -1, 0, W, 0], np.float32), np.array([2.5, 0, 0, 2.5, 0, 0], np.float32),
+                     np.array([1.05, 0.02, 4, 0.01, 1.2, 3, 4e-4, 2e-4], np.float64),
+                     np.array([1.0, 0.1, 5.0, 0.05, 1.0, 3.0, -0.01, 0.002], np.float64)]
+            for inv in cases:
+                for (xo, yo, oW, oH) in ((-20, -16, W + 60, H + 40), (0, 0, W, H), (5, 7, 129, 65)):
+                    c.image_set(img, W, H)
+                    got = c.warp_inverse_matrix(inv, xo, yo, oW, oH)
+                    want = O.warp_inverse_geometric(img, W, H, inv, xo, yo, oW, oH)
+                    assert _diff(got, want) == 0, (W, H, inv.tolist(), xo, yo, oW, oH)
+    finally:
+        c.close()
