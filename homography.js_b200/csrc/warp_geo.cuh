@@ -560,8 +560,52 @@ __device__ __forceinline__ bool geo_fast_mode(const GeoFrame &F, const double (&
            (fabs(m[6]) * Xm + fabs(m[7]) * Ym + 1.0 < 256.0 * dmin);
 }
 
+// Is RN(N / D) >= b, decided exactly WITHOUT the division?  b is a non-zero multiple of 1/2 with |b| < 2^19 (an even
+// mantissa), D is finite, non-zero and of moderate size, N finite.
+//   RN(Q) >= b  <=>  Q >= b - h,   h = half the gap between b and the double just below it (at the exact midpoint the
+//   tie goes to the even neighbour, which is b);  with the sign of D:  N - b D + h D >= 0  (D > 0),  <= 0  (D < 0).
+//   r = fma(-b, D, N) is exact whenever it is small enough to matter: b has <= 20 significant bits, so b*D is a
+//   multiple of 2^-72 |N| and a difference below 2^-30 |N| has fewer than 53 bits; a larger |r| dwarfs h|D| <= 2^-52 |bD|
+//   and only its sign counts.  t = fma(h, D, r) then carries the exact sign (an fma rounds the exact sum once and
+//   never across zero).
+__device__ __forceinline__ bool quotient_at_least(double N, double D, double b)
+{
+    const long long bits = __double_as_longlong(b);
+    const int E = (int)((bits >> 52) & 0x7FF);
+    const bool pow2_pos = (bits > 0) && ((bits & 0xFFFFFFFFFFFFFLL) == 0);  // gap below a positive power of two is halved
+    const double h = __longlong_as_double((long long)(E - 53 - (pow2_pos ? 1 : 0)) << 52);
+    const double t = __fma_rn(h, D, __fma_rn(-b, D, N));
+    return D > 0.0 ? (t >= 0.0) : (t <= 0.0);
+}
+
+// n = floor(2 * RN(N / D) + 1) — the doubled-coordinate integer of geo_fast_body — exactly.  T is the approximate
+// 2q + 1 + delta + magic (error < delta): away from an integer of 2q + 1 its integer part is already right; within
+// delta of one, the only open question is on which side of b = (n_candidate - 1) / 2 the reference's quotient falls.
+__device__ __forceinline__ int exact_doubled_floor(double T, double N, double D)
+{
+    int n = __double2hiint(T) - HG_HI_ZERO;
+    if ((unsigned)__double2loint(T) < 2u * HG_NEAR_DELTA2) {
+        const double b = (double)(n - 1) * 0.5;
+        bool ge;
+        if (b == 0.0) {
+            // RN(Q) >= 0 (also true for -0): the sign of Q unless it underflows — then let the division decide
+            if (N == 0.0) ge = true;
+            else if (fabs(N) < 1e-290) ge = __ddiv_rn(N, D) >= 0.0;
+            else ge = (N > 0.0) == (D > 0.0);
+        } else {
+            ge = quotient_at_least(N, D, b);
+        }
+        n -= ge ? 0 : 1;
+    }
+    return n;
+}
+
 // Resolve the queued pixels of one warp with the reference's own arithmetic (H.js:1401-1404 followed by the bounds
-// test, Math.round and the flat read of H.js:1001-1007), one pixel per lane, and overwrite them in the output.
+// test, Math.round and the flat read of H.js:1001-1007), one queue entry per lane, and overwrite them in the output.
+// FAST (frames that run geo_fast_body: denominator of one sign and moderate size): the reference's numerators and
+// denominator are formed exactly, and instead of two IEEE divisions the side of the one nearby decision boundary is
+// settled by quotient_at_least (two fmas).  Otherwise: the divisions themselves.
+template <bool FAST>
 __device__ __forceinline__ void geo_flush_queue(const GeoFrame &F, const double (&m)[8], const uint2 *q, int n, int s,
                                                 int lane)
 {
@@ -580,8 +624,19 @@ __device__ __forceinline__ void geo_flush_queue(const GeoFrame &F, const double 
             const double nx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), m[2]);
             const double ny = __dadd_rn(__dadd_rn(__dmul_rn(m[3], x), __dmul_rn(m[4], y)), m[5]);
             const double dn = __dadd_rn(__dadd_rn(__dmul_rn(m[6], x), __dmul_rn(m[7], y)), 1.0);
-            const unsigned f = decode_flat(exact_quotient_magic(nx, dn), exact_quotient_magic(ny, dn), W, H, npx_src);
-            F.out[(long long)yy * F.oW + xx] = ldg_or_zero(F.src, f);
+            uint32_t v;
+            if (FAST) {
+                const double MG = HG_MAGIC + 1.0 + (double)HG_NEAR_DELTA2 / 4294967296.0;
+                const double rc = rcp_newton1(dn);
+                const int jx = exact_doubled_floor(__fma_rn(__dadd_rn(nx, nx), rc, MG), nx, dn);
+                const int jy = exact_doubled_floor(__fma_rn(__dadd_rn(ny, ny), rc, MG), ny, dn);
+                const unsigned flat = (unsigned)(jy >> 1) * W + (unsigned)(jx >> 1);
+                const bool in = ((unsigned)(jx - 1) < 2u * W) & ((unsigned)(jy - 1) < 2u * H) & (flat < npx_src);
+                v = in ? __ldg(F.src + flat) : 0u;
+            } else {
+                v = ldg_or_zero(F.src, decode_flat(exact_quotient_magic(nx, dn), exact_quotient_magic(ny, dn), W, H, npx_src));
+            }
+            F.out[(long long)yy * F.oW + xx] = v;
         }
     }
 }
@@ -885,13 +940,13 @@ __global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG
     uint2 *q = s_q[KIND == 1 ? warp_id : 0];
     int *qn = &s_qn[warp_id];
 
+    const bool fast = (KIND == 1) && geo_fast_mode(F, m);  // CTA-uniform: from the matrix and the frame window
     if (active) {
         if (KIND == 0) {
             geo_fast_body<0>(F, m, base, P.niter, s, x_first, mask, q, qn);
         } else {
-            // CTA-uniform mode from the matrix and the frame window
             if (m[6] == 0.0 && m[7] == 0.0) geo_tile_body<1, 2>(F, m, base, P.niter, s, x_first, mask, q, qn);
-            else if (geo_fast_mode(F, m)) geo_fast_body<1>(F, m, base, P.niter, s, x_first, mask, q, qn);
+            else if (fast) geo_fast_body<1>(F, m, base, P.niter, s, x_first, mask, q, qn);
             else geo_tile_body<1, 0>(F, m, base, P.niter, s, x_first, mask, q, qn);
         }
     }
@@ -900,7 +955,10 @@ __global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG
         // corrected ones below
         __syncwarp();
         const int n = min(*qn, GEO_QCAP);
-        if (n > 0) geo_flush_queue(F, m, q, n, s, lane_id);
+        if (n > 0) {
+            if (fast) geo_flush_queue<true>(F, m, q, n, s, lane_id);
+            else geo_flush_queue<false>(F, m, q, n, s, lane_id);
+        }
     }
 }
 
@@ -982,7 +1040,7 @@ __device__ __noinline__ void geo_flush_tile(const GeoStageHdr *hp, const uint2 *
     double m[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) m[i] = hp->m[i];
-    geo_flush_queue(F, m, q, n, s, lane);
+    geo_flush_queue<false>(F, m, q, n, s, lane);
 }
 
 // one ring entry: wait for the slot, publish the header, start the box loads (or just signal)
