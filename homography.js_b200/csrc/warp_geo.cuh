@@ -14,26 +14,21 @@
 // partial and is stored pixel by pixel).  a(yy) repeats with period s = 4/gcd(oW mod 4, 4), so a thread
 // that owns rows yy, yy+s, yy+2s, ... sees the same x for all of them.
 //
-// Work decomposition.  CTA = 128 threads = 16 (x) x 8 (y); thread (tx,ty) owns one quad column and R = 2 rows per
-// iteration, `niter` iterations 16 rows apart -> CTA tile = 64 pixels x 16*niter rows (niter is picked on the host
-// so the grid still fills the 148 SMs >= 16 times).  The terms that depend on x only (h0*x, h3*x, h6*x) are computed
-// once per thread and reused for all its rows, the terms that depend on y only once per row; a warp (16 lanes x 2
-// thread rows) stores 256 contiguous bytes per row.  The iterations form a three-stage software pipeline (store
-// group i-2 | gathers of group i-1 | arithmetic of group i), see geo_tile_body.
+// Work decomposition.  CTA = 128 threads = 16 (x) x 8 (y); thread (tx,ty) owns one quad column and R = 2 rows per row
+// group, `niter` row groups 16 rows apart -> CTA tile = 64 pixels x 16*niter rows (niter is picked on the host so the
+// grid still fills the 148 SMs >= 16 times).  A warp (16 lanes x 2 thread rows) stores 256 contiguous bytes per row.
 //
-// Arithmetic (bit-exact with the reference's unfused doubles):
-//   affine      coefficient(float) * integer products are exact in double, so fma(m0,x,m2*y) equals the
-//               unfused sum; one round-down add of 1.5*2^20 then yields floor, bounds test and Math.round
-//               in integer registers (jsnum.cuh)                                  -> 6 FP64 ops / pixel
-//   projective  numerators / denominator evaluated exactly as the reference does (DMUL + DADD); the two
-//               IEEE divides are replaced by MUFU.RCP64H + ONE Newton step (relative error < 2^-39.9, measured
-//               exhaustively in tests/test_gpu_numerics.py; 2^-36 is what the argument needs) and one DFMA per
-//               coordinate that multiplies and adds the magic constant in a single rounding.  Every decision
-//               of the loop flips only at multiples of 0.5, so the quotient is trusted unless it lies within
-//               2^-20 of such a multiple; those pixels go to a per-warp queue and are redone 32 at a time with
-//               __ddiv_rn, i.e. the reference's own arithmetic (geo_flush_queue).    -> ~11 FP64 ops / pixel
-//   mode        per-CTA uniform dispatch on the matrix: denominator == 1 everywhere (h6 = h7 = 0: exact, no
-//               reciprocal), denominator provably in (0.25, 1.75) (no exponent guard), or general.
+// Pixel loops in this file (all bit-exact with the reference's unfused doubles):
+//   geo_fast_body   the default: doubled coordinates (n = floor(2v + 1) from ONE fma; Math.round = n >> 1, the bounds
+//                   test of H.js:1001 = one unsigned compare), two-stage software pipeline with predicated gathers,
+//                   warp-uniform "end pixels inside" shortcut, L2 prefetch one row group ahead.  Affine: exact, no
+//                   fix-up.  Projective (denominator of one sign and moderate size over the window, geo_fast_mode):
+//                   MUFU.RCP64H + one Newton step, quotients within 2^-19 of a decision boundary are queued per warp
+//                   and resolved exactly after the loop (geo_flush_queue<true>, no division: quotient_at_least).
+//   geo_tile_body   first-generation body, kept for the projective frames geo_fast_mode rejects (horizon inside the
+//                   window, denominator == 1, extreme magnitudes): reference-exact numerators, exponent guard, IEEE
+//                   divisions in the exact path; three-stage pipeline with a sentinel flat index.
+//   geo_smem_body   pixel loop of the opt-in TMA-staged kernel (warp_inverse_geo_staged_kernel, HG_GEO_STAGED=1).
 #pragma once
 #include "jsnum.cuh"
 #include "tma.cuh"
