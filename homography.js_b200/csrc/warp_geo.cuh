@@ -88,7 +88,7 @@ constexpr int GEO_TY = 8;           // thread rows per CTA  -> 128 threads
 constexpr int GEO_ROWS_PER_THREAD = HG_GEO_R;
 constexpr int GEO_THREADS = GEO_TILE_QUADS * GEO_TY;
 constexpr int GEO_GROUP_ROWS = GEO_TY * GEO_ROWS_PER_THREAD;  // rows one CTA covers per iteration
-constexpr int GEO_QCAP = 64;  // queued (thread, row group) entries per warp awaiting exact resolution
+constexpr int GEO_QCAP = 96;  // queued (thread, row group) entries per warp awaiting exact resolution
 
 // host + device: CTAs needed for one frame.  Rows whose flat start is not 16-byte aligned begin with a partial
 // quad, so a row has at most (oW + 3 + 3) / 4 quads; when oW % 4 == 0 every row is aligned.
