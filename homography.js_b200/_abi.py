@@ -24,7 +24,7 @@ SYMBOLS = [
     "hg_image_set", "hg_image_set_device",
     "hg_solve_affine", "hg_solve_projective", "hg_inverse_affine", "hg_transform_limits", "hg_solve_with_limits",
     "hg_warp_inverse_matrix", "hg_warp_inverse_points", "hg_warp_forward_matrix",
-    "hg_delaunay",
+    "hg_delaunay", "hg_png_decode", "hg_png_encode", "hg_png_encode_bound",
     "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_piecewise_extents", "hg_build_index_map",
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
@@ -109,6 +109,10 @@ def load():
     L.hg_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     L.hg_output_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.hg_delaunay.argtypes = [vp, i, vp, i, C.POINTER(i)]
+    L.hg_png_decode.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.POINTER(i), C.POINTER(i)]
+    L.hg_png_encode_bound.argtypes = [i, i]
+    L.hg_png_encode_bound.restype = C.c_size_t
+    L.hg_png_encode.argtypes = [vp, i, i, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L
 
@@ -405,6 +409,33 @@ def delaunay(points) -> np.ndarray:
     if st:
         raise HgError(st, "hg_delaunay failed")
     return out[:3 * cnt.value].copy()
+
+
+def png_decode(data: bytes) -> np.ndarray:
+    """hg_png_decode: PNG file bytes -> (h, w, 4) uint8 RGBA, the layout of ImageData.data.  Host only."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    w, h = C.c_int(), C.c_int()
+    L = load()
+    if L.hg_png_decode(_ptr(buf), buf.size, None, 0, C.byref(w), C.byref(h)):
+        raise HgError(1, "hg_png_decode: not a PNG this decoder supports")
+    out = np.empty((h.value, w.value, 4), np.uint8)
+    if L.hg_png_decode(_ptr(buf), buf.size, _ptr(out), out.size, C.byref(w), C.byref(h)):
+        raise HgError(1, "hg_png_decode: malformed image data")
+    return out
+
+
+def png_encode(rgba) -> bytes:
+    """hg_png_encode: (h, w, 4) uint8 RGBA -> PNG file bytes.  Host only."""
+    a = np.ascontiguousarray(rgba, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("png_encode expects an (h, w, 4) uint8 array")
+    L = load()
+    cap = L.hg_png_encode_bound(a.shape[1], a.shape[0])
+    out = np.empty(cap, np.uint8)
+    n = C.c_size_t()
+    if L.hg_png_encode(_ptr(a), a.shape[1], a.shape[0], _ptr(out), cap, C.byref(n)):
+        raise HgError(1, "hg_png_encode failed")
+    return out[:n.value].tobytes()
 
 
 def device_count() -> int:

@@ -23,6 +23,7 @@
 #include "forward.cuh"
 #include "piecewise_fused.cuh"
 #include "delaunay_host.cuh"
+#include "png_host.cuh"
 
 using namespace hg;
 
@@ -873,6 +874,37 @@ int hg_delaunay(const double *points, int n_points, uint32_t *triangles_out, int
     if (nt > (size_t)capacity_triangles) return HG_ERR_INVALID;
     if (nt) memcpy(triangles_out, t.data(), t.size() * sizeof(uint32_t));
     *n_triangles = (int)nt;
+    return HG_OK;
+}
+
+/* ------------------------------------------------------------------ image files */
+int hg_png_decode(const uint8_t *png, size_t png_bytes, uint8_t *rgba_out, size_t capacity_bytes, int *w, int *h)
+{
+    if (!png || !w || !h) return HG_ERR_INVALID;
+    *w = *h = 0;
+    hg_png_detail::Header hd;
+    if (hg_png_detail::decode(png, png_bytes, hd, nullptr)) return HG_ERR_INVALID;  // header + chunk CRCs
+    *w = (int)hd.w;
+    *h = (int)hd.h;
+    if (!rgba_out) return HG_OK;
+    if (capacity_bytes < (size_t)hd.w * hd.h * 4) return HG_ERR_INVALID;
+    return hg_png_detail::decode(png, png_bytes, hd, rgba_out) ? HG_ERR_INVALID : HG_OK;
+}
+
+size_t hg_png_encode_bound(int w, int h)
+{
+    if (w < 1 || h < 1) return 0;
+    return 8 + 25 + 12 + 12 + (size_t)compressBound((uLong)(((size_t)w * 4 + 1) * (size_t)h));
+}
+
+int hg_png_encode(const uint8_t *rgba, int w, int h, uint8_t *png_out, size_t capacity_bytes, size_t *png_bytes)
+{
+    if (!rgba || !png_out || !png_bytes || w < 1 || h < 1 || w > 65536 || h > 65536) return HG_ERR_INVALID;
+    std::vector<uint8_t> out;
+    if (hg_png_detail::encode(rgba, (uint32_t)w, (uint32_t)h, out)) return HG_ERR_INVALID;
+    if (out.size() > capacity_bytes) return HG_ERR_INVALID;
+    memcpy(png_out, out.data(), out.size());
+    *png_bytes = out.size();
     return HG_OK;
 }
 

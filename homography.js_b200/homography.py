@@ -42,6 +42,17 @@ class ImageData:
     def as_array(self) -> np.ndarray:
         return self.data.reshape(self.height, self.width, 4)
 
+    @classmethod
+    def from_png(cls, png_bytes: bytes) -> "ImageData":
+        """What `loadImage()` + canvas `getImageData` give the reference (test/nodeTest.js:11, H.js:1071-1076):
+        the RGBA8 pixels of a PNG file (hg_png_decode)."""
+        a = _abi.png_decode(png_bytes)
+        return cls(a.reshape(-1), a.shape[1], a.shape[0])
+
+    def to_png(self) -> bytes:
+        """The result as PNG file bytes (the reference's HTMLImageElementFromImageData / toDataURL, H.js:467-496)."""
+        return _abi.png_encode(np.asarray(self.data, dtype=np.uint8).reshape(self.height, self.width, 4))
+
 
 def _js_round(x: float) -> float:
     """Math.round: nearest integer, ties toward +inf (host-side scalar bookkeeping only)."""

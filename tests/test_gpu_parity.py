@@ -656,3 +656,16 @@ def test_staged_tma_kernel_parity():
                     assert _diff(got, want) == 0, (W, H, inv.tolist(), xo, yo, oW, oH)
     finally:
         c.close()
+
+
+def test_node_test_flow_from_png_file_to_png_file(golden):
+    """test/nodeTest.js end to end without a canvas: PNG bytes in (hg_png_decode), projective warp on the GPU, PNG bytes
+    out (hg_png_encode) — the decoded result is the reference's golden transformedImage.png."""
+    src_png = hg._abi.png_encode(np.asarray(golden["src"], np.uint8).reshape(400, 400, 4))
+    h = hg.Homography()
+    h.setReferencePoints(golden["src_points"].tolist(), golden["dst_points"].tolist())
+    h.setImage(hg.ImageData.from_png(src_png))
+    out_png = h.warp().to_png()
+    got = hg._abi.png_decode(out_png)
+    assert got.shape == (200, 400, 4)
+    assert np.array_equal(got.reshape(-1), np.asarray(golden["out"]).reshape(-1))
