@@ -206,6 +206,53 @@ static napi_value Delaunay(napi_env env, napi_callback_info info)
     return arr;
 }
 
+/* pngDecode(Uint8Array file) -> {data: Uint8ClampedArray, width, height}     <- canvas drawImage + getImageData,
+ *                                                                               H.js:1071-1076 / loadImage in nodeTest.js */
+static napi_value PngDecode(napi_env env, napi_callback_info info)
+{
+    ARGS(1);
+    napi_typedarray_type t;
+    size_t n = 0;
+    void *data = NULL;
+    if (napi_get_typedarray_info(env, argv[0], &t, &n, &data, NULL, NULL) != napi_ok || (t != napi_uint8_array && t != napi_uint8_clamped_array))
+        return throw_text(env, "pngDecode(Uint8Array)");
+    int w = 0, h = 0;
+    if (hg_png_decode((const uint8_t *)data, n, NULL, 0, &w, &h) != HG_OK) return throw_text(env, "pngDecode: not a PNG this decoder supports");
+    uint8_t *px = NULL;
+    napi_value arr = new_output(env, w, h, &px), obj, vw, vh;
+    if (hg_png_decode((const uint8_t *)data, n, px, (size_t)w * h * 4, &w, &h) != HG_OK) return throw_text(env, "pngDecode: malformed image data");
+    napi_create_object(env, &obj);
+    napi_create_int32(env, w, &vw);
+    napi_create_int32(env, h, &vh);
+    napi_set_named_property(env, obj, "data", arr);
+    napi_set_named_property(env, obj, "width", vw);
+    napi_set_named_property(env, obj, "height", vh);
+    return obj;
+}
+
+/* pngEncode(Uint8ClampedArray rgba, width, height) -> Uint8Array file        <- toDataURL, H.js:480-483 */
+static napi_value PngEncode(napi_env env, napi_callback_info info)
+{
+    ARGS(3);
+    const int w = i32(env, argv[1]), h = i32(env, argv[2]);
+    const uint8_t *rgba = (w > 0 && h > 0) ? (const uint8_t *)typed(env, argv[0], napi_uint8_array, (size_t)w * h * 4) : NULL;
+    if (!rgba) return throw_text(env, "pngEncode(Uint8ClampedArray, width, height)");
+    const size_t cap = hg_png_encode_bound(w, h);
+    uint8_t *tmp = (uint8_t *)malloc(cap ? cap : 1);
+    size_t n = 0;
+    if (!tmp || hg_png_encode(rgba, w, h, tmp, cap, &n) != HG_OK) {
+        free(tmp);
+        return throw_text(env, "pngEncode failed");
+    }
+    napi_value ab, arr;
+    void *p = NULL;
+    napi_create_arraybuffer(env, n, &p, &ab);
+    memcpy(p, tmp, n);
+    free(tmp);
+    napi_create_typedarray(env, napi_uint8_array, n, ab, 0, &arr);
+    return arr;
+}
+
 /* piecewiseMatrices(ctx, Float32Array dstPts, nTris) -> Float32Array(6*nTris)
  *                                                        <- _calculatePiecewiseAffineTransformMatrices, H.js:785 */
 static napi_value PiecewiseMatrices(napi_env env, napi_callback_info info)
@@ -265,6 +312,8 @@ static napi_value Init(napi_env env, napi_value exports)
         {"warpForwardMatrix", 0, WarpForwardMatrix, 0, 0, 0, napi_default, 0},
         {"setMesh", 0, SetMesh, 0, 0, 0, napi_default, 0},
         {"delaunay", 0, Delaunay, 0, 0, 0, napi_default, 0},
+        {"pngDecode", 0, PngDecode, 0, 0, 0, napi_default, 0},
+        {"pngEncode", 0, PngEncode, 0, 0, 0, napi_default, 0},
         {"piecewiseMatrices", 0, PiecewiseMatrices, 0, 0, 0, napi_default, 0},
         {"warpPiecewiseInverse", 0, WarpPiecewiseInverse, 0, 0, 0, napi_default, 0},
         {"warpPiecewiseForward", 0, WarpPiecewiseForward, 0, 0, 0, napi_default, 0},

@@ -32,4 +32,4 @@ def test_js_shim_calls_match_addon_exports():
     assert called == exported, (called, exported)
     for name in ("setReferencePoints", "setSourcePoints", "setDestinyPoints", "setImage", "setTriangles", "warp"):
         assert re.search(r"\n  %s\(" % name, shim), name
-    assert "export { Homography }" in shim
+    assert "export { Homography" in shim
