@@ -636,8 +636,8 @@ __device__ __forceinline__ void geo_flush_queue(const GeoFrame &F, const double 
     }
 }
 
-// Direct-gather kernel: one CTA per (tile, frame), every tile through geo_tile_body.  Used when the source cannot be
-// described by a tensor map (row pitch or base not 16-byte aligned) and as the A/B baseline (HG_GEO_TMA=0).
+// The default kernel: one CTA per (tile, frame), source pixels gathered directly from global memory through L1 / L2
+// (geo_fast_body; geo_tile_body for the projective frames geo_fast_mode rejects).
 template <int KIND>
 __global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG_GEO_MINB) warp_inverse_geo_kernel(const GeoParams P)
 {
@@ -709,8 +709,6 @@ __global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG
         }
     }
 }
-
-
 }  // namespace hg
 
 #include "warp_geo_staged.cuh"
