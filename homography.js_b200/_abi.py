@@ -29,7 +29,7 @@ SYMBOLS = [
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
     "hg_pipe_create", "hg_pipe_submit", "hg_pipe_wait", "hg_pipe_flush", "hg_pipe_destroy",
-    "hg_debug_rcp_max_error", "hg_debug_force_general", "hg_debug_piecewise_stats",
+    "hg_debug_rcp_max_error", "hg_debug_quotient_at_least", "hg_debug_force_general", "hg_debug_piecewise_stats",
     "hg_dev_alloc", "hg_dev_free", "hg_host_alloc_pinned", "hg_host_free_pinned",
     "hg_memcpy_h2d", "hg_memcpy_d2h", "hg_output_device",
 ]
@@ -101,6 +101,7 @@ def load():
     L.hg_debug_force_general.argtypes = [vp, i]
     L.hg_debug_piecewise_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.hg_debug_rcp_max_error.argtypes = [vp, i, i, C.POINTER(d)]
+    L.hg_debug_quotient_at_least.argtypes = [vp, vp, vp, vp, i, vp]
     L.hg_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.hg_dev_free.argtypes = [vp, vp]
     L.hg_host_alloc_pinned.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -186,6 +187,12 @@ class Context:
         e = C.c_double()
         self._ck(self.L.hg_debug_rcp_max_error(self.h, biased_exponent, int(negative), C.byref(e)))
         return e.value
+
+    def debug_quotient_at_least(self, N, D, b) -> np.ndarray:
+        N, D, b = (np.ascontiguousarray(v, dtype=np.float64) for v in (N, D, b))
+        out = np.zeros(N.size, np.int32)
+        self._ck(self.L.hg_debug_quotient_at_least(self.h, _ptr(N), _ptr(D), _ptr(b), int(N.size), _ptr(out)))
+        return out.astype(bool)
 
     def debug_piecewise_stats(self):
         a, b = C.c_uint64(), C.c_uint64()

@@ -23,4 +23,12 @@ __global__ void rcp_error_kernel(int biased_exp, int negative, unsigned long lon
     atomicMax(max_bits, (unsigned long long)__double_as_longlong(worst));
 }
 
+// quotient_at_least / exact_doubled_floor (warp_geo.cuh) on caller-supplied operands: out[i] = 1 iff the device decides
+// RN(N[i] / D[i]) >= b[i]; tests/test_gpu_numerics.py compares with exact rational arithmetic.
+__global__ void quotient_decision_kernel(const double *N, const double *D, const double *b, int n, int *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = quotient_at_least(N[i], D[i], b[i]) ? 1 : 0;
+}
+
 }  // namespace hg

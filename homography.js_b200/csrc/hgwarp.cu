@@ -1534,6 +1534,30 @@ int hg_debug_rcp_max_error(hg_ctx *c, int biased_exponent, int negative, double 
     return HG_OK;
 }
 
+int hg_debug_quotient_at_least(hg_ctx *c, const double *N, const double *D, const double *b, int n, int *out)
+{
+    BIND(c);
+    NEED(c, N && D && b && out && n >= 1 && n <= (1 << 22), "bad argument");
+    DevBuf buf;
+    const size_t nb = sizeof(double) * (size_t)n;
+    TRY(ensure(c, buf, 3 * nb + sizeof(int) * (size_t)n));
+    char *p = (char *)buf.p;
+    int st = HG_OK;
+    do {
+        if (cudaMemcpyAsync(p, N, nb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync(p + nb, D, nb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync(p + 2 * nb, b, nb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { st = HG_ERR_CUDA; break; }
+        quotient_decision_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>((const double *)p, (const double *)(p + nb),
+                                                                         (const double *)(p + 2 * nb), n, (int *)(p + 3 * nb));
+        c->launches++;
+        if (cudaMemcpyAsync(out, p + 3 * nb, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) st = HG_ERR_CUDA;
+    } while (0);
+    cudaFree(buf.p);
+    if (st) return fail(c, st, "hg_debug_quotient_at_least: %s", cudaGetErrorString(cudaGetLastError()));
+    return HG_OK;
+}
+
 /* ------------------------------------------------------------------ memory helpers */
 int hg_dev_alloc(hg_ctx *c, size_t bytes, void **p)
 {

@@ -189,6 +189,9 @@ int hg_pipe_destroy(hg_pipe *pipe);
 /* max over all 2^20 high-mantissa patterns (x 6 low words) of |1 - d*r|, r = the reciprocal the projective
  * fast path uses (MUFU.RCP64H + one Newton step), for doubles with the given biased exponent / sign */
 int hg_debug_rcp_max_error(hg_ctx *ctx, int biased_exponent, int negative, double *max_rel_err);
+/* out[i] = 1 iff the device's division-free decision says RN(N[i] / D[i]) >= b[i] (b a non-zero multiple of 1/2,
+ * |b| < 2^19; D finite, non-zero): the exact resolution of projective pixels on a decision boundary (warp_geo.cuh) */
+int hg_debug_quotient_at_least(hg_ctx *ctx, const double *N, const double *D, const double *b, int n, int *out);
 /* on != 0: inverse piecewise warps always take the general map-based path (tests compare it with the fused one) */
 int hg_debug_force_general(hg_ctx *ctx, int on);
 /* how many inverse piecewise frames were finished by the fused (map-free) path / by the general map-based path */

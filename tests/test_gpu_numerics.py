@@ -103,3 +103,39 @@ def test_bilinear_extension_within_one_lsb(ctx, kind):
         assert np.array_equal(got, ctx.warp_inverse_matrix(ident, 0, 0, 100, 90))
     finally:
         ctx.set_sampling(hg._abi.HG_NEAREST)
+
+
+def test_division_free_exact_decision_against_rational_arithmetic(ctx):
+    """quotient_at_least: RN(N / D) >= b decided with two fmas instead of the division.  Checked against exact
+    rational arithmetic (float(Fraction) is the correctly rounded quotient) on the cases that matter: N within a few ulp of
+    b * D — including exact ties at the midpoint below b —, b a power of two (the gap below it is halved), negative b,
+    negative D, plus random far-away operands."""
+    from fractions import Fraction
+    rng = np.random.default_rng(9)
+    Ns, Ds, bs = [], [], []
+    halves = np.concatenate([np.arange(-40, 41) * 0.5, [512.0, 1024.0, -2048.0, 4096.5, 65535.5, 131072.0, -131071.5, 262143.5, 0.5, -0.5]])
+    halves = halves[halves != 0.0]
+    for b in halves:
+        for _ in range(60):
+            D = float(rng.uniform(1 / 64, 64)) * (1 if rng.random() < 0.5 else -1)
+            if rng.random() < 0.2:
+                D = float(np.float32(D))  # short mantissas make b * D exactly representable: true ties
+            base = float(Fraction(b) * Fraction(D))  # RN(b * D)
+            for k in (-3, -2, -1, 0, 1, 2, 3):
+                N = base
+                for _ in range(abs(k)):
+                    N = float(np.nextafter(N, np.inf if k > 0 else -np.inf))
+                Ns.append(N); Ds.append(D); bs.append(float(b))
+            # the exact midpoint between pred(b) and b, times D, when representable
+            pb = float(np.nextafter(b, -np.inf))
+            mid = (Fraction(b) + Fraction(pb)) / 2 * Fraction(D)
+            if Fraction(float(mid)) == mid:
+                Ns.append(float(mid)); Ds.append(D); bs.append(float(b))
+    for _ in range(4000):
+        Ns.append(float(rng.uniform(-1e6, 1e6))); Ds.append(float(rng.uniform(0.02, 60)) * (1 if rng.random() < 0.5 else -1))
+        bs.append(float(rng.integers(-500000, 500000)) * 0.5 or 0.5)
+    got = ctx.debug_quotient_at_least(Ns, Ds, bs)
+    want = np.array([float(Fraction(n) / Fraction(d)) >= b for n, d, b in zip(Ns, Ds, bs)])
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, [(Ns[i], Ds[i], bs[i], bool(got[i]), bool(want[i])) for i in bad[:5]]
+    assert want.sum() > 1000 and (~want).sum() > 1000

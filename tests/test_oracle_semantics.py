@@ -205,3 +205,39 @@ def test_index_map_last_triangle_wins_and_x_offset_is_ignored():
     # Q4: columns are absolute x, no x offset is subtracted -> span starts at column round(xmin) = 2
     row1 = m[16:32]
     assert row1[2] == 1 and row1[1] == -1
+
+
+def test_division_free_decision_algorithm_against_rational_arithmetic():
+    """The algorithm behind the CUDA path's exact resolution of projective pixels on a decision boundary
+    (quotient_at_least, csrc/warp_geo.cuh) restated with exact-rational fmas: RN(N / D) >= b  <=>  the sign of
+    fma(h, D, fma(-b, D, N)), h = half the gap below b.  (The CUDA function itself is checked on the same operands by
+    tests/test_gpu_numerics.py::test_division_free_exact_decision_against_rational_arithmetic.)"""
+    import struct
+    from fractions import Fraction
+
+    def fma(a, b, c):
+        return float(Fraction(a) * Fraction(b) + Fraction(c))  # one correctly rounded operation
+
+    def decide(N, D, b):
+        bits = struct.unpack("<q", struct.pack("<d", b))[0]
+        E = (bits >> 52) & 0x7FF
+        pow2_pos = bits > 0 and (bits & 0xFFFFFFFFFFFFF) == 0
+        h = struct.unpack("<d", struct.pack("<q", (E - 53 - (1 if pow2_pos else 0)) << 52))[0]
+        t = fma(h, D, fma(-b, D, N))
+        return t >= 0 if D > 0 else t <= 0
+
+    rng = np.random.default_rng(9)
+    n_checked = 0
+    for b in [v * 0.5 for v in range(-12, 13) if v] + [512.0, 1024.0, -2048.0, 4096.5, 131072.0, -131071.5, 262143.5]:
+        for _ in range(25):
+            D = float(rng.uniform(1 / 64, 64)) * (1 if rng.random() < 0.5 else -1)
+            if rng.random() < 0.3:
+                D = float(np.float32(D))
+            base = float(Fraction(b) * Fraction(D))
+            for k in range(-3, 4):
+                N = base
+                for _ in range(abs(k)):
+                    N = float(np.nextafter(N, np.inf if k > 0 else -np.inf))
+                assert decide(N, D, b) == (float(Fraction(N) / Fraction(D)) >= b), (N, D, b)
+                n_checked += 1
+    assert n_checked > 5000
