@@ -341,6 +341,8 @@ struct GeoFastCtx {
     unsigned W, H, W2, H2, npx;
     unsigned Wi, Hi;         // 2W - 3, 2H - 3 (0 for a 1-pixel dimension): the strictly-inside range of the end-pixel test
     unsigned kflat;          // flat = (hy >> 1) * W + (hx >> 1) - kflat
+    unsigned nkflat;         // -kflat: (hx >> 1) + nkflat is one LEA.HI
+    const uint32_t *srcv;    // src again, pinned to vector registers (the address multiply-add then takes an immediate 4)
     unsigned last[GEO_ROWS_PER_THREAD];  // flat index of the row's first pixel in the previous group (L2 prefetch stride)
     double xs[4];
     double c0, c1, c2, c3, c4, c5, c6, c7;  // affine: m0..m5; projective: 2h0, 2h1, 2h2, 2h3, 2h4, 2h5, h6, h7
@@ -419,7 +421,7 @@ __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g,
         // both variants
         if (__all_sync(__activemask(), ends_inside)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) g.px[j][k] = __ldg(C.src + ((hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat));
+            for (int k = 0; k < 4; ++k) g.px[j][k] = __ldg(C.srcv + ((hy[k] >> 1) * C.W + ((hx[k] >> 1) + C.nkflat)));
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -498,6 +500,9 @@ __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&
     C.Hi = C.H2 >= 3u ? C.H2 - 3u : 0u;
     C.npx = C.W * C.H;
     C.kflat = (unsigned)(HG_HI_ZERO >> 1) * (C.W + 1u);
+    C.nkflat = 0u - C.kflat;
+    C.srcv = F.src;
+    asm volatile("" : "+l"(C.srcv));
     C.xOff = F.xOff;
     C.yOff = F.yOff;
     C.s = s;
