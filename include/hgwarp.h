@@ -21,6 +21,11 @@
  *   - a context is bound to one GPU and one CUDA stream and is not thread-safe; use one per GPU;
  *   - degenerate transforms (NaN / Inf matrices) are NOT errors: like the reference they give an
  *     all-transparent image.
+ * Environment (read once per hg_ctx_create; none is needed in production):
+ *   HG_GEO_STAGED=1     affine / projective inverse warps run the TMA-staged kernel (slower than the default direct-gather
+ *                       kernel on every workload measured); HG_GEO_BOX_BYTES / HG_GEO_STAGES / HG_GEO_CTAS /
+ *                       HG_GEO_NITER size its shared-memory ring, HG_GEO_VERBOSE=1 prints the chosen configuration,
+ *                       HG_GEO_DEBUG=1 traces every ring entry.
  * Supported ranges (anything else returns HG_ERR_UNSUPPORTED, never a wrong image):
  *   1 <= W,H,oW,oH <= 65536, W*H and oW*oH < 2^31, |xOff|,|yOff|,|minSrc*| <= 2^18.
  */
