@@ -293,24 +293,58 @@ int tmaps_device(hg_ctx *c, const void *img, int W, int H, const CUtensorMap **o
 
 // rows per CTA = 64 * niter: long-lived CTAs amortise their start-up and pipeline gathers against arithmetic,
 // but the grid must still fill the machine (>= ~6 CTAs per SM in total)
-int pick_niter(hg_ctx *c, int max_ow, int max_oh, int n_frames)
+int pick_niter(hg_ctx *c, int max_ow, int max_oh, int n_frames, int ltx = 4)
 {
-    int niter = 16;
-    while (niter > 1 &&
-           (long long)geo_tiles_x(max_ow) * geo_tiles_y(max_oh, niter) * n_frames < (long long)c->sm_count * 16)
+    int niter = ltx == 4 ? 16 : 2;  // tall row groups are 128 rows already
+    while (niter > 1 && (long long)geo_tiles_x(max_ow, 1 << ltx) * geo_tiles_y(max_oh, niter, geo_group_rows(ltx)) * n_frames <
+                            (long long)c->sm_count * 16)
         niter >>= 1;
     return niter;
 }
 
+// Does the inverse map turn the image by about a quarter turn (a step in output x is mostly a step in source y)?  Then
+// the "tall" thread layout gathers coalesced (warp_geo.cuh, geo_group_rows).  From the matrix: the derivative of the
+// source coordinates along output x at the centre of the window.
+bool map_is_rotated(int kind, const double *m, int x_off, int y_off, int o_w, int o_h)
+{
+    if (getenv("HG_GEO_NO_TALL")) return false;
+    double dsx, dsy;
+    if (kind == HG_AFFINE) {
+        dsx = m[0];
+        dsy = m[1];
+    } else {
+        const double x = x_off + 0.5 * o_w, y = y_off + 0.5 * o_h;
+        const double dn = m[6] * x + m[7] * y + 1.0, nx = m[0] * x + m[1] * y + m[2], ny = m[3] * x + m[4] * y + m[5];
+        dsx = m[0] * dn - m[6] * nx;
+        dsy = m[3] * dn - m[6] * ny;
+    }
+    return std::isfinite(dsx) && std::isfinite(dsy) && std::fabs(dsy) > 2.0 * std::fabs(dsx);
+}
+
+// the same question from point pairs (the matrix is solved on the device): affine estimate through the first three pairs
+// of the inverse map  from[i] -> to[i]
+bool points_map_is_rotated(const double *from, const double *to)
+{
+    const double ax = from[2] - from[0], ay = from[3] - from[1], bx = from[4] - from[0], by = from[5] - from[1];
+    const double det = ax * by - ay * bx;
+    if (!(std::fabs(det) > 0.0)) return false;
+    // d(to)/d(from.x) of the affine map through the three pairs
+    const double ux = to[2] - to[0], uy = to[3] - to[1], vx = to[4] - to[0], vy = to[5] - to[1];
+    const double m[6] = {(ux * by - vx * ay) / det, (uy * by - vy * ay) / det, 0, 0, 0, 0};
+    return map_is_rotated(HG_AFFINE, m, 0, 0, 1, 1);
+}
+
 // `staged`: the frames carry tensor maps (P.has_tm / GeoFrame::tm), so CTAs cover few rows and stage their source
 // footprint in shared memory; otherwise long-lived CTAs gather directly
-int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_frames, bool staged, cudaStream_t stream)
+int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_frames, bool staged, cudaStream_t stream,
+               bool tall = false)
 {
-    P.niter = staged ? c->geo_niter_staged : pick_niter(c, max_ow, max_oh, n_frames);
+    P.ltx = (tall && !staged && c->sampling != HG_BILINEAR) ? 1 : 4;
+    P.niter = staged ? c->geo_niter_staged : pick_niter(c, max_ow, max_oh, n_frames, P.ltx);
     if (staged && 32 * P.niter > GEO_QCAP) P.niter = GEO_QCAP / 32;  // per-tile exact queue: one entry per thread and row group
     P.box_bytes = staged ? c->geo_box_bytes : 0;
     P.stages = 0;
-    dim3 grid((unsigned)(geo_tiles_x(max_ow) * geo_tiles_y(max_oh, P.niter)), (unsigned)n_frames);
+    dim3 grid((unsigned)(geo_tiles_x(max_ow, 1 << P.ltx) * geo_tiles_y(max_oh, P.niter, geo_group_rows(P.ltx))), (unsigned)n_frames);
     if (c->sampling == HG_BILINEAR) {
         const long long nq = ((long long)max_ow * max_oh + 3) / 4;
         long long blocks = (nq + 255) / 256;
@@ -695,7 +729,7 @@ int hg_solve_with_limits(hg_ctx *c, int kind, const double *src, const double *d
 
 /* ------------------------------------------------------------------ affine / projective warps */
 static int warp_inverse_common(hg_ctx *c, int kind, const void *inv_host, bool solve_on_device, int x_off,
-                               int y_off, int o_w, int o_h, uint8_t *out_host, void *out_dev)
+                               int y_off, int o_w, int o_h, uint8_t *out_host, void *out_dev, bool tall_hint = false)
 {
     NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
     if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
@@ -724,7 +758,8 @@ static int warp_inverse_common(hg_ctx *c, int kind, const void *inv_host, bool s
     }
     P.has_tm = c->img_tm_ok ? 1 : 0;
     if (c->img_tm_ok) memcpy(P.tm_val, c->img_tm, sizeof c->img_tm);
-    TRY(launch_geo(c, kind, P, o_w, o_h, 1, c->img_tm_ok, c->stream));
+    const bool tall = solve_on_device ? tall_hint : map_is_rotated(kind, P.mat_val, x_off, y_off, o_w, o_h);
+    TRY(launch_geo(c, kind, P, o_w, o_h, 1, c->img_tm_ok, c->stream, tall));
     return finish_out(c, dst, bytes, out_host);
 }
 
@@ -754,7 +789,8 @@ int hg_warp_inverse_points(hg_ctx *c, int kind, const double *dst_pts, const dou
     a.n = 1;
     a.op = kind == HG_AFFINE ? 0 : 1;
     TRY(launch_solve(c, a));
-    return warp_inverse_common(c, kind, nullptr, true, x_off, y_off, o_w, o_h, out_host, out_dev);
+    // inverse map: dst -> src
+    return warp_inverse_common(c, kind, nullptr, true, x_off, y_off, o_w, o_h, out_host, out_dev, points_map_is_rotated(dst_pts, src_pts));
 }
 
 static int run_forward(hg_ctx *c, FwdArgs &a, bool piecewise, uint32_t *dst, size_t bytes, uint8_t *out_host)
@@ -858,7 +894,13 @@ int hg_warp_inverse_batch(hg_ctx *c, int kind, const void *inv_matrices, const h
         GeoParams P{};
         P.many = (const GeoFrame *)c->frames.p + f0;
         P.mats_dev = (const char *)c->mats.p + mstride * (size_t)f0;
-        TRY(launch_geo(c, kind, P, max_ow, max_oh, nf, staged, c->stream));
+        double m0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (kind == HG_AFFINE)
+            for (int k = 0; k < 6; ++k) m0[k] = (double)((const float *)inv_matrices)[6 * (size_t)f0 + k];
+        else
+            for (int k = 0; k < 8; ++k) m0[k] = ((const double *)inv_matrices)[8 * (size_t)f0 + k];
+        const bool tall = map_is_rotated(kind, m0, frames[f0].x_off, frames[f0].y_off, frames[f0].o_w, frames[f0].o_h);
+        TRY(launch_geo(c, kind, P, max_ow, max_oh, nf, staged, c->stream, tall));
     }
     return HG_OK;
 }
@@ -1478,7 +1520,7 @@ int hg_pipe_submit(hg_pipe *p, const uint8_t *rgba_host, const double *dst_pts, 
     CU(c, cudaGetLastError());
     const int sampling = c->sampling;
     c->sampling = HG_NEAREST;  // the pipe is the reference's nearest-neighbour path
-    const int lr = launch_geo(c, p->kind, P, o_w, o_h, 1, sl.tm_ok, p->s_k);
+    const int lr = launch_geo(c, p->kind, P, o_w, o_h, 1, sl.tm_ok, p->s_k, points_map_is_rotated(dst_pts, src_pts));
     c->sampling = sampling;
     TRY(lr);
     CU(c, cudaEventRecord(sl.k_done, p->s_k));

@@ -60,7 +60,8 @@ struct GeoParams {
     GeoFrame one;            // used when many == nullptr
     const GeoFrame *many;    // device array, indexed by blockIdx.y
     const void *mats_dev;    // device matrices (float[6] | double[8] per frame) or nullptr
-    int niter;               // row groups (of GEO_GROUP_ROWS rows) per CTA
+    int niter;               // row groups per CTA
+    int ltx;                 // log2(quads per CTA row): 4 = the default 64 x 16 pixel row group; 1 = "tall" 8 x 128 (rotated maps)
     int has_tm;              // tm_val holds the tensor maps of one.src (single-frame launches)
     int box_bytes;           // shared memory for one staged source box (staged kernel)
     int stages;              // ring depth of the staged kernel
@@ -92,12 +93,20 @@ constexpr int GEO_QCAP = 96;  // queued (thread, row group) entries per warp awa
 
 // host + device: CTAs needed for one frame.  Rows whose flat start is not 16-byte aligned begin with a partial
 // quad, so a row has at most (oW + 3 + 3) / 4 quads; when oW % 4 == 0 every row is aligned.
-__host__ __device__ inline int geo_tiles_x(int oW)
+__host__ __device__ inline int geo_tiles_x(int oW, int tile_quads = GEO_TILE_QUADS)
 {
     const int quads = (oW & 3) == 0 ? oW / 4 : (oW + 6) / 4;
-    return (quads + GEO_TILE_QUADS - 1) / GEO_TILE_QUADS;
+    return (quads + tile_quads - 1) / tile_quads;
 }
-__host__ __device__ inline int geo_tiles_y(int oH, int niter) { return (oH + GEO_GROUP_ROWS * niter - 1) / (GEO_GROUP_ROWS * niter); }
+__host__ __device__ inline int geo_tiles_y(int oH, int niter, int group_rows = GEO_GROUP_ROWS)
+{
+    return (oH + group_rows * niter - 1) / (group_rows * niter);
+}
+// The 128 threads of a CTA form 2^ltx quad columns x (128 >> ltx) thread rows.  ltx = 4 is the default (a warp stores
+// 256 contiguous bytes per row).  ltx = 1 ("tall") is for maps that turn the image by about a quarter turn: there a
+// step in output x is a step in source y, so lanes laid out along output ROWS read along a source row — coalesced
+// gathers again — and a warp still stores whole 32-byte sectors (two adjacent quads per row).
+__host__ __device__ inline int geo_group_rows(int ltx) { return (GEO_THREADS >> ltx) * GEO_ROWS_PER_THREAD; }
 
 // hi word of (v + 1.5*2^20) minus the hi word of (0 + 1.5*2^20): equals floor(v) for -2^19 <= v < 2^19 and is
 // >= 2^19 (as unsigned) for everything else incl. NaN / Inf, so `(unsigned)u < W` is the complete test
@@ -164,7 +173,7 @@ __device__ __forceinline__ unsigned decode_flat(double tx, double ty, unsigned W
 // iteration of arithmetic inside the same warp.
 template <int KIND, int MODE>
 __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&m)[8], int base0, int niter, int s,
-                                              int x_first, unsigned mask, uint2 *q, int *qn)
+                                              int x_first, unsigned mask, uint2 *q, int *qn, int group_rows = GEO_GROUP_ROWS)
 {
     static_assert(4 * GEO_ROWS_PER_THREAD + 17 <= 32, "queue entry packs the redo bits above a 17-bit row");
     constexpr int R = GEO_ROWS_PER_THREAD;
@@ -250,7 +259,7 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
             base_idx = -1;
         }
         // ---- A: arithmetic of group it
-        const int base = base0 + it * GEO_GROUP_ROWS;
+        const int base = base0 + it * group_rows;
         if (it < niter && base < oH) {
             redo_bits = 0u;
 #pragma unroll
@@ -488,7 +497,7 @@ __device__ __forceinline__ void geo_fast_retire(const GeoFrame &F, const double 
 
 template <int KIND>
 __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&m)[8], int base0, int niter, int s,
-                                              int x_first, unsigned mask, uint2 *q, int *qn)
+                                              int x_first, unsigned mask, uint2 *q, int *qn, int group_rows)
 {
     GeoFastCtx<KIND> C;
     C.src = F.src;
@@ -524,7 +533,7 @@ __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&
     const int oH = F.oH;
 #pragma unroll 1
     for (int it = 0; it < niter; it += 2) {
-        const int b0 = base0 + it * GEO_GROUP_ROWS, b1 = b0 + GEO_GROUP_ROWS;
+        const int b0 = base0 + it * group_rows, b1 = b0 + group_rows;
         if (b0 >= oH) break;
         geo_fast_issue<KIND>(C, ga, b0, qn);
         geo_fast_retire<KIND>(F, m, C, gb, x_first, mask, q);
@@ -672,19 +681,20 @@ __global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG
     }
 
     const int oW = F.oW, oH = F.oH;
-    const int tiles_x = geo_tiles_x(oW);
+    const int ltx = P.ltx, tile_quads = 1 << ltx, group_rows = geo_group_rows(ltx);
+    const int tiles_x = geo_tiles_x(oW, tile_quads);
     const int tile_y = blockIdx.x / tiles_x;
     const int tile_x = blockIdx.x - tile_y * tiles_x;
-    const int row0 = tile_y * (GEO_GROUP_ROWS * P.niter);
+    const int row0 = tile_y * (group_rows * P.niter);
     if (row0 >= oH) return;  // grid is sized for the largest frame of the batch
 
     // rows with equal flat alignment repeat with period s = 4 / gcd(oW mod 4, 4)
     const int sl = (oW & 3) == 0 ? 0 : ((oW & 1) ? 2 : 1);  // log2(s)
     const int s = 1 << sl;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tx = threadIdx.x & (tile_quads - 1), ty = threadIdx.x >> ltx;
     const int base = row0 + (ty >> sl) * (s * GEO_ROWS_PER_THREAD) + (ty & (s - 1));
     const int shift = (int)(((unsigned)base * (unsigned)oW) & 3u);
-    const int x_first = 4 * (tile_x * GEO_TILE_QUADS + tx) - shift;
+    const int x_first = 4 * (tile_x * tile_quads + tx) - shift;
     const bool active = (base < oH) && (x_first < oW);
     unsigned mask = 0;
 #pragma unroll
@@ -696,11 +706,11 @@ __global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG
     const bool fast = (KIND == 1) && geo_fast_mode(F, m);  // CTA-uniform: from the matrix and the frame window
     if (active) {
         if (KIND == 0) {
-            geo_fast_body<0>(F, m, base, P.niter, s, x_first, mask, q, qn);
+            geo_fast_body<0>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows);
         } else {
-            if (m[6] == 0.0 && m[7] == 0.0) geo_tile_body<1, 2>(F, m, base, P.niter, s, x_first, mask, q, qn);
-            else if (fast) geo_fast_body<1>(F, m, base, P.niter, s, x_first, mask, q, qn);
-            else geo_tile_body<1, 0>(F, m, base, P.niter, s, x_first, mask, q, qn);
+            if (m[6] == 0.0 && m[7] == 0.0) geo_tile_body<1, 2>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows);
+            else if (fast) geo_fast_body<1>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows);
+            else geo_tile_body<1, 0>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows);
         }
     }
     if (KIND == 1) {
