@@ -4,7 +4,7 @@
 // canvas (drawImage + getImageData, H.js:1071-1076) and hands results back as a PNG data URL (toDataURL, H.js:480-483);
 // its Node smoke test reads test/testImgLogoBlack.png and its golden output is test/transformedImage.png
 // (test/nodeTest.js:5-13).  This file is that file I/O for a host without a canvas: PNG (ISO/IEC 15948) chunks, zlib
-// inflate / deflate from the system zlib, the five scanline filters, and expansion of every non-interlaced 8- or 16-bit
+// inflate / deflate from the system zlib, the five scanline filters, Adam7 interlacing, and expansion of every 8- or 16-bit
 // colour type (and 1/2/4-bit grey / palette) to the RGBA8 layout of ImageData.  Pixel values are what any conforming
 // decoder produces (16-bit samples keep their high byte, tRNS keys and palette alpha are honoured); no colour
 // management, no gamma — exactly what getImageData returns for an untagged image.
@@ -70,7 +70,7 @@ inline int parse(const uint8_t *png, size_t n, Header &hd, std::vector<uint8_t> 
         pos += 12 + (size_t)len;
     }
     if (!have_ihdr || !end || hd.w == 0 || hd.h == 0 || hd.w > 65536 || hd.h > 65536) return 1;
-    if (hd.interlace != 0) return 1;  // Adam7 is not supported
+    if (hd.interlace != 0 && hd.interlace != 1) return 1;
     const int d = hd.depth;
     switch (hd.color) {
         case 0: if (d != 1 && d != 2 && d != 4 && d != 8 && d != 16) return 1; break;
@@ -89,87 +89,106 @@ inline int decode(const uint8_t *png, size_t n, Header &hd, uint8_t *rgba)
     if (!rgba) return 0;  // header only
     static const int channels_of[7] = {1, 0, 3, 1, 2, 0, 4};
     const int ch = channels_of[hd.color], bpp_bits = ch * hd.depth;
-    const size_t stride = ((size_t)hd.w * bpp_bits + 7) / 8, bpp = (size_t)(bpp_bits + 7) / 8;
-    std::vector<uint8_t> raw((stride + 1) * hd.h);
+    const size_t bpp = (size_t)(bpp_bits + 7) / 8;
+    // the image as one pass, or the seven Adam7 passes: (x0, y0, dx, dy) of each reduced image
+    static const int adam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    static const int whole[1][4] = {{0, 0, 1, 1}};
+    const int (*passes)[4] = hd.interlace ? adam7 : whole;
+    const int n_pass = hd.interlace ? 7 : 1;
+    size_t total = 0;
+    for (int p = 0; p < n_pass; ++p) {
+        const size_t pw = (hd.w + passes[p][2] - 1 - passes[p][0]) / passes[p][2], ph = (hd.h + passes[p][3] - 1 - passes[p][1]) / passes[p][3];
+        if (pw && ph) total += (((size_t)pw * bpp_bits + 7) / 8 + 1) * ph;
+    }
+    std::vector<uint8_t> raw(total);
     uLongf out_len = (uLongf)raw.size();
     if (uncompress(raw.data(), &out_len, idat.data(), (uLong)idat.size()) != Z_OK || out_len != raw.size()) return 1;
-    // undo the scanline filters in place
-    std::vector<uint8_t> zero(stride, 0);
-    for (uint32_t y = 0; y < hd.h; ++y) {
-        uint8_t *row = raw.data() + (stride + 1) * y + 1;
-        const uint8_t *up = y ? row - (stride + 1) : zero.data();
-        const int ft = row[-1];
-        for (size_t i = 0; i < stride; ++i) {
-            const int a = i >= bpp ? row[i - bpp] : 0, b = up[i], c = i >= bpp ? up[i - bpp] : 0;
-            int add;
-            switch (ft) {
-                case 0: add = 0; break;
-                case 1: add = a; break;
-                case 2: add = b; break;
-                case 3: add = (a + b) >> 1; break;
-                case 4: add = paeth(a, b, c); break;
-                default: return 1;
-            }
-            row[i] = (uint8_t)(row[i] + add);
-        }
-    }
-    // expand to RGBA8
     const int maxv = (1 << (hd.depth < 8 ? hd.depth : 8)) - 1;
-    for (uint32_t y = 0; y < hd.h; ++y) {
-        const uint8_t *row = raw.data() + (stride + 1) * y + 1;
-        uint8_t *o = rgba + (size_t)y * hd.w * 4;
-        for (uint32_t x = 0; x < hd.w; ++x, o += 4) {
-            auto sample = [&](int c, uint16_t &full) -> uint8_t {  // c-th channel of pixel x: 8-bit value (+ raw sample)
-                if (hd.depth == 16) {
-                    const uint8_t *p = row + ((size_t)x * ch + c) * 2;
-                    full = (uint16_t)((p[0] << 8) | p[1]);
-                    return p[0];
+    size_t off = 0;
+    for (int p = 0; p < n_pass; ++p) {
+        const uint32_t pw = (uint32_t)((hd.w + passes[p][2] - 1 - passes[p][0]) / passes[p][2]);
+        const uint32_t ph = (uint32_t)((hd.h + passes[p][3] - 1 - passes[p][1]) / passes[p][3]);
+        if (!pw || !ph) continue;
+        const size_t stride = ((size_t)pw * bpp_bits + 7) / 8;
+        uint8_t *pass = raw.data() + off;
+        off += (stride + 1) * ph;
+        // undo the scanline filters in place
+        std::vector<uint8_t> zero(stride, 0);
+        for (uint32_t y = 0; y < ph; ++y) {
+            uint8_t *row = pass + (stride + 1) * y + 1;
+            const uint8_t *up = y ? row - (stride + 1) : zero.data();
+            const int ft = row[-1];
+            for (size_t i = 0; i < stride; ++i) {
+                const int a = i >= bpp ? row[i - bpp] : 0, b = up[i], c = i >= bpp ? up[i - bpp] : 0;
+                int add;
+                switch (ft) {
+                    case 0: add = 0; break;
+                    case 1: add = a; break;
+                    case 2: add = b; break;
+                    case 3: add = (a + b) >> 1; break;
+                    case 4: add = paeth(a, b, c); break;
+                    default: return 1;
                 }
-                if (hd.depth == 8) {
-                    full = row[(size_t)x * ch + c];
-                    return (uint8_t)full;
+                row[i] = (uint8_t)(row[i] + add);
+            }
+        }
+        // expand to RGBA8 at the pass's pixel positions
+        for (uint32_t y = 0; y < ph; ++y) {
+            const uint8_t *row = pass + (stride + 1) * y + 1;
+            for (uint32_t x = 0; x < pw; ++x) {
+                uint8_t *o = rgba + ((size_t)(passes[p][1] + y * passes[p][3]) * hd.w + (passes[p][0] + x * passes[p][2])) * 4;
+                auto sample = [&](int c, uint16_t &full) -> uint8_t {  // c-th channel of pixel x: 8-bit value (+ raw sample)
+                    if (hd.depth == 16) {
+                        const uint8_t *q = row + ((size_t)x * ch + c) * 2;
+                        full = (uint16_t)((q[0] << 8) | q[1]);
+                        return q[0];
+                    }
+                    if (hd.depth == 8) {
+                        full = row[(size_t)x * ch + c];
+                        return (uint8_t)full;
+                    }
+                    const size_t bit = (size_t)x * hd.depth;
+                    const int v = (row[bit >> 3] >> (8 - hd.depth - (int)(bit & 7))) & maxv;
+                    full = (uint16_t)v;
+                    return (uint8_t)v;
+                };
+                uint16_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+                switch (hd.color) {
+                    case 0: {
+                        uint8_t g = sample(0, f0);
+                        if (hd.depth < 8) g = (uint8_t)(g * 255 / maxv);
+                        o[0] = o[1] = o[2] = g;
+                        o[3] = (trns.size() >= 2 && f0 == (uint16_t)((trns[0] << 8) | trns[1])) ? 0 : 255;
+                        break;
+                    }
+                    case 2: {
+                        o[0] = sample(0, f0);
+                        o[1] = sample(1, f1);
+                        o[2] = sample(2, f2);
+                        o[3] = (trns.size() >= 6 && f0 == (uint16_t)((trns[0] << 8) | trns[1]) && f1 == (uint16_t)((trns[2] << 8) | trns[3]) &&
+                                f2 == (uint16_t)((trns[4] << 8) | trns[5])) ? 0 : 255;
+                        break;
+                    }
+                    case 3: {
+                        const size_t i = sample(0, f0);
+                        if (3 * i + 2 >= plte.size()) return 1;
+                        o[0] = plte[3 * i];
+                        o[1] = plte[3 * i + 1];
+                        o[2] = plte[3 * i + 2];
+                        o[3] = i < trns.size() ? trns[i] : 255;
+                        break;
+                    }
+                    case 4:
+                        o[0] = o[1] = o[2] = sample(0, f0);
+                        o[3] = sample(1, f1);
+                        break;
+                    default:
+                        o[0] = sample(0, f0);
+                        o[1] = sample(1, f1);
+                        o[2] = sample(2, f2);
+                        o[3] = sample(3, f3);
+                        break;
                 }
-                const size_t bit = (size_t)x * hd.depth;
-                const int v = (row[bit >> 3] >> (8 - hd.depth - (int)(bit & 7))) & maxv;
-                full = (uint16_t)v;
-                return (uint8_t)v;
-            };
-            uint16_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
-            switch (hd.color) {
-                case 0: {
-                    uint8_t g = sample(0, f0);
-                    if (hd.depth < 8) g = (uint8_t)(g * 255 / maxv);
-                    o[0] = o[1] = o[2] = g;
-                    o[3] = (trns.size() >= 2 && f0 == (uint16_t)((trns[0] << 8) | trns[1])) ? 0 : 255;
-                    break;
-                }
-                case 2: {
-                    o[0] = sample(0, f0);
-                    o[1] = sample(1, f1);
-                    o[2] = sample(2, f2);
-                    o[3] = (trns.size() >= 6 && f0 == (uint16_t)((trns[0] << 8) | trns[1]) && f1 == (uint16_t)((trns[2] << 8) | trns[3]) &&
-                            f2 == (uint16_t)((trns[4] << 8) | trns[5])) ? 0 : 255;
-                    break;
-                }
-                case 3: {
-                    const size_t i = sample(0, f0);
-                    if (3 * i + 2 >= plte.size()) return 1;
-                    o[0] = plte[3 * i];
-                    o[1] = plte[3 * i + 1];
-                    o[2] = plte[3 * i + 2];
-                    o[3] = i < trns.size() ? trns[i] : 255;
-                    break;
-                }
-                case 4:
-                    o[0] = o[1] = o[2] = sample(0, f0);
-                    o[3] = sample(1, f1);
-                    break;
-                default:
-                    o[0] = sample(0, f0);
-                    o[1] = sample(1, f1);
-                    o[2] = sample(2, f2);
-                    o[3] = sample(3, f3);
-                    break;
             }
         }
     }

@@ -135,8 +135,8 @@ int hg_delaunay(const double *points, int n_points, uint32_t *triangles_out, int
 /* The step either side of the path when there is no canvas: the reference reads its pixels through
  * drawImage + getImageData (H.js:1071-1076) and returns results as a PNG data URL (toDataURL, H.js:480-483); its Node
  * smoke test loads test/testImgLogoBlack.png (test/nodeTest.js:11).  PNG -> the RGBA8 layout of ImageData.data: every
- * non-interlaced colour type and bit depth (16-bit samples keep their high byte, palette / tRNS transparency applied).
- * rgba_out == NULL: only *w / *h are filled.  HG_ERR_INVALID: malformed, interlaced or unsupported file, or capacity
+ * colour type and bit depth, Adam7 interlacing included (16-bit samples keep their high byte, palette / tRNS applied).
+ * rgba_out == NULL: only *w / *h are filled.  HG_ERR_INVALID: malformed or unsupported file, or capacity
  * smaller than w*h*4. */
 int hg_png_decode(const uint8_t *png, size_t png_bytes, uint8_t *rgba_out, size_t capacity_bytes, int *w, int *h);
 /* RGBA8 -> PNG (8-bit RGBA, zlib level 6).  hg_png_encode_bound gives a capacity that always suffices. */

@@ -89,3 +89,28 @@ def test_capacity_and_argument_errors():
     assert L.hg_delaunay(pts.ctypes.data, 4, out.ctypes.data, 1, C.byref(cnt)) == 1  # HG_ERR_INVALID: needs 2 triangles
     assert cnt.value == 0
     assert L.hg_delaunay(None, 4, out.ctypes.data, 1, C.byref(cnt)) == 1
+
+
+def test_benchmark_sized_mesh_is_fast_and_complete():
+    """The reference's largest benchmark mesh: 160 x 80 points -> 23,000+ triangles (test/benchmark.js:48, README.md:317).
+    A jittered grid of that size triangulates in well under a second on the host and is a complete triangulation of its
+    convex hull (Euler: T = 2n - 2 - hull vertices)."""
+    import time
+    from scipy.spatial import ConvexHull
+    rng = np.random.default_rng(12)
+    gx, gy = np.meshgrid(np.arange(160) * 5.0, np.arange(80) * 5.0)
+    pts = (np.stack([gx.ravel(), gy.ravel()], 1) + rng.uniform(-1.5, 1.5, (160 * 80, 2))).astype(np.float32).astype(np.float64)
+    t0 = time.perf_counter()
+    t = _cxx(pts)
+    dt = time.perf_counter() - t0
+    n, hull = len(pts), len(ConvexHull(pts).vertices)
+    assert len(t) // 3 == 2 * n - 2 - hull
+    assert dt < 2.0, dt
+    # every point is used
+    assert len(np.unique(t)) == n
+
+
+def test_medium_mesh_matches_python_restatement():
+    rng = np.random.default_rng(13)
+    pts = rng.uniform(0, 4000, (2500, 2)).astype(np.float32).astype(np.float64)
+    assert np.array_equal(_cxx(pts), _py(pts))

@@ -103,3 +103,42 @@ def test_reference_fixtures_decode_to_the_committed_golden_arrays(golden):
     for name in ("testImg.png", "testImgLogoWhite.png"):
         data = open(os.path.join(REF, name), "rb").read()
         assert np.array_equal(hg._abi.png_decode(data), _pillow_rgba(data))
+
+
+def _interlaced_png(a):
+    """An Adam7-interlaced 8-bit RGBA PNG of `a`, built by hand (Pillow cannot write interlaced files)."""
+    import struct
+    import zlib
+    h, w = a.shape[:2]
+    raw = b""
+    for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+        sub = a[y0::dy, x0::dx]
+        if sub.size == 0:
+            continue
+        prev = np.zeros(sub.shape[1] * 4, np.uint8)
+        for y, row in enumerate(sub.reshape(sub.shape[0], -1)):
+            ft = (0, 2, 1)[y % 3]  # None, Up, Sub in turn
+            if ft == 0:
+                f = row
+            elif ft == 2:
+                f = (row.astype(np.int16) - prev).astype(np.uint8)
+            else:
+                left = np.concatenate([np.zeros(4, np.uint8), row[:-4]])
+                f = (row.astype(np.int16) - left).astype(np.uint8)
+            raw += bytes([ft]) + f.tobytes()
+            prev = row
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 1)) +
+            chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+
+
+def test_adam7_interlaced_files_decode():
+    rng = np.random.default_rng(8)
+    for w, h in ((1, 1), (3, 2), (8, 8), (37, 21), (64, 5)):  # small sizes leave some passes empty
+        a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        data = _interlaced_png(a)
+        assert np.array_equal(_pillow_rgba(data), a)          # the hand-built file is a valid interlaced PNG
+        assert np.array_equal(hg._abi.png_decode(data), a)
