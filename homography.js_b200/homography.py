@@ -2,7 +2,7 @@
 
 This is the Python twin of js/Homography.mjs: the same public surface
 (`Homography(transform, width, height)`, `setReferencePoints`, `setSourcePoints`, `setDestinyPoints`,
-`setImage`, `setTriangles`, `warp`) and the same state machine (normalised-range auto-detection,
+`setImage`, `setTriangles`, `warp`, `getTransformationMatrixAsCSS`, `transformHTMLElement`) and the same state machine (normalised-range auto-detection,
 in-place (de)normalisation of caller-owned point arrays, cache invalidation, forward/inverse dispatch
 thresholds), with every arithmetic step executed by libhgwarp.so on the GPU:
 
@@ -17,6 +17,7 @@ There is no CPU fallback: without the CUDA library / a GPU the constructor raise
 """
 from __future__ import annotations
 
+import decimal
 import math
 
 import numpy as np
@@ -25,6 +26,7 @@ from . import _abi
 
 NORMALIZED_MAX = 8.0  # H.js:36
 DIMS = 2              # H.js:34
+MAX_CSS_DECIMAL = 5   # H.js:31
 
 
 class HomographyError(Exception):
@@ -56,10 +58,29 @@ class ImageData:
 
 def _js_round(x: float) -> float:
     """Math.round: nearest integer, ties toward +inf (host-side scalar bookkeeping only)."""
+    if x is None:   # Math.round(null) === 0
+        return 0.0
     if x != x or x in (math.inf, -math.inf) or abs(x) >= 4503599627370496.0:
         return x
     r = math.floor(x)
     return float(r + 1) if x - r >= 0.5 else float(r)
+
+
+def _js_to_fixed(x: float, digits: int) -> str:
+    """Number.prototype.toFixed: the decimal string of the EXACT binary value, rounded to `digits` places with ties
+    away from zero ("let n be an integer for which n / 10^f - x is as close to zero as possible; if there are two
+    such n, pick the larger n", applied to |x|); -0 prints without a sign, a negative that rounds to zero keeps it."""
+    x = float(x)
+    if x != x:
+        return "NaN"
+    if x in (math.inf, -math.inf):
+        return "Infinity" if x > 0 else "-Infinity"
+    if abs(x) >= 1e21:
+        return repr(x)  # ToString(x): shortest round-trip digits, "1e+21" form — the same text in both languages
+    with decimal.localcontext() as ctx:
+        ctx.prec = 80
+        q = decimal.Decimal(abs(x)).quantize(decimal.Decimal(1).scaleb(-digits), rounding=decimal.ROUND_HALF_UP)
+    return ("-" if x < 0 else "") + format(q, "f")
 
 
 def _positive(v) -> bool:      # JS `v > 0` (null -> false)
@@ -293,6 +314,46 @@ class Homography:
         if empty:
             return ImageData(np.zeros(4, np.uint8), 1, 1)
         return ImageData(out, int(oW), int(oH))
+
+    def getTransformationMatrixAsCSS(self, srcPoints=None, dstPoints=None, width=None, height=None) -> str:
+        """H.js:548-586: the current affine / projective matrix as the value of the CSS `transform` property —
+        `matrix(a, b, c, d, e, f)` from the six float32 coefficients, `matrix3d(...)` from the eight doubles (the 3x3
+        transposed into a column-major 4x4 with the identity's z row / column), every number through toFixed(5)."""
+        if width is not None or height is not None:
+            self._setSrcWidthHeight(width, height)
+        if srcPoints is not None:
+            self.setSourcePoints(srcPoints, None, width, height)
+        if dstPoints is not None:
+            self.setDestinyPoints(dstPoints)
+        if self._srcPoints is None:
+            raise HomographyError("Impossible to calculate a transform when srcPoints are not set")
+        if self._dstPoints is None:
+            raise HomographyError("Impossible to calculate a transform when dstPoints are not set")
+        if self._transformMatrix is None:
+            raise HomographyError("Transform matrix can not be calculated")
+        m = [float(v) for v in self._transformMatrix]
+        if self.transform == "affine":
+            return "matrix(" + ", ".join(_js_to_fixed(v, MAX_CSS_DECIMAL) for v in m) + ")"
+        if self.transform == "projective":
+            cells, i = [], 0
+            for dy in range(4):
+                for dx in range(4):
+                    if (dy == 2 and dx == 2) or (dy == 3 and dx == 3):
+                        cells.append("1")
+                    elif dy == 2 or dx == 2:
+                        cells.append("0")
+                    else:
+                        cells.append(_js_to_fixed(m[(i * 3) % 8], MAX_CSS_DECIMAL))
+                        i += 1
+            return "matrix3d(" + ", ".join(cells) + ")"
+        raise HomographyError('Only "affine" or "projective" transforms can be applied on the CSS transform property, '
+                              f"but {self.transform} selected")
+
+    def transformHTMLElement(self, element, srcPoints=None, dstPoints=None):
+        """H.js:611 — duck-typed outside a browser: `element.getBoundingClientRect()` gives .width / .height and the
+        string lands in `element.style.transform`."""
+        rect = element.getBoundingClientRect()
+        element.style.transform = self.getTransformationMatrixAsCSS(srcPoints, dstPoints, rect.width, rect.height)
 
     # ------------------------------------------------------------------ state plumbing (H.js:637-896)
     def _solve(self, src, dst):

@@ -1,5 +1,6 @@
 // homography_b200.mjs — Node.js face of the engine: the `Homography` class surface of Eric-Canas/Homography.js
-// (constructor, setReferencePoints, setSourcePoints, setDestinyPoints, setImage, setTriangles, warp) with every
+// (constructor, setReferencePoints, setSourcePoints, setDestinyPoints, setImage, setTriangles, warp,
+// getTransformationMatrixAsCSS, transformHTMLElement) with every
 // arithmetic step executed on the GPU through the N-API addon (js/hgwarp_napi.c -> libhgwarp.so).
 //
 // This file is the JavaScript twin of ../homography.py (same state machine, same engine calls); the Python twin
@@ -11,6 +12,7 @@ import { createRequire } from 'node:module';
 const native = createRequire(import.meta.url)('./hgwarp.node');
 
 const NORMALIZED_MAX = 8.0; // H.js:36
+const MAX_CSS_DECIMAL = 5;  // H.js:31
 const KIND = { affine: 0, projective: 1 };
 const positive = (v) => v !== null && v > 0;
 const isTyped = (a) => ArrayBuffer.isView(a);
@@ -171,6 +173,39 @@ class Homography {
     }
     if (empty) return { data: new Uint8ClampedArray(4), width: 1, height: 1 };
     return { data, width: oW, height: oH };
+  }
+
+  // String form of the current affine / projective matrix for the CSS `transform` property (H.js:548-586): pure
+  // string work on the matrix the engine solved (six float32 values -> `matrix(...)`, eight doubles laid out column-major
+  // with the z row / column of the identity -> `matrix3d(...)`), every value through toFixed(5) (maxCSSDecimal, H.js:31).
+  getTransformationMatrixAsCSS(srcPoints = null, dstPoints = null, width = null, height = null) {
+    if (width !== null || height !== null) this._setSrcWidthHeight(width, height);
+    if (srcPoints !== null) this.setSourcePoints(srcPoints, null, width, height);
+    if (dstPoints !== null) this.setDestinyPoints(dstPoints);
+    if (this._srcPoints === null) throw ('Impossible to calculate a transform when srcPoints are not set');
+    else if (this._dstPoints === null) throw ('Impossible to calculate a transform when dstPoints are not set');
+    else if (this._transformMatrix === null) throw ('Transform matrix can not be calculated');
+    const m = this._transformMatrix, D = MAX_CSS_DECIMAL;
+    if (this.transform === 'affine') return `matrix(${Array.from(m, (v) => v.toFixed(D)).join(', ')})`;
+    if (this.transform === 'projective') {
+      const cells = [];
+      let i = 0;
+      for (let dy = 0; dy < 4; dy++) {
+        for (let dx = 0; dx < 4; dx++) {
+          if ((dy === 2 && dx === 2) || (dy === 3 && dx === 3)) cells.push('1');
+          else if (dy === 2 || dx === 2) cells.push('0');
+          else cells.push(m[((i++) * 3) % 8].toFixed(D)); // h0 h3 h6 | h1 h4 h7 | h2 h5: the 3x3 transposed
+        }
+      }
+      return `matrix3d(${cells.join(', ')})`;
+    }
+    throw (`Only "affine" or "projective" transforms can be applied on the CSS transform property, but ${this.transform} selected`);
+  }
+
+  // H.js:611 — any object with getBoundingClientRect() and a style (a DOM element in a browser / jsdom)
+  transformHTMLElement(element, srcPoints = null, dstPoints = null) {
+    const rect = element.getBoundingClientRect();
+    element.style.transform = this.getTransformationMatrixAsCSS(srcPoints, dstPoints, rect.width, rect.height);
   }
 
   // ---------------------------------------------------------------- state plumbing (H.js:637-896)

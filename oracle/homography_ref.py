@@ -5,7 +5,8 @@ reference statement by statement (line numbers cite /root/reference/Homography.j
 every arithmetic loop to the C oracle, so that `tests/` can compare the product's CUDA-backed
 `Homography` with the reference's behaviour at the class surface.
 
-Not restated here: the DOM branches (hidden canvas, HTMLImageElement in/out, CSS export).  The
+Not restated here: the DOM branches (hidden canvas, HTMLImageElement in/out, `element.style`).  The CSS matrix
+string (getTransformationMatrixAsCSS, H.js:548-586) is pure string work on the solved matrix and IS restated.  The
 third-party `delaunator` triangulation (H.js:27, 1216) is restated in oracle/delaunator_ref.py from
 the package's published algorithm — no reference fixture pins it (parity unpinned at that boundary);
 pass triangles through setTriangles (H.js:517) to fix a mesh.
@@ -20,6 +21,28 @@ from . import oracle as O
 
 NORMALIZED_MAX = 8.0  # H.js:36
 DIMS = 2              # H.js:34
+MAX_CSS_DECIMAL = 5   # H.js:31
+
+
+def js_to_fixed(x, digits):
+    """Number.prototype.toFixed (ECMA-262 21.1.3.3) in exact rational arithmetic: n = the integer nearest to
+    |x| * 10^digits (the larger one on a tie), printed with `digits` decimals; sign from `x < 0` (so -0 has none)."""
+    from fractions import Fraction
+    x = float(x)
+    if math.isnan(x):
+        return "NaN"
+    if math.isinf(x):
+        return "Infinity" if x > 0 else "-Infinity"
+    if abs(x) >= 1e21:
+        return repr(x)  # ToString(x)
+    scaled = Fraction(abs(x)) * 10 ** digits
+    n = scaled.numerator // scaled.denominator
+    if scaled - n >= Fraction(1, 2):
+        n += 1
+    text = str(n).rjust(digits + 1, "0")
+    if digits:
+        text = text[:-digits] + "." + text[-digits:]
+    return ("-" if x < 0 else "") + text
 
 
 class RefImageData:
@@ -220,13 +243,50 @@ class RefHomography:
             return RefImageData(out, int(self._objectiveWidth), int(self._objectiveHeight))
         return RefImageData(np.zeros(4, np.uint8), 1, 1)
 
+    def getTransformationMatrixAsCSS(self, srcPoints=None, dstPoints=None, width=None, height=None):  # H.js:548
+        if width is not None or height is not None:
+            self._setSrcWidthHeight(width, height)
+        if srcPoints is not None:
+            self.setSourcePoints(srcPoints, None, width, height)
+        if dstPoints is not None:
+            self.setDestinyPoints(dstPoints)
+        if self._srcPoints is None:
+            raise ValueError("Impossible to calculate a transform when srcPoints are not set")
+        elif self._dstPoints is None:
+            raise ValueError("Impossible to calculate a transform when dstPoints are not set")
+        elif self._transformMatrix is None:
+            raise ValueError("Transform matrix can not be calculated")
+        tm = self._transformMatrix
+        if self.transform == "affine":  # H.js:560-567
+            matrix = "matrix("
+            for i in range(len(tm)):
+                matrix += js_to_fixed(tm[i], MAX_CSS_DECIMAL)
+                matrix += ", " if i < len(tm) - 1 else ")"
+        elif self.transform == "projective":  # H.js:568-581
+            matrix = "matrix3d("
+            i = 0
+            for dy in range(4):
+                for dx in range(4):
+                    if dy == 2 and dx == 2 or dy == 3 and dx == 3:
+                        matrix += "1"
+                    elif dy == 2 or dx == 2:
+                        matrix += "0"
+                    else:
+                        matrix += js_to_fixed(tm[(i * 3) % 8], MAX_CSS_DECIMAL)
+                        i += 1
+                    matrix += ", " if dy * 4 + dx < 4 * 4 - 1 else ")"
+        else:
+            raise ValueError('Only "affine" or "projective" transforms can be applied on the CSS transform property, '
+                             f"but {self.transform} selected")
+        return matrix
+
     # ------------------------------------------------------------------ private plumbing
     def _setSrcWidthHeight(self, width, height):  # H.js:637
         last_w, last_h = self._width, self._height
         self._width, self._height = width, height
         if last_w != width or last_h != height:
-            self._width = O.js_round(width)
-            self._height = O.js_round(height)
+            self._width = O.js_round(0.0 if width is None else width)    # Math.round(null) === 0
+            self._height = O.js_round(0.0 if height is None else height)
             self._trianglesCorrespondencesMatrix = None
             if self.transform == "projective":
                 if self._srcPoints is not None and self._srcPointsAreNormalized:

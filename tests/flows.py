@@ -5,6 +5,8 @@ warp result(s).  They run against the oracle restatement, against the product ov
 and against the product over CUDA (GPU)."""
 import math
 
+import numpy as np
+
 W = H = 400
 
 
@@ -139,3 +141,47 @@ def test5_then_forward(mk, img):  # inverse piecewise warp, then a same-size for
 ALL = [node_test, test1, test2, test3, test4, test5, test6, test7, test8, test9, test10, test11, test12,
        test6_inverse, test5_then_forward]
 INVERSE_ONLY = [node_test, test1, test2, test3, test4, test5, test8, test9, test10, test11, test12, test6_inverse]
+
+
+# ------------------------------------------------------------------ getTransformationMatrixAsCSS flows: mk -> string
+sq4 = [[0, 0], [0, 1], [1, 0], [1, 1]]
+
+
+
+def css1(mk):  # test/test.js:354-380 (testCSS1): element rect 300 x 150
+    return mk("auto").getTransformationMatrixAsCSS([[0, 0], [0, 1], [1, 0]], [[0, 0], [1 / 2, 1], [1, 1 / 8]], 300.0, 150.0)
+
+
+def css2(mk):  # test/test.js:383-425 (testCSS2): setters first, then the string, then the element's size
+    hm = mk("projective")
+    hm.setSourcePoints([list(p) for p in sq4])
+    hm.setDestinyPoints([[0, 0], [0, 1], [1, 0.1], [1, 1]])
+    return hm.getTransformationMatrixAsCSS() + " | " + hm.getTransformationMatrixAsCSS(None, None, 203.4, 150.0)
+
+
+def bench_affine(mk):  # test/benchmark.js:358-434 shape: pixel-range points
+    w = h = 400
+    hm = mk("affine")
+    hm.setSourcePoints([[0, 0], [0, h], [w, 0]])
+    return hm.getTransformationMatrixAsCSS(None, [[0, h / 2], [w / 2, h * 0.8], [w / 2, 0]])
+
+
+def bench_projective(mk):
+    w = h = 400
+    hm = mk("projective")
+    hm.setSourcePoints([[0, 0], [0, h], [w, 0], [w, h]])
+    return hm.getTransformationMatrixAsCSS(None, [[w / 10, 0], [w / 10, h], [w, h / 4], [w, 3 * h / 4]])
+
+
+def random_ones(mk):
+    rng = np.random.default_rng(91)
+    out = []
+    for k in range(40):
+        n = 3 if k % 2 else 4
+        src = rng.uniform(0, 900, (n, 2)).tolist()
+        dst = rng.uniform(0, 900, (n, 2)).tolist()
+        out.append(mk("auto").getTransformationMatrixAsCSS(src, dst, float(rng.integers(50, 900)), float(rng.integers(50, 900))))
+    return "\n".join(out)
+
+
+CSS = [css1, css2, bench_affine, bench_projective, random_ones]

@@ -328,6 +328,12 @@ def test_reference_test_page_flows_over_cuda(ctx, flow, golden):
         assert _diff(g.data, r.data) == 0
 
 
+@pytest.mark.parametrize("flow", flows.CSS, ids=lambda f: f.__name__)
+def test_css_matrix_strings_over_cuda(ctx, flow):
+    """getTransformationMatrixAsCSS (H.js:548): the device-solved matrices print the same strings as the reference's."""
+    assert flow(lambda *a: hg.Homography(*a, context=ctx)) == flow(lambda *a: RefHomography(*a))
+
+
 def test_node_golden_over_cuda(ctx, golden):
     res, _ = flows.node_test(lambda *a: hg.Homography(*a, context=ctx), hg.ImageData(golden["src"].reshape(-1).copy(), 400, 400))
     assert np.array_equal(res[0].as_array(), golden["out"])

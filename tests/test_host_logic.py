@@ -86,3 +86,41 @@ def test_dispatch_thresholds(golden):
     hm.setDestinyPoints([[0, 0], [0, 401], [400, 0]])
     hm.warp()
     assert hm.last_path == "inverse_geometric"
+
+
+# ------------------------------------------------------------------ getTransformationMatrixAsCSS / transformHTMLElement
+@pytest.mark.parametrize("flow", flows.CSS, ids=lambda f: f.__name__)
+def test_css_matrix_matches_reference_restatement(flow):
+    want = flow(lambda *a: RefHomography(*a))
+    got = flow(lambda *a: hg.Homography(*a, context=OracleContext()))
+    assert got == want
+    assert got.startswith("matrix")
+
+
+def test_css_errors_and_element_form():
+    with pytest.raises(hg.HomographyError, match="srcPoints are not set"):
+        hg.Homography("affine", context=OracleContext()).getTransformationMatrixAsCSS()
+    hm = hg.Homography("affine", context=OracleContext())
+    hm.setSourcePoints([[0, 0], [0, 1], [1, 0]])
+    with pytest.raises(hg.HomographyError, match="dstPoints are not set"):
+        hm.getTransformationMatrixAsCSS()
+    pw = hg.Homography("piecewiseaffine", 10, 10, context=OracleContext())
+    pw.setReferencePoints([[0, 0], [0, 1], [1, 0], [1, 1], [0.5, 0.5]], [[0, 0], [0, 1], [1, 0], [1, 1], [0.4, 0.6]])
+    pw._transformMatrix = np.zeros(6, np.float32)   # the reference checks the matrix field before the transform kind
+    with pytest.raises(hg.HomographyError, match='Only "affine" or "projective" transforms'):
+        pw.getTransformationMatrixAsCSS()
+
+    class Style:
+        transform = None
+
+    class Element:  # what transformHTMLElement touches of a DOM element (H.js:611-614)
+        style = Style()
+
+        def getBoundingClientRect(self):
+            class R:
+                width, height = 320.0, 200.0
+            return R()
+
+    el = Element()
+    hg.Homography("auto", context=OracleContext()).transformHTMLElement(el, [[0, 0], [0, 1], [1, 0]], [[0, 0], [1 / 2, 1], [1, 1 / 8]])
+    assert el.style.transform == "matrix(1.00000, 0.12500, 0.50000, 1.00000, 0.00000, 0.00000)"

@@ -30,6 +30,7 @@ def test_js_shim_calls_match_addon_exports():
     shim = open(os.path.join(JS, "homography_b200.mjs")).read()
     called = set(re.findall(r"\bnative\.([A-Za-z]+)\(", shim))
     assert called == exported, (called, exported)
-    for name in ("setReferencePoints", "setSourcePoints", "setDestinyPoints", "setImage", "setTriangles", "warp"):
+    for name in ("setReferencePoints", "setSourcePoints", "setDestinyPoints", "setImage", "setTriangles", "warp",
+                 "getTransformationMatrixAsCSS", "transformHTMLElement"):
         assert re.search(r"\n  %s\(" % name, shim), name
     assert "export { Homography" in shim

@@ -241,3 +241,66 @@ def test_division_free_decision_algorithm_against_rational_arithmetic():
                 assert decide(N, D, b) == (float(Fraction(N) / Fraction(D)) >= b), (N, D, b)
                 n_checked += 1
     assert n_checked > 5000
+
+
+# ------------------------------------------------------------------ getTransformationMatrixAsCSS (H.js:548-586)
+# Number.prototype.toFixed known answers (ECMA-262: exact binary value, ties to the larger n, sign from x < 0)
+TO_FIXED_KATS = [(1.0, "1.00000"), (0.125, "0.12500"), (0.015625, "0.01563"), (-0.015625, "-0.01563"), (2.5, "2.50000"),
+                 (1.005, "1.00500"), (0.000005, "0.00001"), (-0.0, "0.00000"), (-1e-7, "-0.00000"), (1e21, "1e+21"),
+                 (123456.7891251, "123456.78913"), (1e-300, "0.00000"), (float("nan"), "NaN"), (float("inf"), "Infinity"),
+                 (float("-inf"), "-Infinity"), (999999.999995, "999999.99999"), (0.1 + 0.2, "0.30000")]
+
+
+@pytest.mark.parametrize("x,want", TO_FIXED_KATS)
+def test_to_fixed_oracle_and_host(x, want):
+    from oracle.homography_ref import js_to_fixed
+    from homography_js_b200.homography import _js_to_fixed   # host string code of the product: no GPU involved
+    assert js_to_fixed(x, 5) == want
+    assert _js_to_fixed(x, 5) == want
+
+
+def test_to_fixed_oracle_equals_host_on_random_doubles():
+    from oracle.homography_ref import js_to_fixed
+    from homography_js_b200.homography import _js_to_fixed
+    rng = np.random.default_rng(77)
+    xs = np.concatenate([rng.uniform(-3, 3, 2000), rng.uniform(-5000, 5000, 1000), rng.uniform(-1e-4, 1e-4, 500),
+                         np.arange(-64, 64) / 64.0 + 2.0 ** -6,      # exactly representable ...5 ties
+                         rng.uniform(-3, 3, 500).astype(np.float32).astype(np.float64)])
+    for x in xs:
+        for d in (0, 2, 5):
+            assert js_to_fixed(float(x), d) == _js_to_fixed(float(x), d), (x, d)
+
+
+def test_css_matrix_strings_known_answers(oracle_lib):
+    from oracle.homography_ref import RefHomography
+    # test/test.js:354-380 (testCSS1): affine from normalised points, element 300 x 150 -> matrix stays in the
+    # normalised space (Q11); columns of [[1, .5], [.125, 1]]
+    h = RefHomography("auto")
+    assert h.getTransformationMatrixAsCSS([[0, 0], [0, 1], [1, 0]], [[0, 0], [1 / 2, 1], [1, 1 / 8]], 300.0, 150.0) == \
+        "matrix(1.00000, 0.12500, 0.50000, 1.00000, 0.00000, 0.00000)"
+    # identity projective: the 4x4 identity with toFixed(5) on the eight solved entries
+    h = RefHomography("projective")
+    sq = [[0, 0], [0, 1], [1, 0], [1, 1]]
+    h.setSourcePoints(sq)
+    h.setDestinyPoints([list(p) for p in sq])
+    assert h.getTransformationMatrixAsCSS() == \
+        "matrix3d(1.00000, 0.00000, 0, 0.00000, 0.00000, 1.00000, 0, 0.00000, 0, 0, 1, 0, 0.00000, 0.00000, 0, 1)"
+    # test/test.js:383-425 (testCSS2): cells are h0 h3 0 h6 | h1 h4 0 h7 | 0 0 1 0 | h2 h5 0 1
+    h = RefHomography("projective")
+    h.setSourcePoints(sq)
+    h.setDestinyPoints([[0, 0], [0, 1], [1, 0.1], [1, 1]])
+    css = h.getTransformationMatrixAsCSS()
+    m = h._transformMatrix
+    cells = css[len("matrix3d("):-1].split(", ")
+    assert len(cells) == 16 and [cells[i] for i in (2, 6, 8, 9, 10, 11, 14, 15)] == ["0", "0", "0", "0", "1", "0", "0", "1"]
+    for cell, k in zip([cells[i] for i in (0, 1, 3, 4, 5, 7, 12, 13)], (0, 3, 6, 1, 4, 7, 2, 5)):
+        assert abs(float(cell) - m[k]) <= 0.5e-5 + 1e-12
+    # piecewise has no CSS form; missing points raise the reference's texts
+    with pytest.raises(ValueError, match="srcPoints are not set"):
+        RefHomography("affine").getTransformationMatrixAsCSS()
+    h = RefHomography("piecewiseaffine")
+    with pytest.raises(ValueError, match="Only \"affine\" or \"projective\""):
+        h.setSourcePoints([[0, 0], [0, 1], [1, 0], [1, 1], [0.5, 0.5]], None, 10, 10)
+        h._dstPoints = h._srcPoints.copy()
+        h._transformMatrix = np.zeros(6, np.float32)
+        h.getTransformationMatrixAsCSS()
