@@ -229,6 +229,95 @@ def run_piecewise(args, which):
     ctx.close()
 
 
+def run_secondary(args, which):
+    """Secondary bench lines for the remaining pixel kernels (not the headline), 1 GPU, device-resident rings > L2:
+       affine_forward       _geometricWarp (H.js:911): 1080p translation by (100, 50) — the case warp() dispatches to the
+                            forward loop (oW == W, oH == H) — one hg_warp_forward_matrix per frame = winner-plane
+                            memset + forward_scatter_kernel + forward_gather_kernel
+       projective_bilinear  config 2 through the bilinear extension (warp_inverse_geo_bilinear_kernel), one batched
+                            launch per step; gate: <= 1 LSB per channel against the oracle's f64 definition"""
+    import torch
+    import homography_js_b200 as hg
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = hg.Context(0)
+    from oracle import oracle as O
+    O.build()
+    F = args.frames
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    peak, peak_src = measured_peak_gbs()
+    if which == "affine_forward":
+        W, H, xo, yo = 1920, 1080, 100, 50
+        oW, oH = W, H
+        src_pts = np.array([0, 0, 0, H, W, 0], np.float64)
+        fwd = ctx.solve_affine(src_pts, src_pts + np.array([xo, yo] * 3, np.float64))   # [1,0,0,1,100,50] (test.js:167-192 shape)
+        src_ring = torch.randint(0, 256, (F, H * W * 4), dtype=torch.uint8, device=dev, generator=g)
+        out_ring = torch.zeros((F, oW * oH * 4), dtype=torch.uint8, device=dev)
+
+        def step():
+            for f in range(F):
+                ctx.image_set_device(src_ring[f].data_ptr(), W, H)
+                ctx.warp_forward_matrix(fwd, xo, yo, oW, oH, to_host=False, out_dev=out_ring[f].data_ptr())
+
+        torch.cuda.synchronize()   # the rings were filled on torch's stream; the context has its own
+        step()
+        ctx.synchronize()
+        want = O.warp_forward_geometric(src_ring[0].cpu().numpy(), W, H, fwd, xo, yo, oW, oH)
+        parity = bool(np.array_equal(out_ring[0].cpu().numpy(), want))
+        name = "affine forward scatter (translation), 1920x1080 RGBA8 -> 1920x1080"
+        kernel = "forward_gather_kernel (timed); whole step = memset + forward_scatter_kernel + forward_gather_kernel"
+    else:
+        wl = hg.workloads.projective_1080p()
+        W, H, oW, oH = wl["W"], wl["H"], wl["o_w"], wl["o_h"]
+        inv = ctx.solve_projective(wl["dst"], wl["src"])
+        src_ring = torch.randint(0, 256, (F, H * W * 4), dtype=torch.uint8, device=dev, generator=g)
+        out_ring = torch.zeros((F, oW * oH * 4), dtype=torch.uint8, device=dev)
+        mats = np.tile(inv, (F, 1))
+        frames = [hg.HgFrame(src_ring[f].data_ptr(), out_ring[f].data_ptr(), W, H, wl["x_off"], wl["y_off"], oW, oH) for f in range(F)]
+        ctx.set_sampling(hg._abi.HG_BILINEAR)
+
+        def step():
+            ctx.warp_inverse_batch(1, mats, frames)
+
+        torch.cuda.synchronize()
+        step()
+        ctx.synchronize()
+        want = O.warp_inverse_geometric_bilinear(src_ring[0].cpu().numpy(), W, H, O.projective_from_squares(wl["dst"], wl["src"]),
+                                                 wl["x_off"], wl["y_off"], oW, oH, threads=os.cpu_count() or 1)
+        got = out_ring[0].cpu().numpy()
+        parity = bool(np.abs(got.astype(np.int16) - want.astype(np.int16)).max() <= 1)
+        name = "projective 4-point warp, BILINEAR sampling (extension), 1920x1080 RGBA8 -> 1728x1080"
+        kernel = "warp_inverse_geo_bilinear_kernel<projective>"
+    if not parity:
+        raise SystemExit("parity gate failed: CUDA output differs from the oracle")
+    for _ in range(args.warmup):
+        step()
+    ctx.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ctx.profile_enable(True)
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop()
+    sampler.sample_once()
+    sampler.stop()
+    kms, kn = ctx.profile_read()
+    ctx.profile_enable(False)
+    npix = F * oW * oH
+    val = npix * args.steps / (ms * 1e-3) / 1e6
+    print(json.dumps({"metric": "Mpix/s warped", "value": val, "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms / args.steps, "workload": name, "frames_per_step": F, "parity_gate": parity,
+                      "l2": f"ring of {F} distinct sources + {F} distinct outputs ({(src_ring.numel() + out_ring.numel()) / 1e6:.0f} MB) > 126 MB L2",
+                      "timed_kernel": kernel, "timed_kernel_ms_per_step": kms / args.steps, "timed_kernels": kn,
+                      "roofline_frac_timed_kernel": ALG_BYTES_PER_PIXEL * npix / (kms / args.steps * 1e-3) / 1e9 / peak,
+                      "roofline_frac_whole_step": ALG_BYTES_PER_PIXEL * npix / (ms / args.steps * 1e-3) / 1e9 / peak,
+                      "peak_source": peak_src, "gpu_launches": int(ctx.launch_count() - l0), "clocks": sampler.summary()}), flush=True)
+    ctx.close()
+
+
 def run_video5(args):
     """Secondary line: BASELINE config 5 — video stream, 1920x1080, 30-point piecewise mesh, per-frame destiny points
     (a different output window every frame), ONE source image shared by all GPUs: rank 0 owns it and it is broadcast
@@ -332,7 +421,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="projective", choices=["projective", "affine", "projective_generic", "affine_rot90", "piecewise3", "piecewise4", "video5"],
+    ap.add_argument("--workload", default="projective", choices=["projective", "affine", "projective_generic", "affine_rot90", "piecewise3", "piecewise4", "video5",
+                             "affine_forward", "projective_bilinear"],
                     help="projective = BASELINE config 2 (the headline); affine = same sizes through the affine kernel")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -346,6 +436,9 @@ def main():
         return
     if args.workload.startswith("piecewise"):
         run_piecewise(args, args.workload)
+        return
+    if args.workload in ("affine_forward", "projective_bilinear"):
+        run_secondary(args, args.workload)
         return
 
     rank = int(os.environ.get("RANK", "0"))

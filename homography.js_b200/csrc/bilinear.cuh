@@ -27,11 +27,10 @@ __device__ __forceinline__ uint32_t bilerp_px(uint32_t p00, uint32_t p10, uint32
     return out;
 }
 
+// the frame's inverse matrix: per-frame device array (batches) or by value (floats widened to double)
 template <int KIND>
-__global__ void __launch_bounds__(256) warp_inverse_geo_bilinear_kernel(const GeoParams P)
+__device__ __forceinline__ void bilinear_load_matrix(const GeoParams &P, double (&m)[8])
 {
-    const GeoFrame F = P.many ? P.many[blockIdx.y] : P.one;
-    double m[8];
     if (P.mats_dev) {
         if (KIND == 0) {
             const float *mf = (const float *)P.mats_dev + 6 * (size_t)blockIdx.y;
@@ -47,6 +46,13 @@ __global__ void __launch_bounds__(256) warp_inverse_geo_bilinear_kernel(const Ge
 #pragma unroll
         for (int k = 0; k < 8; ++k) m[k] = P.mat_val[k];
     }
+}
+
+// first-generation pixel loop: every pixel on its own (64-bit flat index -> row / column, the reference's arithmetic with
+// IEEE divisions, I2F / F2I conversions).  Still the path of outputs narrower than four pixels in the second generation.
+template <int KIND>
+__device__ __forceinline__ void bilinear_v1_body(const GeoFrame &F, const double (&m)[8])
+{
     const long long npix = (long long)F.oW * F.oH;
     const long long nquad = (npix + 3) >> 2;
     const unsigned W = (unsigned)F.W, H = (unsigned)F.H;
@@ -90,6 +96,156 @@ __global__ void __launch_bounds__(256) warp_inverse_geo_bilinear_kernel(const Ge
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (p0 + k < npix) F.out[p0 + k] = px[k];
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) warp_inverse_geo_bilinear_kernel(const GeoParams P)
+{
+    const GeoFrame F = P.many ? P.many[blockIdx.y] : P.one;
+    double m[8];
+    bilinear_load_matrix<KIND>(P, m);
+    bilinear_v1_body<KIND>(F, m);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Second-generation kernel (the default; HG_BILINEAR_V1=1 selects the one above).  Same definition, same <= 1 LSB
+// bound, about half the instructions per pixel:
+//   * one 32-bit division per QUAD (flat quad -> row, column) instead of a 64-bit one per pixel; a quad that runs over
+//     the end of a row (oW % 4 != 0) switches to the next row's terms per pixel;
+//   * projective frames that pass geo_fast_mode (denominator of one sign and moderate size over the window) take the
+//     reciprocal from MUFU.RCP64H + one Newton step (2^-39.9 relative) and one fma per coordinate with per-row constants:
+//     |error| < 2^-21.9 pixel, far below anything a weight can show in 8 bits.  The only decision that must stay exact
+//     is the window test of H.js:1001 at 0 and W (H): a coordinate within 2^-20 of one of those integers is recomputed
+//     with the reference's own arithmetic (IEEE division), in place — such pixels lie on the image's border curve only;
+//     an interior floor() that lands one pixel off at an integer coordinate moves a weight of < 2^-20 between two
+//     neighbours and cannot change a byte beyond the rounding tie the tolerance already covers;
+//   * bytes become floats through PRMT (byte -> mantissa of 2^23 + byte, exact; differences of two such values are the
+//     exact byte differences, so only the two lerp bases are un-biased), and floats become bytes through the
+//     round-to-nearest-even of one more add (v + 1.5 * 2^23 leaves round(v) in the low byte): no I2F / F2I, no clamps
+//     (a convex combination of bytes stays in [0, 255]).
+__device__ __forceinline__ uint32_t bilerp_px2(uint32_t p00, uint32_t p10, uint32_t p01, uint32_t p11, float fx, float fy,
+                                               unsigned bias_word /* 0x4B000000 in a register: PRMT's immediate slot is the selector's */)
+{
+    const float BIAS = 8388608.0f;         // 2^23
+    const float ROUND = 12582912.0f;       // 1.5 * 2^23: ulp = 1, the add rounds half to even like a Uint8ClampedArray store
+    float r[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const unsigned sel = 0x7440u | (unsigned)c;  // out = { 0x4B, 0x00, 0x00, byte c of the pixel }
+        const float a = __uint_as_float(__byte_perm(p00, bias_word, sel));
+        const float b = __uint_as_float(__byte_perm(p10, bias_word, sel));
+        const float d = __uint_as_float(__byte_perm(p01, bias_word, sel));
+        const float e = __uint_as_float(__byte_perm(p11, bias_word, sel));
+        const float top = fmaf(fx, __fsub_rn(b, a), __fsub_rn(a, BIAS));
+        const float bot = fmaf(fx, __fsub_rn(e, d), __fsub_rn(d, BIAS));
+        const float v = fmaf(fy, __fsub_rn(bot, top), top);
+        r[c] = __fadd_rn(v, ROUND);
+    }
+    const uint32_t lo = __byte_perm(__float_as_uint(r[0]), __float_as_uint(r[1]), 0x0040u);
+    const uint32_t hi = __byte_perm(__float_as_uint(r[2]), __float_as_uint(r[3]), 0x0040u);
+    return __byte_perm(lo, hi, 0x5410u);
+}
+
+#define HG_BIL_NEAR 4096u  // 2^-20 pixel in the 2^-32 fixed-point low word
+
+template <int KIND>
+__global__ void __launch_bounds__(256) warp_inverse_geo_bilinear2_kernel(const GeoParams P)
+{
+    const GeoFrame F = P.many ? P.many[blockIdx.y] : P.one;
+    double m[8];
+    bilinear_load_matrix<KIND>(P, m);
+    if (F.oW < 4) {  // a quad would span more than two rows: the per-pixel loop handles it
+        bilinear_v1_body<KIND>(F, m);
+        return;
+    }
+    const unsigned W = (unsigned)F.W, H = (unsigned)F.H, oW = (unsigned)F.oW;
+    const unsigned npix = (unsigned)F.oW * (unsigned)F.oH;  // < 2^31 (check_window)
+    const unsigned nquad = (npix + 3u) >> 2;
+    // the image base lives in a vector register pair (the address multiply-add then takes the immediate 4) and so does
+    // the float bias word of bilerp_px2
+    const uint32_t *src = F.src;
+    unsigned bias_word = 0x4B000000u;
+    const bool fast = (KIND == 1) && geo_fast_mode(F, m);  // CTA-uniform
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += stride) {
+        asm volatile("" : "+l"(src), "+r"(bias_word));  // opaque per iteration: they stay in vector registers
+        const unsigned p0 = q << 2;
+        const unsigned yy = p0 / oW, xx = p0 - yy * oW;
+        // the quad's row and the one after it (entered when xx + k reaches oW)
+        const double ya = (double)(F.yOff + (int)yy), yb = (double)(F.yOff + (int)yy + 1);
+        double r0a, r1a, r2a = 0.0, r0b, r1b, r2b = 0.0;
+        if (KIND == 0) {
+            r0a = __dmul_rn(m[2], ya); r1a = __dmul_rn(m[3], ya);
+            r0b = __dmul_rn(m[2], yb); r1b = __dmul_rn(m[3], yb);
+        } else {
+            r0a = __fma_rn(m[1], ya, m[2]); r1a = __fma_rn(m[4], ya, m[5]); r2a = __fma_rn(m[7], ya, 1.0);
+            r0b = __fma_rn(m[1], yb, m[2]); r1b = __fma_rn(m[4], yb, m[5]); r2b = __fma_rn(m[7], yb, 1.0);
+        }
+        unsigned i00[4], i10[4], i01[4], i11[4];
+        float fx[4], fy[4];
+        bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned xk = xx + (unsigned)k;
+            const bool wrap = xk >= oW;  // oW >= 4: a quad touches at most two rows
+            xk -= wrap ? oW : 0u;
+            const double x = (double)(F.xOff + (int)xk), y = wrap ? yb : ya;
+            const double r0 = wrap ? r0b : r0a, r1 = wrap ? r1b : r1a, r2 = wrap ? r2b : r2a;
+            double tx, ty;
+            bool exact = (KIND == 1) && !fast;
+            if (KIND == 0) {
+                tx = __dadd_rd(affine_coord_exact(m[0], x, r0, m[4]), HG_MAGIC);
+                ty = __dadd_rd(affine_coord_exact(m[1], x, r1, m[5]), HG_MAGIC);
+            } else if (fast) {
+                const double rc = rcp_newton1(__fma_rn(m[6], x, r2));
+                tx = __fma_rn(__fma_rn(m[0], x, r0), rc, HG_MAGIC);
+                ty = __fma_rn(__fma_rn(m[3], x, r1), rc, HG_MAGIC);
+                const unsigned fxi = (unsigned)__double2hiint(tx) - (unsigned)HG_HI_ZERO;
+                const unsigned fyi = (unsigned)__double2hiint(ty) - (unsigned)HG_HI_ZERO;
+                const bool near_x = ((unsigned)__double2loint(tx) + HG_BIL_NEAR) < 2u * HG_BIL_NEAR;
+                const bool near_y = ((unsigned)__double2loint(ty) + HG_BIL_NEAR) < 2u * HG_BIL_NEAR;
+                // floor in {-1, 0} or {W - 1, W}: the integer next to the coordinate is a bound of the window test
+                const bool crit_x = (fxi + 1u < 2u) | (fxi + 1u - W < 2u);
+                const bool crit_y = (fyi + 1u < 2u) | (fyi + 1u - H < 2u);
+                exact = (near_x & crit_x) | (near_y & crit_y);
+            }
+            if (KIND == 1 && exact) {
+                // the reference's own arithmetic (H.js:1401-1404): unfused sums, IEEE divisions
+                const double nxe = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), m[2]);
+                const double nye = __dadd_rn(__dadd_rn(__dmul_rn(m[3], x), __dmul_rn(m[4], y)), m[5]);
+                const double dne = __dadd_rn(__dadd_rn(__dmul_rn(m[6], x), __dmul_rn(m[7], y)), 1.0);
+                tx = exact_quotient_magic(nxe, dne);
+                ty = exact_quotient_magic(nye, dne);
+            }
+            const unsigned ux = (unsigned)__double2hiint(tx) - (unsigned)HG_HI_ZERO;
+            const unsigned uy = (unsigned)__double2hiint(ty) - (unsigned)HG_HI_ZERO;
+            ok[k] = (ux < W) & (uy < H) & (p0 + (unsigned)k < npix);
+            fx[k] = (float)((unsigned)__double2loint(tx)) * 2.3283064365386963e-10f;  // * 2^-32
+            fy[k] = (float)((unsigned)__double2loint(ty)) * 2.3283064365386963e-10f;
+            const unsigned x1 = min(ux + 1u, W - 1u), y1 = min(uy + 1u, H - 1u);
+            const unsigned row0 = uy * W, row1 = y1 * W;
+            i00[k] = row0 + ux; i10[k] = row0 + x1; i01[k] = row1 + ux; i11[k] = row1 + x1;
+        }
+        uint32_t a[4], b[4], d[4], e[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[k] = b[k] = d[k] = e[k] = 0u;
+            if (ok[k]) {
+                a[k] = __ldg(src + i00[k]); b[k] = __ldg(src + i10[k]);
+                d[k] = __ldg(src + i01[k]); e[k] = __ldg(src + i11[k]);
+            }
+        }
+        uint32_t px[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) px[k] = bilerp_px2(a[k], b[k], d[k], e[k], fx[k], fy[k], bias_word);  // four zero pixels blend to zero
+        if (p0 + 3u < npix) {
+            *reinterpret_cast<uint4 *>(F.out + p0) = make_uint4(px[0], px[1], px[2], px[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (p0 + (unsigned)k < npix) F.out[p0 + k] = px[k];
         }
     }
 }

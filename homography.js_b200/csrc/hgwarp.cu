@@ -351,8 +351,13 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
         if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
         dim3 g2((unsigned)blocks, (unsigned)n_frames);
         TRY(prof_begin(c));
-        if (kind == HG_AFFINE) warp_inverse_geo_bilinear_kernel<0><<<g2, 256, 0, stream>>>(P);
-        else warp_inverse_geo_bilinear_kernel<1><<<g2, 256, 0, stream>>>(P);
+        if (getenv("HG_BILINEAR_V1")) {  // first-generation kernel, kept for A/B runs
+            if (kind == HG_AFFINE) warp_inverse_geo_bilinear_kernel<0><<<g2, 256, 0, stream>>>(P);
+            else warp_inverse_geo_bilinear_kernel<1><<<g2, 256, 0, stream>>>(P);
+        } else {
+            if (kind == HG_AFFINE) warp_inverse_geo_bilinear2_kernel<0><<<g2, 256, 0, stream>>>(P);
+            else warp_inverse_geo_bilinear2_kernel<1><<<g2, 256, 0, stream>>>(P);
+        }
         c->launches++;
         CU(c, cudaGetLastError());
         TRY(prof_end(c));

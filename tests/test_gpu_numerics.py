@@ -139,3 +139,90 @@ def test_division_free_exact_decision_against_rational_arithmetic(ctx):
     bad = np.nonzero(got != want)[0]
     assert bad.size == 0, [(Ns[i], Ds[i], bs[i], bool(got[i]), bool(want[i])) for i in bad[:5]]
     assert want.sum() > 1000 and (~want).sum() > 1000
+
+
+def _bilinear_check(ctx, img, W, H, inv, window, max_mismatch=0.02):
+    got = ctx.warp_inverse_matrix(inv, *window).astype(np.int16)
+    want = O.warp_inverse_geometric_bilinear(img, W, H, inv, *window).astype(np.int16)
+    diff = np.abs(got - want)
+    assert diff.max() <= 1, (diff.max(), int((diff > 1).sum()))
+    if diff.size >= 4000:   # rounding ties are rare, not impossible: only a statistic over many values means something
+        assert (diff > 0).mean() <= max_mismatch
+    return want
+
+
+def test_bilinear_window_bounds_stay_exact_under_the_fast_reciprocal(ctx):
+    """Second-generation bilinear kernel: projective frames take the reciprocal from MUFU + one Newton step; the window test
+    of H.js:1001 must still be the reference's.  Matrices built so that the quotient is mathematically W (or H) for EVERY
+    pixel — numerator = W * denominator up to rounding — which puts the reference's RN(N / D) on either side of the bound
+    pixel by pixel: one wrong decision shows as a whole transparent / opaque pixel, far more than 1 LSB."""
+    rng = np.random.default_rng(4242)
+    W, H = 180, 130
+    img = rng.integers(1, 256, (H, W, 4), dtype=np.uint8)   # no zero bytes: transparent vs sampled always differs
+    ctx.image_set(img, W, H)
+    ctx.set_sampling(hg._abi.HG_BILINEAR)
+    try:
+        seen_in = seen_out = 0
+        for h6, h7 in ((1e-3, 2e-3), (-7e-4, 1.3e-3), (3.3e-3, -1e-3), (1 / 1024, 1 / 2048)):
+            for bound_on in ("x", "y"):
+                if bound_on == "x":
+                    inv = np.array([W * h6, W * h7, float(W), 0.37 * h6, 1.0 + 0.37 * h7, 2.37, h6, h7])
+                else:
+                    inv = np.array([1.0 + 0.61 * h6, 0.61 * h7, 3.61, H * h6, H * h7, float(H), h6, h7])
+                want = _bilinear_check(ctx, img, W, H, inv, (-5, -4, 150, 100), max_mismatch=0.05)
+                opaque = (want.reshape(-1, 4)[:, 3] != 0).mean()
+                seen_in += opaque > 0
+                seen_out += opaque < 1
+                # the same with the quotient sitting on 0 from both sides: numerators of a few ulp
+                tiny = np.array([1e-17, -2e-17, 1e-16, 0.0, 1.0, 2.0, h6, h7]) if bound_on == "x" else \
+                    np.array([1.0, 0.0, 3.0, -1e-17, 3e-17, -1e-16, h6, h7])
+                _bilinear_check(ctx, img, W, H, tiny, (-5, -4, 150, 100), max_mismatch=0.05)
+        assert seen_in and seen_out   # both sides of the bound actually occurred
+    finally:
+        ctx.set_sampling(hg._abi.HG_NEAREST)
+
+
+@pytest.mark.parametrize("kind", ["affine", "projective"])
+def test_bilinear_narrow_and_odd_output_widths(ctx, kind):
+    """Flat quads run over row ends when oW % 4 != 0, and span several rows when oW < 4."""
+    rng = np.random.default_rng(99)
+    W, H = 64, 48
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    ctx.image_set(img, W, H)
+    ctx.set_sampling(hg._abi.HG_BILINEAR)
+    try:
+        for o_w in (1, 2, 3, 4, 5, 6, 7, 9, 13, 66):
+            for o_h in (1, 3, 50):
+                if kind == "affine":
+                    inv = np.array([0.83, 0.11, -0.07, 0.91, 1.3, 0.6], np.float32)
+                else:
+                    inv = np.array([0.83, -0.07, 1.3, 0.11, 0.91, 0.6, 1.5e-3, -0.8e-3])
+                _bilinear_check(ctx, img, W, H, inv, (-2, -1, o_w, o_h), max_mismatch=0.05)
+    finally:
+        ctx.set_sampling(hg._abi.HG_NEAREST)
+
+
+def test_bilinear_batch_with_mixed_frame_sizes(ctx):
+    """hg_warp_inverse_batch under HG_BILINEAR: frames of different sizes (one narrower than a quad) in one launch."""
+    import torch
+    rng = np.random.default_rng(7)
+    W, H = 96, 70
+    dev = torch.device("cuda", 0)
+    imgs = [rng.integers(0, 256, (H, W, 4), dtype=np.uint8) for _ in range(3)]
+    windows = [(-3, -2, 120, 80), (0, 0, 3, 40), (5, 7, 57, 33)]
+    mats = np.stack([O.projective_from_squares(np.array([0, 0, 0, H, W, 0, W, H], np.float64) + rng.uniform(-6, 6, 8),
+                                               np.array([0, 0, 0, H, W, 0, W, H], np.float64)) for _ in range(3)])
+    srcs = [torch.from_numpy(i.reshape(-1).copy()).to(dev) for i in imgs]
+    outs = [torch.zeros(w[2] * w[3] * 4, dtype=torch.uint8, device=dev) for w in windows]
+    torch.cuda.synchronize()
+    frames = [hg.HgFrame(s.data_ptr(), o.data_ptr(), W, H, *w) for s, o, w in zip(srcs, outs, windows)]
+    ctx.set_sampling(hg._abi.HG_BILINEAR)
+    try:
+        ctx.warp_inverse_batch(1, mats, frames)
+        ctx.synchronize()
+    finally:
+        ctx.set_sampling(hg._abi.HG_NEAREST)
+    for img, o, w, m in zip(imgs, outs, windows, mats):
+        want = O.warp_inverse_geometric_bilinear(img, W, H, m, *w).astype(np.int16)
+        diff = np.abs(o.cpu().numpy().astype(np.int16) - want)
+        assert diff.max() <= 1
