@@ -288,7 +288,7 @@ def run_secondary(args, which):
         got = out_ring[0].cpu().numpy()
         parity = bool(np.abs(got.astype(np.int16) - want.astype(np.int16)).max() <= 1)
         name = "projective 4-point warp, BILINEAR sampling (extension), 1920x1080 RGBA8 -> 1728x1080"
-        kernel = "warp_inverse_geo_bilinear_kernel<projective>"
+        kernel = "warp_inverse_geo_bilinear2_kernel<projective>"
     if not parity:
         raise SystemExit("parity gate failed: CUDA output differs from the oracle")
     for _ in range(args.warmup):

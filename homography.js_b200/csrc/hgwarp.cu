@@ -348,6 +348,11 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
     if (c->sampling == HG_BILINEAR) {
         const long long nq = ((long long)max_ow * max_oh + 3) / 4;
         long long blocks = (nq + 255) / 256;
+        // several quads per thread amortise the per-thread set-up (frame and matrix loads, geo_fast_mode) as long as the
+        // grid still fills the machine several times over
+        int qpt = 4;
+        while (qpt > 1 && (blocks / qpt) * n_frames < (long long)c->sm_count * 8) qpt >>= 1;
+        blocks = (blocks + qpt - 1) / qpt;
         if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
         dim3 g2((unsigned)blocks, (unsigned)n_frames);
         TRY(prof_begin(c));

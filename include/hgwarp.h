@@ -26,6 +26,8 @@
  *                       kernel on every workload measured); HG_GEO_BOX_BYTES / HG_GEO_STAGES / HG_GEO_CTAS /
  *                       HG_GEO_NITER size its shared-memory ring, HG_GEO_VERBOSE=1 prints the chosen configuration,
  *                       HG_GEO_DEBUG=1 traces every ring entry.
+ *   HG_GEO_NO_TALL=1    keep the default thread layout for quarter-turn maps (A/B runs).
+ *   HG_BILINEAR_V1=1    HG_BILINEAR warps run the first-generation per-pixel kernel (A/B runs).
  * Supported ranges (anything else returns HG_ERR_UNSUPPORTED, never a wrong image):
  *   1 <= W,H,oW,oH <= 65536, W*H and oW*oH < 2^31, |xOff|,|yOff|,|minSrc*| <= 2^18.
  */
