@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <new>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -921,12 +922,18 @@ int hg_delaunay(const double *points, int n_points, uint32_t *triangles_out, int
     if (!points || !n_triangles || n_points < 0 || capacity_triangles < 0 || (capacity_triangles > 0 && !triangles_out))
         return HG_ERR_INVALID;
     *n_triangles = 0;
-    const std::vector<uint32_t> t = hg_delaunay_detail::triangulate(points, (size_t)n_points);
-    const size_t nt = t.size() / 3;
-    if (nt > (size_t)capacity_triangles) return HG_ERR_INVALID;
-    if (nt) memcpy(triangles_out, t.data(), t.size() * sizeof(uint32_t));
-    *n_triangles = (int)nt;
-    return HG_OK;
+    try {  // nothing may unwind through the C ABI
+        const std::vector<uint32_t> t = hg_delaunay_detail::triangulate(points, (size_t)n_points);
+        const size_t nt = t.size() / 3;
+        if (nt > (size_t)capacity_triangles) return HG_ERR_INVALID;
+        if (nt) memcpy(triangles_out, t.data(), t.size() * sizeof(uint32_t));
+        *n_triangles = (int)nt;
+        return HG_OK;
+    } catch (const std::bad_alloc &) {
+        return HG_ERR_NOMEM;
+    } catch (...) {
+        return HG_ERR_INVALID;
+    }
 }
 
 /* ------------------------------------------------------------------ image files */
@@ -934,30 +941,43 @@ int hg_png_decode(const uint8_t *png, size_t png_bytes, uint8_t *rgba_out, size_
 {
     if (!png || !w || !h) return HG_ERR_INVALID;
     *w = *h = 0;
-    hg_png_detail::Header hd;
-    if (hg_png_detail::decode(png, png_bytes, hd, nullptr)) return HG_ERR_INVALID;  // header + chunk CRCs
-    *w = (int)hd.w;
-    *h = (int)hd.h;
-    if (!rgba_out) return HG_OK;
-    if (capacity_bytes < (size_t)hd.w * hd.h * 4) return HG_ERR_INVALID;
-    return hg_png_detail::decode(png, png_bytes, hd, rgba_out) ? HG_ERR_INVALID : HG_OK;
+    try {  // the bytes are untrusted: nothing may unwind through the C ABI
+        hg_png_detail::Header hd;
+        if (hg_png_detail::decode(png, png_bytes, hd, nullptr)) return HG_ERR_INVALID;  // header + chunk CRCs
+        *w = (int)hd.w;
+        *h = (int)hd.h;
+        if (!rgba_out) return HG_OK;
+        if (capacity_bytes < (size_t)hd.w * hd.h * 4) return HG_ERR_INVALID;
+        return hg_png_detail::decode(png, png_bytes, hd, rgba_out) ? HG_ERR_INVALID : HG_OK;
+    } catch (const std::bad_alloc &) {
+        return HG_ERR_NOMEM;
+    } catch (...) {
+        return HG_ERR_INVALID;
+    }
 }
 
 size_t hg_png_encode_bound(int w, int h)
 {
     if (w < 1 || h < 1) return 0;
-    return 8 + 25 + 12 + 12 + (size_t)compressBound((uLong)(((size_t)w * 4 + 1) * (size_t)h));
+    const size_t z = (size_t)compressBound((uLong)(((size_t)w * 4 + 1) * (size_t)h));
+    return 8 + 25 + 12 + z + 12 * (z >> 30) + 12;  // signature, IHDR, IDAT chunk(s) of <= 2^30 bytes, IEND
 }
 
 int hg_png_encode(const uint8_t *rgba, int w, int h, uint8_t *png_out, size_t capacity_bytes, size_t *png_bytes)
 {
     if (!rgba || !png_out || !png_bytes || w < 1 || h < 1 || w > 65536 || h > 65536) return HG_ERR_INVALID;
-    std::vector<uint8_t> out;
-    if (hg_png_detail::encode(rgba, (uint32_t)w, (uint32_t)h, out)) return HG_ERR_INVALID;
-    if (out.size() > capacity_bytes) return HG_ERR_INVALID;
-    memcpy(png_out, out.data(), out.size());
-    *png_bytes = out.size();
-    return HG_OK;
+    try {
+        std::vector<uint8_t> out;
+        if (hg_png_detail::encode(rgba, (uint32_t)w, (uint32_t)h, out)) return HG_ERR_INVALID;
+        if (out.size() > capacity_bytes) return HG_ERR_INVALID;
+        memcpy(png_out, out.data(), out.size());
+        *png_bytes = out.size();
+        return HG_OK;
+    } catch (const std::bad_alloc &) {
+        return HG_ERR_NOMEM;
+    } catch (...) {
+        return HG_ERR_INVALID;
+    }
 }
 
 /* ------------------------------------------------------------------ piecewise */

@@ -100,6 +100,9 @@ inline int decode(const uint8_t *png, size_t n, Header &hd, uint8_t *rgba)
         const size_t pw = (hd.w + passes[p][2] - 1 - passes[p][0]) / passes[p][2], ph = (hd.h + passes[p][3] - 1 - passes[p][1]) / passes[p][3];
         if (pw && ph) total += (((size_t)pw * bpp_bits + 7) / 8 + 1) * ph;
     }
+    // deflate cannot expand beyond ~1032 : 1: a header that promises more than the IDAT bytes can hold is malformed —
+    // reject it before allocating what it asks for (a 65536 x 65536 header in a 100-byte file)
+    if (total / 1040 > idat.size() + 1) return 1;
     std::vector<uint8_t> raw(total);
     uLongf out_len = (uLongf)raw.size();
     if (uncompress(raw.data(), &out_len, idat.data(), (uLong)idat.size()) != Z_OK || out_len != raw.size()) return 1;
@@ -236,7 +239,14 @@ inline int encode(const uint8_t *rgba, uint32_t w, uint32_t h, std::vector<uint8
     uLongf zlen = compressBound((uLong)raw.size());
     std::vector<uint8_t> z(zlen);
     if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return 1;
-    chunk(out, "IDAT", z.data(), zlen);
+    // a chunk length is a 31-bit field: large images leave as several IDAT chunks
+    const size_t piece = (size_t)1 << 30;
+    size_t at = 0;
+    do {
+        const size_t len = (size_t)zlen - at < piece ? (size_t)zlen - at : piece;
+        chunk(out, "IDAT", z.data() + at, len);
+        at += len;
+    } while (at < (size_t)zlen);
     chunk(out, "IEND", nullptr, 0);
     return 0;
 }
