@@ -114,3 +114,26 @@ def test_medium_mesh_matches_python_restatement():
     rng = np.random.default_rng(13)
     pts = rng.uniform(0, 4000, (2500, 2)).astype(np.float32).astype(np.float64)
     assert np.array_equal(_cxx(pts), _py(pts))
+
+
+def test_hostile_point_sets_under_sanitizers(tmp_path):
+    """hg_delaunay takes caller data as is: duplicates, collinear sets, 1e300, denormals, NaN and Inf run through the C++
+    under AddressSanitizer + UBSan with a time limit (no out-of-bounds access, no endless hull walk)."""
+    import os
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    exe = tmp_path / "delaunay_fuzz"
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    build = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fsanitize=address,undefined",
+                            "-fno-sanitize-recover=all", os.path.join(ROOT, "tests", "delaunay_fuzz_harness.cpp"), "-o", str(exe)],
+                           capture_output=True, text=True, env=env)
+    if build.returncode != 0 and "sanitize" in build.stderr:
+        pytest.skip("sanitizer runtime not available")
+    assert build.returncode == 0, build.stderr[-3000:]
+    run = subprocess.run([str(exe), "1500"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, (run.stdout[-500:], run.stderr[-3000:])
+    assert run.stdout.startswith("triangles ")
