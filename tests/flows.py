@@ -185,3 +185,14 @@ def random_ones(mk):
 
 
 CSS = [css1, css2, bench_affine, bench_projective, random_ones]
+
+
+# ------------------------------------------------------------------ BASELINE.json config 1: affine 3-point, 256 x 256
+def config1(mk, mk_image):
+    """image = default_rng(1) bytes; src [[0,0],[0,256],[256,0]] -> dst [[0,128],[128,204.8],[128,0]] (benchmark.js:204-205
+    shape): pixel-range points, output size != input size -> the inverse loop."""
+    w = h = 256
+    data = np.random.default_rng(1).integers(0, 256, (h, w, 4), dtype=np.uint8).reshape(-1)
+    hm = mk("affine")
+    hm.setReferencePoints([[0, 0], [0, h], [w, 0]], [[0, h / 2], [w / 2, h * 0.8], [w / 2, 0]])
+    return [hm.warp(mk_image(data.copy(), w, h))], hm

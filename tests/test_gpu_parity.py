@@ -328,6 +328,15 @@ def test_reference_test_page_flows_over_cuda(ctx, flow, golden):
         assert _diff(g.data, r.data) == 0
 
 
+def test_config1_affine_256_over_cuda(ctx):
+    """BASELINE.json configs[0] (affine 3-point warp, 256 x 256) through the class surface over CUDA."""
+    ref_res, ref = flows.config1(lambda *a: RefHomography(*a), RefImageData)
+    got_res, got = flows.config1(lambda *a: hg.Homography(*a, context=ctx), hg.ImageData)
+    assert got.last_path == ref.last_path == "inverse_geometric"
+    assert (got_res[0].width, got_res[0].height) == (ref_res[0].width, ref_res[0].height) == (256, 205)
+    assert _diff(got_res[0].data, ref_res[0].data) == 0
+
+
 @pytest.mark.parametrize("flow", flows.CSS, ids=lambda f: f.__name__)
 def test_css_matrix_strings_over_cuda(ctx, flow):
     """getTransformationMatrixAsCSS (H.js:548): the device-solved matrices print the same strings as the reference's."""

@@ -124,3 +124,13 @@ def test_css_errors_and_element_form():
     el = Element()
     hg.Homography("auto", context=OracleContext()).transformHTMLElement(el, [[0, 0], [0, 1], [1, 0]], [[0, 0], [1 / 2, 1], [1, 1 / 8]])
     assert el.style.transform == "matrix(1.00000, 0.12500, 0.50000, 1.00000, 0.00000, 0.00000)"
+
+
+def test_config1_affine_256_plumbing():
+    """BASELINE.json configs[0]: the class surface end to end on the CPU (engine calls answered by the oracle)."""
+    ref_res, ref = flows.config1(lambda *a: RefHomography(*a), RefImageData)
+    got_res, got = flows.config1(lambda *a: hg.Homography(*a, context=OracleContext()), hg.ImageData)
+    assert got.last_path == ref.last_path == "inverse_geometric"
+    assert (got_res[0].width, got_res[0].height) == (ref_res[0].width, ref_res[0].height) == (256, 205)
+    assert np.array_equal(got_res[0].data, ref_res[0].data)
+    assert ref_res[0].data.reshape(-1, 4)[:, 3].any()   # not an empty image
