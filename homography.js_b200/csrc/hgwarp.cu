@@ -85,6 +85,9 @@ struct hg_ctx {
     int geo_niter_staged = 2;       // row groups (16 rows) per tile of the staged kernel (HG_GEO_NITER)
     int geo_stages = 3;             // ring depth per CTA (HG_GEO_STAGES)
     int geo_ctas_per_sm = 5;        // persistent CTAs per SM (HG_GEO_CTAS; bounded by registers / shared memory)
+    int geo_debug = 0;              // HG_GEO_DEBUG: the staged kernel's producer traces its ring
+    bool no_tall = false;           // HG_GEO_NO_TALL: never pick the tall thread layout (A/B runs)
+    bool bilinear_v1 = false;       // HG_BILINEAR_V1: first-generation bilinear kernel (A/B runs)
     CUtensorMap img_tm[GEO_NBOX];
     bool img_tm_ok = false;
     DevBuf tm_dev;                   // TM_CACHE_SLOTS x GEO_NBOX tensor maps
@@ -308,7 +311,6 @@ int pick_niter(hg_ctx *c, int max_ow, int max_oh, int n_frames, int ltx = 4)
 // source coordinates along output x at the centre of the window.
 bool map_is_rotated(int kind, const double *m, int x_off, int y_off, int o_w, int o_h)
 {
-    if (getenv("HG_GEO_NO_TALL")) return false;
     double dsx, dsy;
     if (kind == HG_AFFINE) {
         dsx = m[0];
@@ -340,7 +342,7 @@ bool points_map_is_rotated(const double *from, const double *to)
 int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_frames, bool staged, cudaStream_t stream,
                bool tall = false)
 {
-    P.ltx = (tall && !staged && c->sampling != HG_BILINEAR) ? 1 : 4;
+    P.ltx = (tall && !c->no_tall && !staged && c->sampling != HG_BILINEAR) ? 1 : 4;
     P.niter = staged ? c->geo_niter_staged : pick_niter(c, max_ow, max_oh, n_frames, P.ltx);
     if (staged && 32 * P.niter > GEO_QCAP) P.niter = GEO_QCAP / 32;  // per-tile exact queue: one entry per thread and row group
     P.box_bytes = staged ? c->geo_box_bytes : 0;
@@ -357,7 +359,7 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
         if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
         dim3 g2((unsigned)blocks, (unsigned)n_frames);
         TRY(prof_begin(c));
-        if (getenv("HG_BILINEAR_V1")) {  // first-generation kernel, kept for A/B runs
+        if (c->bilinear_v1) {  // first-generation kernel, kept for A/B runs
             if (kind == HG_AFFINE) warp_inverse_geo_bilinear_kernel<0><<<g2, 256, 0, stream>>>(P);
             else warp_inverse_geo_bilinear_kernel<1><<<g2, 256, 0, stream>>>(P);
         } else {
@@ -376,7 +378,7 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
         P.tiles_x = geo_tiles_x(max_ow);
         P.tiles_y = geo_tiles_y(max_oh, P.niter);
         P.n_frames = n_frames;
-        P.debug = getenv("HG_GEO_DEBUG") ? atoi(getenv("HG_GEO_DEBUG")) : 0;  // 1: trace ring entries, 2: no 32-row boxes
+        P.debug = c->geo_debug;  // 1: trace ring entries, 2: no 32-row boxes
         const long long total = (long long)P.tiles_x * P.tiles_y * n_frames;
         long long ctas = (long long)c->sm_count * c->geo_ctas_per_sm;
         if (ctas > total) ctas = total;
@@ -491,6 +493,9 @@ int hg_ctx_create(int device, hg_ctx **out)
         env_int("HG_GEO_NITER", 1, 16, c->geo_niter_staged);
         env_int("HG_GEO_STAGES", 2, GEO_MAX_STAGES, c->geo_stages);
         env_int("HG_GEO_CTAS", 1, 8, c->geo_ctas_per_sm);
+        env_int("HG_GEO_DEBUG", 0, 2, c->geo_debug);
+        c->no_tall = getenv("HG_GEO_NO_TALL") != nullptr;
+        c->bilinear_v1 = getenv("HG_BILINEAR_V1") != nullptr;
         // the ring must fit a CTA's shared memory: shrink the depth (the CTA count follows from the occupancy below)
         const size_t cta_max = prop.sharedMemPerBlockOptin;
         auto ring = [&]() { return (size_t)c->geo_stages * (size_t)(GEO_HDR_BYTES + c->geo_box_bytes); };
