@@ -455,7 +455,8 @@ int hg_ctx_create(int device, hg_ctx **out)
         cudaError_t e_ = (call);                                                                        \
         if (e_ != cudaSuccess) {                                                                        \
             fail(nullptr, HG_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                 \
-            delete c;                                                                                   \
+            cudaGetLastError();                                                                         \
+            hg_ctx_destroy(c); /* releases whatever was created so far */                               \
             return HG_ERR_CUDA;                                                                         \
         }                                                                                               \
     } while (0)

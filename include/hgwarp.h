@@ -92,7 +92,9 @@ int hg_profile_enable(hg_ctx *ctx, int on);
 int hg_profile_read(hg_ctx *ctx, double *total_ms, uint64_t *n_kernels);
 
 /* ------------------------------------------------------------------ image (this._image, H.js:298) */
-int hg_image_set(hg_ctx *ctx, const uint8_t *rgba_host, int w, int h);      /* H2D copy, stays resident */
+/* H2D copy, stays resident.  Pageable memory is staged before the call returns; a PINNED buffer is copied asynchronously on
+ * the context stream and must stay unchanged until the next call that synchronizes (a warp with out_host, hg_ctx_synchronize) */
+int hg_image_set(hg_ctx *ctx, const uint8_t *rgba_host, int w, int h);
 int hg_image_set_device(hg_ctx *ctx, const void *rgba_dev, int w, int h);   /* borrow a device buffer */
 
 /* ------------------------------------------------------------------ transform solves (one in-register kernel) */
