@@ -34,3 +34,23 @@ def test_js_shim_calls_match_addon_exports():
                  "getTransformationMatrixAsCSS", "transformHTMLElement"):
         assert re.search(r"\n  %s\(" % name, shim), name
     assert "export { Homography" in shim
+
+
+def test_js_shim_lexes_cleanly_and_brackets_balance():
+    """No JavaScript engine here: at least the shim must tokenize without error tokens (pygments' ECMAScript lexer) and its
+    brackets must balance outside strings, template literals and comments."""
+    pygments = __import__("pytest").importorskip("pygments")
+    from pygments.lexers import JavascriptLexer
+    from pygments.token import Error, Punctuation
+    src = open(os.path.join(JS, "homography_b200.mjs")).read()
+    stack, pairs = [], {")": "(", "]": "[", "}": "{"}
+    for tok, text in JavascriptLexer().get_tokens(src):
+        assert tok is not Error, repr(text)
+        if tok in Punctuation:
+            for ch in text:
+                if ch in "([{":
+                    stack.append(ch)
+                elif ch in ")]}":
+                    assert stack and stack.pop() == pairs[ch], "unbalanced " + ch
+    # template literals `${...}` are lexed as string parts with their own interpolation tokens; whatever remains must be closed
+    assert not stack, stack
