@@ -304,3 +304,126 @@ def test_css_matrix_strings_known_answers(oracle_lib):
         h._dstPoints = h._srcPoints.copy()
         h._transformMatrix = np.zeros(6, np.float32)
         h.getTransformationMatrixAsCSS()
+
+
+# ------------------------------------------------------------------ the other three loops, restated literally in Python
+def _js_round_py(v):
+    if v != v or v in (math.inf, -math.inf):
+        return v
+    return float(math.floor(v + 0.5))
+
+
+def _to_int32(v):
+    if v != v or v in (math.inf, -math.inf):
+        return 0
+    v = int(math.trunc(v)) & 0xFFFFFFFF
+    return v - (1 << 32) if v >= (1 << 31) else v
+
+
+def _shl2(v):  # JS `v << 2`
+    r = (_to_int32(v) << 2) & 0xFFFFFFFF
+    return r - (1 << 32) if r >= (1 << 31) else r
+
+
+def _typed_get(arr, i):  # typed-array read: a non-integer / out-of-range index gives undefined -> stored as 0
+    return int(arr[int(i)]) if (0 <= i < len(arr) and i == math.floor(i)) else 0
+
+
+def _typed_set(arr, i, v):  # typed-array write: silently dropped unless the index is an in-range integer
+    if 0 <= i < len(arr) and i == math.floor(i):   # NaN and +-Inf fail the range test
+        arr[int(i)] = v
+
+
+def _py_forward(flat, W, H, point_fn, xo, yo, oW, oH, domain):
+    """H.js:911-932 / 948-972: for every (x, y) of `domain` (raster order) scatter src pixel to round(T(x, y) - offset)."""
+    dst_row = _shl2(oW)
+    out = [0] * int(dst_row * oH)
+    src_row = _shl2(W)
+    for x, y in domain:
+        p = point_fn(x, y)
+        if p is None:
+            continue
+        idx = y * src_row + _shl2(x)
+        nx, ny = _js_round_py(p[0] - xo), _js_round_py(p[1] - yo)
+        nidx = ny * dst_row + _shl2(nx)
+        for c in range(4):
+            _typed_set(out, nidx + c, _typed_get(flat, idx + c))
+    return np.array(out, np.uint8)
+
+
+def test_forward_geometric_matches_python_loop_small():
+    """_geometricWarp restated as the literal double loop: collisions (last writer wins), writes wrapped into neighbouring
+    rows and dropped outside the buffer (Q3), NaN targets."""
+    rng = np.random.default_rng(5)
+    W, H = 19, 13
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    flat = img.reshape(-1)
+    dom = [(x, y) for y in range(H) for x in range(W)]
+    cases = [(np.array([1, 0, 0, 1, 3, 2], np.float32), (3, 2, W, H)),                # translation: a copy
+             (np.array([0.6, 0.1, -0.2, 0.7, 1.5, 0.5], np.float32), (0, 0, 15, 11)),  # shrink: many collisions
+             (np.array([1.3, 0, 0, 1.2, -4, -3], np.float32), (0, 0, W, H)),           # negative / overflowing columns wrap
+             (np.array([0, 1, -1, 0, 12, 0], np.float32), (0, 0, H, W)),               # quarter turn
+             (np.array([1.0, 0.02, -3.0, 0.03, 0.98, 2.0, 1e-3, -2e-3], np.float64), (-2, 1, 21, 14)),
+             (np.array([1, 0, 0, 0, 1, 0, 0, -1.0], np.float64), (0, 0, W, H))]        # denominator 0 on row y = 1: Inf / NaN
+    for m, (xo, yo, oW, oH) in cases:
+        mm = [float(v) for v in m]
+        if m.size == 6:
+            fn = lambda x, y: (mm[0] * x + mm[2] * y + mm[4], mm[1] * x + mm[3] * y + mm[5])
+        else:
+            def fn(x, y):
+                den = mm[6] * x + mm[7] * y + 1
+                with np.errstate(all="ignore"):
+                    return (float(np.float64(mm[0] * x + mm[1] * y + mm[2]) / np.float64(den)),
+                            float(np.float64(mm[3] * x + mm[4] * y + mm[5]) / np.float64(den)))
+        want = _py_forward(flat, W, H, fn, xo, yo, oW, oH, dom)
+        got = O.warp_forward_geometric(img, W, H, m, xo, yo, oW, oH)
+        assert np.array_equal(got, want), m
+
+
+def test_piecewise_loops_match_python_restatement_small():
+    """_inversePiecewiseAffineWarp (H.js:1029-1058) and _piecewiseAffineWarp (H.js:948-972) as literal Python loops over the
+    oracle's own map and matrices (both pinned separately above): window test on [minSrc, W + minSrc), Int16 ids, the flat
+    source index, reads past the image, forward collisions."""
+    rng = np.random.default_rng(8)
+    W, H = 24, 18
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    flat = img.reshape(-1)
+    src = np.array([[0, 0], [W, 0], [0, H], [W, H], [W / 2, H / 2]], np.float32)
+    tris = np.array([[0, 1, 4], [1, 3, 4], [3, 2, 4], [2, 0, 4]], np.uint32)
+    for trial in range(4):
+        dst = (src.astype(np.float64) * [1.4, 1.25] + rng.uniform(-2, 2, src.shape) + [3, 1]).astype(np.float32)
+        fwd = O.piecewise_matrices(src, dst, tris)
+        inv = O.inverse_matrices(fwd)
+        mm = O.minmax_xy(dst)
+        xo, yo, oW, oH = int(mm[0]), int(mm[1]), int(mm[2] - mm[0]), int(mm[3] - mm[1])
+        min_sx, min_sy = (0, 0) if trial % 2 == 0 else (2, 1)       # Q14: the window moves with minSrc
+        imap = O.build_index_map(dst, tris, oW, yo, oW * oH)
+        want = [0] * (oW * oH * 4)
+        for y in range(yo, yo + oH):
+            for x in range(xo, xo + oW):
+                t = int(imap[(y - yo) * oW + (x - xo)])
+                if t >= 0:
+                    m = [float(v) for v in inv[t]]
+                    sx, sy = m[0] * x + m[2] * y + m[4], m[1] * x + m[3] * y + m[5]
+                    if min_sx <= sx < W + min_sx and min_sy <= sy < H + min_sy:
+                        si = _js_round_py(sy) * (W * 4) + _js_round_py(sx) * 4
+                        di = ((y - yo) * oW + (x - xo)) * 4
+                        for c in range(4):
+                            want[di + c] = _typed_get(flat, si + c)
+        got = O.warp_inverse_piecewise(img, W, H, imap, inv, xo, yo, oW, oH, min_sx, min_sy)
+        assert np.array_equal(got, np.array(want, np.uint8)), trial
+        # forward loop over the source-point bounding box, through the forward map
+        bx0, by0, bx1, by1 = 0, 0, W, H
+        fmap = O.build_index_map(src, tris, bx1 - bx0, by0, (bx1 - bx0) * (by1 - by0))
+
+        def fn(x, y):
+            t = int(fmap[(y - by0) * (bx1 - bx0) + (x - bx0)])
+            if t <= -1:
+                return None
+            m = [float(v) for v in fwd[t]]
+            return m[0] * x + m[2] * y + m[4], m[1] * x + m[3] * y + m[5]
+
+        dom = [(x, y) for y in range(by0, by1) for x in range(bx0, bx1)]
+        want_f = _py_forward(flat, W, H, fn, xo, yo, oW, oH, dom)
+        got_f = O.warp_forward_piecewise(img, W, H, fmap, fwd, xo, yo, oW, oH, bx0, by0, bx1, by1)
+        assert np.array_equal(got_f, want_f), trial
