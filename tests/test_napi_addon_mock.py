@@ -98,3 +98,48 @@ def test_class_surface_through_the_addon_over_cuda(native_gpu, flow, golden):
     for r, g in zip(ref_res, got_res):
         assert (g.width, g.height) == (r.width, r.height)
         assert np.array_equal(g.data, r.data)
+
+
+# ------------------------------------------------------------------ the JS shim's own control flow (transliterated)
+def _shim_factory(native):
+    import js_shim_transliteration as T
+    return lambda *a: T.Homography(native, *a)
+
+
+@pytest.mark.parametrize("flow", flows.ALL, ids=lambda f: f.__name__)
+def test_js_shim_control_flow_through_the_addon_cpu_double(native_cpu, flow, golden):
+    """js/homography_b200.mjs rendered statement by statement into Python (tests/js_shim_transliteration.py), driving the real
+    addon: the shim's call protocol (solveWithLimits for every solve, re-solve in _induceObjective, f64 / f32 conversions)
+    gives the reference's bytes for every flow of the reference's test page."""
+    ref_res, ref = flow(lambda *a: RefHomography(*a), RefImageData(golden["src"].reshape(-1).copy(), 400, 400))
+    got_res, got = flow(_shim_factory(native_cpu), hg.ImageData(golden["src"].reshape(-1).copy(), 400, 400))
+    assert got.transform == ref.transform and got.last_path == ref.last_path
+    for r, g in zip(ref_res, got_res):
+        assert (g.width, g.height) == (r.width, r.height)
+        assert np.array_equal(g.data, r.data)
+    assert np.array_equal(got._srcPoints, ref._srcPoints) and np.array_equal(got._dstPoints, ref._dstPoints)
+    for name in ("_xOutputOffset", "_yOutputOffset", "_objectiveWidth", "_objectiveHeight", "_width", "_height"):
+        assert getattr(got, name) == getattr(ref, name), name
+
+
+@pytest.mark.parametrize("flow", flows.CSS, ids=lambda f: f.__name__)
+def test_js_shim_css_strings_through_the_addon_cpu_double(native_cpu, flow):
+    assert flow(_shim_factory(native_cpu)) == flow(lambda *a: RefHomography(*a))
+
+
+def test_transliteration_covers_the_shim():
+    """Every method of the .mjs class and every native.* call it makes exists in the transliteration, and vice versa."""
+    import os
+    import re
+    from conftest import ROOT
+    mjs = open(os.path.join(ROOT, "homography.js_b200", "js", "homography_b200.mjs")).read()
+    py = open(os.path.join(ROOT, "tests", "js_shim_transliteration.py")).read()
+    js_methods = set(re.findall(r"\n  (_?[A-Za-z]+)\(", mjs)) - {"constructor", "if", "for", "switch", "return"}
+    py_methods = set(re.findall(r"\n    def (_?[A-Za-z]+)\(", py)) - {"__init__"}
+    assert js_methods == py_methods, js_methods ^ py_methods
+    js_calls = set(re.findall(r"\bnative\.([A-Za-z]+)\(", mjs)) - {"pngDecode", "pngEncode"}   # module-level helpers
+    py_calls = set(re.findall(r"\bnative\.([A-Za-z]+)\(", py))
+    assert js_calls == py_calls, js_calls ^ py_calls
+    # the same reference-defined throw texts
+    for text in re.findall(r"throw \('([^'$]{30,})'\)", mjs):
+        assert text in py, text
