@@ -169,22 +169,29 @@ def run_reference(args):
 
 def run_piecewise(args, which):
     """Secondary bench lines (not the headline): BASELINE configs 3 / 4 through hg_warp_piecewise_inverse_batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import torch
+    import torch.distributed as dist
     import homography_js_b200 as hg
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
-    ctx = hg.Context(0)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:   # frames are independent: block-partitioned over ranks, NCCL only for the barrier / max / sum below
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = hg.Context(local_rank)
     w, h = 3840, 2160
     nx = ny = 10 if which == "piecewise3" else 64
-    F = args.frames if args.frames != 64 else 16
+    F = args.frames if args.frames != 64 else 16      # frames per step PER GPU (weak scaling)
     src, _, tris = hg.workloads.piecewise_sinusoid(nx, ny, w, h)
     ctx.piecewise_set_mesh(src, tris)
     g = torch.Generator(device=dev)
-    g.manual_seed(3)
+    g.manual_seed(3 + rank)
     src_ring = torch.randint(0, 256, (F, h * w * 4), dtype=torch.uint8, device=dev, generator=g)
     dsts, frames, outs, npix = [], [], [], 0
+    lo, _ = hg.workloads.shard_range(F * world, rank, world)
     for f in range(F):
-        _, dst, _ = hg.workloads.piecewise_sinusoid(nx, ny, w, h, phase=2 * np.pi * f / max(F, 1))
+        _, dst, _ = hg.workloads.piecewise_sinusoid(nx, ny, w, h, phase=2 * np.pi * (lo + f) / max(F * world, 1))
         xo, yo, oW, oH = hg.workloads.piecewise_extent(dst)
         o = torch.zeros(oW * oH * 4, dtype=torch.uint8, device=dev)
         outs.append(o)
@@ -193,6 +200,20 @@ def run_piecewise(args, which):
         npix += oW * oH
     dst_all = np.stack(dsts)
     torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(v, op):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    npix_all = reduce(npix, dist.ReduceOp.SUM)
     res = {}
     for mode in ("fused", "general"):
         ctx.debug_force_general(mode == "general")
@@ -200,6 +221,7 @@ def run_piecewise(args, which):
             ctx.warp_piecewise_inverse_batch(dst_all, frames, 0, 0)
         ctx.synchronize()
         l0 = ctx.launch_count()
+        barrier()
         ctx.profile_enable(True)
         t0 = time.perf_counter()
         ctx.timer_start()
@@ -209,23 +231,31 @@ def run_piecewise(args, which):
         wall = (time.perf_counter() - t0) * 1e3
         kms, kn = ctx.profile_read()
         ctx.profile_enable(False)
-        res[mode] = {"Mpix/s": npix * args.steps / (max(ms, wall) * 1e-3) / 1e6, "ms_per_step": max(ms, wall) / args.steps,
+        barrier()
+        step_ms = reduce(max(ms, wall), dist.ReduceOp.MAX)       # the slowest rank sets the job's time
+        res[mode] = {"Mpix/s": npix_all * args.steps / (step_ms * 1e-3) / 1e6, "ms_per_step": step_ms / args.steps,
                      "pixel_kernel_ms_per_step": kms / args.steps, "pixel_kernels": kn, "launches": ctx.launch_count() - l0}
     ctx.debug_force_general(False)
-    # parity of frame 0 against the oracle
-    from oracle import oracle as O
-    xo, yo, oW, oH = frames[0].x_off, frames[0].y_off, frames[0].o_w, frames[0].o_h
-    fwd = O.piecewise_matrices(src, dsts[0], tris)
-    imap = O.build_index_map(dsts[0], tris, oW, yo, oW * oH)
-    want = O.warp_inverse_piecewise(src_ring[0].cpu().numpy(), w, h, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, 0, 0,
-                                    threads=os.cpu_count() or 1)
-    parity = bool(np.array_equal(outs[0].cpu().numpy(), want))
-    peak, _ = measured_peak_gbs()
-    fr = res["fused"]
-    print(json.dumps({"metric": "Mpix/s warped", "workload": f"piecewiseaffine {nx}x{ny} grid ({len(tris)} tris), 3840x2160, {F} frames/step",
-                      "value": fr["Mpix/s"], "unit": "Mpix/s", "parity_gate": parity, "fused": fr, "general": res["general"],
-                      "roofline_frac_pixel_kernel": ALG_BYTES_PER_PIXEL * npix / (fr["pixel_kernel_ms_per_step"] * 1e-3) / 1e9 / peak,
-                      "roofline_frac_whole_step": ALG_BYTES_PER_PIXEL * npix / (fr["ms_per_step"] * 1e-3) / 1e9 / peak}), flush=True)
+    if rank == 0:
+        # parity of frame 0 against the oracle
+        from oracle import oracle as O
+        O.build()
+        xo, yo, oW, oH = frames[0].x_off, frames[0].y_off, frames[0].o_w, frames[0].o_h
+        fwd = O.piecewise_matrices(src, dsts[0], tris)
+        imap = O.build_index_map(dsts[0], tris, oW, yo, oW * oH)
+        want = O.warp_inverse_piecewise(src_ring[0].cpu().numpy(), w, h, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, 0, 0,
+                                        threads=os.cpu_count() or 1)
+        parity = bool(np.array_equal(outs[0].cpu().numpy(), want))
+        peak, _ = measured_peak_gbs()
+        fr = res["fused"]
+        print(json.dumps({"metric": "Mpix/s warped", "n_gpus": world, "scaling": "weak",
+                          "workload": f"piecewiseaffine {nx}x{ny} grid ({len(tris)} tris), 3840x2160, {F} frames/step per GPU, sharded over {world} GPU(s)",
+                          "value": fr["Mpix/s"], "unit": "Mpix/s", "parity_gate": parity, "fused": fr, "general": res["general"],
+                          # rank 0's pixel kernel against ONE GPU's peak; the whole job against the peak of all of them
+                          "roofline_frac_pixel_kernel": ALG_BYTES_PER_PIXEL * npix / (fr["pixel_kernel_ms_per_step"] * 1e-3) / 1e9 / peak,
+                          "roofline_frac_whole_step": ALG_BYTES_PER_PIXEL * npix_all / (fr["ms_per_step"] * 1e-3) / 1e9 / (peak * world)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
     ctx.close()
 
 
