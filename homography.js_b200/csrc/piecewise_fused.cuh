@@ -247,7 +247,6 @@ __device__ __forceinline__ void pwf_body(const FusedFrame &F, int niter, int til
     int nvalid[2];
     nvalid[0] = min(4, F.oW - xx0[0]);
     nvalid[1] = max(0, min(4, F.oW - xx0[1]));
-    const int n_tris = F.n_tris;
 
     double xs[2][4];
 #pragma unroll
