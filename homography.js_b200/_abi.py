@@ -24,7 +24,7 @@ SYMBOLS = [
     "hg_image_set", "hg_image_set_device",
     "hg_solve_affine", "hg_solve_projective", "hg_inverse_affine", "hg_transform_limits", "hg_solve_with_limits",
     "hg_warp_inverse_matrix", "hg_warp_inverse_points", "hg_warp_forward_matrix",
-    "hg_delaunay", "hg_png_decode", "hg_png_encode", "hg_png_encode_bound",
+    "hg_delaunay", "hg_png_decode", "hg_jpeg_decode", "hg_png_encode", "hg_png_encode_bound",
     "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_piecewise_extents", "hg_build_index_map",
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
@@ -111,6 +111,7 @@ def load():
     L.hg_output_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.hg_delaunay.argtypes = [vp, i, vp, i, C.POINTER(i)]
     L.hg_png_decode.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.POINTER(i), C.POINTER(i)]
+    L.hg_jpeg_decode.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.POINTER(i), C.POINTER(i)]
     L.hg_png_encode_bound.argtypes = [i, i]
     L.hg_png_encode_bound.restype = C.c_size_t
     L.hg_png_encode.argtypes = [vp, i, i, vp, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -428,6 +429,22 @@ def png_decode(data: bytes) -> np.ndarray:
     out = np.empty((h.value, w.value, 4), np.uint8)
     if L.hg_png_decode(_ptr(buf), buf.size, _ptr(out), out.size, C.byref(w), C.byref(h)):
         raise HgError(1, "hg_png_decode: malformed image data")
+    return out
+
+
+def jpeg_decode(data: bytes) -> np.ndarray:
+    """hg_jpeg_decode: baseline JPEG file bytes -> (h, w, 4) uint8 RGBA (alpha 255), the bytes getImageData returns.  Host only.
+    Raises HgError with status HG_ERR_UNSUPPORTED for progressive / CMYK / arithmetic-coded files."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    w, h = C.c_int(), C.c_int()
+    L = load()
+    st = L.hg_jpeg_decode(_ptr(buf), buf.size, None, 0, C.byref(w), C.byref(h))
+    if st:
+        raise HgError(st, "hg_jpeg_decode: not a JPEG this decoder supports")
+    out = np.empty((h.value, w.value, 4), np.uint8)
+    st = L.hg_jpeg_decode(_ptr(buf), buf.size, _ptr(out), out.size, C.byref(w), C.byref(h))
+    if st:
+        raise HgError(st, "hg_jpeg_decode: malformed or unsupported image data")
     return out
 
 

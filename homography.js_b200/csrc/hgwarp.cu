@@ -25,6 +25,7 @@
 #include "piecewise_fused.cuh"
 #include "delaunay_host.cuh"
 #include "png_host.cuh"
+#include "jpeg_host.cuh"
 
 using namespace hg;
 
@@ -955,6 +956,27 @@ int hg_png_decode(const uint8_t *png, size_t png_bytes, uint8_t *rgba_out, size_
         if (!rgba_out) return HG_OK;
         if (capacity_bytes < (size_t)hd.w * hd.h * 4) return HG_ERR_INVALID;
         return hg_png_detail::decode(png, png_bytes, hd, rgba_out) ? HG_ERR_INVALID : HG_OK;
+    } catch (const std::bad_alloc &) {
+        return HG_ERR_NOMEM;
+    } catch (...) {
+        return HG_ERR_INVALID;
+    }
+}
+
+int hg_jpeg_decode(const uint8_t *jpg, size_t jpg_bytes, uint8_t *rgba_out, size_t capacity_bytes, int *w, int *h)
+{
+    if (!jpg || !w || !h) return HG_ERR_INVALID;
+    *w = *h = 0;
+    try {  // the bytes are untrusted: nothing may unwind through the C ABI
+        int ww = 0, hh = 0;
+        int r = hg_jpeg_detail::decode(jpg, jpg_bytes, ww, hh, nullptr);  // frame header
+        if (r) return r == hg_jpeg_detail::UNSUPPORTED ? HG_ERR_UNSUPPORTED : HG_ERR_INVALID;
+        *w = ww;
+        *h = hh;
+        if (!rgba_out) return HG_OK;
+        if (capacity_bytes < (size_t)ww * hh * 4) return HG_ERR_INVALID;
+        r = hg_jpeg_detail::decode(jpg, jpg_bytes, ww, hh, rgba_out);
+        return r == 0 ? HG_OK : (r == hg_jpeg_detail::UNSUPPORTED ? HG_ERR_UNSUPPORTED : HG_ERR_INVALID);
     } catch (const std::bad_alloc &) {
         return HG_ERR_NOMEM;
     } catch (...) {

@@ -51,6 +51,12 @@ class ImageData:
         a = _abi.png_decode(png_bytes)
         return cls(a.reshape(-1), a.shape[1], a.shape[0])
 
+    @classmethod
+    def from_jpeg(cls, jpeg_bytes: bytes) -> "ImageData":
+        """The RGBA8 pixels of a baseline JPEG file, as a browser's canvas returns them (hg_jpeg_decode)."""
+        a = _abi.jpeg_decode(jpeg_bytes)
+        return cls(a.reshape(-1), a.shape[1], a.shape[0])
+
     def to_png(self) -> bytes:
         """The result as PNG file bytes (the reference's HTMLImageElementFromImageData / toDataURL, H.js:467-496)."""
         return _abi.png_encode(np.asarray(self.data, dtype=np.uint8).reshape(self.height, self.width, 4))

@@ -230,6 +230,35 @@ static napi_value PngDecode(napi_env env, napi_callback_info info)
     return obj;
 }
 
+/* jpegDecode(Uint8Array file) -> {data: Uint8ClampedArray, width, height}    <- the same canvas path for a JPEG file */
+static napi_value JpegDecode(napi_env env, napi_callback_info info)
+{
+    ARGS(1);
+    napi_typedarray_type t;
+    size_t n = 0;
+    void *data = NULL;
+    if (napi_get_typedarray_info(env, argv[0], &t, &n, &data, NULL, NULL) != napi_ok || (t != napi_uint8_array && t != napi_uint8_clamped_array))
+        return throw_text(env, "jpegDecode(Uint8Array)");
+    int w = 0, h = 0;
+    int st = hg_jpeg_decode((const uint8_t *)data, n, NULL, 0, &w, &h);
+    if (st != HG_OK)
+        return throw_text(env, st == HG_ERR_UNSUPPORTED ? "jpegDecode: a JPEG mode this decoder does not support (progressive, CMYK, ...)"
+                                                        : "jpegDecode: not a JPEG file");
+    uint8_t *px = NULL;
+    napi_value arr = new_output(env, w, h, &px), obj, vw, vh;
+    st = hg_jpeg_decode((const uint8_t *)data, n, px, (size_t)w * h * 4, &w, &h);
+    if (st != HG_OK)
+        return throw_text(env, st == HG_ERR_UNSUPPORTED ? "jpegDecode: a JPEG mode this decoder does not support (progressive, CMYK, ...)"
+                                                        : "jpegDecode: malformed image data");
+    napi_create_object(env, &obj);
+    napi_create_int32(env, w, &vw);
+    napi_create_int32(env, h, &vh);
+    napi_set_named_property(env, obj, "data", arr);
+    napi_set_named_property(env, obj, "width", vw);
+    napi_set_named_property(env, obj, "height", vh);
+    return obj;
+}
+
 /* pngEncode(Uint8ClampedArray rgba, width, height) -> Uint8Array file        <- toDataURL, H.js:480-483 */
 static napi_value PngEncode(napi_env env, napi_callback_info info)
 {
@@ -313,6 +342,7 @@ static napi_value Init(napi_env env, napi_value exports)
         {"setMesh", 0, SetMesh, 0, 0, 0, napi_default, 0},
         {"delaunay", 0, Delaunay, 0, 0, 0, napi_default, 0},
         {"pngDecode", 0, PngDecode, 0, 0, 0, napi_default, 0},
+        {"jpegDecode", 0, JpegDecode, 0, 0, 0, napi_default, 0},
         {"pngEncode", 0, PngEncode, 0, 0, 0, napi_default, 0},
         {"piecewiseMatrices", 0, PiecewiseMatrices, 0, 0, 0, napi_default, 0},
         {"warpPiecewiseInverse", 0, WarpPiecewiseInverse, 0, 0, 0, napi_default, 0},

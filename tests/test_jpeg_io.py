@@ -1,0 +1,130 @@
+"""hg_jpeg_decode (host-side JPEG ingest) against libjpeg-turbo through Pillow — byte for byte: the
+bytes a browser's getImageData returns for the file.  Host only: runs without a GPU."""
+import io
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import homography_js_b200 as hg
+from conftest import ROOT
+
+PIL = pytest.importorskip("PIL.Image")
+
+
+def _picture(h, w, seed=0):
+    """Smooth gradients with a block of noise: every frequency, saturated chroma at the edges."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    a = np.stack([(np.sin(x / 7.0) + 1) * 127, (np.cos(y / 5.0) + 1) * 127, (x + y) % 256], -1).astype(np.uint8)
+    if h > 6 and w > 8:
+        a[h // 3:h // 2, w // 4:w // 2] = rng.integers(0, 256, (h // 2 - h // 3, w // 2 - w // 4, 3), dtype=np.uint8)
+    return a
+
+
+def _jpeg(img, **kw):
+    b = io.BytesIO()
+    img.save(b, format="JPEG", **kw)
+    return b.getvalue()
+
+
+def _same_as_pillow(data):
+    want = np.asarray(PIL.open(io.BytesIO(data)).convert("RGB"))
+    got = hg._abi.jpeg_decode(data)
+    assert got.shape == want.shape[:2] + (4,)
+    assert (got[..., 3] == 255).all()
+    assert np.array_equal(got[..., :3], want)
+
+
+@pytest.mark.parametrize("subsampling", [0, 1, 2], ids=["444", "422", "420"])
+def test_decode_matches_libjpeg_turbo_for_every_size_and_quality(subsampling):
+    """Odd sizes (partial MCUs), components one or two samples wide (no triangle filter there), whole-MCU sizes."""
+    for h, w in [(64, 64), (37, 53), (1, 1), (8, 9), (17, 3), (2, 2), (100, 255), (131, 97), (5, 4), (16, 5), (3, 6)]:
+        for q in (1, 30, 75, 95, 100):
+            _same_as_pillow(_jpeg(PIL.fromarray(_picture(h, w), "RGB"), quality=q, subsampling=subsampling))
+
+
+def test_grey_custom_huffman_restart_intervals_rgb_files_and_noise():
+    img = PIL.fromarray(_picture(97, 133), "RGB")
+    _same_as_pillow(_jpeg(img.convert("L"), quality=80))
+    _same_as_pillow(_jpeg(img, quality=80, optimize=True, subsampling=2))            # per-image Huffman tables
+    for kw in ({"restart_marker_blocks": 3}, {"restart_marker_rows": 1}, {"restart_marker_blocks": 1, "subsampling": 2}):
+        try:
+            data = _jpeg(img, quality=70, **kw)
+        except TypeError:
+            continue   # an older Pillow without the restart options
+        assert b"\xff\xdd" in data
+        _same_as_pillow(data)
+    try:
+        _same_as_pillow(_jpeg(img, quality=90, keep_rgb=True, subsampling=0))        # RGB components, Adobe transform 0
+    except TypeError:
+        pass
+    rng = np.random.default_rng(4)
+    noise = PIL.fromarray(rng.integers(0, 256, (63, 65, 3), dtype=np.uint8), "RGB")
+    _same_as_pillow(_jpeg(noise, quality=100, subsampling=2))
+    _same_as_pillow(_jpeg(noise, quality=10, subsampling=1))
+
+
+def test_full_hd_frame():
+    _same_as_pillow(_jpeg(PIL.fromarray(_picture(1080, 1920), "RGB"), quality=85))
+
+
+def test_unsupported_and_malformed_files_are_refused_not_guessed():
+    img = PIL.fromarray(_picture(40, 40), "RGB")
+    for data in (_jpeg(img, quality=80, progressive=True), _jpeg(img.convert("CMYK"), quality=80)):
+        with pytest.raises(hg.HgError) as e:
+            hg._abi.jpeg_decode(data)
+        assert e.value.status == hg._abi.HG_ERR_UNSUPPORTED
+    good = _jpeg(img, quality=80)
+    for data in (b"", b"\xff\xd8", good[:40], b"\x89PNG\r\n\x1a\n" + good, good[:200]):
+        with pytest.raises(hg.HgError):
+            hg._abi.jpeg_decode(data)
+    # without its JFIF segment the file is still a JPEG (component ids 1, 2, 3 -> YCbCr): same pixels
+    assert good[2:4] == b"\xff\xe0"
+    assert np.array_equal(hg._abi.jpeg_decode(good[:2] + good[20:]), hg._abi.jpeg_decode(good))
+    # a frame header that promises 65535 x 65535 pixels in a 700-byte file: refused before anything is allocated
+    i = good.index(b"\xff\xc0")
+    bomb = good[:i + 5] + b"\xff\xff\xff\xff" + good[i + 9:]
+    import ctypes as C
+    w, h = C.c_int(), C.c_int()
+    assert hg._abi.load().hg_jpeg_decode(bomb, len(bomb), None, 0, C.byref(w), C.byref(h)) == 0 and w.value == 65535
+    big = np.empty(1, np.uint8)
+    assert hg._abi.load().hg_jpeg_decode(bomb, len(bomb), big.ctypes.data, 65535 * 65535 * 4, C.byref(w), C.byref(h)) != 0
+
+
+def test_truncated_file_without_eoi_is_decoded_when_complete():
+    good = _jpeg(PIL.fromarray(_picture(24, 24), "RGB"), quality=90)
+    assert good.endswith(b"\xff\xd9")
+    assert np.array_equal(hg._abi.jpeg_decode(good[:-2]), hg._abi.jpeg_decode(good))
+
+
+def test_mutated_jpegs_under_sanitizers(tmp_path):
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    exe = tmp_path / "jpeg_fuzz"
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    build = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                            os.path.join(ROOT, "tests", "jpeg_fuzz_harness.cpp"), "-o", str(exe)], capture_output=True, text=True, env=env)
+    if build.returncode != 0 and "sanitize" in build.stderr:
+        pytest.skip("sanitizer runtime not available")
+    assert build.returncode == 0, build.stderr[-3000:]
+    files = []
+    img = PIL.fromarray(_picture(29, 43), "RGB")
+    for name, kw in (("a", dict(quality=75, subsampling=2)), ("b", dict(quality=90, subsampling=1, optimize=True)),
+                     ("c", dict(quality=60, subsampling=0)), ("d", dict(quality=80))):
+        p = tmp_path / (name + ".jpg")
+        p.write_bytes(_jpeg(img.convert("L") if name == "d" else img, **kw))
+        files.append(str(p))
+    try:
+        p = tmp_path / "r.jpg"
+        p.write_bytes(_jpeg(img, quality=70, restart_marker_blocks=2, subsampling=2))
+        files.append(str(p))
+    except TypeError:
+        pass
+    run = subprocess.run([str(exe), "1500"] + files, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, (run.stdout[-500:], run.stderr[-3000:])
+    decoded, rejected = [int(t.rstrip(",")) for t in run.stdout.split() if t.rstrip(",").isdigit()]
+    assert decoded > 100 and rejected > 100

@@ -24,7 +24,7 @@ def native_cpu():
 def test_addon_registers_the_exports_the_shim_calls(native_cpu):
     assert M.build(True).mock_module_name() == b"hgwarp"
     assert set(native_cpu.exports) == {"createContext", "setImage", "solveWithLimits", "warpInversePoints", "warpForwardMatrix",
-                                       "setMesh", "delaunay", "pngDecode", "pngEncode", "piecewiseMatrices",
+                                       "setMesh", "delaunay", "pngDecode", "jpegDecode", "pngEncode", "piecewiseMatrices",
                                        "warpPiecewiseInverse", "warpPiecewiseForward"}
 
 
@@ -40,6 +40,16 @@ def test_host_only_exports_match_the_c_abi(native_cpu):
     assert bytes(png) == hg._abi.png_encode(img)
     back = native_cpu.pngDecode(png)
     assert (back["width"], back["height"]) == (13, 9) and np.array_equal(back["data"].reshape(9, 13, 4), img)
+    PIL = pytest.importorskip("PIL.Image")
+    import io
+    b = io.BytesIO()
+    PIL.fromarray(img[..., :3].copy(), "RGB").save(b, format="JPEG", quality=85)
+    jpg = np.frombuffer(b.getvalue(), np.uint8)
+    back = native_cpu.jpegDecode(jpg)
+    assert (back["width"], back["height"]) == (13, 9)
+    assert np.array_equal(back["data"].reshape(9, 13, 4), hg._abi.jpeg_decode(b.getvalue()))
+    with pytest.raises(M.JsError, match="not a JPEG"):
+        native_cpu.jpegDecode(np.arange(64, dtype=np.uint8))
 
 
 def test_argument_errors_become_js_exceptions(native_cpu):
@@ -137,7 +147,7 @@ def test_transliteration_covers_the_shim():
     js_methods = set(re.findall(r"\n  (_?[A-Za-z]+)\(", mjs)) - {"constructor", "if", "for", "switch", "return"}
     py_methods = set(re.findall(r"\n    def (_?[A-Za-z]+)\(", py)) - {"__init__"}
     assert js_methods == py_methods, js_methods ^ py_methods
-    js_calls = set(re.findall(r"\bnative\.([A-Za-z]+)\(", mjs)) - {"pngDecode", "pngEncode"}   # module-level helpers
+    js_calls = set(re.findall(r"\bnative\.([A-Za-z]+)\(", mjs)) - {"pngDecode", "jpegDecode", "pngEncode"}   # module-level helpers
     py_calls = set(re.findall(r"\bnative\.([A-Za-z]+)\(", py))
     assert js_calls == py_calls, js_calls ^ py_calls
     # the same reference-defined throw texts
