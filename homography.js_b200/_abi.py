@@ -433,8 +433,8 @@ def png_decode(data: bytes) -> np.ndarray:
 
 
 def jpeg_decode(data: bytes) -> np.ndarray:
-    """hg_jpeg_decode: baseline JPEG file bytes -> (h, w, 4) uint8 RGBA (alpha 255), the bytes getImageData returns.  Host only.
-    Raises HgError with status HG_ERR_UNSUPPORTED for progressive / CMYK / arithmetic-coded files."""
+    """hg_jpeg_decode: JPEG file bytes (baseline or progressive) -> (h, w, 4) uint8 RGBA (alpha 255), the bytes getImageData returns.  Host only.
+    Raises HgError with status HG_ERR_UNSUPPORTED for CMYK / arithmetic-coded / lossless files."""
     buf = np.frombuffer(data, dtype=np.uint8)
     w, h = C.c_int(), C.c_int()
     L = load()

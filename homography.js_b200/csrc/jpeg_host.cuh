@@ -1,19 +1,20 @@
-// jpeg_host.cuh — host-side baseline JPEG ingest behind hg_jpeg_decode (include/hgwarp.h).
+// jpeg_host.cuh — host-side JPEG ingest (baseline and progressive) behind hg_jpeg_decode (include/hgwarp.h).
 //
 // The step before the hot path when there is no canvas: in a browser the reference gets the RGBA bytes
 // of ANY image the browser can decode through drawImage + getImageData (H.js:1071-1076), and for JPEG files every major
 // browser (and Pillow, the checker used by the tests) decodes with libjpeg-turbo's defaults.  This file restates that
 // pipeline from the published algorithms (ITU-T T.81 and the Independent JPEG Group's reference arithmetic) so that the
 // bytes are the ones getImageData returns:
-//   * sequential DCT, Huffman coding, 8-bit samples (SOF0 / SOF1), 1 or 3 components, any number of scans, restart
-//     intervals, 8- and 16-bit quantisation tables;
+//   * sequential AND progressive DCT (SOF0 / SOF1 / SOF2: spectral selection and successive approximation, end-of-band runs),
+//     Huffman coding, 8-bit samples, 1 or 3 components, any number of scans, restart intervals, 8- and 16-bit quantisation
+//     tables;
 //   * dequantisation + the accurate integer inverse DCT ("islow": 13-bit constants, two passes, the zero-AC shortcuts give
 //     the same numbers as the general path);
 //   * chroma upsampling as libjpeg does by default: the triangle ("fancy") filters for 2:1 horizontal and 2:1 x 2:1 when the
 //     component is wider than two samples, with the edge rows / columns replicated; pixel replication for other integer ratios;
 //   * YCbCr -> RGB with the 16-bit fixed-point tables (1.40200, 0.34414, 0.71414, 1.77200), or RGB passed through when an
 //     Adobe marker / the component ids say so; grey -> R = G = B; alpha = 255.
-// Not decoded (HG_ERR_UNSUPPORTED, never a wrong image): progressive and lossless modes, arithmetic coding, 12-bit samples,
+// Not decoded (HG_ERR_UNSUPPORTED, never a wrong image): lossless and hierarchical modes, arithmetic coding, 12-bit samples,
 // four-component (CMYK / YCCK) files, 1:2 vertical-only subsampling, fractional sampling ratios.
 #pragma once
 #include <cstdint>
@@ -39,6 +40,8 @@ struct Component {
     int real_w = 0, real_h = 0;  // downsampled_width / downsampled_height: ceil(W * hs / max_h), ceil(H * vs / max_v)
     int pred = 0;
     std::vector<uint8_t> plane;  // blocks_w*8 x blocks_h*8 samples
+    std::vector<short> coefs;    // progressive mode: blocks_w*blocks_h blocks of 64 coefficients (natural order), undequantised
+    bool dc_seen = false;        // progressive mode: a first DC scan covered this component
 };
 
 struct BitReader {
@@ -218,7 +221,8 @@ struct Decoder {
     const uint8_t *data;
     size_t n;
     int W = 0, H = 0, ncomp = 0, max_h = 1, max_v = 1;
-    bool have_sof = false, jfif = false, adobe = false;
+    bool have_sof = false, jfif = false, adobe = false, progressive = false;
+    int eobrun = 0;  // progressive AC scans: blocks still covered by the current end-of-band run
     int adobe_transform = 0;
     int restart_interval = 0;
     uint16_t qt[4][64];
@@ -259,6 +263,78 @@ struct Decoder {
         return OK;
     }
 
+    // ---- progressive mode (T.81 annex G): one call per block and scan; `b` = the block's 64 stored coefficients
+    void prog_dc_first(BitReader &br, Component &c, short *b, int al)
+    {
+        const int s = decode_symbol(br, dc[c.td]);
+        int diff = 0;
+        if (s && s <= 15) diff = extend(br.get(s), s);
+        c.pred += diff;
+        b[0] = (short)(c.pred * (1 << al));
+    }
+    static void prog_dc_refine(BitReader &br, short *b, int al)
+    {
+        if (br.get(1)) b[0] = (short)(b[0] | (1 << al));
+    }
+    void prog_ac_first(BitReader &br, Component &c, short *b, int ss, int se, int al)
+    {
+        if (eobrun > 0) {
+            --eobrun;
+            return;
+        }
+        for (int k = ss; k <= se; ++k) {
+            const int rs = decode_symbol(br, ac[c.ta]), r = rs >> 4, s = rs & 15;
+            if (s) {
+                k += r;
+                const int v = extend(br.get(s), s);
+                b[kZigzag[k > 63 ? 63 : k]] = (short)(v * (1 << al));
+            } else if (r == 15) {
+                k += 15;
+            } else {
+                eobrun = 1 << r;
+                if (r) eobrun += br.get(r);
+                --eobrun;
+                break;
+            }
+        }
+    }
+    void prog_ac_refine(BitReader &br, Component &c, short *b, int ss, int se, int al)
+    {
+        const int p1 = 1 << al, m1 = -(1 << al);
+        auto correct = [&](short &coef) {  // one correction bit for an already-nonzero coefficient
+            if (br.get(1) && (coef & p1) == 0) coef = (short)(coef >= 0 ? coef + p1 : coef + m1);
+        };
+        int k = ss;
+        if (eobrun == 0) {
+            for (; k <= se; ++k) {
+                const int rs = decode_symbol(br, ac[c.ta]);
+                int r = rs >> 4, s = rs & 15;
+                if (s) {
+                    s = br.get(1) ? p1 : m1;  // a new coefficient is always +-1 at this bit position
+                } else if (r != 15) {
+                    eobrun = 1 << r;
+                    if (r) eobrun += br.get(r);
+                    break;  // the rest of the band is handled by the end-of-band branch below
+                }
+                // skip r still-zero coefficients, correcting the nonzero ones passed on the way
+                do {
+                    short &coef = b[kZigzag[k]];
+                    if (coef != 0) correct(coef);
+                    else if (--r < 0) break;
+                    ++k;
+                } while (k <= se);
+                if (s && k <= 63) b[kZigzag[k]] = (short)s;
+            }
+        }
+        if (eobrun > 0) {
+            for (; k <= se; ++k) {
+                short &coef = b[kZigzag[k]];
+                if (coef != 0) correct(coef);
+            }
+            --eobrun;
+        }
+    }
+
     int scan(size_t &pos)
     {
         if (pos + 2 > n) return MALFORMED;
@@ -277,12 +353,26 @@ struct Decoder {
                 if (sc[j] == c) return MALFORMED;
             c->td = tt >> 4;
             c->ta = tt & 15;
-            if (c->td > 3 || c->ta > 3 || !dc[c->td].present || !ac[c->ta].present || !qt_present[c->tq]) return MALFORMED;
-            if (comp_done[c - comp]) return MALFORMED;  // sequential mode: one scan per component
+            if (c->td > 3 || c->ta > 3 || !qt_present[c->tq]) return MALFORMED;
+            if (!progressive) {
+                if (!dc[c->td].present || !ac[c->ta].present) return MALFORMED;
+                if (comp_done[c - comp]) return MALFORMED;  // sequential mode: one scan per component
+            }
             sc[i] = c;
         }
         const int ss = data[pos + 3 + 2 * ns], se = data[pos + 4 + 2 * ns], ahal = data[pos + 5 + 2 * ns];
-        if (ss != 0 || se != 63 || ahal != 0) return MALFORMED;  // sequential: full spectrum, no successive approximation
+        const int ah = ahal >> 4, al = ahal & 15;
+        if (!progressive) {
+            if (ss != 0 || se != 63 || ahal != 0) return MALFORMED;  // sequential: full spectrum, no successive approximation
+        } else {
+            if (ss > se || se > 63 || al > 13 || ah > 13) return MALFORMED;
+            if (ss == 0 ? se != 0 : ns != 1) return MALFORMED;      // DC scans carry only DC; AC scans one component
+            for (int i = 0; i < ns; ++i) {
+                if (ss == 0 && ah == 0 && !dc[sc[i]->td].present) return MALFORMED;
+                if (ss != 0 && !ac[sc[i]->ta].present) return MALFORMED;
+            }
+        }
+        eobrun = 0;
         pos += (size_t)len;
         BitReader br(data + pos, data + n);
         for (int i = 0; i < ns; ++i) sc[i]->pred = 0;
@@ -308,6 +398,7 @@ struct Decoder {
                     br.p = p;
                     next_rst = (next_rst + 1) & 7;
                     for (int i = 0; i < ns; ++i) sc[i]->pred = 0;
+                    eobrun = 0;
                     until_restart = restart_interval;
                 }
                 for (int i = 0; i < ns; ++i) {
@@ -315,9 +406,21 @@ struct Decoder {
                     const int bh = ns == 1 ? 1 : c.hs, bv = ns == 1 ? 1 : c.vs;
                     for (int by = 0; by < bv; ++by)
                         for (int bx = 0; bx < bh; ++bx) {
+                            const int X = mx * bh + bx, Y = my * bv + by;
+                            if (progressive) {
+                                short dummy[64] = {0};
+                                short *b = (X < c.blocks_w && Y < c.blocks_h) ? c.coefs.data() + ((size_t)Y * c.blocks_w + X) * 64 : dummy;
+                                if (ss == 0) {
+                                    if (ah == 0) prog_dc_first(br, c, b, al);
+                                    else prog_dc_refine(br, b, al);
+                                } else {
+                                    if (ah == 0) prog_ac_first(br, c, b, ss, se, al);
+                                    else prog_ac_refine(br, c, b, ss, se, al);
+                                }
+                                continue;
+                            }
                             const int r = decode_block(br, c, blk);
                             if (r) return r;
-                            const int X = mx * bh + bx, Y = my * bv + by;
                             if (X < c.blocks_w && Y < c.blocks_h)
                                 idct_islow(blk, c.plane.data() + ((size_t)Y * 8 * c.blocks_w + X) * 8, (size_t)c.blocks_w * 8);
                         }
@@ -325,7 +428,10 @@ struct Decoder {
                 if (restart_interval) --until_restart;
             }
         }
-        for (int i = 0; i < ns; ++i) comp_done[sc[i] - comp] = true;
+        for (int i = 0; i < ns; ++i) {
+            if (!progressive) comp_done[sc[i] - comp] = true;
+            else if (ss == 0 && ah == 0) sc[i]->dc_seen = true;
+        }
         // the scan's entropy-coded segment ends at the next marker that is not a restart
         const uint8_t *p = br.p;
         while (p + 1 < data + n && !(p[0] == 0xFF && p[1] != 0x00 && p[1] != 0xFF && !(p[1] >= 0xD0 && p[1] <= 0xD7))) ++p;
@@ -351,7 +457,8 @@ struct Decoder {
             if (len < 2 || pos + (size_t)len > n) return MALFORMED;
             const uint8_t *p = data + pos + 2;
             const int body = len - 2;
-            if (m == 0xC0 || m == 0xC1) {
+            if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+                progressive = (m == 0xC2);
                 if (have_sof || body < 6) return MALFORMED;
                 if (p[0] != 8) return UNSUPPORTED;
                 H = be16(p + 1);
@@ -387,9 +494,10 @@ struct Decoder {
                     c.real_w = (W * c.hs + max_h - 1) / max_h;
                     c.real_h = (H * c.vs + max_v - 1) / max_v;
                     c.plane.assign((size_t)c.blocks_w * 8 * c.blocks_h * 8, 128);
+                    if (progressive) c.coefs.assign((size_t)c.blocks_w * c.blocks_h * 64, 0);
                 }
-            } else if (m == 0xC2 || m == 0xC3 || (m >= 0xC5 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
-                return UNSUPPORTED;  // progressive, lossless, differential, arithmetic-coded frames
+            } else if (m == 0xC3 || (m >= 0xC5 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
+                return UNSUPPORTED;  // lossless, differential, arithmetic-coded frames
             } else if (m == 0xCC) {
                 return UNSUPPORTED;  // arithmetic conditioning
             } else if (m == 0xC4) {  // DHT
@@ -436,6 +544,23 @@ struct Decoder {
         }
         if (!have_sof) return MALFORMED;
         if (header_only) return OK;
+        if (progressive) {
+            // every scan has refined the stored coefficients: dequantise and transform each block once.  (libjpeg's
+            // inter-block smoothing only acts while low-frequency coefficients are still missing precision, i.e. on files
+            // whose scans have not all arrived.)
+            for (int i = 0; i < ncomp; ++i) {
+                Component &c = comp[i];
+                if (!c.dc_seen || !qt_present[c.tq]) return MALFORMED;
+                int blk[64];
+                for (int Y = 0; Y < c.blocks_h; ++Y)
+                    for (int X = 0; X < c.blocks_w; ++X) {
+                        const short *b = c.coefs.data() + ((size_t)Y * c.blocks_w + X) * 64;
+                        for (int k = 0; k < 64; ++k) blk[kZigzag[k]] = (int)b[kZigzag[k]] * qt[c.tq][k];
+                        idct_islow(blk, c.plane.data() + ((size_t)Y * 8 * c.blocks_w + X) * 8, (size_t)c.blocks_w * 8);
+                    }
+            }
+            return OK;
+        }
         for (int i = 0; i < ncomp; ++i)
             if (!comp_done[i]) return MALFORMED;
         return OK;

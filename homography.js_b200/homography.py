@@ -53,7 +53,7 @@ class ImageData:
 
     @classmethod
     def from_jpeg(cls, jpeg_bytes: bytes) -> "ImageData":
-        """The RGBA8 pixels of a baseline JPEG file, as a browser's canvas returns them (hg_jpeg_decode)."""
+        """The RGBA8 pixels of a JPEG file, as a browser's canvas returns them (hg_jpeg_decode)."""
         a = _abi.jpeg_decode(jpeg_bytes)
         return cls(a.reshape(-1), a.shape[1], a.shape[0])
 

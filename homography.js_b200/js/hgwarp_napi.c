@@ -242,13 +242,13 @@ static napi_value JpegDecode(napi_env env, napi_callback_info info)
     int w = 0, h = 0;
     int st = hg_jpeg_decode((const uint8_t *)data, n, NULL, 0, &w, &h);
     if (st != HG_OK)
-        return throw_text(env, st == HG_ERR_UNSUPPORTED ? "jpegDecode: a JPEG mode this decoder does not support (progressive, CMYK, ...)"
+        return throw_text(env, st == HG_ERR_UNSUPPORTED ? "jpegDecode: a JPEG mode this decoder does not support (CMYK, arithmetic coding, ...)"
                                                         : "jpegDecode: not a JPEG file");
     uint8_t *px = NULL;
     napi_value arr = new_output(env, w, h, &px), obj, vw, vh;
     st = hg_jpeg_decode((const uint8_t *)data, n, px, (size_t)w * h * 4, &w, &h);
     if (st != HG_OK)
-        return throw_text(env, st == HG_ERR_UNSUPPORTED ? "jpegDecode: a JPEG mode this decoder does not support (progressive, CMYK, ...)"
+        return throw_text(env, st == HG_ERR_UNSUPPORTED ? "jpegDecode: a JPEG mode this decoder does not support (CMYK, arithmetic coding, ...)"
                                                         : "jpegDecode: malformed image data");
     napi_create_object(env, &obj);
     napi_create_int32(env, w, &vw);

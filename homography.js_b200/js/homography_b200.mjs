@@ -329,7 +329,7 @@ class Homography {
 // File I/O for hosts without a canvas (the reference reads pixels through drawImage + getImageData, H.js:1071-1076, and
 // returns PNG data URLs, H.js:480-483): PNG bytes <-> the {data, width, height} form setImage() / warp() use.
 function imageDataFromPNG(bytes) { return native.pngDecode(bytes); }
-function imageDataFromJPEG(bytes) { return native.jpegDecode(bytes); } // baseline JPEG; throws for progressive / CMYK files
+function imageDataFromJPEG(bytes) { return native.jpegDecode(bytes); } // baseline and progressive JPEG; throws for CMYK / arithmetic-coded files
 function pngFromImageData(image) { return native.pngEncode(image.data, image.width, image.height); }
 
 export { Homography, imageDataFromPNG, imageDataFromJPEG, pngFromImageData };

@@ -1,4 +1,5 @@
-"""hg_jpeg_decode (host-side JPEG ingest) against libjpeg-turbo through Pillow — byte for byte: the
+"""hg_jpeg_decode (host-side JPEG ingest, baseline and progressive) against libjpeg-turbo through Pillow —
+byte for byte: the
 bytes a browser's getImageData returns for the file.  Host only: runs without a GPU."""
 import io
 import os
@@ -38,19 +39,26 @@ def _same_as_pillow(data):
     assert np.array_equal(got[..., :3], want)
 
 
+@pytest.mark.parametrize("progressive", [False, True], ids=["baseline", "progressive"])
 @pytest.mark.parametrize("subsampling", [0, 1, 2], ids=["444", "422", "420"])
-def test_decode_matches_libjpeg_turbo_for_every_size_and_quality(subsampling):
-    """Odd sizes (partial MCUs), components one or two samples wide (no triangle filter there), whole-MCU sizes."""
+def test_decode_matches_libjpeg_turbo_for_every_size_and_quality(subsampling, progressive):
+    """Odd sizes (partial MCUs), components one or two samples wide (no triangle filter there), whole-MCU sizes; progressive
+    files exercise all four scan kinds (DC / AC, first / refinement) and end-of-band runs."""
     for h, w in [(64, 64), (37, 53), (1, 1), (8, 9), (17, 3), (2, 2), (100, 255), (131, 97), (5, 4), (16, 5), (3, 6)]:
         for q in (1, 30, 75, 95, 100):
-            _same_as_pillow(_jpeg(PIL.fromarray(_picture(h, w), "RGB"), quality=q, subsampling=subsampling))
+            data = _jpeg(PIL.fromarray(_picture(h, w), "RGB"), quality=q, subsampling=subsampling, progressive=progressive,
+                         optimize=progressive and q == 75)
+            assert (b"\xff\xc2" in data) == progressive
+            _same_as_pillow(data)
 
 
 def test_grey_custom_huffman_restart_intervals_rgb_files_and_noise():
     img = PIL.fromarray(_picture(97, 133), "RGB")
     _same_as_pillow(_jpeg(img.convert("L"), quality=80))
+    _same_as_pillow(_jpeg(img.convert("L"), quality=80, progressive=True))
     _same_as_pillow(_jpeg(img, quality=80, optimize=True, subsampling=2))            # per-image Huffman tables
-    for kw in ({"restart_marker_blocks": 3}, {"restart_marker_rows": 1}, {"restart_marker_blocks": 1, "subsampling": 2}):
+    for kw in ({"restart_marker_blocks": 3}, {"restart_marker_rows": 1}, {"restart_marker_blocks": 1, "subsampling": 2},
+               {"restart_marker_blocks": 2, "subsampling": 2, "progressive": True}):
         try:
             data = _jpeg(img, quality=70, **kw)
         except TypeError:
@@ -69,11 +77,17 @@ def test_grey_custom_huffman_restart_intervals_rgb_files_and_noise():
 
 def test_full_hd_frame():
     _same_as_pillow(_jpeg(PIL.fromarray(_picture(1080, 1920), "RGB"), quality=85))
+    _same_as_pillow(_jpeg(PIL.fromarray(_picture(1080, 1920), "RGB"), quality=85, progressive=True))
 
 
 def test_unsupported_and_malformed_files_are_refused_not_guessed():
     img = PIL.fromarray(_picture(40, 40), "RGB")
-    for data in (_jpeg(img, quality=80, progressive=True), _jpeg(img.convert("CMYK"), quality=80)):
+    base = _jpeg(img, quality=80)
+    i = base.index(b"\xff\xc0")
+    for data in (_jpeg(img.convert("CMYK"), quality=80),          # four components
+                 base[:i + 1] + b"\xc9" + base[i + 2:],            # the same frame declared arithmetic-coded (SOF9)
+                 base[:i + 1] + b"\xc3" + base[i + 2:],            # lossless (SOF3)
+                 base[:i + 4] + b"\x0c" + base[i + 5:]):           # 12-bit samples
         with pytest.raises(hg.HgError) as e:
             hg._abi.jpeg_decode(data)
         assert e.value.status == hg._abi.HG_ERR_UNSUPPORTED
@@ -114,7 +128,8 @@ def test_mutated_jpegs_under_sanitizers(tmp_path):
     files = []
     img = PIL.fromarray(_picture(29, 43), "RGB")
     for name, kw in (("a", dict(quality=75, subsampling=2)), ("b", dict(quality=90, subsampling=1, optimize=True)),
-                     ("c", dict(quality=60, subsampling=0)), ("d", dict(quality=80))):
+                     ("c", dict(quality=60, subsampling=0)), ("d", dict(quality=80)),
+                     ("e", dict(quality=75, subsampling=2, progressive=True)), ("f", dict(quality=50, subsampling=0, progressive=True))):
         p = tmp_path / (name + ".jpg")
         p.write_bytes(_jpeg(img.convert("L") if name == "d" else img, **kw))
         files.append(str(p))
