@@ -13,7 +13,9 @@
 //   * chroma upsampling as libjpeg does by default: the triangle ("fancy") filters for 2:1 horizontal and 2:1 x 2:1 when the
 //     component is wider than two samples, with the edge rows / columns replicated; pixel replication for other integer ratios;
 //   * YCbCr -> RGB with the 16-bit fixed-point tables (1.40200, 0.34414, 0.71414, 1.77200), or RGB passed through when an
-//     Adobe marker / the component ids say so; grey -> R = G = B; alpha = 255.
+//     Adobe marker / the component ids say so; grey -> R = G = B; alpha = 255;
+//   * the Exif Orientation tag (APP1) is applied, as browsers do when an image is drawn (CSS image-orientation: from-image is
+//     the default): the returned width / height are those of the picture as shown.
 // Not decoded (HG_ERR_UNSUPPORTED, never a wrong image): lossless and hierarchical modes, arithmetic coding, 12-bit samples,
 // four-component (CMYK / YCCK) files, 1:2 vertical-only subsampling, fractional sampling ratios.
 #pragma once
@@ -223,6 +225,7 @@ struct Decoder {
     int W = 0, H = 0, ncomp = 0, max_h = 1, max_v = 1;
     bool have_sof = false, jfif = false, adobe = false, progressive = false;
     int eobrun = 0;  // progressive AC scans: blocks still covered by the current end-of-band run
+    int orientation = 1;  // Exif tag 0x0112 (1..8); browsers apply it when the image is drawn (image-orientation: from-image)
     int adobe_transform = 0;
     int restart_interval = 0;
     uint16_t qt[4][64];
@@ -439,6 +442,36 @@ struct Decoder {
         return OK;
     }
 
+    // APP1 "Exif\0\0" + TIFF header + IFD0: the Orientation entry (tag 0x0112, SHORT).  Anything odd leaves orientation 1.
+    void parse_exif_orientation(const uint8_t *p, int body)
+    {
+        if (body < 14 || memcmp(p, "Exif\0\0", 6) != 0) return;
+        const uint8_t *t = p + 6;
+        const int tl = body - 6;
+        const bool le = t[0] == 'I' && t[1] == 'I', be = t[0] == 'M' && t[1] == 'M';
+        if (!le && !be) return;
+        auto u16 = [&](int o) { return le ? (t[o] | (t[o + 1] << 8)) : ((t[o] << 8) | t[o + 1]); };
+        auto u32 = [&](int o) {
+            return le ? ((uint32_t)t[o] | ((uint32_t)t[o + 1] << 8) | ((uint32_t)t[o + 2] << 16) | ((uint32_t)t[o + 3] << 24))
+                      : (((uint32_t)t[o] << 24) | ((uint32_t)t[o + 1] << 16) | ((uint32_t)t[o + 2] << 8) | (uint32_t)t[o + 3]);
+        };
+        if (u16(2) != 42) return;
+        const uint32_t ifd = u32(4);
+        if (ifd > (uint32_t)tl || (uint32_t)tl - ifd < 2) return;
+        const int count = u16((int)ifd);
+        for (int i = 0; i < count; ++i) {
+            const uint32_t e = ifd + 2 + 12u * (uint32_t)i;
+            if (e + 12 > (uint32_t)tl) return;
+            if (u16((int)e) == 0x0112) {
+                if (u16((int)e + 2) == 3 && u32((int)e + 4) == 1) {
+                    const int v = u16((int)e + 8);
+                    if (v >= 1 && v <= 8) orientation = v;
+                }
+                return;
+            }
+        }
+    }
+
     int parse_headers_and_scans(bool header_only)
     {
         if (n < 4 || data[0] != 0xFF || data[1] != 0xD8) return MALFORMED;
@@ -529,6 +562,8 @@ struct Decoder {
                 restart_interval = be16(p);
             } else if (m == 0xE0) {
                 if (body >= 5 && !memcmp(p, "JFIF\0", 5)) jfif = true;
+            } else if (m == 0xE1) {
+                parse_exif_orientation(p, body);
             } else if (m == 0xEE) {
                 if (body >= 12 && !memcmp(p, "Adobe", 5)) {
                     adobe = true;
@@ -657,10 +692,32 @@ inline int decode(const uint8_t *jpg, size_t n, int &w, int &h, uint8_t *rgba)
     d.data = jpg;
     d.n = n;
     const int r = d.parse_headers_and_scans(rgba == nullptr);
-    w = d.W;
-    h = d.H;
-    if (r) return r;
-    return rgba ? d.output(rgba) : OK;
+    const bool turned = d.orientation >= 5;  // orientations 5..8 exchange the axes
+    w = turned ? d.H : d.W;
+    h = turned ? d.W : d.H;
+    if (r || !rgba) return r;
+    if (d.orientation == 1) return d.output(rgba);
+    // decode upright-as-stored, then lay the pixels out the way the Exif orientation says the picture is to be shown
+    std::vector<uint8_t> tmp((size_t)d.W * d.H * 4);
+    const int r2 = d.output(tmp.data());
+    if (r2) return r2;
+    const int W = d.W, H = d.H;
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(tmp.data());
+    for (int oy = 0; oy < h; ++oy)
+        for (int ox = 0; ox < w; ++ox) {
+            int x, y;
+            switch (d.orientation) {
+                case 2: x = W - 1 - ox; y = oy; break;           // mirrored left-right
+                case 3: x = W - 1 - ox; y = H - 1 - oy; break;   // rotated 180
+                case 4: x = ox; y = H - 1 - oy; break;           // mirrored top-bottom
+                case 5: x = oy; y = ox; break;                   // transposed
+                case 6: x = oy; y = H - 1 - ox; break;           // to be shown rotated 90 clockwise
+                case 7: x = W - 1 - oy; y = H - 1 - ox; break;   // transversed
+                default: x = W - 1 - oy; y = ox; break;          // 8: to be shown rotated 90 counter-clockwise
+            }
+            memcpy(rgba + ((size_t)oy * w + ox) * 4, &in[(size_t)y * W + x], 4);
+        }
+    return OK;
 }
 
 }  // namespace hg_jpeg_detail

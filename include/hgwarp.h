@@ -146,7 +146,8 @@ int hg_png_decode(const uint8_t *png, size_t png_bytes, uint8_t *rgba_out, size_
 /* JPEG -> RGBA8 (alpha 255), the bytes getImageData returns for the file: sequential and progressive Huffman JPEG, 8-bit,
  * grey or three components (YCbCr / RGB), any scan layout, restart intervals; accurate integer IDCT, libjpeg's default ("fancy")
  * chroma upsampling and fixed-point colour conversion (csrc/jpeg_host.cuh; checked byte for byte against libjpeg-turbo
- * through Pillow).  Same calling convention as hg_png_decode.  HG_ERR_UNSUPPORTED: lossless / arithmetic-coded /
+ * through Pillow).  The Exif Orientation tag is applied the way a browser draws the image (w / h are those of the picture as
+ * shown).  Same calling convention as hg_png_decode.  HG_ERR_UNSUPPORTED: lossless / arithmetic-coded /
  * 12-bit / four-component files and 1:2 vertical-only subsampling; HG_ERR_INVALID: malformed data or capacity too small. */
 int hg_jpeg_decode(const uint8_t *jpg, size_t jpg_bytes, uint8_t *rgba_out, size_t capacity_bytes, int *w, int *h);
 /* RGBA8 -> PNG (8-bit RGBA, zlib level 6).  hg_png_encode_bound gives a capacity that always suffices. */

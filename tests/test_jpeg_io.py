@@ -139,7 +139,41 @@ def test_mutated_jpegs_under_sanitizers(tmp_path):
         files.append(str(p))
     except TypeError:
         pass
+    p = tmp_path / "x.jpg"
+    p.write_bytes(_with_exif_orientation(_jpeg(img, quality=70), 6, True))
+    files.append(str(p))
     run = subprocess.run([str(exe), "1500"] + files, capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, (run.stdout[-500:], run.stderr[-3000:])
     decoded, rejected = [int(t.rstrip(",")) for t in run.stdout.split() if t.rstrip(",").isdigit()]
     assert decoded > 100 and rejected > 100
+
+
+def _with_exif_orientation(jpeg: bytes, orientation: int, big_endian: bool) -> bytes:
+    """Splice a minimal APP1 Exif segment (TIFF header + IFD0 with the Orientation entry) in after SOI."""
+    import struct
+    e = ">" if big_endian else "<"
+    tiff = (b"MM" if big_endian else b"II") + struct.pack(e + "HI", 42, 8) + struct.pack(e + "H", 1) + \
+        struct.pack(e + "HHIHH", 0x0112, 3, 1, orientation, 0) + struct.pack(e + "I", 0)
+    body = b"Exif\0\0" + tiff
+    return jpeg[:2] + b"\xff\xe1" + struct.pack(">H", len(body) + 2) + body + jpeg[2:]
+
+
+@pytest.mark.parametrize("big_endian", [False, True], ids=["II", "MM"])
+def test_exif_orientation_is_applied_like_a_browser_canvas(big_endian):
+    """Browsers draw a JPEG the way its Exif Orientation says (image-orientation: from-image): getImageData returns the turned
+    picture.  Checker: Pillow's exif_transpose on libjpeg-turbo's pixels."""
+    ops = pytest.importorskip("PIL.ImageOps")
+    base = _jpeg(PIL.fromarray(_picture(37, 53), "RGB"), quality=90, subsampling=2)
+    upright = hg._abi.jpeg_decode(base)
+    for o in range(1, 9):
+        data = _with_exif_orientation(base, o, big_endian)
+        im = PIL.open(io.BytesIO(data))
+        assert im.getexif().get(0x0112) == o
+        want = np.asarray(ops.exif_transpose(im).convert("RGB"))
+        got = hg._abi.jpeg_decode(data)
+        assert got.shape[:2] == ((53, 37) if o >= 5 else (37, 53))
+        assert np.array_equal(got[..., :3], want), o
+    # out-of-range values and damaged segments leave the picture as stored
+    for data in (_with_exif_orientation(base, 9, big_endian), _with_exif_orientation(base, 0, big_endian),
+                 _with_exif_orientation(base, 6, big_endian)[:2] + b"\xff\xe1\x00\x10Exif\0\0II*\0\xff\xff\xff\x7f" + base[2:]):
+        assert np.array_equal(hg._abi.jpeg_decode(data), upright)
