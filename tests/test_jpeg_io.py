@@ -177,3 +177,142 @@ def test_exif_orientation_is_applied_like_a_browser_canvas(big_endian):
     for data in (_with_exif_orientation(base, 9, big_endian), _with_exif_orientation(base, 0, big_endian),
                  _with_exif_orientation(base, 6, big_endian)[:2] + b"\xff\xe1\x00\x10Exif\0\0II*\0\xff\xff\xff\x7f" + base[2:]):
         assert np.array_equal(hg._abi.jpeg_decode(data), upright)
+
+
+# ------------------------------------------------------------------ one scan per component (non-interleaved sequential)
+def _reencode_non_interleaved(jpeg: bytes) -> bytes:
+    """Pillow only writes interleaved baseline scans.  This transcodes one losslessly into the other legal sequential layout —
+    one scan per component over the component's own block raster — by Huffman-decoding the coefficients and re-encoding them
+    with the file's own tables (T.81 F.1.2 / F.2.2)."""
+    import struct
+    segs, pos = [], 2
+    while True:
+        assert jpeg[pos] == 0xFF
+        m = jpeg[pos + 1]
+        ln = struct.unpack(">H", jpeg[pos + 2:pos + 4])[0]
+        segs.append((m, jpeg[pos + 4:pos + 2 + ln]))
+        pos += 2 + ln
+        if m == 0xDA:
+            break
+    end = jpeg.rindex(b"\xff\xd9")
+    ecs = jpeg[pos:end].replace(b"\xff\x00", b"\xff")
+    sof = next(b for m, b in segs if m == 0xC0)
+    H, W, nc = struct.unpack(">HHB", sof[1:6])
+    comps = [(sof[6 + 3 * i], sof[7 + 3 * i] >> 4, sof[7 + 3 * i] & 15) for i in range(nc)]
+    max_h, max_v = max(c[1] for c in comps), max(c[2] for c in comps)
+    dec, enc = {}, {}
+    for m, b in segs:
+        if m != 0xC4:
+            continue
+        o = 0
+        while o < len(b):
+            tc_th, counts = b[o], b[o + 1:o + 17]
+            vals = b[o + 17:o + 17 + sum(counts)]
+            o += 17 + sum(counts)
+            code, k, d, e = 0, 0, {}, {}
+            for ln in range(1, 17):
+                for _ in range(counts[ln - 1]):
+                    d[(ln, code)] = vals[k]
+                    e[vals[k]] = (code, ln)
+                    code += 1
+                    k += 1
+                code <<= 1
+            dec[tc_th], enc[tc_th] = d, e
+    sos = segs[-1][1]
+    sel = {sos[1 + 2 * i]: (sos[2 + 2 * i] >> 4, sos[2 + 2 * i] & 15) for i in range(sos[0])}
+    bits = "".join(f"{byte:08b}" for byte in ecs)
+    cur = 0
+
+    def sym(table):
+        nonlocal cur
+        code = ln = 0
+        while True:
+            code = (code << 1) | int(bits[cur])
+            cur += 1
+            ln += 1
+            if (ln, code) in table:
+                return table[(ln, code)]
+
+    def receive(s):
+        nonlocal cur
+        if s == 0:
+            return 0
+        v = int(bits[cur:cur + s], 2)
+        cur += s
+        return v if v >= (1 << (s - 1)) else v - (1 << s) + 1
+
+    mcus_x, mcus_y = -(-W // (8 * max_h)), -(-H // (8 * max_v))
+    blocks = {cid: {} for cid, _, _ in comps}
+    pred = {cid: 0 for cid, _, _ in comps}
+    for my in range(mcus_y):
+        for mx in range(mcus_x):
+            for cid, hs, vs in comps:
+                td, ta = sel[cid]
+                for by in range(vs):
+                    for bx in range(hs):
+                        zz = [0] * 64
+                        pred[cid] += receive(sym(dec[td]))
+                        zz[0] = pred[cid]
+                        k = 1
+                        while k < 64:
+                            rs = sym(dec[0x10 | ta])
+                            r, s = rs >> 4, rs & 15
+                            if s == 0:
+                                if r != 15:
+                                    break
+                                k += 16
+                                continue
+                            k += r
+                            zz[k] = receive(s)
+                            k += 1
+                        blocks[cid][(mx * hs + bx, my * vs + by)] = zz
+    out = bytearray(b"\xff\xd8")
+    for m, b in segs[:-1]:
+        out += bytes([0xFF, m]) + struct.pack(">H", len(b) + 2) + b
+
+    def put_bits(acc, value, n):
+        acc.append(f"{value:0{n}b}" if n else "")
+
+    def category(v):
+        return 0 if v == 0 else abs(v).bit_length()
+
+    for cid, hs, vs in comps:
+        td, ta = sel[cid]
+        acc, last = [], 0
+        bw, bh = -(-(-(-W * hs // max_h)) // 8), -(-(-(-H * vs // max_v)) // 8)   # ceil(ceil(W hs / max_h) / 8)
+        for Y in range(bh):
+            for X in range(bw):
+                zz = blocks[cid][(X, Y)]
+                diff, last = zz[0] - last, zz[0]
+                s = category(diff)
+                put_bits(acc, *enc[td][s])
+                put_bits(acc, diff if diff >= 0 else diff + (1 << s) - 1, s)
+                run = 0
+                for k in range(1, 64):
+                    if zz[k] == 0:
+                        run += 1
+                        continue
+                    while run > 15:
+                        put_bits(acc, *enc[0x10 | ta][0xF0])
+                        run -= 16
+                    s = category(zz[k])
+                    put_bits(acc, *enc[0x10 | ta][(run << 4) | s])
+                    put_bits(acc, zz[k] if zz[k] >= 0 else zz[k] + (1 << s) - 1, s)
+                    run = 0
+                if run:
+                    put_bits(acc, *enc[0x10 | ta][0x00])
+        stream = "".join(acc)
+        stream += "1" * (-len(stream) % 8)
+        data = bytes(int(stream[i:i + 8], 2) for i in range(0, len(stream), 8)).replace(b"\xff", b"\xff\x00")
+        out += b"\xff\xda" + struct.pack(">HB", 8, 1) + bytes([cid, (td << 4) | ta, 0, 63, 0]) + data
+    return bytes(out + b"\xff\xd9")
+
+
+@pytest.mark.parametrize("subsampling", [0, 1, 2], ids=["444", "422", "420"])
+def test_one_scan_per_component_layout(subsampling):
+    src = _jpeg(PIL.fromarray(_picture(45, 61), "RGB"), quality=80, subsampling=subsampling)
+    multi = _reencode_non_interleaved(src)
+    assert multi.count(b"\xff\xda") == 3
+    want = np.asarray(PIL.open(io.BytesIO(src)).convert("RGB"))
+    assert np.array_equal(np.asarray(PIL.open(io.BytesIO(multi)).convert("RGB")), want)   # the transcoding is lossless
+    assert np.array_equal(hg._abi.jpeg_decode(multi)[..., :3], want)
