@@ -7,7 +7,8 @@
  * Build (with a Node toolchain):
  *   cc -O2 -fPIC -shared -DHG_USE_SYSTEM_NAPI -I$(node -p "process.execPath+'/../../include/node'") \
  *      -I../../include hgwarp_napi.c -L.. -lhgwarp -Wl,-rpath,'$ORIGIN/..' -o hgwarp.node
- * In this image (no Node) it is only compile-checked against js/napi_min.h (tests/test_js_binding_sources.py).
+ * In this image (no Node) it is compiled against js/napi_min.h and executed under the miniature Node-API runtime of
+ * tests/napi_mock/ (tests/test_napi_addon_mock.py).
  */
 #include <stdio.h>
 #include <stdlib.h>
