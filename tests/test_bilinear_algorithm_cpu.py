@@ -4,7 +4,6 @@ DESIGN on the build machine (no GPU there): flat quad -> row / column with the r
 the exact re-computation of coordinates next to a window bound, the PRMT byte -> float conversion, the float blend and the
 magic-add rounding.  The CUDA kernel itself is checked on the device by tests/test_gpu_numerics.py."""
 import numpy as np
-import pytest
 
 from oracle import oracle as O
 
