@@ -8,7 +8,7 @@ that ABI), homography.py (host mirror of the reference class), js/ (the Node.js 
 source a maintainer would ship), build.py (nvcc recipe).
 """
 from . import _abi, workloads
-from ._abi import Context, HgError, HgFrame, Pipe, device_count
+from ._abi import Context, HgError, HgFrame, HgStreamInfo, Pipe, device_count
 from .homography import Homography, HomographyError, ImageData
 
-__all__ = ["Homography", "HomographyError", "ImageData", "Context", "HgError", "HgFrame", "Pipe", "device_count", "_abi", "workloads"]
+__all__ = ["Homography", "HomographyError", "ImageData", "Context", "HgError", "HgFrame", "HgStreamInfo", "Pipe", "device_count", "_abi", "workloads"]

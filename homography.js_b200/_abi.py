@@ -28,7 +28,11 @@ SYMBOLS = [
     "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_piecewise_extents", "hg_build_index_map",
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
+    "hg_warp_inverse_points_batch", "hg_warp_forward_batch", "hg_warp_piecewise_forward_batch",
+    "hg_warp_piecewise_stream", "hg_stream_slot_bytes", "hg_checksum_frames",
     "hg_pipe_create", "hg_pipe_submit", "hg_pipe_wait", "hg_pipe_flush", "hg_pipe_destroy",
+    "hg_pipe_create_piecewise", "hg_pipe_submit_piecewise",
+    "hg_host_alloc_pinned_ex", "hg_pcie_probe",
     "hg_debug_rcp_max_error", "hg_debug_quotient_at_least", "hg_debug_force_general", "hg_debug_piecewise_stats",
     "hg_dev_alloc", "hg_dev_free", "hg_host_alloc_pinned", "hg_host_free_pinned",
     "hg_memcpy_h2d", "hg_memcpy_d2h", "hg_output_device",
@@ -39,6 +43,25 @@ class HgFrame(C.Structure):
     _fields_ = [("src_dev", C.c_void_p), ("out_dev", C.c_void_p),
                 ("src_w", C.c_int32), ("src_h", C.c_int32),
                 ("x_off", C.c_int32), ("y_off", C.c_int32), ("o_w", C.c_int32), ("o_h", C.c_int32)]
+
+
+class HgStreamInfo(C.Structure):
+    _fields_ = [("x_off", C.c_int32), ("y_off", C.c_int32), ("o_w", C.c_int32), ("o_h", C.c_int32),
+                ("slot", C.c_int32), ("status", C.c_int32)]
+
+
+CHECKSUM_MUL = 2654435761
+CHECKSUM_LEN_MUL = 0x9E3779B97F4A7C15
+
+
+def checksum_reference(rgba_bytes: np.ndarray) -> int:
+    """The checksum hg_checksum_frames computes, in numpy (for comparing device frames with oracle frames):
+    sum_i pixel_i * (((i * 2654435761) mod 2^32) | 1) + n * 0x9E3779B97F4A7C15 (mod 2^64), pixel_i = little-endian RGBA8 word."""
+    px = np.ascontiguousarray(rgba_bytes, dtype=np.uint8).reshape(-1).view("<u4").astype(np.uint64)
+    n = px.size
+    w = ((np.arange(n, dtype=np.uint64) * np.uint64(CHECKSUM_MUL)) & np.uint64(0xFFFFFFFF)) | np.uint64(1)
+    with np.errstate(over="ignore"):
+        return (int((px * w).sum(dtype=np.uint64)) + n * CHECKSUM_LEN_MUL) & 0xFFFFFFFFFFFFFFFF
 
 
 class HgError(RuntimeError):
@@ -93,6 +116,17 @@ def load():
     L.hg_warp_piecewise_forward.argtypes = [vp, vp, i, i, i, i, i, i, i, i, i, vp, vp]
     L.hg_warp_inverse_batch.argtypes = [vp, i, vp, C.POINTER(HgFrame), i]
     L.hg_warp_piecewise_inverse_batch.argtypes = [vp, vp, C.POINTER(HgFrame), i, i, i]
+    L.hg_warp_inverse_points_batch.argtypes = [vp, i, vp, vp, C.POINTER(HgFrame), i]
+    L.hg_warp_forward_batch.argtypes = [vp, i, vp, C.POINTER(HgFrame), i]
+    L.hg_warp_piecewise_forward_batch.argtypes = [vp, vp, C.POINTER(HgFrame), i, i, i, i, i]
+    L.hg_warp_piecewise_stream.argtypes = [vp, vp, i, C.c_int64, i, i, vp, i, i, i, vp, i, i, i, C.POINTER(HgStreamInfo)]
+    L.hg_stream_slot_bytes.argtypes = [i, i]
+    L.hg_stream_slot_bytes.restype = C.c_size_t
+    L.hg_checksum_frames.argtypes = [vp, C.POINTER(HgFrame), i, vp]
+    L.hg_pipe_create_piecewise.argtypes = [vp, i, i, i, i, i, C.POINTER(vp)]
+    L.hg_pipe_submit_piecewise.argtypes = [vp, vp, vp, i, i, vp, vp, C.POINTER(C.c_uint64)]
+    L.hg_host_alloc_pinned_ex.argtypes = [vp, C.c_size_t, i, C.POINTER(vp)]
+    L.hg_pcie_probe.argtypes = [vp, C.c_size_t, i, C.POINTER(d), C.POINTER(d), C.POINTER(d)]
     L.hg_pipe_create.argtypes = [vp, i, i, i, i, i, i, C.POINTER(vp)]
     L.hg_pipe_submit.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, C.POINTER(C.c_uint64)]
     L.hg_pipe_wait.argtypes = [vp, C.c_uint64]
@@ -134,9 +168,13 @@ class Context:
             raise HgError(st, (self.L.hg_last_error(None) or b"").decode())
         self.h = h
         self.device = device
+        self._pinned = []
 
     def close(self):
         if getattr(self, "h", None):
+            for ptr in getattr(self, "_pinned", []):
+                self.L.hg_host_free_pinned(self.h, ptr)
+            self._pinned = []
             self.L.hg_ctx_destroy(self.h)
             self.h = None
 
@@ -215,6 +253,23 @@ class Context:
         p = C.c_void_p()
         self._ck(self.L.hg_host_alloc_pinned(self.h, nbytes, C.byref(p)))
         return p.value
+
+    def host_alloc_pinned_ex(self, nbytes: int, write_combined: bool = False) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.hg_host_alloc_pinned_ex(self.h, nbytes, int(write_combined), C.byref(p)))
+        return p.value
+
+    def pinned_array(self, nbytes: int, write_combined: bool = False) -> np.ndarray:
+        """A uint8 numpy view over page-locked host memory owned by the library (freed by the context's close())."""
+        ptr = self.host_alloc_pinned_ex(nbytes, write_combined)
+        self._pinned.append(ptr)
+        return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr))
+
+    def pcie_probe(self, nbytes: int = 64 << 20, iters: int = 8):
+        """(h2d, d2h, bidirectional) GB/s of raw pinned copies on this GPU's host link (hg_pcie_probe)."""
+        a, b, cc = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.hg_pcie_probe(self.h, nbytes, iters, C.byref(a), C.byref(b), C.byref(cc)))
+        return a.value, b.value, cc.value
 
     def host_free_pinned(self, p: int):
         self._ck(self.L.hg_host_free_pinned(self.h, p))
@@ -317,6 +372,43 @@ class Context:
         arr = (HgFrame * len(frames))(*frames)
         self._ck(self.L.hg_warp_inverse_batch(self.h, kind, _ptr(m), arr, len(frames)))
 
+    def warp_inverse_points_batch(self, kind, dst_pts: np.ndarray, src_pts: np.ndarray, frames):
+        """Per-frame solve + pixel loop for a batch (hg_warp_inverse_points_batch); points: (n_frames, 6 | 8) doubles."""
+        dd = np.ascontiguousarray(dst_pts, dtype=np.float64)
+        ss = np.ascontiguousarray(src_pts, dtype=np.float64)
+        arr = frames if isinstance(frames, C.Array) else (HgFrame * len(frames))(*frames)
+        self._ck(self.L.hg_warp_inverse_points_batch(self.h, kind, _ptr(dd), _ptr(ss), arr, len(arr)))
+
+    def warp_forward_batch(self, kind, fwd_matrices: np.ndarray, frames):
+        m = np.ascontiguousarray(fwd_matrices, dtype=np.float32 if kind == HG_AFFINE else np.float64)
+        arr = frames if isinstance(frames, C.Array) else (HgFrame * len(frames))(*frames)
+        self._ck(self.L.hg_warp_forward_batch(self.h, kind, _ptr(m), arr, len(arr)))
+
+    def warp_piecewise_forward_batch(self, dst_pts, frames, min_src_x, min_src_y, max_src_x, max_src_y):
+        dd = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(-1)
+        arr = frames if isinstance(frames, C.Array) else (HgFrame * len(frames))(*frames)
+        self._ck(self.L.hg_warp_piecewise_forward_batch(self.h, _ptr(dd), arr, len(arr), min_src_x, min_src_y, max_src_x, max_src_y))
+
+    def checksum_frames(self, frames) -> np.ndarray:
+        arr = frames if isinstance(frames, C.Array) else (HgFrame * len(frames))(*frames)
+        out = np.zeros(len(arr), np.uint64)
+        self._ck(self.L.hg_checksum_frames(self.h, arr, len(arr), _ptr(out)))
+        return out
+
+    def stream_slot_bytes(self, max_out_w: int, max_out_h: int) -> int:
+        return int(self.L.hg_stream_slot_bytes(max_out_w, max_out_h))
+
+    def warp_piecewise_stream(self, dst_pts, first_frame, min_src_x, min_src_y, out_ring_dev, n_slots, max_out_w, max_out_h,
+                              src_ring_dev=None, n_src=0, src_w=0, src_h=0, info=None):
+        """hg_warp_piecewise_stream: dst_pts (n_frames, n_pts, 2) float32; returns the HgStreamInfo array."""
+        dd = np.ascontiguousarray(dst_pts, dtype=np.float32)
+        n = dd.shape[0]
+        if info is None:
+            info = (HgStreamInfo * n)()
+        self._ck(self.L.hg_warp_piecewise_stream(self.h, _ptr(dd), n, int(first_frame), min_src_x, min_src_y, src_ring_dev, n_src,
+                                                 src_w, src_h, out_ring_dev, n_slots, max_out_w, max_out_h, info))
+        return info
+
     # ---- piecewise
     def piecewise_set_mesh(self, src_pts, tris):
         p = np.ascontiguousarray(src_pts, dtype=np.float32).reshape(-1)
@@ -348,11 +440,15 @@ class Context:
         return out
 
     def warp_piecewise_inverse(self, dst_pts, x_off, y_off, o_w, o_h, min_src_x, min_src_y, to_host=True,
-                               out_dev=None):
+                               out_dev=None, out_host_ptr=None):
         d = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(-1)
-        out = np.empty(o_w * o_h * 4, np.uint8) if to_host else None
+        out = None
+        hp = out_host_ptr
+        if hp is None and to_host:
+            out = np.empty(o_w * o_h * 4, np.uint8)
+            hp = out.ctypes.data
         self._ck(self.L.hg_warp_piecewise_inverse(self.h, _ptr(d), x_off, y_off, o_w, o_h, min_src_x, min_src_y,
-                                                  _ptr(out), out_dev))
+                                                  hp, out_dev))
         return out
 
     def warp_piecewise_forward(self, dst_pts, x_off, y_off, o_w, o_h, min_src_x, min_src_y, max_src_x, max_src_y,
@@ -390,6 +486,26 @@ class Pipe:
 
     def wait(self, ticket: int):
         self.ctx._ck(self.L.hg_pipe_wait(self.h, ticket))
+
+    @classmethod
+    def piecewise(cls, ctx: "Context", src_w: int, src_h: int, max_out_w: int, max_out_h: int, depth: int = 3) -> "Pipe":
+        """hg_pipe_create_piecewise: the same pipeline for inverse piecewise frames of the context mesh."""
+        self = cls.__new__(cls)
+        self.ctx, self.L = ctx, ctx.L
+        h = C.c_void_p()
+        ctx._ck(self.L.hg_pipe_create_piecewise(ctx.h, src_w, src_h, max_out_w, max_out_h, depth, C.byref(h)))
+        self.h = h
+        self.npts = 0
+        return self
+
+    def submit_piecewise(self, rgba_host_ptr, dst_pts, min_src_x, min_src_y, out_host_ptr: int):
+        """Returns (ticket, (x_off, y_off, o_w, o_h)); rgba_host_ptr None = the context image."""
+        d = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(-1)
+        t = C.c_uint64()
+        win = (C.c_int32 * 4)()
+        self.ctx._ck(self.L.hg_pipe_submit_piecewise(self.h, rgba_host_ptr, d.ctypes.data, min_src_x, min_src_y, out_host_ptr,
+                                                      win, C.byref(t)))
+        return t.value, tuple(win)
 
     def flush(self):
         self.ctx._ck(self.L.hg_pipe_flush(self.h))

@@ -7,9 +7,20 @@
 //
 // The reference runs sequentially, so when several source pixels land on one output pixel the LAST one in loop
 // order wins, and writes whose flat index falls outside [0, len) are dropped while in-range-but-wrapped ones land
-// (Q3).  Here: pass 1 scatters the loop-order KEY of every source element with atomicMax into a 32-bit "winner"
-// plane (an order-independent reduction with the same result), pass 2 gathers the winning source pixel for every
-// output pixel and writes the whole output once with 128-bit stores (untouched pixels become transparent).
+// (Q3).  Here:
+//   general     pass 1 scatters the loop-order KEY of every source element with a 32-bit atomic max into a "winner"
+//               plane (an order-independent reduction with the same result; RED, no return value), pass 2 gathers the
+//               winning source pixel for every output pixel, writes the whole output once with 128-bit stores
+//               (untouched pixels become transparent) and RESETS the plane entry it read — so the plane is clean for
+//               the next frame without a memset pass, and a small ring of planes stays resident in the 126 MB L2
+//               while a batch streams through it (DRAM sees the 4 B read + 4 B write per pixel only).
+//   lattice     affine matrices whose linear part is a signed permutation with exact 0 / +-1 entries (translations,
+//               mirrors, quarter turns: what warp() actually dispatches here — the forward loop is only chosen when
+//               the output has the size of the input, H.js:426) map the pixel lattice onto itself one to one:
+//               round((+-x) + e - xOff) = +-x + round(e - xOff) exactly.  No collisions, no ordering question: one
+//               gather pass with the integer inverse, 8 B per pixel, no atomics (forward_lattice_kernel; the host
+//               proves the preconditions per frame, see forward_lattice_plan in hgwarp.cu).
+// Both kernels take a batch: blockIdx.y = frame.
 #pragma once
 #include "piecewise.cuh"
 
@@ -39,7 +50,7 @@ __device__ __forceinline__ long long forward_target(double tx, double ty, int xO
 struct FwdArgs {
     const uint32_t *src;
     uint32_t *out;
-    int *winner;             // oW*oH ints, initialised to -1
+    int *winner;             // oW*oH ints, all -1 between frames
     const int *map32;        // piecewise only
     const TriRec *rec;       // piecewise only
     long long map_len;
@@ -48,14 +59,30 @@ struct FwdArgs {
     int W, H, xOff, yOff, oW, oH;
     int minX, minY, domW, domH;  // loop domain: x in [minX, minX+domW), y in [minY, minY+domH)
     int n_tris;
+    // lattice plan (forward_lattice_kernel): source pixel of output (X, Y) is
+    //   x = ixx * (X - rx) + ixy * (Y - ry),  y = iyx * (X - rx) + iyy * (Y - ry)     (integer inverse of the permutation)
+    int lattice;             // 1: this frame takes the lattice kernel
+    int ixx, ixy, iyx, iyy, rx, ry;
+};
+
+struct FwdParams {
+    FwdArgs one;             // used when many == nullptr
+    const FwdArgs *many;     // device array, indexed by blockIdx.y
 };
 
 template <bool PIECEWISE>
-__global__ void __launch_bounds__(256) forward_scatter_kernel(const FwdArgs a)
+__global__ void __launch_bounds__(256) forward_scatter_kernel(const FwdParams P)
 {
+    const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
+    if (a.lattice) return;
     const long long n = (long long)a.domW * a.domH;
     const long long npix_out = (long long)a.oW * a.oH;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    float mf[6];
+    if (!PIECEWISE) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) mf[k] = (float)a.mat[k];
+    }
     for (long long key = (long long)blockIdx.x * blockDim.x + threadIdx.x; key < n; key += stride) {
         const int yy = (int)(key / a.domW);
         const int xx = (int)(key - (long long)yy * a.domW);
@@ -63,15 +90,12 @@ __global__ void __launch_bounds__(256) forward_scatter_kernel(const FwdArgs a)
         double tx, ty;
         if (PIECEWISE) {
             if (key >= a.map_len) continue;  // read past the map: undefined > -1 is false
-            const int raw = a.map32[key];
+            const int raw = __ldg(a.map32 + key);
             const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);  // Int16Array semantics
             if (t < 0 || t >= a.n_tris) continue;
             apply_affine_general(a.rec[t].fwd, x, y, tx, ty);
         } else if (a.kind == 0) {
-            float m[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) m[k] = (float)a.mat[k];
-            apply_affine_general(m, x, y, tx, ty);
+            apply_affine_general(mf, x, y, tx, ty);
         } else {
             apply_projective_general(a.mat, x, y, tx, ty);
         }
@@ -80,28 +104,44 @@ __global__ void __launch_bounds__(256) forward_scatter_kernel(const FwdArgs a)
     }
 }
 
-// pass 2: every output pixel takes the source pixel of its winning key (or stays transparent)
-__global__ void __launch_bounds__(256) forward_gather_kernel(const FwdArgs a)
+// pass 2: every output pixel takes the source pixel of its winning key (or stays transparent) and hands the plane
+// entry back as -1
+__global__ void __launch_bounds__(256) forward_gather_kernel(const FwdParams P)
 {
+    const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
+    if (a.lattice) return;
     const long long npix = (long long)a.oW * a.oH;
     const long long nquad = (npix + 3) >> 2;
     const long long npx_src = (long long)a.W * a.H;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += stride) {
         const long long p0 = q << 2;
+        int key[4];
+        if (p0 + 3 < npix) {
+            int4 *wp = reinterpret_cast<int4 *>(a.winner + p0);
+            const int4 kv = *wp;
+            key[0] = kv.x; key[1] = kv.y; key[2] = kv.z; key[3] = kv.w;
+            if ((kv.x & kv.y & kv.z & kv.w) != -1) *wp = make_int4(-1, -1, -1, -1);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                key[k] = -1;
+                if (p0 + k < npix) {
+                    key[k] = a.winner[p0 + k];
+                    if (key[k] != -1) a.winner[p0 + k] = -1;
+                }
+            }
+        }
         uint32_t px[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             uint32_t v = 0u;
-            if (p0 + k < npix) {
-                const int key = a.winner[p0 + k];
-                if (key >= 0) {
-                    const int yy = key / a.domW;
-                    const int xx = key - yy * a.domW;
-                    // idx = y*(W<<2) + (x<<2): flat, so x >= W runs into the next row; outside the image -> 0
-                    const long long flat = (long long)(a.minY + yy) * a.W + (a.minX + xx);
-                    if (flat >= 0 && flat < npx_src) v = __ldg(a.src + flat);
-                }
+            if (key[k] >= 0) {
+                const int yy = key[k] / a.domW;
+                const int xx = key[k] - yy * a.domW;
+                // idx = y*(W<<2) + (x<<2): flat, so x >= W runs into the next row; outside the image -> 0
+                const long long flat = (long long)(a.minY + yy) * a.W + (a.minX + xx);
+                if (flat >= 0 && flat < npx_src) v = __ldg(a.src + flat);
             }
             px[k] = v;
         }
@@ -113,6 +153,47 @@ __global__ void __launch_bounds__(256) forward_gather_kernel(const FwdArgs a)
                 if (p0 + k < npix) a.out[p0 + k] = px[k];
         }
     }
+}
+
+// lattice frames: out(X, Y) = src(x, y) with the integer inverse of the plan, transparent where (x, y) leaves the
+// loop domain [0, W) x [0, H).  One flat quad per thread and step (a quad may run over a row end: (X, Y) per pixel).
+__global__ void __launch_bounds__(256) forward_lattice_kernel(const FwdParams P)
+{
+    const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
+    if (!a.lattice) return;
+    const long long npix = (long long)a.oW * a.oH;
+    const long long nquad = (npix + 3) >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const uint32_t *__restrict__ src = a.src;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += stride) {
+        const long long p0 = q << 2;
+        int Y = (int)(p0 / a.oW);
+        int X = (int)(p0 - (long long)Y * a.oW);
+        uint32_t px[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int u = X - a.rx, v = Y - a.ry;
+            const int x = a.ixx * u + a.ixy * v, y = a.iyx * u + a.iyy * v;
+            uint32_t w = 0u;
+            if ((unsigned)x < (unsigned)a.W && (unsigned)y < (unsigned)a.H && p0 + k < npix) w = __ldg(src + (size_t)y * a.W + x);
+            px[k] = w;
+            if (++X == a.oW) { X = 0; ++Y; }
+        }
+        if (p0 + 3 < npix) {
+            *reinterpret_cast<uint4 *>(a.out + p0) = make_uint4(px[0], px[1], px[2], px[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (p0 + k < npix) a.out[p0 + k] = px[k];
+        }
+    }
+}
+
+// fills a buffer of ints with -1 (a fresh winner plane)
+__global__ void fill_minus_one_kernel(int *p, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = -1;
 }
 
 }  // namespace hg

@@ -23,6 +23,7 @@
 #include "bilinear.cuh"
 #include "forward.cuh"
 #include "piecewise_fused.cuh"
+#include "stream.cuh"
 #include "delaunay_host.cuh"
 #include "png_host.cuh"
 #include "jpeg_host.cuh"
@@ -68,6 +69,11 @@ struct hg_ctx {
     // mesh
     DevBuf src_pts, dst_pts, tris, rec, map32, map16, frames, mats, winner;
     DevBuf invd, bin_cnt, bin_ent, bin_run, fstatus, fframes;  // fused piecewise path
+    DevBuf fwd_args, cs_frames, cs_out, sinfo, pts_batch;     // forward batches, checksums, stream bookkeeping, point batches
+    bool winner_clean = false;  // every entry of `winner` is -1 (the gather pass hands the plane back clean)
+    void *pin_big = nullptr;    // pinned host staging for per-frame status / info read-backs
+    cudaEvent_t ev_chunk[2] = {nullptr, nullptr};  // chunk boundaries of hg_warp_piecewise_stream
+    size_t pin_big_cap = 0;
     // parameters of the last inverse index map (rebuilt on demand for the aliasing forward read, Q8)
     std::vector<float> last_inv_pts;
     double last_inv_mw = 0, last_inv_yoff = 0;
@@ -89,6 +95,7 @@ struct hg_ctx {
     int geo_debug = 0;              // HG_GEO_DEBUG: the staged kernel's producer traces its ring
     bool no_tall = false;           // HG_GEO_NO_TALL: never pick the tall thread layout (A/B runs)
     bool bilinear_v1 = false;       // HG_BILINEAR_V1: first-generation bilinear kernel (A/B runs)
+    bool pwf_v1 = false;            // HG_PWF_V1: first-generation fused piecewise pixel kernel (A/B runs)
     CUtensorMap img_tm[GEO_NBOX];
     bool img_tm_ok = false;
     DevBuf tm_dev;                   // TM_CACHE_SLOTS x GEO_NBOX tensor maps
@@ -140,6 +147,23 @@ int ensure(hg_ctx *c, DevBuf &b, size_t bytes)
         return fail(c, HG_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
     }
     b.cap = want;
+    return HG_OK;
+}
+
+int ensure_pinned(hg_ctx *c, size_t bytes)
+{
+    if (bytes <= c->pin_big_cap) return HG_OK;
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (c->pin_big) CU(c, cudaFreeHost(c->pin_big));
+    c->pin_big = nullptr;
+    c->pin_big_cap = 0;
+    const size_t want = bytes + bytes / 2 + 4096;
+    cudaError_t e = cudaHostAlloc(&c->pin_big, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, HG_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    c->pin_big_cap = want;
     return HG_OK;
 }
 
@@ -498,6 +522,7 @@ int hg_ctx_create(int device, hg_ctx **out)
         env_int("HG_GEO_DEBUG", 0, 2, c->geo_debug);
         c->no_tall = getenv("HG_GEO_NO_TALL") != nullptr;
         c->bilinear_v1 = getenv("HG_BILINEAR_V1") != nullptr;
+        c->pwf_v1 = getenv("HG_PWF_V1") != nullptr;
         // the ring must fit a CTA's shared memory: shrink the depth (the CTA count follows from the occupancy below)
         const size_t cta_max = prop.sharedMemPerBlockOptin;
         auto ring = [&]() { return (size_t)c->geo_stages * (size_t)(GEO_HDR_BYTES + c->geo_box_bytes); };
@@ -529,10 +554,14 @@ int hg_ctx_destroy(hg_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->img_own, &c->out, &c->scratch, &c->src_pts, &c->dst_pts, &c->tris,
                       &c->rec, &c->map32, &c->map16, &c->frames, &c->mats, &c->winner,
-                      &c->invd, &c->bin_cnt, &c->bin_ent, &c->bin_run, &c->fstatus, &c->fframes, &c->tm_dev};
+                      &c->invd, &c->bin_cnt, &c->bin_ent, &c->bin_run, &c->fstatus, &c->fframes, &c->tm_dev,
+                      &c->fwd_args, &c->cs_frames, &c->cs_out, &c->sinfo, &c->pts_batch};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->pin_big) cudaFreeHost(c->pin_big);
+    for (cudaEvent_t e : c->ev_chunk)
+        if (e) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto &pr : c->prof_ev) {
@@ -811,28 +840,168 @@ int hg_warp_inverse_points(hg_ctx *c, int kind, const double *dst_pts, const dou
     return warp_inverse_common(c, kind, nullptr, true, x_off, y_off, o_w, o_h, out_host, out_dev, points_map_is_rotated(dst_pts, src_pts));
 }
 
+// a winner plane of `ints` entries, all -1 (the gather pass resets what it reads, so a fill is only needed after the
+// buffer grew or a failed call left it dirty)
+static int ensure_winner(hg_ctx *c, size_t ints)
+{
+    if (sizeof(int) * ints <= c->winner.cap && c->winner_clean) return HG_OK;
+    TRY(ensure(c, c->winner, sizeof(int) * ints));
+    const long long n = (long long)(c->winner.cap / sizeof(int));
+    fill_minus_one_kernel<<<(unsigned)(c->sm_count * 8), 256, 0, c->stream>>>((int *)c->winner.p, n);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    c->winner_clean = true;
+    return HG_OK;
+}
+
+// Does the forward affine matrix map the pixel lattice onto itself one to one (forward.cuh, "lattice")?  Linear part a
+// signed permutation with exact 0 / +-1 entries; translation e with e == 0 or 2^-8 <= |e| <= 2^18, so that
+// (+-x) + e and the subtraction of the offset are exact in double and round((+-x) + e - xOff) = +-x + round(e - xOff);
+// and no source pixel of the loop domain lands outside [0, oW) in x (the flat-index wrap of Q3 would otherwise fold
+// several (nx, ny) onto one output pixel).  Fills the plan fields of `a` when it does.
+static bool forward_lattice_plan(FwdArgs &a)
+{
+    a.lattice = 0;
+    if (a.kind != HG_AFFINE) return false;
+    const double m0 = a.mat[0], m1 = a.mat[1], m2 = a.mat[2], m3 = a.mat[3], e = a.mat[4], f = a.mat[5];
+    auto unit = [](double v) { return v == 0.0 || v == 1.0 || v == -1.0; };
+    if (!unit(m0) || !unit(m1) || !unit(m2) || !unit(m3)) return false;
+    const int sxx = (int)m0, syx = (int)m1, sxy = (int)m2, syy = (int)m3;
+    if (std::abs(sxx) + std::abs(sxy) != 1 || std::abs(syx) + std::abs(syy) != 1 || std::abs(sxx) + std::abs(syx) != 1) return false;
+    auto exact = [](double v) { return v == 0.0 || (std::fabs(v) >= 0.00390625 && std::fabs(v) <= 262144.0); };
+    if (!exact(e) || !exact(f)) return false;
+    if (a.W > 65536 || a.H > 65536) return false;
+    auto round_half_up = [](double v) { const double fl = std::floor(v); return (long long)fl + ((v - fl) >= 0.5 ? 1 : 0); };
+    const long long rx = round_half_up(e - (double)a.xOff), ry = round_half_up(f - (double)a.yOff);
+    // nx over the loop domain x in [0, W), y in [0, H)
+    const long long xs[2] = {0, a.W - 1}, ys[2] = {0, a.H - 1};
+    long long nmin = (1LL << 62), nmax = -(1LL << 62);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            const long long nx = sxx * xs[i] + sxy * ys[j] + rx;
+            if (nx < nmin) nmin = nx;
+            if (nx > nmax) nmax = nx;
+        }
+    if (nmin < 0 || nmax >= a.oW) return false;
+    if (std::llabs(rx) > (1LL << 20) || std::llabs(ry) > (1LL << 20)) return false;
+    a.lattice = 1;
+    a.ixx = sxx; a.ixy = syx; a.iyx = sxy; a.iyy = syy;  // inverse of a signed permutation = its transpose
+    a.rx = (int)rx; a.ry = (int)ry;
+    return true;
+}
+
+static unsigned fwd_blocks(hg_ctx *c, long long items, int n_frames)
+{
+    long long blocks = (items + 255) / 256;
+    long long cap = (long long)c->sm_count * (n_frames > 1 ? 4 : 16);
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
 static int run_forward(hg_ctx *c, FwdArgs &a, bool piecewise, uint32_t *dst, size_t bytes, uint8_t *out_host)
 {
     const long long npix = (long long)a.oW * a.oH;
-    TRY(ensure(c, c->winner, sizeof(int) * (size_t)npix));
-    CU(c, cudaMemsetAsync(c->winner.p, 0xFF, sizeof(int) * (size_t)npix, c->stream));
-    a.winner = (int *)c->winner.p;
     a.out = dst;
+    FwdParams P{};
+    P.many = nullptr;
+    if (!piecewise && forward_lattice_plan(a)) {
+        P.one = a;
+        TRY(prof_begin(c));
+        forward_lattice_kernel<<<dim3(fwd_blocks(c, (npix + 3) / 4, 1), 1), 256, 0, c->stream>>>(P);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        TRY(prof_end(c));
+        return finish_out(c, dst, bytes, out_host);
+    }
+    TRY(ensure_winner(c, (size_t)npix));
+    a.winner = (int *)c->winner.p;
+    P.one = a;
+    c->winner_clean = false;
     const long long n = (long long)a.domW * a.domH;
+    TRY(prof_begin(c));
     if (n > 0) {
-        long long blocks = (n + 255) / 256;
-        if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
-        if (piecewise) forward_scatter_kernel<true><<<(unsigned)blocks, 256, 0, c->stream>>>(a);
-        else forward_scatter_kernel<false><<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+        const dim3 g(fwd_blocks(c, n, 1), 1);
+        if (piecewise) forward_scatter_kernel<true><<<g, 256, 0, c->stream>>>(P);
+        else forward_scatter_kernel<false><<<g, 256, 0, c->stream>>>(P);
         c->launches++;
         CU(c, cudaGetLastError());
     }
-    TRY(prof_begin(c));
-    forward_gather_kernel<<<grid_for(c, npix, 1), 256, 0, c->stream>>>(a);
+    forward_gather_kernel<<<dim3(fwd_blocks(c, (npix + 3) / 4, 1), 1), 256, 0, c->stream>>>(P);
     c->launches++;
     CU(c, cudaGetLastError());
     TRY(prof_end(c));
+    c->winner_clean = true;
     return finish_out(c, dst, bytes, out_host);
+}
+
+// a batch of forward frames whose FwdArgs (winner still unset) are in `fa`: lattice frames in one launch, the others
+// through a small ring of winner planes that stays resident in L2
+static int run_forward_batch(hg_ctx *c, std::vector<FwdArgs> &fa, bool piecewise)
+{
+    const int n_frames = (int)fa.size();
+    long long max_npix = 1, max_dom = 1;
+    int n_lattice = 0;
+    for (auto &a : fa) {
+        if (!piecewise && forward_lattice_plan(a)) { n_lattice++; continue; }
+        const long long npix = (long long)a.oW * a.oH, dom = (long long)a.domW * a.domH;
+        if (npix > max_npix) max_npix = npix;
+        if (dom > max_dom) max_dom = dom;
+    }
+    max_npix = (max_npix + 3) & ~3LL;  // planes start 16-byte aligned (the gather pass reads and resets them four at a time)
+    // planes: as many as fit ~48 MB (they are read, reset and re-used while L2-resident), between 1 and 8
+    int planes = (int)((48ll << 20) / (max_npix * 4));
+    if (planes < 1) planes = 1;
+    if (planes > 8) planes = 8;
+    if (n_lattice < n_frames) {
+        TRY(ensure_winner(c, (size_t)max_npix * planes));
+        int k = 0;
+        for (auto &a : fa)
+            if (!a.lattice) a.winner = (int *)c->winner.p + (size_t)max_npix * (k++ % planes);
+    }
+    TRY(ensure(c, c->fwd_args, sizeof(FwdArgs) * (size_t)n_frames));
+    // general frames first in device order? no: keep frame order, kernels skip frames of the other kind
+    CU(c, cudaMemcpyAsync(c->fwd_args.p, fa.data(), sizeof(FwdArgs) * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
+    TRY(prof_begin(c));
+    if (n_lattice > 0) {
+        long long max_q = 1;
+        for (auto &a : fa)
+            if (a.lattice && ((long long)a.oW * a.oH + 3) / 4 > max_q) max_q = ((long long)a.oW * a.oH + 3) / 4;
+        for (int f0 = 0; f0 < n_frames; f0 += 32768) {
+            const int nf = n_frames - f0 < 32768 ? n_frames - f0 : 32768;
+            FwdParams P{};
+            P.many = (const FwdArgs *)c->fwd_args.p + f0;
+            forward_lattice_kernel<<<dim3(fwd_blocks(c, max_q, nf), (unsigned)nf), 256, 0, c->stream>>>(P);
+            c->launches++;
+        }
+        CU(c, cudaGetLastError());
+    }
+    if (n_lattice < n_frames) {
+        c->winner_clean = false;
+        // sub-batches of consecutive frames that together hold at most `planes` general frames
+        int f0 = 0;
+        while (f0 < n_frames) {
+            int f1 = f0, g = 0;
+            while (f1 < n_frames && f1 - f0 < 32768 && (g < planes || fa[(size_t)f1].lattice)) {
+                if (!fa[(size_t)f1].lattice) g++;
+                f1++;
+            }
+            if (g > 0) {
+                const int nf = f1 - f0;
+                FwdParams P{};
+                P.many = (const FwdArgs *)c->fwd_args.p + f0;
+                const dim3 gs(fwd_blocks(c, max_dom, nf), (unsigned)nf), gg(fwd_blocks(c, (max_npix + 3) / 4, nf), (unsigned)nf);
+                if (piecewise) forward_scatter_kernel<true><<<gs, 256, 0, c->stream>>>(P);
+                else forward_scatter_kernel<false><<<gs, 256, 0, c->stream>>>(P);
+                forward_gather_kernel<<<gg, 256, 0, c->stream>>>(P);
+                c->launches += 2;
+            }
+            f0 = f1;
+        }
+        CU(c, cudaGetLastError());
+        c->winner_clean = true;
+    }
+    TRY(prof_end(c));
+    return HG_OK;
 }
 
 int hg_warp_forward_matrix(hg_ctx *c, int kind, const void *fwd_matrix, int x_off, int y_off, int o_w, int o_h,
@@ -1019,6 +1188,16 @@ static int check_points(hg_ctx *c, const float *p, int n, const char *what)
     return HG_OK;
 }
 
+static int check_point_floats(hg_ctx *c, const float *p, size_t n_floats, const char *what)
+{
+    for (size_t i = 0; i < n_floats; ++i) {
+        const float v = p[i];
+        if (!(v >= -1048576.f && v <= 1048576.f))  // also rejects NaN / Inf
+            return fail(c, HG_ERR_UNSUPPORTED, "%s[%zu] = %g: piecewise points must be finite and |v| <= 2^20", what, i, (double)v);
+    }
+    return HG_OK;
+}
+
 int hg_piecewise_set_mesh(hg_ctx *c, const float *src_pts, int n_pts, const uint32_t *tris, int n_tris)
 {
     BIND(c);
@@ -1186,6 +1365,49 @@ static int pw_inverse_general_frame(hg_ctx *c, const float *dst_dev, const PwFra
     return HG_OK;
 }
 
+// the kernel chain of the fused path over the nF FusedFrame descriptors in c->fframes (written by the host or by
+// pw_stream_frames_kernel); bin counters and status flags are already zeroed.  Grids are sized for a max_ow x max_oh
+// window: CTAs beyond a smaller frame's extent exit at once.
+static int pw_fused_launch(hg_ctx *c, const float *dst_dev, int nF, int max_ow, int max_oh, size_t max_bins)
+{
+    const size_t T = (size_t)c->n_tris;
+    // rows per CTA = 16 * niter: long-lived CTAs amortise their start-up and keep the software pipeline full
+    int niter = 16;
+    while (niter > 1 && (long long)pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter) * nF < (long long)c->sm_count * 16) niter >>= 1;
+    const int max_tiles = pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter);
+    if (T > 0) {
+        PwSetupArgs a{};
+        a.src_pts = (const float *)c->src_pts.p;
+        a.dst_pts = dst_dev;
+        a.map_pts = dst_dev;
+        a.tris = (const uint32_t *)c->tris.p;
+        a.rec = (TriRec *)c->rec.p;
+        a.invd_out = (double *)c->invd.p;
+        a.n_tris = c->n_tris;
+        a.dst_stride = 2 * (size_t)c->n_pts;
+        a.rec_stride = T;
+        pw_setup_kernel<<<dim3((unsigned)((T + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>(a);
+        // warps per triangle: a mesh of T triangles over oH rows has triangles ~ oH / sqrt(T/2) rows tall
+        int split = (int)((double)max_oh / (32.0 * sqrt((double)T / 2.0 + 1.0)) + 0.5);
+        if (split < 1) split = 1;
+        if (split > 16) split = 16;
+        pw_span_bin_kernel<<<dim3((unsigned)((T * split + 3) / 4), (unsigned)nF), 128, 0, c->stream>>>(
+            (const FusedFrame *)c->fframes.p, split);
+        c->launches += 2;
+        CU(c, cudaGetLastError());
+    }
+    pw_bin_runs_kernel<<<dim3((unsigned)((max_bins + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    TRY(prof_begin(c));
+    if (c->pwf_v1) pw_warp_fused_v1_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p, niter);
+    else pw_warp_fused_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p, niter);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    TRY(prof_end(c));
+    return HG_OK;
+}
+
 // fused (map-free) inverse piecewise warp of nF frames in four launches; status_dev[f] != 0 afterwards means
 // frame f could not be represented and must be redone with pw_inverse_general_frame
 static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrameHost *fr, int nF, int min_src_x,
@@ -1194,20 +1416,15 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
     const size_t T = (size_t)c->n_tris;
     std::vector<FusedFrame> ff((size_t)nF);
     size_t total_bins = 0;
-    int max_tiles = 1;
     for (int f = 0; f < nF; ++f) {
-        const int bx = pwf_tiles_x(fr[f].oW);
+        const int bx = pwf_bins_x(fr[f].oW);
         total_bins += (size_t)bx * fr[f].oH;
     }
-    // rows per CTA = 16 * niter: long-lived CTAs amortise their start-up and keep the software pipeline full
     int max_ow = 1, max_oh = 1;
     for (int f = 0; f < nF; ++f) {
         if (fr[f].oW > max_ow) max_ow = fr[f].oW;
         if (fr[f].oH > max_oh) max_oh = fr[f].oH;
     }
-    int niter = 16;
-    while (niter > 1 && (long long)pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter) * nF < (long long)c->sm_count * 16) niter >>= 1;
-    max_tiles = pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter);
     TRY(ensure(c, c->rec, sizeof(TriRec) * T * nF));
     TRY(ensure(c, c->invd, sizeof(double) * 6 * T * nF));
     // + one row group of slack: the pixel kernel's bin pointers may step (and read, but never use) past the last row
@@ -1231,49 +1448,18 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         F.xOff = fr[f].xOff; F.yOff = fr[f].yOff; F.oW = fr[f].oW; F.oH = fr[f].oH;
         F.minSrcX = min_src_x; F.minSrcY = min_src_y;
         F.n_tris = c->n_tris;
-        F.bins_x = pwf_tiles_x(fr[f].oW);
+        F.bins_x = pwf_bins_x(fr[f].oW);
         bin0 += (size_t)F.bins_x * fr[f].oH;
     }
     CU(c, cudaMemcpyAsync(c->fframes.p, ff.data(), sizeof(FusedFrame) * (size_t)nF, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * total_bins, c->stream));
     CU(c, cudaMemsetAsync(c->fstatus.p, 0, sizeof(int) * (size_t)nF, c->stream));
-    if (T > 0) {
-        PwSetupArgs a{};
-        a.src_pts = (const float *)c->src_pts.p;
-        a.dst_pts = dst_dev;
-        a.map_pts = dst_dev;
-        a.tris = (const uint32_t *)c->tris.p;
-        a.rec = (TriRec *)c->rec.p;
-        a.invd_out = (double *)c->invd.p;
-        a.n_tris = c->n_tris;
-        a.dst_stride = 2 * (size_t)c->n_pts;
-        a.rec_stride = T;
-        pw_setup_kernel<<<dim3((unsigned)((T + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>(a);
-        // warps per triangle: a mesh of T triangles over oH rows has triangles ~ oH / sqrt(T/2) rows tall
-        int split = (int)((double)max_oh / (32.0 * sqrt((double)T / 2.0 + 1.0)) + 0.5);
-        if (split < 1) split = 1;
-        if (split > 16) split = 16;
-        pw_span_bin_kernel<<<dim3((unsigned)((T * split + 3) / 4), (unsigned)nF), 128, 0, c->stream>>>(
-            (const FusedFrame *)c->fframes.p, split);
-        c->launches += 2;
-        CU(c, cudaGetLastError());
+    size_t max_bins = 1;
+    for (int f = 0; f < nF; ++f) {
+        const size_t nb = (size_t)pwf_bins_x(fr[f].oW) * fr[f].oH;
+        if (nb > max_bins) max_bins = nb;
     }
-    {
-        size_t max_bins = 1;
-        for (int f = 0; f < nF; ++f) {
-            const size_t nb = (size_t)pwf_tiles_x(fr[f].oW) * fr[f].oH;
-            if (nb > max_bins) max_bins = nb;
-        }
-        pw_bin_runs_kernel<<<dim3((unsigned)((max_bins + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
-        c->launches++;
-        CU(c, cudaGetLastError());
-    }
-    TRY(prof_begin(c));
-    pw_warp_fused_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p, niter);
-    c->launches++;
-    CU(c, cudaGetLastError());
-    TRY(prof_end(c));
-    return HG_OK;
+    return pw_fused_launch(c, dst_dev, nF, max_ow, max_oh, max_bins);
 }
 
 static bool pw_fused_possible(hg_ctx *c, const PwFrameHost &f)
@@ -1396,18 +1582,14 @@ int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *dst_pts, const hg_fr
         g.xOff = h.x_off; g.yOff = h.y_off; g.oW = h.o_w; g.oH = h.o_h;
     }
     const size_t pts_per_frame = 2 * (size_t)c->n_pts;
-    for (size_t i = 0; i < pts_per_frame * (size_t)n_frames; ++i) {
-        const float v = dst_pts[i];
-        if (!(v >= -1048576.f && v <= 1048576.f))
-            return fail(c, HG_ERR_UNSUPPORTED, "dst_pts[%zu] = %g: piecewise points must be finite and |v| <= 2^20", i, (double)v);
-    }
+    TRY(check_point_floats(c, dst_pts, pts_per_frame * (size_t)n_frames, "dst_pts"));
     TRY(upload_dst_points(c, dst_pts, (size_t)n_frames));
     c->map32_current = false;
     c->last_inv_len = -1;
     // chunk so that the per-frame scratch (triangle records, inverse matrices, bins) stays below ~1.5 GB
     size_t per_frame = (sizeof(TriRec) + 48) * (size_t)c->n_tris;
     for (int f = 0; f < n_frames; ++f) {
-        const size_t b = (size_t)pwf_tiles_x(fr[(size_t)f].oW) * fr[(size_t)f].oH * (4 + 4 * PW_BIN_CAP);
+        const size_t b = (size_t)pwf_bins_x(fr[(size_t)f].oW) * fr[(size_t)f].oH * (4 + 4 * PW_BIN_CAP + 32);
         if (b + (sizeof(TriRec) + 48) * (size_t)c->n_tris > per_frame) per_frame = b + (sizeof(TriRec) + 48) * (size_t)c->n_tris;
     }
     int chunk = (int)((1500ull << 20) / (per_frame ? per_frame : 1));
@@ -1467,6 +1649,7 @@ struct hg_pipe_slot {
 
 struct hg_pipe {
     hg_ctx *c = nullptr;
+    bool piecewise = false;
     int kind = 0, W = 0, H = 0, max_ow = 0, max_oh = 0, depth = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     std::vector<hg_pipe_slot> slots;
@@ -1545,6 +1728,7 @@ int hg_pipe_submit(hg_pipe *p, const uint8_t *rgba_host, const double *dst_pts, 
     hg_ctx *c = p->c;
     BIND(c);
     NEED(c, rgba_host && dst_pts && src_pts && out_host, "NULL argument");
+    NEED(c, !p->piecewise, "a piecewise pipe takes hg_pipe_submit_piecewise");
     TRY(check_window(c, x_off, y_off, o_w, o_h));
     if (o_w > p->max_ow || o_h > p->max_oh || (long long)o_w * o_h > (long long)p->max_ow * p->max_oh)
         return fail(c, HG_ERR_INVALID, "output %dx%d exceeds the pipe's maximum %dx%d", o_w, o_h, p->max_ow, p->max_oh);
@@ -1592,6 +1776,97 @@ int hg_pipe_submit(hg_pipe *p, const uint8_t *rgba_host, const double *dst_pts, 
     return HG_OK;
 }
 
+int hg_pipe_create_piecewise(hg_ctx *c, int src_w, int src_h, int max_out_w, int max_out_h, int depth, hg_pipe **out)
+{
+    const int r = hg_pipe_create(c, HG_AFFINE, src_w, src_h, max_out_w, max_out_h, depth, out);
+    if (r == HG_OK) (*out)->piecewise = true;
+    return r;
+}
+
+namespace {
+// the fused / general piecewise helpers enqueue on c->stream: run them on another stream for the length of a scope
+struct StreamSwap {
+    hg_ctx *c;
+    cudaStream_t saved;
+    StreamSwap(hg_ctx *ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { c->stream = s; }
+    ~StreamSwap() { c->stream = saved; }
+};
+}  // namespace
+
+int hg_pipe_submit_piecewise(hg_pipe *p, const uint8_t *rgba_host, const float *dst_pts, int min_src_x, int min_src_y,
+                             uint8_t *out_host, int32_t window_out[4], uint64_t *ticket)
+{
+    if (!p) return HG_ERR_INVALID;
+    hg_ctx *c = p->c;
+    BIND(c);
+    NEED(c, p->piecewise, "not a piecewise pipe (hg_pipe_create_piecewise)");
+    NEED(c, dst_pts && out_host && window_out, "NULL argument");
+    if (c->n_pts == 0) return fail(c, HG_ERR_STATE, "no mesh set (hg_piecewise_set_mesh)");
+    if (min_src_x > (1 << 18) || min_src_x < -(1 << 18) || min_src_y > (1 << 18) || min_src_y < -(1 << 18))
+        return fail(c, HG_ERR_UNSUPPORTED, "min_src (%d,%d) outside the supported range", min_src_x, min_src_y);
+    TRY(check_points(c, dst_pts, c->n_pts, "dst_pts"));
+    // output window on the host, the arithmetic of H.js:706-710 + minmaxXYofArray H.js:1558 (floats compare exactly;
+    // Math.round of a float32 value is exact in double): the copy-out below needs its size before the frame runs
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = 0; i < c->n_pts; ++i) {
+        const float x = dst_pts[2 * i], y = dst_pts[2 * i + 1];
+        if (x > mxx) mxx = x;
+        if (x < mnx) mnx = x;
+        if (y > mxy) mxy = y;
+        if (y < mny) mny = y;
+    }
+    auto jsr = [](double v) { const double fl = std::floor(v); return (v - fl) >= 0.5 ? fl + 1.0 : fl; };
+    const double x0 = jsr((double)mnx), y0 = jsr((double)mny), w = jsr((double)mxx) - x0, h = jsr((double)mxy) - y0;
+    if (!(w >= 1.0 && h >= 1.0 && w <= (double)p->max_ow && h <= (double)p->max_oh && std::fabs(x0) <= 262144.0 &&
+          std::fabs(y0) <= 262144.0))
+        return fail(c, HG_ERR_UNSUPPORTED, "output window %gx%g at (%g,%g) is empty or exceeds the pipe's maximum %dx%d", w, h, x0,
+                    y0, p->max_ow, p->max_oh);
+    const int xo = (int)x0, yo = (int)y0, oW = (int)w, oH = (int)h;
+    if (!rgba_host && !c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set) and no frame image given");
+    hg_pipe_slot &sl = p->slots[(size_t)(p->next % (uint64_t)p->depth)];
+    if (sl.busy) CU(c, cudaEventSynchronize(sl.out_done));  // the slot's previous frame has left the device
+    const uint32_t *src = c->img;
+    int W = c->W, H = c->H;
+    if (rgba_host) {
+        CU(c, cudaMemcpyAsync(sl.d_src, rgba_host, (size_t)p->W * p->H * 4, cudaMemcpyHostToDevice, p->s_in));
+        CU(c, cudaEventRecord(sl.in_done, p->s_in));
+        CU(c, cudaStreamWaitEvent(p->s_k, sl.in_done, 0));
+        src = (const uint32_t *)sl.d_src;
+        W = p->W;
+        H = p->H;
+    }
+    {
+        StreamSwap swap(c, p->s_k);  // the context's piecewise scratch is used in s_k order by every frame of the pipe
+        TRY(upload_dst_points(c, dst_pts, 1));
+        c->map32_current = false;
+        c->last_inv_len = -1;
+        PwFrameHost f{src, (uint32_t *)sl.d_out, W, H, xo, yo, oW, oH};
+        bool general = !pw_fused_possible(c, f);
+        if (!general) {
+            TRY(pw_inverse_fused_chunk(c, (const float *)c->dst_pts.p, &f, 1, min_src_x, min_src_y));
+            int *st = (int *)c->pinned;
+            CU(c, cudaMemcpyAsync(st, c->fstatus.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));  // compute stream only: the previous frame's copy-out keeps running
+            general = (*st != 0);
+        }
+        if (general) {
+            TRY(pw_inverse_general_frame(c, (const float *)c->dst_pts.p, f, min_src_x, min_src_y));
+            c->n_general++;
+        } else {
+            c->n_fused++;
+        }
+    }
+    CU(c, cudaEventRecord(sl.k_done, p->s_k));
+    CU(c, cudaStreamWaitEvent(p->s_out, sl.k_done, 0));
+    CU(c, cudaMemcpyAsync(out_host, sl.d_out, (size_t)oW * oH * 4, cudaMemcpyDeviceToHost, p->s_out));
+    CU(c, cudaEventRecord(sl.out_done, p->s_out));
+    sl.busy = true;
+    window_out[0] = xo; window_out[1] = yo; window_out[2] = oW; window_out[3] = oH;
+    if (ticket) *ticket = p->next;
+    p->next++;
+    return HG_OK;
+}
+
 int hg_pipe_wait(hg_pipe *p, uint64_t ticket)
 {
     if (!p) return HG_ERR_INVALID;
@@ -1613,6 +1888,309 @@ int hg_pipe_flush(hg_pipe *p)
     CU(c, cudaStreamSynchronize(p->s_k));
     CU(c, cudaStreamSynchronize(p->s_in));
     for (auto &sl : p->slots) sl.busy = false;
+    return HG_OK;
+}
+
+/* ------------------------------------------------------------------ batches: per-frame solve, forward loops */
+int hg_warp_inverse_points_batch(hg_ctx *c, int kind, const double *dst_pts, const double *src_pts, const hg_frame *frames,
+                                 int n_frames)
+{
+    BIND(c);
+    NEED(c, dst_pts && src_pts && frames, "NULL argument");
+    NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
+    NEED(c, n_frames >= 1 && n_frames <= 32768, "n_frames must be in [1, 32768]");
+    std::vector<GeoFrame> gf((size_t)n_frames);
+    int max_ow = 1, max_oh = 1;
+    for (int f = 0; f < n_frames; ++f) {
+        const hg_frame &h = frames[f];
+        TRY(check_window(c, h.x_off, h.y_off, h.o_w, h.o_h));
+        NEED(c, h.out_dev && ((uintptr_t)h.out_dev & 15) == 0, "frame out_dev must be a 16-byte aligned device pointer");
+        GeoFrame &g = gf[(size_t)f];
+        if (h.src_dev) {
+            TRY(check_image_dims(c, h.src_w, h.src_h));
+            g.src = (const uint32_t *)h.src_dev; g.W = h.src_w; g.H = h.src_h;
+        } else {
+            if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
+            g.src = c->img; g.W = c->W; g.H = c->H;
+        }
+        g.tm = nullptr;  // direct-gather kernel (the staged kernel is an opt-in experiment of the matrix entry points)
+        g.out = (uint32_t *)h.out_dev;
+        g.xOff = h.x_off; g.yOff = h.y_off; g.oW = h.o_w; g.oH = h.o_h;
+        if (h.o_w > max_ow) max_ow = h.o_w;
+        if (h.o_h > max_oh) max_oh = h.o_h;
+    }
+    const size_t pb = kind == HG_AFFINE ? 48 : 64, mstride = kind == HG_AFFINE ? 24 : 64;
+    TRY(ensure(c, c->frames, sizeof(GeoFrame) * (size_t)n_frames));
+    TRY(ensure(c, c->mats, mstride * (size_t)n_frames));
+    TRY(ensure(c, c->pts_batch, 2 * pb * (size_t)n_frames));
+    char *pd = (char *)c->pts_batch.p;
+    CU(c, cudaMemcpyAsync(c->frames.p, gf.data(), sizeof(GeoFrame) * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
+    // inverse matrix of frame f = calculateTransformMatrix(kind, dstPoints_f, srcPoints_f)  (H.js:994)
+    CU(c, cudaMemcpyAsync(pd, dst_pts, pb * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(pd + pb * (size_t)n_frames, src_pts, pb * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
+    SolveArgs a{};
+    a.src = (const double *)pd;
+    a.dst = (const double *)(pd + pb * (size_t)n_frames);
+    a.out_f = (float *)c->mats.p;
+    a.out_d = (double *)c->mats.p;
+    a.n = n_frames;
+    a.op = kind == HG_AFFINE ? 0 : 1;
+    TRY(launch_solve(c, a));
+    GeoParams P{};
+    P.many = (const GeoFrame *)c->frames.p;
+    P.mats_dev = c->mats.p;
+    return launch_geo(c, kind, P, max_ow, max_oh, n_frames, false, c->stream, points_map_is_rotated(dst_pts, src_pts));
+}
+
+static int fill_fwd_frame(hg_ctx *c, const hg_frame &h, FwdArgs &a)
+{
+    TRY(check_window(c, h.x_off, h.y_off, h.o_w, h.o_h));
+    NEED(c, h.out_dev && ((uintptr_t)h.out_dev & 15) == 0, "frame out_dev must be a 16-byte aligned device pointer");
+    if (h.src_dev) {
+        TRY(check_image_dims(c, h.src_w, h.src_h));
+        a.src = (const uint32_t *)h.src_dev; a.W = h.src_w; a.H = h.src_h;
+    } else {
+        if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
+        a.src = c->img; a.W = c->W; a.H = c->H;
+    }
+    a.out = (uint32_t *)h.out_dev;
+    a.xOff = h.x_off; a.yOff = h.y_off; a.oW = h.o_w; a.oH = h.o_h;
+    return HG_OK;
+}
+
+int hg_warp_forward_batch(hg_ctx *c, int kind, const void *fwd_matrices, const hg_frame *frames, int n_frames)
+{
+    BIND(c);
+    NEED(c, fwd_matrices && frames, "NULL argument");
+    NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
+    NEED(c, n_frames >= 1, "n_frames must be >= 1");
+    std::vector<FwdArgs> fa((size_t)n_frames);
+    for (int f = 0; f < n_frames; ++f) {
+        FwdArgs &a = fa[(size_t)f];
+        a = FwdArgs{};
+        TRY(fill_fwd_frame(c, frames[f], a));
+        a.kind = kind;
+        if (kind == HG_AFFINE)
+            for (int k = 0; k < 6; ++k) a.mat[k] = (double)((const float *)fwd_matrices)[6 * (size_t)f + k];
+        else
+            for (int k = 0; k < 8; ++k) a.mat[k] = ((const double *)fwd_matrices)[8 * (size_t)f + k];
+        a.minX = 0; a.minY = 0; a.domW = a.W; a.domH = a.H;  // for (y < H) for (x < W), H.js:919-920
+    }
+    return run_forward_batch(c, fa, false);
+}
+
+int hg_warp_piecewise_forward_batch(hg_ctx *c, const float *dst_pts, const hg_frame *frames, int n_frames, int min_src_x,
+                                    int min_src_y, int max_src_x, int max_src_y)
+{
+    BIND(c);
+    NEED(c, dst_pts && frames, "NULL argument");
+    NEED(c, n_frames >= 1, "n_frames must be >= 1");
+    if (c->n_pts == 0) return fail(c, HG_ERR_STATE, "no mesh set (hg_piecewise_set_mesh)");
+    const long long dom_w = (long long)max_src_x - min_src_x, dom_h = (long long)max_src_y - min_src_y;
+    if (min_src_x > (1 << 18) || min_src_x < -(1 << 18) || min_src_y > (1 << 18) || min_src_y < -(1 << 18) ||
+        dom_w > 65536 || dom_h > 65536 || dom_w * dom_h >= (1LL << 31))
+        return fail(c, HG_ERR_UNSUPPORTED, "source-point bounding box outside the supported range");
+    const size_t T = (size_t)c->n_tris, pts_per_frame = 2 * (size_t)c->n_pts;
+    TRY(check_point_floats(c, dst_pts, pts_per_frame * (size_t)n_frames, "dst_pts"));
+    TRY(upload_dst_points(c, dst_pts, (size_t)n_frames));
+    c->map32_current = false;
+    c->last_inv_len = -1;
+    // chunks: the per-frame triangle records (forward matrices) stay below ~1 GB
+    int chunk = (int)((1000ull << 20) / (sizeof(TriRec) * (T ? T : 1)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > 4096) chunk = 4096;
+    const long long len = dom_w > 0 && dom_h > 0 ? dom_w * dom_h : 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        TRY(ensure(c, c->rec, sizeof(TriRec) * (T ? T : 1) * (size_t)nf));
+        if (T > 0) {
+            // forward matrices from (src, dst_f); edge equations of the SOURCE triangles for the forward map (H.js:817-832)
+            PwSetupArgs s{};
+            s.src_pts = (const float *)c->src_pts.p;
+            s.dst_pts = (const float *)c->dst_pts.p + pts_per_frame * (size_t)f0;
+            s.map_pts = (const float *)c->src_pts.p;
+            s.tris = (const uint32_t *)c->tris.p;
+            s.rec = (TriRec *)c->rec.p;
+            s.n_tris = c->n_tris;
+            s.dst_stride = pts_per_frame;
+            s.rec_stride = T;
+            pw_setup_kernel<<<dim3((unsigned)((T + 127) / 128), (unsigned)nf), 128, 0, c->stream>>>(s);
+            c->launches++;
+            CU(c, cudaGetLastError());
+        }
+        // the forward map depends on the source points only: built once per call from the first chunk's records (the
+        // reference builds it once per source-point set, H.js:759)
+        if (f0 == 0) TRY(launch_fill(c, (double)dom_w, (double)min_src_y, len));
+        std::vector<FwdArgs> fa((size_t)nf);
+        for (int f = 0; f < nf; ++f) {
+            FwdArgs &a = fa[(size_t)f];
+            a = FwdArgs{};
+            TRY(fill_fwd_frame(c, frames[f0 + f], a));
+            a.map32 = (const int *)c->map32.p;
+            a.map_len = c->map_len;
+            a.rec = (const TriRec *)c->rec.p + T * (size_t)f;
+            a.n_tris = c->n_tris;
+            a.minX = min_src_x; a.minY = min_src_y;
+            a.domW = dom_w > 0 ? (int)dom_w : 0;
+            a.domH = dom_h > 0 ? (int)dom_h : 0;
+        }
+        TRY(run_forward_batch(c, fa, true));
+    }
+    return HG_OK;
+}
+
+/* ------------------------------------------------------------------ checksums */
+int hg_checksum_frames(hg_ctx *c, const hg_frame *frames, int n_frames, uint64_t *out_host)
+{
+    BIND(c);
+    NEED(c, frames && out_host, "NULL argument");
+    NEED(c, n_frames >= 1 && n_frames <= 65535, "n_frames must be in [1, 65535]");
+    std::vector<ChecksumFrame> cf((size_t)n_frames);
+    long long max_n = 1;
+    for (int f = 0; f < n_frames; ++f) {
+        NEED(c, frames[f].out_dev && frames[f].o_w >= 0 && frames[f].o_h >= 0, "bad frame");
+        cf[(size_t)f].px = (const uint32_t *)frames[f].out_dev;
+        cf[(size_t)f].n = (long long)frames[f].o_w * frames[f].o_h;
+        if (cf[(size_t)f].n > max_n) max_n = cf[(size_t)f].n;
+    }
+    TRY(ensure(c, c->cs_frames, sizeof(ChecksumFrame) * (size_t)n_frames));
+    TRY(ensure(c, c->cs_out, sizeof(uint64_t) * (size_t)n_frames));
+    TRY(ensure_pinned(c, sizeof(uint64_t) * (size_t)n_frames));
+    CU(c, cudaMemcpyAsync(c->cs_frames.p, cf.data(), sizeof(ChecksumFrame) * (size_t)n_frames, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemsetAsync(c->cs_out.p, 0, sizeof(uint64_t) * (size_t)n_frames, c->stream));
+    long long blocks = (max_n + 256 * 8 - 1) / (256 * 8);
+    const long long cap = (long long)c->sm_count * 8 / (n_frames < 8 ? 1 : 4);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    checksum_frames_kernel<<<dim3((unsigned)blocks, (unsigned)n_frames), 256, 0, c->stream>>>((const ChecksumFrame *)c->cs_frames.p,
+                                                                                            (unsigned long long *)c->cs_out.p);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(c->pin_big, c->cs_out.p, sizeof(uint64_t) * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    memcpy(out_host, c->pin_big, sizeof(uint64_t) * (size_t)n_frames);
+    return HG_OK;
+}
+
+/* ------------------------------------------------------------------ streamed piecewise frames */
+size_t hg_stream_slot_bytes(int max_out_w, int max_out_h)
+{
+    if (max_out_w < 1 || max_out_h < 1) return 0;
+    return (((size_t)max_out_w * (size_t)max_out_h * 4) + 255) & ~(size_t)255;
+}
+
+int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int64_t first_frame, int min_src_x, int min_src_y,
+                             const void *src_ring_dev, int n_src, int src_w, int src_h, void *out_ring_dev, int n_slots,
+                             int max_out_w, int max_out_h, hg_stream_info *info_out)
+{
+    BIND(c);
+    NEED(c, dst_pts && out_ring_dev, "NULL argument");
+    NEED(c, n_frames >= 1 && first_frame >= 0, "n_frames must be >= 1 and first_frame >= 0");
+    NEED(c, n_slots >= 1, "n_slots must be >= 1");
+    NEED(c, ((uintptr_t)out_ring_dev & 255) == 0, "out_ring_dev must be 256-byte aligned");
+    if (c->n_pts == 0) return fail(c, HG_ERR_STATE, "no mesh set (hg_piecewise_set_mesh)");
+    if (min_src_x > (1 << 18) || min_src_x < -(1 << 18) || min_src_y > (1 << 18) || min_src_y < -(1 << 18))
+        return fail(c, HG_ERR_UNSUPPORTED, "min_src (%d,%d) outside the supported range", min_src_x, min_src_y);
+    TRY(check_window(c, 0, 0, max_out_w, max_out_h));
+    const uint32_t *src = nullptr;
+    int W = 0, H = 0;
+    if (src_ring_dev) {
+        NEED(c, n_src >= 1 && ((uintptr_t)src_ring_dev & 3) == 0, "src_ring_dev must be 4-byte aligned, n_src >= 1");
+        TRY(check_image_dims(c, src_w, src_h));
+        src = (const uint32_t *)src_ring_dev; W = src_w; H = src_h;
+    } else {
+        if (!c->img) return fail(c, HG_ERR_STATE, "no image set (hg_image_set)");
+        src = c->img; W = c->W; H = c->H; n_src = 1;
+    }
+    const size_t T = (size_t)c->n_tris, pts_per_frame = 2 * (size_t)c->n_pts;
+    const size_t slot_px = hg_stream_slot_bytes(max_out_w, max_out_h) / 4;
+    const size_t bin_stride = (size_t)pwf_bins_x(max_out_w) * (size_t)max_out_h;
+    TRY(upload_dst_points(c, dst_pts, (size_t)n_frames));
+    c->map32_current = false;
+    c->last_inv_len = -1;
+    // chunk: frames in flight never share a ring slot, and the per-frame scratch stays below ~1.5 GB
+    const size_t per_frame = (sizeof(TriRec) + 48) * T + bin_stride * (4 + 4 * PW_BIN_CAP + 32);
+    int chunk = (int)((1500ull << 20) / (per_frame ? per_frame : 1));
+    if (n_frames > n_slots) {
+        // the stream wraps around the ring inside this call: a chunk covers at most half of it, so the deferred redo of a
+        // flagged frame (one chunk later) still finds its slot untouched
+        NEED(c, n_slots >= 2, "a stream longer than the ring needs n_slots >= 2");
+        if (chunk > n_slots / 2) chunk = n_slots / 2;
+    } else if (chunk > n_slots) {
+        chunk = n_slots;
+    }
+    if (chunk > 1024) chunk = 1024;
+    if (chunk < 1) chunk = 1;
+    const bool fused = !c->force_general && c->n_tris < PW_MAX_TRIS;
+    const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
+    TRY(ensure(c, c->rec, sizeof(TriRec) * (T ? T : 1) * (size_t)chunk));
+    TRY(ensure(c, c->invd, sizeof(double) * 6 * (T ? T : 1) * (size_t)chunk));
+    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * (bin_stride * chunk + slack)));
+    TRY(ensure(c, c->bin_ent, sizeof(unsigned) * (bin_stride * chunk + slack) * PW_BIN_CAP));
+    TRY(ensure(c, c->bin_run, sizeof(uint4) * 2 * (bin_stride * chunk + slack)));
+    TRY(ensure(c, c->fstatus, sizeof(int) * (size_t)chunk));
+    TRY(ensure(c, c->fframes, sizeof(FusedFrame) * (size_t)chunk));
+    TRY(ensure(c, c->sinfo, sizeof(StreamInfo) * (size_t)n_frames));
+    TRY(ensure_pinned(c, (sizeof(StreamInfo) + sizeof(int)) * (size_t)n_frames));
+    StreamInfo *h_info = (StreamInfo *)c->pin_big;
+    int *h_status = (int *)((char *)c->pin_big + sizeof(StreamInfo) * (size_t)n_frames);
+    for (auto &e : c->ev_chunk)
+        if (!e) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // frames of chunk [f0, f0 + nf) the span bins could not express: the general, map-based path (exact for everything)
+    bool any_general = false;
+    auto redo_flagged = [&](int f0, int nf) -> int {
+        for (int f = f0; f < f0 + nf; ++f) {
+            const StreamInfo &I = h_info[f];
+            if (I.status == 2) continue;  // skipped: reported to the caller
+            if (!fused || h_status[f] == 1) {
+                PwFrameHost g{src + (n_src > 1 ? (size_t)(((long long)first_frame + f) % n_src) * (size_t)W * H : 0),
+                              (uint32_t *)out_ring_dev + (size_t)I.slot * slot_px, W, H, I.x_off, I.y_off, I.o_w, I.o_h};
+                TRY(pw_inverse_general_frame(c, (const float *)c->dst_pts.p + pts_per_frame * (size_t)f, g, min_src_x, min_src_y));
+                c->n_general++;
+                any_general = true;
+            } else {
+                c->n_fused++;
+            }
+        }
+        return HG_OK;
+    };
+    int prev_f0 = -1, prev_nf = 0, k = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++k) {
+        const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        const float *dd = (const float *)c->dst_pts.p + pts_per_frame * (size_t)f0;
+        CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * bin_stride * (size_t)nf, c->stream));
+        CU(c, cudaMemsetAsync(c->fstatus.p, 0, sizeof(int) * (size_t)nf, c->stream));
+        StreamArgs a{};
+        a.dst_pts = dd; a.n_pts = c->n_pts; a.n_frames = nf; a.frame0 = (long long)first_frame + f0;
+        a.src = src; a.src_stride_px = (size_t)W * H; a.n_src = n_src; a.W = W; a.H = H;
+        a.out_ring = (uint32_t *)out_ring_dev; a.slot_px = slot_px; a.n_slots = n_slots; a.max_w = max_out_w; a.max_h = max_out_h;
+        a.rec = (const TriRec *)c->rec.p; a.invd = (const double *)c->invd.p;
+        a.bin_cnt = (unsigned *)c->bin_cnt.p; a.bin_ent = (unsigned *)c->bin_ent.p; a.bin_run = (uint4 *)c->bin_run.p;
+        a.status = (int *)c->fstatus.p; a.bin_stride = bin_stride;
+        a.n_tris = c->n_tris; a.minSrcX = min_src_x; a.minSrcY = min_src_y;
+        a.frames_out = (FusedFrame *)c->fframes.p;
+        a.info_out = (StreamInfo *)c->sinfo.p + f0;
+        pw_stream_frames_kernel<<<(unsigned)((nf + 3) / 4), 128, 0, c->stream>>>(a);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        if (fused) TRY(pw_fused_launch(c, dd, nf, max_out_w, max_out_h, bin_stride));
+        // the scratch is reused by the next chunk: collect this chunk's status and windows first (stream-ordered copies)
+        CU(c, cudaMemcpyAsync(h_status + f0, c->fstatus.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(h_info + f0, (StreamInfo *)c->sinfo.p + f0, sizeof(StreamInfo) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaEventRecord(c->ev_chunk[k & 1], c->stream));
+        // while this chunk runs, look at the previous one: its flagged frames are redone behind this chunk in stream
+        // order, and their slots are not touched by it (a chunk covers at most half of the ring when the stream wraps)
+        if (prev_f0 >= 0) {
+            CU(c, cudaEventSynchronize(c->ev_chunk[(k - 1) & 1]));
+            TRY(redo_flagged(prev_f0, prev_nf));
+        }
+        prev_f0 = f0;
+        prev_nf = nf;
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    TRY(redo_flagged(prev_f0, prev_nf));
+    if (any_general) CU(c, cudaStreamSynchronize(c->stream));
+    if (info_out) memcpy(info_out, h_info, sizeof(StreamInfo) * (size_t)n_frames);
     return HG_OK;
 }
 
@@ -1691,6 +2269,86 @@ int hg_host_alloc_pinned(hg_ctx *c, size_t bytes, void **p)
         cudaGetLastError();
         *p = nullptr;
         return fail(c, HG_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return HG_OK;
+}
+
+int hg_host_alloc_pinned_ex(hg_ctx *c, size_t bytes, int write_combined, void **p)
+{
+    BIND(c);
+    NEED(c, p, "host_ptr is NULL");
+    cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return fail(c, HG_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return HG_OK;
+}
+
+int hg_pcie_probe(hg_ctx *c, size_t bytes, int iters, double *h2d_gbs, double *d2h_gbs, double *bidir_gbs)
+{
+    BIND(c);
+    NEED(c, h2d_gbs && d2h_gbs && bidir_gbs, "NULL argument");
+    NEED(c, bytes >= 4096 && bytes <= (1ull << 31) && iters >= 1 && iters <= 4096, "bytes in [4 KiB, 2 GiB], iters in [1, 4096]");
+    void *h_a = nullptr, *h_b = nullptr, *d_a = nullptr, *d_b = nullptr;
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; return r == cudaSuccess; };
+    ok(cudaHostAlloc(&h_a, bytes, cudaHostAllocDefault));
+    ok(cudaHostAlloc(&h_b, bytes, cudaHostAllocDefault));
+    ok(cudaMalloc(&d_a, bytes));
+    ok(cudaMalloc(&d_b, bytes));
+    ok(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    ok(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    ok(cudaEventCreate(&e0)); ok(cudaEventCreate(&e1)); ok(cudaEventCreate(&e2)); ok(cudaEventCreate(&e3));
+    if (e == cudaSuccess) {
+        memset(h_a, 1, bytes);
+        memset(h_b, 2, bytes);
+        ok(cudaMemsetAsync(d_b, 3, bytes, s2));
+        // warm-up of both directions
+        ok(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s1));
+        ok(cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s2));
+        ok(cudaStreamSynchronize(s1)); ok(cudaStreamSynchronize(s2));
+        float ms = 0.f;
+        ok(cudaEventRecord(e0, s1));
+        for (int i = 0; i < iters; ++i) ok(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s1));
+        ok(cudaEventRecord(e1, s1));
+        ok(cudaStreamSynchronize(s1));
+        if (ok(cudaEventElapsedTime(&ms, e0, e1))) *h2d_gbs = (double)bytes * iters / (ms * 1e-3) / 1e9;
+        ok(cudaEventRecord(e2, s2));
+        for (int i = 0; i < iters; ++i) ok(cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s2));
+        ok(cudaEventRecord(e3, s2));
+        ok(cudaStreamSynchronize(s2));
+        if (ok(cudaEventElapsedTime(&ms, e2, e3))) *d2h_gbs = (double)bytes * iters / (ms * 1e-3) / 1e9;
+        // both directions at once: each stream timed by its own events, the pair by the longer of the two
+        ok(cudaEventRecord(e0, s1));
+        ok(cudaEventRecord(e2, s2));
+        for (int i = 0; i < iters; ++i) {
+            ok(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s1));
+            ok(cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s2));
+        }
+        ok(cudaEventRecord(e1, s1));
+        ok(cudaEventRecord(e3, s2));
+        ok(cudaStreamSynchronize(s1)); ok(cudaStreamSynchronize(s2));
+        float ma = 0.f, mb = 0.f;
+        if (ok(cudaEventElapsedTime(&ma, e0, e1)) && ok(cudaEventElapsedTime(&mb, e2, e3)))
+            *bidir_gbs = 2.0 * (double)bytes * iters / ((ma > mb ? ma : mb) * 1e-3) / 1e9;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
+    if (e3) cudaEventDestroy(e3);
+    if (s1) cudaStreamDestroy(s1);
+    if (s2) cudaStreamDestroy(s2);
+    if (d_a) cudaFree(d_a);
+    if (d_b) cudaFree(d_b);
+    if (h_a) cudaFreeHost(h_a);
+    if (h_b) cudaFreeHost(h_b);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, HG_ERR_CUDA, "hg_pcie_probe: %s", cudaGetErrorString(e));
     }
     return HG_OK;
 }

@@ -185,7 +185,11 @@ constexpr int PWF_TY = 16;                      // thread rows per CTA
 constexpr int PWF_THREADS = PWF_TX * PWF_TY;    // 128
 constexpr int PWF_GROUP_ROWS = PWF_TY;          // rows one CTA covers per iteration (one row per thread)
 
-__host__ __device__ inline int pwf_tiles_x(int oW) { return (oW + PW_BIN_W - 1) / PW_BIN_W; }
+// 64-column bins of a map row (what the span / run kernels fill) ...
+__host__ __device__ inline int pwf_bins_x(int oW) { return (oW + PW_BIN_W - 1) / PW_BIN_W; }
+// ... and CTA tiles of an output row.  The pixel kernel walks rows in FLAT-aligned quads (like warp_geo.cuh): row yy is
+// shifted left by a(yy) = (yy * oW) & 3 columns, so when oW % 4 != 0 its last pixels may sit up to 3 columns further right
+__host__ __device__ inline int pwf_tiles_x(int oW) { return ((oW & 3) ? (oW + 3 + PW_BIN_W - 1) : (oW + PW_BIN_W - 1)) / PW_BIN_W; }
 __host__ __device__ inline int pwf_tiles_y(int oH, int niter) { return (oH + PWF_GROUP_ROWS * niter - 1) / (PWF_GROUP_ROWS * niter); }
 
 __device__ __forceinline__ void pwf_load_matrix(const double *inv, int t, double (&m)[6])
@@ -370,14 +374,224 @@ __device__ __forceinline__ void pwf_body(const FusedFrame &F, int niter, int til
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second-generation pixel loop (the default).  Same decomposition — CTA = one 64-column tile x (16 * niter) rows, thread
+// = one row x two quads per row group — with four changes measured against the first generation (profiles/r02_*):
+//   * FLAT-ALIGNED QUADS.  Row yy is walked in quads that start at column 4i - a(yy), a(yy) = (yy * oW) & 3, so every
+//     interior quad is one aligned 128-bit store for ANY output width (per-frame video windows have arbitrary widths);
+//     16 | PWF_GROUP_ROWS, so a(yy) is the same for every row a thread owns.
+//   * ONE TRIANGLE PER QUAD in the loop.  A quad is computed with the triangle of its first pixel; quads a span boundary
+//     cuts through (a run starts inside them) or that reach back into the previous bin are ALSO noted in a per-warp
+//     queue (slot = popcount of a ballot: no atomics) and redone after the loop, one PIXEL per lane with the pixel's own
+//     triangle — dense lanes instead of a per-pixel path that every warp of a fine mesh had to walk through.
+//   * the doubled-coordinate decode of warp_geo.cuh with its warp-uniform "end pixels inside => quad inside" shortcut
+//     (both source coordinates are monotone along the quad: one triangle, one affine map), loads predicated directly.
+//   * four pipeline stages instead of five (S0 run record -> S1 triangle id + matrix loads -> S2 coordinates + gathers
+//     -> S3 stores), ids through one PRMT.
+constexpr int PWF_QCAP = 1024;  // per warp: 16 row groups x 32 lanes x 2 quads, the most a CTA can ever queue
+
+// id of run r (0..7) from the eight packed int16 ids: one byte permute, sign-extended
+__device__ __forceinline__ int pwf_run_id2(const uint4 &ids, unsigned r)
+{
+    const unsigned lo = (r & 4u) ? ids.z : ids.x, hi = (r & 4u) ? ids.w : ids.y;
+    return (int)__byte_perm(lo, hi, (r & 3u) * 0x2222u + 0x9910u);
+}
+
+template <bool ZERO_OFF>
+__device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int tile_x, int row0, unsigned short *wq)
+{
+    const int lane = threadIdx.x & 31, warp_id = threadIdx.x >> 5;
+    const int tx = threadIdx.x & (PWF_TX - 1), ty = threadIdx.x / PWF_TX;
+    const int oW = F.oW, oH = F.oH;
+    const int base0 = row0 + ty;
+    const int ngroups = min(niter, (oH - row0 + PWF_GROUP_ROWS - 1) / PWF_GROUP_ROWS);  // CTA-uniform
+    const bool has_bin = tile_x < F.bins_x;
+    const int a = (oW & 3) ? (int)(((unsigned)base0 * (unsigned)oW) & 3u) : 0;
+    const uint32_t *__restrict__ src = F.src;
+    const unsigned W = (unsigned)F.W, H = (unsigned)F.H, npx_src = W * H;
+    const unsigned W2 = 2u * W, H2 = 2u * H, Wi = W2 >= 3u ? W2 - 3u : 0u, Hi = H2 >= 3u ? H2 - 3u : 0u;
+    const unsigned kflat = (unsigned)(HG_HI_ZERO >> 1) * (W + 1u);
+
+    int xx0[2];
+    unsigned vmask[2];
+    unsigned long long below[2], inner[2];
+    double xs[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int c = 4 * tx + 32 * q - a;        // first column of the quad inside its bin (negative: previous bin)
+        xx0[q] = tile_x * PW_BIN_W + c;
+        vmask[q] = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (xx0[q] + k >= 0 && xx0[q] + k < oW) vmask[q] |= 1u << k;
+            xs[q][k] = (double)(F.xOff + xx0[q] + k);
+        }
+        const int c0 = c < 0 ? 0 : c, c3 = c + 3;                       // own-bin columns of the quad: c0 .. c3 (<= 63)
+        below[q] = (2ull << c0) - 1ull;                                 // bits 0 .. c0
+        inner[q] = ((c3 >= 63 ? 0ull : (1ull << (c3 + 1))) - 1ull) & ~below[q];  // bits c0+1 .. c3
+    }
+    // pixels of quad 0 left of the tile belong to the previous bin (only when they are pixels of the image at all)
+    const bool prev_bin = (a > 0) && (tx == 0) && (tile_x > 0);
+
+    const uint4 *p_run = F.bin_run + 2 * ((size_t)base0 * F.bins_x + tile_x);
+    const size_t run_step = 2 * (size_t)PWF_GROUP_ROWS * F.bins_x;
+    uint32_t *p_out = F.out + ((long long)base0 * oW + xx0[0]);
+    const long long out_step = (long long)PWF_GROUP_ROWS * oW;
+
+    uint4 be0 = make_uint4(1u, 0u, 0u, 0u), be1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    int t0[2] = {-1, -1};
+    double mq[2][6];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) mq[q][k] = 0.0;
+    uint32_t px[2][4];
+    int qn = 0;  // warp-uniform: entries in this warp's queue
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+#pragma unroll 1
+    for (int it = 0; it < ngroups + 3; ++it) {
+        // ---- S3: store row group it-3
+        if (it >= 3) {
+            if (base0 + (it - 3) * PWF_GROUP_ROWS < oH) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t *dst = p_out + 32 * q;
+                    if (vmask[q] == 0xFu) {
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(px[q][0], px[q][1], px[q][2], px[q][3]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (vmask[q] & (1u << k)) dst[k] = px[q][k];
+                    }
+                }
+            }
+            p_out += out_step;
+        }
+        // ---- S2: coordinates (H.js:1046) + window test, Math.round, flat gather (H.js:1047-1052) of group it-2
+        if (it >= 2 && it - 2 < ngroups) {
+            const int row = base0 + (it - 2) * PWF_GROUP_ROWS;
+            const double y = (double)(F.yOff + row);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const bool live = (t0[q] >= 0) && (row < oH) && (vmask[q] != 0u);
+                const double r0 = __dmul_rn(mq[q][2], y), r1 = __dmul_rn(mq[q][3], y);
+                if (ZERO_OFF) {
+                    unsigned hx[4], hy[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        hx[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(mq[q][0], xs[q][k], r0, mq[q][4]), 2.0, HG_MAGIC + 1.0));
+                        hy[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(mq[q][1], xs[q][k], r1, mq[q][5]), 2.0, HG_MAGIC + 1.0));
+                    }
+                    const unsigned cz = (unsigned)(HG_HI_ZERO + 2);
+                    const bool ends_inside = live && ((hx[0] - cz) < Wi) & ((hy[0] - cz) < Hi) & ((hx[3] - cz) < Wi) & ((hy[3] - cz) < Hi);
+                    if (__all_sync(0xffffffffu, ends_inside)) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) px[q][k] = __ldg(src + ((hy[k] >> 1) * W + (hx[k] >> 1) - kflat));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const unsigned flat = (hy[k] >> 1) * W + (hx[k] >> 1) - kflat;
+                            const bool in = live & ((hx[k] - (unsigned)(HG_HI_ZERO + 1)) < W2) & ((hy[k] - (unsigned)(HG_HI_ZERO + 1)) < H2) &
+                                            (flat < npx_src);
+                            uint32_t v = 0u;
+                            if (in) v = __ldg(src + flat);
+                            px[q][k] = v;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        unsigned f = HG_OUTSIDE;
+                        if (live)
+                            f = pwf_decode<false>(affine_coord_exact(mq[q][0], xs[q][k], r0, mq[q][4]),
+                                                  affine_coord_exact(mq[q][1], xs[q][k], r1, mq[q][5]), F, npx_src);
+                        px[q][k] = ldg_or_zero(src, f);
+                    }
+                }
+            }
+        }
+        // ---- S1: triangle of each quad's first pixel from the run record of group it-1, its matrix; note cut quads
+        if (it >= 1 && it - 1 < ngroups) {
+            const bool row_ok = base0 + (it - 1) * PWF_GROUP_ROWS < oH;
+            const unsigned long long m64 = ((unsigned long long)be0.y << 32) | (unsigned long long)be0.x;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const unsigned r = (unsigned)__popcll(m64 & below[q]) - 1u;
+                const int t = pwf_run_id2(be1, r);
+                t0[q] = t;
+                if (t >= 0) pwf_load_matrix(F.inv, t, mq[q]);
+                const bool cut = row_ok && (vmask[q] != 0u) && (((m64 & inner[q]) != 0ull) || (q == 0 && prev_bin));
+                const unsigned bal = __ballot_sync(0xffffffffu, cut);
+                if (cut) wq[qn + __popc(bal & lt_mask)] = (unsigned short)(((it - 1) << 6) | (lane << 1) | q);
+                qn += __popc(bal);
+            }
+        }
+        // ---- S0: run record of group it
+        if (it < ngroups) {
+            if (has_bin && base0 + it * PWF_GROUP_ROWS < oH) {
+                be0 = __ldg(p_run);
+                be1 = __ldg(p_run + 1);
+            } else {
+                be0 = make_uint4(1u, 0u, 0u, 0u);
+                be1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            }
+            p_run += run_step;
+        }
+    }
+
+    // ---- the queued quads again, one pixel per lane, each with the triangle of its own run (H.js:1044-1052 verbatim)
+    __syncwarp();  // also orders the provisional stores above before the final ones below
+    for (int e0 = 0; e0 < qn; e0 += 8) {
+        const int e = e0 + (lane >> 2), k = lane & 3;
+        if (e >= qn) continue;
+        const unsigned ent = wq[e];
+        const int qq = (int)(ent & 1u), sl = (int)((ent >> 1) & 31u), g = (int)(ent >> 6);
+        const int row = row0 + warp_id * 4 + (sl >> 3) + g * PWF_GROUP_ROWS;
+        const int ae = (oW & 3) ? (int)(((unsigned)row * (unsigned)oW) & 3u) : 0;
+        const int X = tile_x * PW_BIN_W + 4 * (sl & 7) + 32 * qq - ae + k;
+        if (X < 0 || X >= oW) continue;
+        const uint4 *pr = F.bin_run + 2 * ((size_t)row * F.bins_x + (X >> 6));
+        const uint4 b0 = __ldg(pr), b1 = __ldg(pr + 1);
+        const unsigned long long m64 = ((unsigned long long)b0.y << 32) | (unsigned long long)b0.x;
+        const int t = pwf_run_id2(b1, (unsigned)__popcll(m64 & ((2ull << (X & 63)) - 1ull)) - 1u);
+        uint32_t v = 0u;
+        if (t >= 0) {
+            double m[6];
+            pwf_load_matrix(F.inv, t, m);
+            const double x = (double)(F.xOff + X), y = (double)(F.yOff + row);
+            v = ldg_or_zero(src, pwf_decode<ZERO_OFF>(affine_coord_exact(m[0], x, __dmul_rn(m[2], y), m[4]),
+                                                      affine_coord_exact(m[1], x, __dmul_rn(m[3], y), m[5]), F, npx_src));
+        }
+        F.out[(long long)row * oW + X] = v;
+    }
+}
+
 __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel(const FusedFrame *frames, int niter)
 {
+    __shared__ unsigned short s_q[PWF_THREADS / 32][PWF_QCAP];
     const FusedFrame F = frames[blockIdx.y];
+    if (F.oW <= 0 || F.oH <= 0) return;
     const int tiles_x = pwf_tiles_x(F.oW);
     const int tile_y = blockIdx.x / tiles_x;
     const int tile_x = blockIdx.x - tile_y * tiles_x;
     const int row0 = tile_y * PWF_GROUP_ROWS * niter;
     if (row0 >= F.oH) return;
+    unsigned short *wq = s_q[threadIdx.x >> 5];
+    if (F.minSrcX == 0 && F.minSrcY == 0) pwf_body2<true>(F, niter, tile_x, row0, wq);
+    else pwf_body2<false>(F, niter, tile_x, row0, wq);
+}
+
+// first-generation kernel, kept for A/B runs (HG_PWF_V1=1); needs oW-wide rows of bins == tiles
+__global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_v1_kernel(const FusedFrame *frames, int niter)
+{
+    const FusedFrame F = frames[blockIdx.y];
+    if (F.oW <= 0 || F.oH <= 0) return;
+    const int tiles_x = pwf_tiles_x(F.oW);
+    const int tile_y = blockIdx.x / tiles_x;
+    const int tile_x = blockIdx.x - tile_y * tiles_x;
+    const int row0 = tile_y * PWF_GROUP_ROWS * niter;
+    if (row0 >= F.oH || tile_x >= F.bins_x) return;
     if (F.minSrcX == 0 && F.minSrcY == 0) pwf_body<true>(F, niter, tile_x, row0);
     else pwf_body<false>(F, niter, tile_x, row0);
 }

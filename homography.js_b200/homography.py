@@ -168,10 +168,16 @@ class Homography:
     _KIND = {"affine": _abi.HG_AFFINE, "projective": _abi.HG_PROJECTIVE}
 
     def __init__(self, transform: str = "auto", width=None, height=None, device: int = 0, context=None,
-                 sampling: str = "nearest"):
+                 sampling: str = "nearest", pinned_output: bool = False):
         """`sampling="bilinear"` is an EXTENSION (the reference only has Math.round sampling): it applies to the
-        inverse affine / projective loop and is accurate to <= 1 LSB per channel (see csrc/bilinear.cuh)."""
+        inverse affine / projective loop and is accurate to <= 1 LSB per channel (see csrc/bilinear.cuh).
+        `pinned_output=True`: the inverse warps return their ImageData over page-locked memory owned by this object (two
+        buffers used alternately, so a result stays valid until the warp after next) — the copy engine then writes the
+        result at link speed instead of staging it through the driver (in Node: an external ArrayBuffer)."""
         self._ctx = context if context is not None else _abi.Context(device)
+        self._pinned_output = bool(pinned_output)
+        self._out_ring = [None, None]
+        self._out_next = 0
         if sampling not in ("nearest", "bilinear"):
             raise HomographyError(f'sampling "{sampling}" is unknown')
         self._sampling = _abi.HG_BILINEAR if sampling == "bilinear" else _abi.HG_NEAREST
@@ -480,6 +486,16 @@ class Homography:
                 "3. Give Source and Destiny points in the same range (both normalized or both in image dimensions)")
 
     # ------------------------------------------------------------------ the four loops -> device
+    def _pinned_out(self, nbytes: int):
+        """The next page-locked result buffer (None when the object returns ordinary arrays)."""
+        if not self._pinned_output:
+            return None
+        i = self._out_next
+        self._out_next ^= 1
+        if self._out_ring[i] is None or self._out_ring[i].size < nbytes:
+            self._out_ring[i] = self._ctx.pinned_array(nbytes + nbytes // 8)
+        return self._out_ring[i][:nbytes]
+
     def _window(self):
         return (int(self._xOutputOffset), int(self._yOutputOffset), int(self._objectiveWidth), int(self._objectiveHeight))
 
@@ -493,6 +509,11 @@ class Homography:
         if self._sampling != _abi.HG_NEAREST:
             self._ctx.set_sampling(self._sampling)
         try:
+            buf = self._pinned_out(oW * oH * 4)
+            if buf is not None:
+                self._ctx.warp_inverse_points(self._KIND[self.transform], self._dstPoints, self._srcPoints, xo, yo, oW, oH,
+                                              out_host_ptr=buf.ctypes.data)
+                return buf
             return self._ctx.warp_inverse_points(self._KIND[self.transform], self._dstPoints, self._srcPoints, xo, yo, oW, oH)
         finally:
             if self._sampling != _abi.HG_NEAREST:
@@ -514,6 +535,11 @@ class Homography:
             return None
         xo, yo, oW, oH = self._window()
         self._upload_mesh()
+        buf = self._pinned_out(oW * oH * 4)
+        if buf is not None:
+            self._ctx.warp_piecewise_inverse(self._dstPoints, xo, yo, oW, oH, int(self._minSrcX), int(self._minSrcY),
+                                             out_host_ptr=buf.ctypes.data)
+            return buf
         return self._ctx.warp_piecewise_inverse(self._dstPoints, xo, yo, oW, oH, int(self._minSrcX), int(self._minSrcY))
 
     def _piecewiseAffineWarp(self, empty):

@@ -189,6 +189,48 @@ int hg_warp_inverse_batch(hg_ctx *ctx, int kind, const void *inv_matrices, const
 int hg_warp_piecewise_inverse_batch(hg_ctx *ctx, const float *dst_pts, const hg_frame *frames, int n_frames,
                                     int min_src_x, int min_src_y);
 
+/* n_frames complete _inverseGeometricWarp calls (H.js:987-1013) in TWO launches: frame f solves
+ * calculateTransformMatrix(kind, dst_pts_f, src_pts_f) on the device (H.js:994; points are n_frames x (6 | 8) HOST
+ * doubles) and the pixel loop of all frames follows with no host round trip — the per-frame setDestinyPoints() + warp()
+ * protocol of test/benchmark.js:96-113 for a batch of independent frames.  Results stay on the device. */
+int hg_warp_inverse_points_batch(hg_ctx *ctx, int kind, const double *dst_pts, const double *src_pts,
+                                 const hg_frame *frames, int n_frames);
+/* _geometricWarp (H.js:911-932) for n_frames independent frames: fwd_matrices = n_frames x (float[6] | double[8]) on
+ * the HOST, frames[f].src_dev / out_dev / window as in hg_warp_inverse_batch.  Results stay on the device. */
+int hg_warp_forward_batch(hg_ctx *ctx, int kind, const void *fwd_matrices, const hg_frame *frames, int n_frames);
+/* _piecewiseAffineWarp (H.js:948-972) for n_frames frames sharing the context mesh and its forward map (built once
+ * per source-point set, H.js:759/817), frame f using dst_pts + f*2*n_pts; min/max_src_* as in the single call. */
+int hg_warp_piecewise_forward_batch(hg_ctx *ctx, const float *dst_pts, const hg_frame *frames, int n_frames,
+                                    int min_src_x, int min_src_y, int max_src_x, int max_src_y);
+
+/* ------------------------------------------------------------------ streamed piecewise frames (video) */
+/* per-frame result of hg_warp_piecewise_stream */
+typedef struct {
+    int32_t x_off, y_off, o_w, o_h; /* the frame's output window (H.js:706-710), computed on the device */
+    int32_t slot;                   /* ring slot holding its o_w*o_h*4 bytes (dense rows of o_w pixels) */
+    int32_t status;                 /* 0 = warped; 2 = skipped: empty / non-finite window, or larger than a ring slot */
+} hg_stream_info;
+/* The video protocol of the reference (README "250 different transforms", test/benchmark.js:96-113): one mesh, a new set
+ * of destiny points per frame, setDestinyPoints() + warp() per frame.  For frames first_frame .. first_frame+n_frames-1 of
+ * a stream, everything a frame needs happens on the device, in order: its output window from its destiny points
+ * (_induceBestObjectiveWidthAndHeight, H.js:706-710), its placement in the caller's output ring (slot = frame index mod
+ * n_slots, each slot max_out_w*max_out_h*4 bytes rounded up to 256), the per-triangle matrices and their inverses, the
+ * inverse triangle map and the pixel loop (_inversePiecewiseAffineWarp, H.js:1029-1058).  dst_pts: n_frames x n_pts x 2
+ * HOST floats.  src_ring_dev == NULL: every frame reads the context image; otherwise frame i reads image (i mod n_src)
+ * of n_src W x H images stored back to back.  info_out (HOST, n_frames entries, may be NULL) receives each frame's window
+ * and slot.  Returns after the stream has been synchronized (frames a compact span list cannot express are redone by the
+ * general map-based path before the call returns, never approximated). */
+int hg_warp_piecewise_stream(hg_ctx *ctx, const float *dst_pts, int n_frames, int64_t first_frame, int min_src_x,
+                             int min_src_y, const void *src_ring_dev, int n_src, int src_w, int src_h, void *out_ring_dev,
+                             int n_slots, int max_out_w, int max_out_h, hg_stream_info *info_out);
+/* bytes of one ring slot for hg_warp_piecewise_stream */
+size_t hg_stream_slot_bytes(int max_out_w, int max_out_h);
+
+/* 64-bit checksum of each frame's output (frames[f].out_dev, o_w*o_h pixels):
+ *   sum_i pixel_i * (((i * 2654435761) mod 2^32) | 1) + n * 0x9E3779B97F4A7C15  (mod 2^64), pixel_i little-endian RGBA8.
+ * For parity gates over batches too large to compare pixel by pixel.  out_host: n_frames values. */
+int hg_checksum_frames(hg_ctx *ctx, const hg_frame *frames, int n_frames, uint64_t *out_host);
+
 /* ------------------------------------------------------------------ pipelined host-to-host stream (video) */
 /* Independent frames arriving in HOST memory (pinned for full overlap) and leaving to HOST memory: up to `depth`
  * frames in flight, H2D of frame i+1, solve+warp of frame i and D2H of frame i-1 overlap on three CUDA streams.
@@ -200,6 +242,14 @@ int hg_pipe_submit(hg_pipe *pipe, const uint8_t *rgba_host, const double *dst_pt
 int hg_pipe_wait(hg_pipe *pipe, uint64_t ticket); /* returns once that frame's out_host is complete */
 int hg_pipe_flush(hg_pipe *pipe);                 /* returns once every submitted frame is complete */
 int hg_pipe_destroy(hg_pipe *pipe);
+/* The same pipeline for piecewise frames (hg_warp_piecewise_inverse per frame, mesh = the context mesh at submit time):
+ * rgba_host == NULL warps the context image (hg_image_set) — the reference's video protocol keeps one image and moves
+ * the destiny points.  The output window is computed on the host exactly as H.js:706-710 does and
+ * returned in window_out[4] = {x_off, y_off, o_w, o_h}; out_host must hold max_out_w*max_out_h*4 bytes.  Returns
+ * HG_ERR_UNSUPPORTED (nothing submitted) when the window is empty or exceeds the pipe's maximum. */
+int hg_pipe_create_piecewise(hg_ctx *ctx, int src_w, int src_h, int max_out_w, int max_out_h, int depth, hg_pipe **out);
+int hg_pipe_submit_piecewise(hg_pipe *pipe, const uint8_t *rgba_host, const float *dst_pts, int min_src_x, int min_src_y,
+                             uint8_t *out_host, int32_t window_out[4], uint64_t *ticket);
 
 /* ------------------------------------------------------------------ diagnostics */
 /* max over all 2^20 high-mantissa patterns (x 6 low words) of |1 - d*r|, r = the reciprocal the projective
@@ -218,6 +268,13 @@ int hg_dev_alloc(hg_ctx *ctx, size_t bytes, void **dev_ptr);
 int hg_dev_free(hg_ctx *ctx, void *dev_ptr);
 int hg_host_alloc_pinned(hg_ctx *ctx, size_t bytes, void **host_ptr);
 int hg_host_free_pinned(hg_ctx *ctx, void *host_ptr);
+/* write_combined != 0: cudaHostAllocWriteCombined — for buffers the host only writes and the GPU's copy engine only
+ * reads (a source ring): reads over PCIe skip the CPU cache snoop */
+int hg_host_alloc_pinned_ex(hg_ctx *ctx, size_t bytes, int write_combined, void **host_ptr);
+/* Raw copy-engine ceiling of this GPU's host link, for judging end-to-end numbers: `iters` pinned copies of `bytes`
+ * host->device alone, device->host alone, and both directions at once on two streams; GB/s each (bidir = sum of both
+ * directions).  Several processes calling this at the same moment (one per GPU) measure the box's shared host fabric. */
+int hg_pcie_probe(hg_ctx *ctx, size_t bytes, int iters, double *h2d_gbs, double *d2h_gbs, double *bidir_gbs);
 int hg_memcpy_h2d(hg_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on the ctx stream */
 int hg_memcpy_d2h(hg_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async on the ctx stream */
 /* the context's own output buffer of the last non-batched warp (device pointer + byte size) */
