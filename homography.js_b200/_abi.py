@@ -25,7 +25,7 @@ SYMBOLS = [
     "hg_solve_affine", "hg_solve_projective", "hg_inverse_affine", "hg_transform_limits", "hg_solve_with_limits",
     "hg_warp_inverse_matrix", "hg_warp_inverse_points", "hg_warp_forward_matrix",
     "hg_delaunay", "hg_png_decode", "hg_jpeg_decode", "hg_png_encode", "hg_png_encode_bound",
-    "hg_piecewise_set_mesh", "hg_piecewise_matrices", "hg_piecewise_extents", "hg_build_index_map",
+    "hg_piecewise_set_mesh", "hg_piecewise_mesh_size", "hg_piecewise_matrices", "hg_piecewise_extents", "hg_build_index_map",
     "hg_warp_piecewise_inverse", "hg_warp_piecewise_forward",
     "hg_warp_inverse_batch", "hg_warp_piecewise_inverse_batch",
     "hg_warp_inverse_points_batch", "hg_warp_forward_batch", "hg_warp_piecewise_forward_batch",
@@ -109,6 +109,7 @@ def load():
     L.hg_warp_inverse_points.argtypes = [vp, i, vp, vp, i, i, i, i, vp, vp]
     L.hg_warp_forward_matrix.argtypes = [vp, i, vp, i, i, i, i, vp, vp]
     L.hg_piecewise_set_mesh.argtypes = [vp, vp, i, vp, i]
+    L.hg_piecewise_mesh_size.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
     L.hg_piecewise_matrices.argtypes = [vp, vp, vp, vp]
     L.hg_piecewise_extents.argtypes = [vp, vp, i, i, vp]
     L.hg_build_index_map.argtypes = [vp, vp, d, d, C.c_int64, vp]

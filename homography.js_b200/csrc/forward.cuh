@@ -75,21 +75,22 @@ __global__ void __launch_bounds__(256) forward_scatter_kernel(const FwdParams P)
 {
     const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
     if (a.lattice) return;
-    const long long n = (long long)a.domW * a.domH;
+    const int n = a.domW * a.domH;  // < 2^31 (checked on the host)
     const long long npix_out = (long long)a.oW * a.oH;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int stride = (int)(gridDim.x * blockDim.x);
     float mf[6];
     if (!PIECEWISE) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) mf[k] = (float)a.mat[k];
     }
-    for (long long key = (long long)blockIdx.x * blockDim.x + threadIdx.x; key < n; key += stride) {
-        const int yy = (int)(key / a.domW);
-        const int xx = (int)(key - (long long)yy * a.domW);
+    // key - stride may wrap past 2^31 only after the loop condition has failed: the unsigned compare ends the loop
+    for (unsigned key = blockIdx.x * blockDim.x + threadIdx.x; key < (unsigned)n; key += (unsigned)stride) {
+        const int yy = (int)(key / (unsigned)a.domW);
+        const int xx = (int)(key - (unsigned)yy * (unsigned)a.domW);
         const double x = (double)(a.minX + xx), y = (double)(a.minY + yy);
         double tx, ty;
         if (PIECEWISE) {
-            if (key >= a.map_len) continue;  // read past the map: undefined > -1 is false
+            if ((long long)key >= a.map_len) continue;  // read past the map: undefined > -1 is false
             const int raw = __ldg(a.map32 + key);
             const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);  // Int16Array semantics
             if (t < 0 || t >= a.n_tris) continue;
@@ -156,36 +157,48 @@ __global__ void __launch_bounds__(256) forward_gather_kernel(const FwdParams P)
 }
 
 // lattice frames: out(X, Y) = src(x, y) with the integer inverse of the plan, transparent where (x, y) leaves the
-// loop domain [0, W) x [0, H).  One flat quad per thread and step (a quad may run over a row end: (X, Y) per pixel).
+// loop domain [0, W) x [0, H).  Flat quads (a quad may run over a row end: (X, Y) per pixel); a thread takes TWO quads
+// per step, a grid stride apart, and issues the eight gathers before the two 128-bit stores.
+__device__ __forceinline__ void lattice_quad_load(const FwdArgs &a, const uint32_t *__restrict__ src, int p0, int npix, uint32_t (&px)[4])
+{
+    int Y = p0 / a.oW;
+    int X = p0 - Y * a.oW;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int u = X - a.rx, v = Y - a.ry;
+        const int x = a.ixx * u + a.ixy * v, y = a.iyx * u + a.iyy * v;
+        uint32_t w = 0u;
+        if ((unsigned)x < (unsigned)a.W && (unsigned)y < (unsigned)a.H && p0 + k < npix) w = __ldg(src + (size_t)y * a.W + x);
+        px[k] = w;
+        if (++X == a.oW) { X = 0; ++Y; }
+    }
+}
+__device__ __forceinline__ void lattice_quad_store(uint32_t *out, int p0, int npix, const uint32_t (&px)[4])
+{
+    if (p0 + 3 < npix) {
+        *reinterpret_cast<uint4 *>(out + p0) = make_uint4(px[0], px[1], px[2], px[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (p0 + k < npix) out[p0 + k] = px[k];
+    }
+}
+
 __global__ void __launch_bounds__(256) forward_lattice_kernel(const FwdParams P)
 {
     const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
     if (!a.lattice) return;
-    const long long npix = (long long)a.oW * a.oH;
-    const long long nquad = (npix + 3) >> 2;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int npix = a.oW * a.oH;  // < 2^31 (checked on the host)
+    const int nquad = (npix + 3) >> 2;
+    const int stride = (int)(gridDim.x * blockDim.x);
     const uint32_t *__restrict__ src = a.src;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += stride) {
-        const long long p0 = q << 2;
-        int Y = (int)(p0 / a.oW);
-        int X = (int)(p0 - (long long)Y * a.oW);
-        uint32_t px[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int u = X - a.rx, v = Y - a.ry;
-            const int x = a.ixx * u + a.ixy * v, y = a.iyx * u + a.iyy * v;
-            uint32_t w = 0u;
-            if ((unsigned)x < (unsigned)a.W && (unsigned)y < (unsigned)a.H && p0 + k < npix) w = __ldg(src + (size_t)y * a.W + x);
-            px[k] = w;
-            if (++X == a.oW) { X = 0; ++Y; }
-        }
-        if (p0 + 3 < npix) {
-            *reinterpret_cast<uint4 *>(a.out + p0) = make_uint4(px[0], px[1], px[2], px[3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (p0 + k < npix) a.out[p0 + k] = px[k];
-        }
+    for (int q = (int)(blockIdx.x * blockDim.x + threadIdx.x); q < nquad; q += 2 * stride) {
+        uint32_t pa[4], pb[4];
+        const int q2 = q + stride;
+        lattice_quad_load(a, src, q << 2, npix, pa);
+        if (q2 < nquad) lattice_quad_load(a, src, q2 << 2, npix, pb);
+        lattice_quad_store(a.out, q << 2, npix, pa);
+        if (q2 < nquad) lattice_quad_store(a.out, q2 << 2, npix, pb);
     }
 }
 

@@ -305,11 +305,10 @@ int tmaps_device(hg_ctx *c, const void *img, int W, int H, const CUtensorMap **o
     if (!encode_tmaps(c, img, W, H, tm)) return HG_OK;
     if (!c->tm_dev.p) TRY(ensure(c, c->tm_dev, sizeof(CUtensorMap) * GEO_NBOX * (size_t)TM_CACHE_SLOTS));
     if (c->tm_used == TM_CACHE_SLOTS) {
-        // cache full: drop everything once no kernel can still be reading it
-        CU(c, cudaDeviceSynchronize());
-        c->tm_index.clear();
-        c->tm_used = 0;
-        return tmaps_device(c, img, W, H, out);
+        // cache full: this frame gathers directly (*out stays nullptr).  Slots are never recycled — frames resolved
+        // earlier in the same batch still point at them until their launch
+        if (bucket.empty()) c->tm_index.erase(key);
+        return HG_OK;
     }
     const int slot = c->tm_used++;
     CUtensorMap *dst = (CUtensorMap *)c->tm_dev.p + (size_t)slot * GEO_NBOX;
@@ -1144,7 +1143,9 @@ int hg_jpeg_decode(const uint8_t *jpg, size_t jpg_bytes, uint8_t *rgba_out, size
         *h = hh;
         if (!rgba_out) return HG_OK;
         if (capacity_bytes < (size_t)ww * hh * 4) return HG_ERR_INVALID;
-        r = hg_jpeg_detail::decode(jpg, jpg_bytes, ww, hh, rgba_out);
+        int w2 = 0, h2 = 0;
+        r = hg_jpeg_detail::decode(jpg, jpg_bytes, w2, h2, rgba_out);
+        if (r == 0 && (w2 != ww || h2 != hh)) return HG_ERR_INVALID;  // the two passes must agree on the picture's size
         return r == 0 ? HG_OK : (r == hg_jpeg_detail::UNSUPPORTED ? HG_ERR_UNSUPPORTED : HG_ERR_INVALID);
     } catch (const std::bad_alloc &) {
         return HG_ERR_NOMEM;
@@ -1215,6 +1216,14 @@ int hg_piecewise_set_mesh(hg_ctx *c, const float *src_pts, int n_pts, const uint
     CU(c, cudaStreamSynchronize(c->stream));
     c->n_pts = n_pts;
     c->n_tris = n_tris;
+    return HG_OK;
+}
+
+int hg_piecewise_mesh_size(hg_ctx *c, int *n_pts, int *n_tris)
+{
+    if (!c || !n_pts || !n_tris) return HG_ERR_INVALID;
+    *n_pts = c->n_pts;
+    *n_tris = c->n_tris;
     return HG_OK;
 }
 

@@ -228,6 +228,9 @@ struct Decoder {
     int orientation = 1;  // Exif tag 0x0112 (1..8); browsers apply it when the image is drawn (image-orientation: from-image)
     int adobe_transform = 0;
     int restart_interval = 0;
+    // the bytes are untrusted: work is bounded by what they can pay for (see parse_headers_and_scans)
+    int n_scans = 0;
+    unsigned long long block_visits = 0, visit_budget = 0;
     uint16_t qt[4][64];
     bool qt_present[4] = {false, false, false, false};
     Huff dc[4], ac[4];
@@ -338,6 +341,9 @@ struct Decoder {
         }
     }
 
+    static constexpr int kMaxScans = 100;
+    static constexpr unsigned long long kMaxPixels = 1ull << 28;  // 16384 x 16384: planes + coefficients stay below ~2.5 GB
+
     int scan(size_t &pos)
     {
         if (pos + 2 > n) return MALFORMED;
@@ -374,6 +380,16 @@ struct Decoder {
                 if (ss == 0 && ah == 0 && !dc[sc[i]->td].present) return MALFORMED;
                 if (ss != 0 && !ac[sc[i]->ta].present) return MALFORMED;
             }
+        }
+        // a scan walks every block of its components even when its entropy-coded segment is empty (the bit reader feeds
+        // zeros after a marker, like libjpeg): bound the scans and the blocks they may walk by the size of the file, so a
+        // few kilobytes cannot buy minutes of decoding (encoders emit about 10 scans; libjpeg-turbo's fuzzers stop at 500)
+        if (++n_scans > kMaxScans) return MALFORMED;
+        {
+            unsigned long long blocks = 0;
+            for (int i = 0; i < ns; ++i) blocks += (unsigned long long)sc[i]->blocks_w * (unsigned long long)sc[i]->blocks_h;
+            block_visits += blocks;
+            if (block_visits > visit_budget) return MALFORMED;
         }
         eobrun = 0;
         pos += (size_t)len;
@@ -514,10 +530,17 @@ struct Decoder {
                     max_h = max_v = 1;
                 }
                 have_sof = true;
-                if (header_only) return OK;
+                if ((unsigned long long)W * (unsigned long long)H > kMaxPixels) return UNSUPPORTED;
+                if (header_only) {   // keep reading markers up to the first scan: an Exif segment may follow the frame header
+                    pos += (size_t)len;
+                    continue;
+                }
                 // a block costs at least two bits per component: a frame far larger than the bytes that follow could
                 // encode is refused before its planes are allocated
                 if ((unsigned long long)W * (unsigned long long)H / 4096ull > (unsigned long long)n) return MALFORMED;
+                // every scan of an honest file pays for the blocks it walks with entropy-coded bytes, or skips them in long
+                // end-of-band runs: 256 block visits per file byte (+ a floor for tiny files) is far beyond any encoder
+                visit_budget = 256ull * (unsigned long long)n + (1ull << 20);
                 const int mcus_x = (W + 8 * max_h - 1) / (8 * max_h), mcus_y = (H + 8 * max_v - 1) / (8 * max_v);
                 for (int i = 0; i < ncomp; ++i) {
                     Component &c = comp[i];
@@ -571,6 +594,7 @@ struct Decoder {
                 }
             } else if (m == 0xDA) {  // SOS
                 if (!have_sof) return MALFORMED;
+                if (header_only) return OK;  // size and orientation are known once the first scan begins
                 const int r = scan(pos);
                 if (r) return r;
                 continue;  // pos already sits on the next marker

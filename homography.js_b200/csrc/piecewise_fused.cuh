@@ -386,184 +386,285 @@ __device__ __forceinline__ void pwf_body(const FusedFrame &F, int niter, int til
 //     triangle — dense lanes instead of a per-pixel path that every warp of a fine mesh had to walk through.
 //   * the doubled-coordinate decode of warp_geo.cuh with its warp-uniform "end pixels inside => quad inside" shortcut
 //     (both source coordinates are monotone along the quad: one triangle, one affine map), loads predicated directly.
-//   * four pipeline stages instead of five (S0 run record -> S1 triangle id + matrix loads -> S2 coordinates + gathers
-//     -> S3 stores), ids through one PRMT.
-constexpr int PWF_QCAP = 1024;  // per warp: 16 row groups x 32 lanes x 2 quads, the most a CTA can ever queue
+//   * run ids through one PRMT; the gathers of a quad carry no per-pixel predicate when its whole warp reads inside;
+//     pixel registers double-buffered (stores two iterations behind their gathers) and run records L2-prefetched: with
+//     ~30 % fewer instructions than the first generation the loop was latency-bound (ncu: issue-active 47 %, the store
+//     stage waiting on its gathers) until two row groups of gathers were kept in flight per thread.
+constexpr int PWF_QCAP = 1024;
+#ifndef PWF_PREFETCH
+#define PWF_PREFETCH 3   // run records are L2-prefetched this many row groups ahead
+#endif  // per warp: 16 row groups x 32 lanes x 2 quads, the most a CTA can ever queue
 
 // id of run r (0..7) from the eight packed int16 ids: one byte permute, sign-extended
 __device__ __forceinline__ int pwf_run_id2(const uint4 &ids, unsigned r)
 {
     const unsigned lo = (r & 4u) ? ids.z : ids.x, hi = (r & 4u) ? ids.w : ids.y;
-    return (int)__byte_perm(lo, hi, (r & 3u) * 0x2222u + 0x9910u);
+    // bytes {2k, 2k+1} of {lo, hi}, the upper half filled with the sign of byte 2k+1 (selector bit 3 = replicate the sign;
+    // __byte_perm() masks that bit away, hence the PTX form)
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"((r & 3u) * 0x2222u + 0x9910u));
+    return (int)d;
+}
+
+// per-thread constants and pipeline registers of pwf_body2
+template <bool ZERO_OFF>
+struct PwfCtx {
+    const uint32_t *src;
+    const double *inv;
+    unsigned W, npx_src, W2, H2, Wi, Hi, kflat;
+    int oW, oH, yOff, base0;
+    double xs[2][4];
+    unsigned vmask[2];
+    unsigned long long below[2], inner[2];
+    bool prev_bin, has_bin;
+    int lane;
+    unsigned lt_mask;
+    // pipeline state
+    uint4 be0, be1;      // run record (S0 -> S1)
+    int t0[2];           // triangle of each quad's first pixel (S1 -> S2)
+    double mq[2][6];     // its inverse matrix (S1 -> S2)
+    int qn;              // warp-uniform: entries in this warp's queue
+};
+
+// S2: coordinates (H.js:1046), window test and Math.round (H.js:1047-1048), flat gather (H.js:1049-1052) of one row group
+template <bool ZERO_OFF>
+__device__ __forceinline__ void pwf_issue(PwfCtx<ZERO_OFF> &C, const FusedFrame &F, int g, uint32_t (&px)[2][4])
+{
+    const int row = C.base0 + g * PWF_GROUP_ROWS;
+    const double y = (double)(C.yOff + row);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const bool live = (C.t0[q] >= 0) && (row < C.oH) && (C.vmask[q] != 0u);
+        const double r0 = __dmul_rn(C.mq[q][2], y), r1 = __dmul_rn(C.mq[q][3], y);
+        if (ZERO_OFF) {
+            unsigned hx[4], hy[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                hx[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(C.mq[q][0], C.xs[q][k], r0, C.mq[q][4]), 2.0, HG_MAGIC + 1.0));
+                hy[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(C.mq[q][1], C.xs[q][k], r1, C.mq[q][5]), 2.0, HG_MAGIC + 1.0));
+            }
+            const unsigned cz = (unsigned)(HG_HI_ZERO + 2);
+            const bool ends_inside = live && ((hx[0] - cz) < C.Wi) & ((hy[0] - cz) < C.Hi) & ((hx[3] - cz) < C.Wi) & ((hy[3] - cz) < C.Hi);
+            if (__all_sync(0xffffffffu, ends_inside)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) px[q][k] = __ldg(C.src + ((hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned flat = (hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat;
+                    const bool in = live & ((hx[k] - (unsigned)(HG_HI_ZERO + 1)) < C.W2) & ((hy[k] - (unsigned)(HG_HI_ZERO + 1)) < C.H2) &
+                                    (flat < C.npx_src);
+                    uint32_t v = 0u;
+                    if (in) v = __ldg(C.src + flat);
+                    px[q][k] = v;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned f = HG_OUTSIDE;
+                if (live)
+                    f = pwf_decode<false>(affine_coord_exact(C.mq[q][0], C.xs[q][k], r0, C.mq[q][4]),
+                                          affine_coord_exact(C.mq[q][1], C.xs[q][k], r1, C.mq[q][5]), F, C.npx_src);
+                px[q][k] = ldg_or_zero(C.src, f);
+            }
+        }
+    }
+}
+
+// S1: triangle of each quad's first pixel from the run record of row group g, its matrix; note cut quads in the queue
+template <bool ZERO_OFF>
+__device__ __forceinline__ void pwf_resolve(PwfCtx<ZERO_OFF> &C, int g, unsigned short *wq)
+{
+    const bool row_ok = C.base0 + g * PWF_GROUP_ROWS < C.oH;
+    const unsigned long long m64 = ((unsigned long long)C.be0.y << 32) | (unsigned long long)C.be0.x;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const unsigned r = (unsigned)__popcll(m64 & C.below[q]) - 1u;
+        const int t = pwf_run_id2(C.be1, r);
+        C.t0[q] = t;
+        if (t >= 0) pwf_load_matrix(C.inv, t, C.mq[q]);
+        const bool cut = row_ok && (C.vmask[q] != 0u) && (((m64 & C.inner[q]) != 0ull) || (q == 0 && C.prev_bin));
+        const unsigned bal = __ballot_sync(0xffffffffu, cut);
+        if (cut) wq[C.qn + __popc(bal & C.lt_mask)] = (unsigned short)((g << 6) | (C.lane << 1) | q);
+        C.qn += __popc(bal);
+    }
+}
+
+// S3: stores of one row group
+template <bool ZERO_OFF>
+__device__ __forceinline__ void pwf_retire(const PwfCtx<ZERO_OFF> &C, int g, uint32_t *p_out, const uint32_t (&px)[2][4])
+{
+    if (C.base0 + g * PWF_GROUP_ROWS >= C.oH) return;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        uint32_t *dst = p_out + 32 * q;
+        if (C.vmask[q] == 0xFu) {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(px[q][0], px[q][1], px[q][2], px[q][3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (C.vmask[q] & (1u << k)) dst[k] = px[q][k];
+        }
+    }
 }
 
 template <bool ZERO_OFF>
 __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int tile_x, int row0, unsigned short *wq)
 {
-    const int lane = threadIdx.x & 31, warp_id = threadIdx.x >> 5;
+    const int warp_id = threadIdx.x >> 5;
     const int tx = threadIdx.x & (PWF_TX - 1), ty = threadIdx.x / PWF_TX;
+    PwfCtx<ZERO_OFF> C;
+    C.lane = threadIdx.x & 31;
+    C.lt_mask = (1u << C.lane) - 1u;
+    C.src = F.src;
+    C.inv = F.inv;
+    C.oW = F.oW;
+    C.oH = F.oH;
+    C.yOff = F.yOff;
+    C.base0 = row0 + ty;
     const int oW = F.oW, oH = F.oH;
-    const int base0 = row0 + ty;
     const int ngroups = min(niter, (oH - row0 + PWF_GROUP_ROWS - 1) / PWF_GROUP_ROWS);  // CTA-uniform
-    const bool has_bin = tile_x < F.bins_x;
-    const int a = (oW & 3) ? (int)(((unsigned)base0 * (unsigned)oW) & 3u) : 0;
-    const uint32_t *__restrict__ src = F.src;
-    const unsigned W = (unsigned)F.W, H = (unsigned)F.H, npx_src = W * H;
-    const unsigned W2 = 2u * W, H2 = 2u * H, Wi = W2 >= 3u ? W2 - 3u : 0u, Hi = H2 >= 3u ? H2 - 3u : 0u;
-    const unsigned kflat = (unsigned)(HG_HI_ZERO >> 1) * (W + 1u);
-
-    int xx0[2];
-    unsigned vmask[2];
-    unsigned long long below[2], inner[2];
-    double xs[2][4];
+    C.has_bin = tile_x < F.bins_x;
+    const int a = (oW & 3) ? (int)(((unsigned)C.base0 * (unsigned)oW) & 3u) : 0;
+    C.W = (unsigned)F.W;
+    const unsigned H = (unsigned)F.H;
+    C.npx_src = C.W * H;
+    C.W2 = 2u * C.W;
+    C.H2 = 2u * H;
+    C.Wi = C.W2 >= 3u ? C.W2 - 3u : 0u;
+    C.Hi = C.H2 >= 3u ? C.H2 - 3u : 0u;
+    C.kflat = (unsigned)(HG_HI_ZERO >> 1) * (C.W + 1u);
+    int xx00 = 0;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const int c = 4 * tx + 32 * q - a;        // first column of the quad inside its bin (negative: previous bin)
-        xx0[q] = tile_x * PW_BIN_W + c;
-        vmask[q] = 0u;
+        const int xx0 = tile_x * PW_BIN_W + c;
+        if (q == 0) xx00 = xx0;
+        C.vmask[q] = 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (xx0[q] + k >= 0 && xx0[q] + k < oW) vmask[q] |= 1u << k;
-            xs[q][k] = (double)(F.xOff + xx0[q] + k);
+            if (xx0 + k >= 0 && xx0 + k < oW) C.vmask[q] |= 1u << k;
+            C.xs[q][k] = (double)(F.xOff + xx0 + k);
         }
         const int c0 = c < 0 ? 0 : c, c3 = c + 3;                       // own-bin columns of the quad: c0 .. c3 (<= 63)
-        below[q] = (2ull << c0) - 1ull;                                 // bits 0 .. c0
-        inner[q] = ((c3 >= 63 ? 0ull : (1ull << (c3 + 1))) - 1ull) & ~below[q];  // bits c0+1 .. c3
+        C.below[q] = (2ull << c0) - 1ull;                               // bits 0 .. c0
+        C.inner[q] = ((c3 >= 63 ? 0ull : (1ull << (c3 + 1))) - 1ull) & ~C.below[q];  // bits c0+1 .. c3
     }
     // pixels of quad 0 left of the tile belong to the previous bin (only when they are pixels of the image at all)
-    const bool prev_bin = (a > 0) && (tx == 0) && (tile_x > 0);
-
-    const uint4 *p_run = F.bin_run + 2 * ((size_t)base0 * F.bins_x + tile_x);
-    const size_t run_step = 2 * (size_t)PWF_GROUP_ROWS * F.bins_x;
-    uint32_t *p_out = F.out + ((long long)base0 * oW + xx0[0]);
-    const long long out_step = (long long)PWF_GROUP_ROWS * oW;
-
-    uint4 be0 = make_uint4(1u, 0u, 0u, 0u), be1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-    int t0[2] = {-1, -1};
-    double mq[2][6];
+    C.prev_bin = (a > 0) && (tx == 0) && (tile_x > 0);
+    C.be0 = make_uint4(1u, 0u, 0u, 0u);
+    C.be1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    C.t0[0] = C.t0[1] = -1;
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) mq[q][k] = 0.0;
-    uint32_t px[2][4];
-    int qn = 0;  // warp-uniform: entries in this warp's queue
-    const unsigned lt_mask = (1u << lane) - 1u;
+        for (int k = 0; k < 6; ++k) C.mq[q][k] = 0.0;
+    C.qn = 0;
 
-#pragma unroll 1
-    for (int it = 0; it < ngroups + 3; ++it) {
-        // ---- S3: store row group it-3
-        if (it >= 3) {
-            if (base0 + (it - 3) * PWF_GROUP_ROWS < oH) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    uint32_t *dst = p_out + 32 * q;
-                    if (vmask[q] == 0xFu) {
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(px[q][0], px[q][1], px[q][2], px[q][3]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (vmask[q] & (1u << k)) dst[k] = px[q][k];
-                    }
-                }
-            }
-            p_out += out_step;
+    const uint4 *p_run = F.bin_run + 2 * ((size_t)C.base0 * F.bins_x + tile_x);
+    const size_t run_step = 2 * (size_t)PWF_GROUP_ROWS * F.bins_x;
+    uint32_t *p_out = F.out + ((long long)C.base0 * oW + xx00);
+    const long long out_step = (long long)PWF_GROUP_ROWS * oW;
+
+    // S0: the run record of row group g (L2-prefetched PWF_PREFETCH groups earlier: the records of a frame were written
+    // by the run kernel just before and mostly sit in DRAM by now)
+    auto load_record = [&](int g) {
+        if (g >= ngroups) return;
+        if (C.has_bin && C.base0 + g * PWF_GROUP_ROWS < oH) {
+            C.be0 = __ldg(p_run);
+            C.be1 = __ldg(p_run + 1);
+            if (g + PWF_PREFETCH < ngroups && C.base0 + (g + PWF_PREFETCH) * PWF_GROUP_ROWS < oH && tx == 0)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p_run + PWF_PREFETCH * run_step));
+        } else {
+            C.be0 = make_uint4(1u, 0u, 0u, 0u);
+            C.be1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         }
-        // ---- S2: coordinates (H.js:1046) + window test, Math.round, flat gather (H.js:1047-1052) of group it-2
-        if (it >= 2 && it - 2 < ngroups) {
-            const int row = base0 + (it - 2) * PWF_GROUP_ROWS;
-            const double y = (double)(F.yOff + row);
+        p_run += run_step;
+    };
+    if (C.has_bin && tx == 0) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const bool live = (t0[q] >= 0) && (row < oH) && (vmask[q] != 0u);
-                const double r0 = __dmul_rn(mq[q][2], y), r1 = __dmul_rn(mq[q][3], y);
-                if (ZERO_OFF) {
-                    unsigned hx[4], hy[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        hx[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(mq[q][0], xs[q][k], r0, mq[q][4]), 2.0, HG_MAGIC + 1.0));
-                        hy[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(mq[q][1], xs[q][k], r1, mq[q][5]), 2.0, HG_MAGIC + 1.0));
-                    }
-                    const unsigned cz = (unsigned)(HG_HI_ZERO + 2);
-                    const bool ends_inside = live && ((hx[0] - cz) < Wi) & ((hy[0] - cz) < Hi) & ((hx[3] - cz) < Wi) & ((hy[3] - cz) < Hi);
-                    if (__all_sync(0xffffffffu, ends_inside)) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) px[q][k] = __ldg(src + ((hy[k] >> 1) * W + (hx[k] >> 1) - kflat));
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const unsigned flat = (hy[k] >> 1) * W + (hx[k] >> 1) - kflat;
-                            const bool in = live & ((hx[k] - (unsigned)(HG_HI_ZERO + 1)) < W2) & ((hy[k] - (unsigned)(HG_HI_ZERO + 1)) < H2) &
-                                            (flat < npx_src);
-                            uint32_t v = 0u;
-                            if (in) v = __ldg(src + flat);
-                            px[q][k] = v;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        unsigned f = HG_OUTSIDE;
-                        if (live)
-                            f = pwf_decode<false>(affine_coord_exact(mq[q][0], xs[q][k], r0, mq[q][4]),
-                                                  affine_coord_exact(mq[q][1], xs[q][k], r1, mq[q][5]), F, npx_src);
-                        px[q][k] = ldg_or_zero(src, f);
-                    }
-                }
-            }
-        }
-        // ---- S1: triangle of each quad's first pixel from the run record of group it-1, its matrix; note cut quads
-        if (it >= 1 && it - 1 < ngroups) {
-            const bool row_ok = base0 + (it - 1) * PWF_GROUP_ROWS < oH;
-            const unsigned long long m64 = ((unsigned long long)be0.y << 32) | (unsigned long long)be0.x;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const unsigned r = (unsigned)__popcll(m64 & below[q]) - 1u;
-                const int t = pwf_run_id2(be1, r);
-                t0[q] = t;
-                if (t >= 0) pwf_load_matrix(F.inv, t, mq[q]);
-                const bool cut = row_ok && (vmask[q] != 0u) && (((m64 & inner[q]) != 0ull) || (q == 0 && prev_bin));
-                const unsigned bal = __ballot_sync(0xffffffffu, cut);
-                if (cut) wq[qn + __popc(bal & lt_mask)] = (unsigned short)(((it - 1) << 6) | (lane << 1) | q);
-                qn += __popc(bal);
-            }
-        }
-        // ---- S0: run record of group it
-        if (it < ngroups) {
-            if (has_bin && base0 + it * PWF_GROUP_ROWS < oH) {
-                be0 = __ldg(p_run);
-                be1 = __ldg(p_run + 1);
-            } else {
-                be0 = make_uint4(1u, 0u, 0u, 0u);
-                be1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            }
-            p_run += run_step;
-        }
+        for (int g = 1; g < PWF_PREFETCH; ++g)
+            if (g < ngroups && C.base0 + g * PWF_GROUP_ROWS < oH) asm volatile("prefetch.global.L2 [%0];" ::"l"(p_run + g * run_step));
     }
 
-    // ---- the queued quads again, one pixel per lane, each with the triangle of its own run (H.js:1044-1052 verbatim)
+    // FOUR STAGES, the pixel registers double-buffered (the loop is unrolled by two so that pa / pb alternate without
+    // moves): the gathers of a row group are stored TWO iterations after they were issued, so two groups of gathers
+    // (16 loads per thread) are in flight while the arithmetic of the following groups runs.
+    //   iteration g:  S3 store group g-4 | S2 coordinates + gathers of g-2 | S1 ids + matrix loads of g-1 | S0 record of g
+    uint32_t pa[2][4], pb[2][4];
+#pragma unroll 1
+    for (int it = 0; it < ngroups + 4; it += 2) {
+        // even step: group it-2 gathers into pa, which group it-4 has just left
+        if (it >= 4) {
+            pwf_retire(C, it - 4, p_out, pa);
+            p_out += out_step;
+        }
+        if (it >= 2 && it - 2 < ngroups) pwf_issue(C, F, it - 2, pa);
+        if (it >= 1 && it - 1 < ngroups) pwf_resolve(C, it - 1, wq);
+        load_record(it);
+        // odd step: the same with pb
+        const int i1 = it + 1;
+        if (i1 >= 4 && i1 - 4 < ngroups) {
+            pwf_retire(C, i1 - 4, p_out, pb);
+            p_out += out_step;
+        }
+        if (i1 >= 2 && i1 - 2 < ngroups) pwf_issue(C, F, i1 - 2, pb);
+        if (i1 - 1 < ngroups) pwf_resolve(C, i1 - 1, wq);
+        load_record(i1);
+    }
+
+    // ---- the queued quads again, one QUAD per lane, every pixel with the triangle of its own run (H.js:1044-1052
+    // verbatim): the run record(s) once, then up to four matrices, four gathers and one 128-bit store
     __syncwarp();  // also orders the provisional stores above before the final ones below
-    for (int e0 = 0; e0 < qn; e0 += 8) {
-        const int e = e0 + (lane >> 2), k = lane & 3;
+    const int qn = C.qn;
+    for (int e0 = 0; e0 < qn; e0 += 32) {
+        const int e = e0 + C.lane;
         if (e >= qn) continue;
         const unsigned ent = wq[e];
         const int qq = (int)(ent & 1u), sl = (int)((ent >> 1) & 31u), g = (int)(ent >> 6);
         const int row = row0 + warp_id * 4 + (sl >> 3) + g * PWF_GROUP_ROWS;
         const int ae = (oW & 3) ? (int)(((unsigned)row * (unsigned)oW) & 3u) : 0;
-        const int X = tile_x * PW_BIN_W + 4 * (sl & 7) + 32 * qq - ae + k;
-        if (X < 0 || X >= oW) continue;
-        const uint4 *pr = F.bin_run + 2 * ((size_t)row * F.bins_x + (X >> 6));
-        const uint4 b0 = __ldg(pr), b1 = __ldg(pr + 1);
-        const unsigned long long m64 = ((unsigned long long)b0.y << 32) | (unsigned long long)b0.x;
-        const int t = pwf_run_id2(b1, (unsigned)__popcll(m64 & ((2ull << (X & 63)) - 1ull)) - 1u);
-        uint32_t v = 0u;
-        if (t >= 0) {
-            double m[6];
-            pwf_load_matrix(F.inv, t, m);
-            const double x = (double)(F.xOff + X), y = (double)(F.yOff + row);
-            v = ldg_or_zero(src, pwf_decode<ZERO_OFF>(affine_coord_exact(m[0], x, __dmul_rn(m[2], y), m[4]),
-                                                      affine_coord_exact(m[1], x, __dmul_rn(m[3], y), m[5]), F, npx_src));
+        const int X0 = tile_x * PW_BIN_W + 4 * (sl & 7) + 32 * qq - ae;
+        const double y = (double)(F.yOff + row);
+        // the quad lies in one bin, except a first quad that reaches back into the previous one
+        const int binA = X0 < 0 ? 0 : (X0 >> 6), binB = (X0 + 3) >> 6;
+        const uint4 *pr = F.bin_run + 2 * ((size_t)row * F.bins_x + binA);
+        const uint4 a0 = __ldg(pr), a1 = __ldg(pr + 1);
+        uint4 b0 = a0, b1 = a1;
+        if (binB != binA && binB < F.bins_x) {
+            b0 = __ldg(pr + 2);
+            b1 = __ldg(pr + 3);
         }
-        F.out[(long long)row * oW + X] = v;
+        uint32_t v[4];
+        int t_prev = -2;
+        double m[6];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int X = X0 + k;
+            v[k] = 0u;
+            if (X < 0 || X >= oW) continue;
+            const bool inB = (X >> 6) != binA;
+            const uint4 &r0 = inB ? b0 : a0, &r1 = inB ? b1 : a1;
+            const unsigned long long m64 = ((unsigned long long)r0.y << 32) | (unsigned long long)r0.x;
+            const int t = pwf_run_id2(r1, (unsigned)__popcll(m64 & ((2ull << (X & 63)) - 1ull)) - 1u);
+            if (t < 0) continue;
+            if (t != t_prev) {
+                pwf_load_matrix(F.inv, t, m);
+                t_prev = t;
+            }
+            const double x = (double)(F.xOff + X);
+            v[k] = ldg_or_zero(C.src, pwf_decode<ZERO_OFF>(affine_coord_exact(m[0], x, __dmul_rn(m[2], y), m[4]),
+                                                          affine_coord_exact(m[1], x, __dmul_rn(m[3], y), m[5]), F, C.npx_src));
+        }
+        uint32_t *dst = F.out + ((long long)row * oW + X0);
+        if (X0 >= 0 && X0 + 3 < oW) {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (X0 + k >= 0 && X0 + k < oW) dst[k] = v[k];
+        }
     }
 }
 

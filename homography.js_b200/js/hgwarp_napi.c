@@ -122,14 +122,29 @@ static napi_value SolveWithLimits(napi_env env, napi_callback_info info)
     return out;
 }
 
+/* a fresh Uint8ClampedArray of ow*oh*4 bytes; NULL (with a pending exception) when the window is empty or the engine
+ * cannot allocate it — the warp must not run with a NULL result buffer */
 static napi_value new_output(napi_env env, int ow, int oh, uint8_t **data)
 {
     napi_value ab, arr;
     void *p = NULL;
-    napi_create_arraybuffer(env, (size_t)ow * oh * 4, &p, &ab);
-    napi_create_typedarray(env, napi_uint8_clamped_array, (size_t)ow * oh * 4, ab, 0, &arr);
+    *data = NULL;
+    if (ow < 1 || oh < 1) return throw_text(env, "output window must be at least 1x1");
+    if (napi_create_arraybuffer(env, (size_t)ow * oh * 4, &p, &ab) != napi_ok || !p ||
+        napi_create_typedarray(env, napi_uint8_clamped_array, (size_t)ow * oh * 4, ab, 0, &arr) != napi_ok)
+        return throw_text(env, "out of memory for the result image");
     *data = (uint8_t *)p;
     return arr;
+}
+
+/* the destiny points of a piecewise call: a Float32Array holding at least the 2*n_pts floats the library will read for
+ * the mesh this context holds (NULL when there is no mesh or the array is too short) */
+static const float *mesh_points(napi_env env, hg_ctx *ctx, napi_value v, int *n_tris)
+{
+    int np = 0, nt = 0;
+    if (!ctx || hg_piecewise_mesh_size(ctx, &np, &nt) != HG_OK || np < 3) return NULL;
+    if (n_tris) *n_tris = nt;
+    return (const float *)typed(env, v, napi_float32_array, (size_t)np * 2);
 }
 
 /* warpInversePoints(ctx, kind, Float64Array dst, Float64Array src, xOff, yOff, oW, oH) -> Uint8ClampedArray
@@ -146,6 +161,7 @@ static napi_value WarpInversePoints(napi_env env, napi_callback_info info)
     int ow = i32(env, argv[6]), oh = i32(env, argv[7]);
     uint8_t *out = NULL;
     napi_value arr = new_output(env, ow, oh, &out);
+    if (!out) return NULL;
     int st = hg_warp_inverse_points(ctx, kind, dst, src, i32(env, argv[4]), i32(env, argv[5]), ow, oh, out, NULL);
     return st == HG_OK ? arr : check(env, ctx, st);
 }
@@ -161,6 +177,7 @@ static napi_value WarpForwardMatrix(napi_env env, napi_callback_info info)
     int ow = i32(env, argv[5]), oh = i32(env, argv[6]);
     uint8_t *out = NULL;
     napi_value arr = new_output(env, ow, oh, &out);
+    if (!out) return NULL;
     int st = hg_warp_forward_matrix(ctx, kind, m, i32(env, argv[3]), i32(env, argv[4]), ow, oh, out, NULL);
     return st == HG_OK ? arr : check(env, ctx, st);
 }
@@ -197,7 +214,10 @@ static napi_value Delaunay(napi_env env, napi_callback_info info)
     const int cap = 2 * n > 5 ? 2 * n - 5 : 0;
     napi_value ab, arr;
     void *p = NULL;
-    napi_create_arraybuffer(env, (size_t)cap * 12, &p, &ab);
+    if (napi_create_arraybuffer(env, (size_t)cap * 12, &p, &ab) != napi_ok || (cap > 0 && !p)) {
+        free(pts);
+        return throw_text(env, "out of memory");
+    }
     int nt = 0;
     const int st = hg_delaunay(pts, n, (uint32_t *)p, cap, &nt);
     free(pts);
@@ -221,6 +241,7 @@ static napi_value PngDecode(napi_env env, napi_callback_info info)
     if (hg_png_decode((const uint8_t *)data, n, NULL, 0, &w, &h) != HG_OK) return throw_text(env, "pngDecode: not a PNG this decoder supports");
     uint8_t *px = NULL;
     napi_value arr = new_output(env, w, h, &px), obj, vw, vh;
+    if (!px) return NULL;
     if (hg_png_decode((const uint8_t *)data, n, px, (size_t)w * h * 4, &w, &h) != HG_OK) return throw_text(env, "pngDecode: malformed image data");
     napi_create_object(env, &obj);
     napi_create_int32(env, w, &vw);
@@ -247,6 +268,7 @@ static napi_value JpegDecode(napi_env env, napi_callback_info info)
                                                         : "jpegDecode: not a JPEG file");
     uint8_t *px = NULL;
     napi_value arr = new_output(env, w, h, &px), obj, vw, vh;
+    if (!px) return NULL;
     st = hg_jpeg_decode((const uint8_t *)data, n, px, (size_t)w * h * 4, &w, &h);
     if (st != HG_OK)
         return throw_text(env, st == HG_ERR_UNSUPPORTED ? "jpegDecode: a JPEG mode this decoder does not support (CMYK, arithmetic coding, ...)"
@@ -289,13 +311,17 @@ static napi_value PiecewiseMatrices(napi_env env, napi_callback_info info)
 {
     ARGS(3);
     hg_ctx *ctx = ctx_of(env, argv[0]);
-    const float *dst = (const float *)typed(env, argv[1], napi_float32_array, 6);
+    int mesh_tris = -1;
+    const float *dst = mesh_points(env, ctx, argv[1], &mesh_tris);
     int nt = i32(env, argv[2]);
-    if (!ctx || !dst || nt < 0) return throw_text(env, "piecewiseMatrices(ctx, Float32Array, nTris)");
+    /* the library writes 6 floats per triangle OF THE CONTEXT MESH: the caller's count must be that one */
+    if (!ctx || !dst || nt < 0 || nt != mesh_tris)
+        return throw_text(env, "piecewiseMatrices(ctx, Float32Array dstPts (2 per mesh point), nTris of the mesh)");
     napi_value ab, arr;
     void *p = NULL;
-    napi_create_arraybuffer(env, (size_t)nt * 24, &p, &ab);
-    napi_create_typedarray(env, napi_float32_array, (size_t)nt * 6, ab, 0, &arr);
+    if (napi_create_arraybuffer(env, (size_t)nt * 24, &p, &ab) != napi_ok || (nt > 0 && !p) ||
+        napi_create_typedarray(env, napi_float32_array, (size_t)nt * 6, ab, 0, &arr) != napi_ok)
+        return throw_text(env, "out of memory");
     int st = hg_piecewise_matrices(ctx, dst, (float *)p, NULL);
     return st == HG_OK ? arr : check(env, ctx, st);
 }
@@ -306,11 +332,12 @@ static napi_value WarpPiecewiseInverse(napi_env env, napi_callback_info info)
 {
     ARGS(8);
     hg_ctx *ctx = ctx_of(env, argv[0]);
-    const float *dst = (const float *)typed(env, argv[1], napi_float32_array, 6);
-    if (!ctx || !dst) return throw_text(env, "warpPiecewiseInverse(ctx, Float32Array, ...)");
+    const float *dst = mesh_points(env, ctx, argv[1], NULL);
+    if (!ctx || !dst) return throw_text(env, "warpPiecewiseInverse(ctx, Float32Array dstPts (2 per mesh point), ...)");
     int ow = i32(env, argv[4]), oh = i32(env, argv[5]);
     uint8_t *out = NULL;
     napi_value arr = new_output(env, ow, oh, &out);
+    if (!out) return NULL;
     int st = hg_warp_piecewise_inverse(ctx, dst, i32(env, argv[2]), i32(env, argv[3]), ow, oh, i32(env, argv[6]),
                                        i32(env, argv[7]), out, NULL);
     return st == HG_OK ? arr : check(env, ctx, st);
@@ -322,11 +349,12 @@ static napi_value WarpPiecewiseForward(napi_env env, napi_callback_info info)
 {
     ARGS(11);
     hg_ctx *ctx = ctx_of(env, argv[0]);
-    const float *dst = (const float *)typed(env, argv[1], napi_float32_array, 6);
-    if (!ctx || !dst) return throw_text(env, "warpPiecewiseForward(ctx, Float32Array, ...)");
+    const float *dst = mesh_points(env, ctx, argv[1], NULL);
+    if (!ctx || !dst) return throw_text(env, "warpPiecewiseForward(ctx, Float32Array dstPts (2 per mesh point), ...)");
     int ow = i32(env, argv[4]), oh = i32(env, argv[5]);
     uint8_t *out = NULL;
     napi_value arr = new_output(env, ow, oh, &out);
+    if (!out) return NULL;
     int st = hg_warp_piecewise_forward(ctx, dst, i32(env, argv[2]), i32(env, argv[3]), ow, oh, i32(env, argv[6]),
                                        i32(env, argv[7]), i32(env, argv[8]), i32(env, argv[9]), i32(env, argv[10]), out, NULL);
     return st == HG_OK ? arr : check(env, ctx, st);

@@ -148,7 +148,11 @@ int hg_png_decode(const uint8_t *png, size_t png_bytes, uint8_t *rgba_out, size_
  * chroma upsampling and fixed-point colour conversion (csrc/jpeg_host.cuh; checked byte for byte against libjpeg-turbo
  * through Pillow).  The Exif Orientation tag is applied the way a browser draws the image (w / h are those of the picture as
  * shown).  Same calling convention as hg_png_decode.  HG_ERR_UNSUPPORTED: lossless / arithmetic-coded /
- * 12-bit / four-component files and 1:2 vertical-only subsampling; HG_ERR_INVALID: malformed data or capacity too small. */
+ * 12-bit / four-component files, 1:2 vertical-only subsampling, more than 2^28 pixels; HG_ERR_INVALID: malformed data or
+ * capacity too small.  The bytes may be hostile: decoding work is bounded by the file size (at most 100 scans, at most 256
+ * block visits per file byte), so a small crafted file cannot buy minutes of CPU or gigabytes of memory.  Files whose scans
+ * have not all arrived (truncated progressive files) decode without libjpeg's inter-block smoothing: byte-exactness with a
+ * browser holds for complete files. */
 int hg_jpeg_decode(const uint8_t *jpg, size_t jpg_bytes, uint8_t *rgba_out, size_t capacity_bytes, int *w, int *h);
 /* RGBA8 -> PNG (8-bit RGBA, zlib level 6).  hg_png_encode_bound gives a capacity that always suffices. */
 size_t hg_png_encode_bound(int w, int h);
@@ -157,6 +161,9 @@ int hg_png_encode(const uint8_t *rgba, int w, int h, uint8_t *png_out, size_t ca
 /* ------------------------------------------------------------------ piecewise affine */
 /* mesh = this._srcPoints (pixel range) + this._triangles (H.js:1216 / setTriangles H.js:517) */
 int hg_piecewise_set_mesh(hg_ctx *ctx, const float *src_pts, int n_pts, const uint32_t *tris, int n_tris);
+/* number of points / triangles of the mesh the context holds (0, 0 before hg_piecewise_set_mesh): what bindings check the
+ * lengths of caller-owned point arrays and result buffers against */
+int hg_piecewise_mesh_size(hg_ctx *ctx, int *n_pts, int *n_tris);
 /* _calculatePiecewiseAffineTransformMatrices, H.js:785: T forward 2x3 float matrices; optionally
  * also their inverses (inverseAffineMatrix, H.js:1036-1038).  Either output may be NULL. */
 int hg_piecewise_matrices(hg_ctx *ctx, const float *dst_pts, float *fwd_out, float *inv_out);

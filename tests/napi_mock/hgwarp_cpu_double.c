@@ -128,6 +128,14 @@ int hg_piecewise_set_mesh(hg_ctx *c, const float *src_pts, int n_pts, const uint
     return HG_OK;
 }
 
+int hg_piecewise_mesh_size(hg_ctx *c, int *n_pts, int *n_tris)
+{
+    if (!c || !n_pts || !n_tris) return HG_ERR_INVALID;
+    *n_pts = c->n_pts;
+    *n_tris = c->n_tris;
+    return HG_OK;
+}
+
 int hg_piecewise_matrices(hg_ctx *c, const float *dst_pts, float *fwd_out, float *inv_out)
 {
     if (!c || !c->src_pts || !dst_pts) return fail(c, HG_ERR_STATE, "no mesh");

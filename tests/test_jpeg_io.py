@@ -103,9 +103,13 @@ def test_unsupported_and_malformed_files_are_refused_not_guessed():
     bomb = good[:i + 5] + b"\xff\xff\xff\xff" + good[i + 9:]
     import ctypes as C
     w, h = C.c_int(), C.c_int()
-    assert hg._abi.load().hg_jpeg_decode(bomb, len(bomb), None, 0, C.byref(w), C.byref(h)) == 0 and w.value == 65535
+    assert hg._abi.load().hg_jpeg_decode(bomb, len(bomb), None, 0, C.byref(w), C.byref(h)) == hg._abi.HG_ERR_UNSUPPORTED  # > 2^28 pixels
     big = np.empty(1, np.uint8)
     assert hg._abi.load().hg_jpeg_decode(bomb, len(bomb), big.ctypes.data, 65535 * 65535 * 4, C.byref(w), C.byref(h)) != 0
+    # within the pixel ceiling the size query answers, and the decode refuses a frame its bytes cannot pay for
+    bomb = good[:i + 5] + b"\x3f\xff\x3f\xff" + good[i + 9:]
+    assert hg._abi.load().hg_jpeg_decode(bomb, len(bomb), None, 0, C.byref(w), C.byref(h)) == 0 and w.value == 0x3fff
+    assert hg._abi.load().hg_jpeg_decode(bomb, len(bomb), big.ctypes.data, 0x3fff * 0x3fff * 4, C.byref(w), C.byref(h)) != 0
 
 
 def test_truncated_file_without_eoi_is_decoded_when_complete():
@@ -316,3 +320,65 @@ def test_one_scan_per_component_layout(subsampling):
     want = np.asarray(PIL.open(io.BytesIO(src)).convert("RGB"))
     assert np.array_equal(np.asarray(PIL.open(io.BytesIO(multi)).convert("RGB")), want)   # the transcoding is lossless
     assert np.array_equal(hg._abi.jpeg_decode(multi)[..., :3], want)
+
+
+# ------------------------------------------------------------------ hostile files: work bounded by the file size
+def _segments(jpeg: bytes):
+    """(marker, start, end) of every marker segment up to and including the first SOS header."""
+    out, pos = [], 2
+    while pos + 4 <= len(jpeg):
+        assert jpeg[pos] == 0xFF
+        m = jpeg[pos + 1]
+        ln = (jpeg[pos + 2] << 8) | jpeg[pos + 3]
+        out.append((m, pos, pos + 2 + ln))
+        pos += 2 + ln
+        if m == 0xDA:
+            break
+    return out
+
+
+def test_crafted_progressive_file_cannot_buy_minutes_of_decoding():
+    """The advisor's denial-of-service file: a frame header claiming 4096 x 4096 followed by hundreds of AC scans with no
+    entropy-coded data.  Every scan used to walk all 262,144 blocks (5 KB -> 4.7 s, 70 KB -> more than 10 minutes); now the
+    scan count and the blocks walked are bounded by the file size and the file is refused at once."""
+    import struct
+    import time
+    base = _jpeg(PIL.fromarray(_picture(64, 64)[..., 0], "L"), quality=80, progressive=True)
+    segs = _segments(base)
+    sof = next(s for s in segs if s[0] == 0xC2)
+    sos = segs[-1]
+    data = bytearray(base)
+    data[sof[1] + 5: sof[1] + 9] = struct.pack(">HH", 4096, 4096)          # height, width
+    # an AC-first scan header of the single component (Ss=1, Se=63), repeated with no data behind it
+    empty_scan = b"\xff\xda" + struct.pack(">HBBBBBB", 8, 1, data[sos[1] + 5], 0x00, 1, 63, 0)
+    pad = b"\xff\xfe" + struct.pack(">H", 4098) + bytes(4096)               # a comment, so the size guard of the header passes
+    crafted = bytes(data[:sof[1]]) + pad + bytes(data[sof[1]:-2]) + empty_scan * 500 + b"\xff\xd9"
+    t0 = time.perf_counter()
+    with pytest.raises(hg.HgError):
+        hg._abi.jpeg_decode(crafted)
+    assert time.perf_counter() - t0 < 2.0
+    # a header claiming more pixels than the decoder supports is refused before anything is allocated
+    huge = bytearray(base)
+    huge[sof[1] + 5: sof[1] + 9] = struct.pack(">HH", 65535, 65535)
+    t0 = time.perf_counter()
+    with pytest.raises(hg.HgError) as e:
+        hg._abi.jpeg_decode(bytes(huge))
+    assert e.value.status == hg._abi.HG_ERR_UNSUPPORTED and time.perf_counter() - t0 < 0.5
+    # honest progressive files are untouched by the bounds
+    _same_as_pillow(_jpeg(PIL.fromarray(_picture(300, 200), "RGB"), quality=85, progressive=True))
+
+
+def test_exif_segment_after_the_frame_header_still_turns_the_picture():
+    """An APP1 Exif segment between SOF and SOS: the size query must report the turned size (it used to stop at SOF and
+    report 30 x 20 for pixels laid out 20 x 30)."""
+    ops = pytest.importorskip("PIL.ImageOps")
+    base = _jpeg(PIL.fromarray(_picture(20, 30), "RGB"), quality=90)
+    exif = _with_exif_orientation(base, 6, False)
+    app1_end = 4 + ((exif[4] << 8) | exif[5])
+    app1 = exif[2:app1_end]
+    segs = _segments(base)
+    sos = segs[-1]
+    moved = base[:sos[1]] + app1 + base[sos[1]:]          # Exif right in front of SOS, after SOF / DHT
+    got = hg._abi.jpeg_decode(moved)
+    assert got.shape[:2] == (30, 20)
+    assert np.array_equal(got[..., :3], np.asarray(ops.exif_transpose(PIL.open(io.BytesIO(exif))).convert("RGB")))
