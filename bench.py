@@ -244,10 +244,9 @@ class Env:
         """sum mod 2^64 over ranks (two 32-bit halves through an int64 all-reduce)."""
         if self.world == 1:
             return v & 0xFFFFFFFFFFFFFFFF
-        t = self.torch.tensor([v & 0xFFFFFFFF, (v >> 32) & 0xFFFFFFFF], dtype=self.torch.int64, device=self.dev)
+        t = self.torch.tensor(list(self.hg.workloads.u64_to_halves(v)), dtype=self.torch.int64, device=self.dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-        lo, hi = int(t[0].item()), int(t[1].item())
-        return (lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF
+        return self.hg.workloads.halves_to_u64(int(t[0].item()), int(t[1].item()))
 
     def oracle_threads(self) -> int:
         return max(1, (os.cpu_count() or 1) // max(self.world, 1))
@@ -799,7 +798,7 @@ def run_headline(env, wl_name: str, with_secondary: bool):
     # ---- end to end.  (a) the class surface a user of the reference calls: setImage + setDestinyPoints + warp per frame,
     #      synchronous, frame images in pinned host memory, results in pinned host memory (H2D + solve + limits + warp + D2H)
     Fe = args.e2e_frames
-    h_src = [ctx.pinned_array(H * W * 4) for _ in range(Fe)]
+    h_src = [ctx.pinned_array(H * W * 4, write_combined=args.wc_src) for _ in range(Fe)]
     rs = np.random.default_rng(100 + rank)
     for a in h_src:
         a[:] = rs.integers(0, 256, a.size, dtype=np.uint8)
@@ -923,7 +922,7 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="headline frames per step (per GPU)")
     ap.add_argument("--e2e-frames", type=int, default=16, help="frames per end-to-end step (per GPU)")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
-    ap.add_argument("--pw-frames", type=int, default=16, help="frames per step per GPU of the piecewise3 / piecewise4 batches")
+    ap.add_argument("--pw-frames", type=int, default=64, help="frames per step per GPU of the piecewise3 / piecewise4 batches")
     ap.add_argument("--c4-frames", type=int, default=512, help="config 4: frames per GPU per step (4096 / 8)")
     ap.add_argument("--c5-frames", type=int, default=12500, help="config 5: frames per GPU per step (100000 / 8)")
     ap.add_argument("--fwd-frames", type=int, default=64, help="frames per step per GPU of the forward / bilinear lines")
@@ -931,6 +930,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (parity gates + cpu_baseline)")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--wc-src", action="store_true", help="end-to-end source frames in write-combined pinned memory (A/B)")
     ap.add_argument("--skip", nargs="*", default=[], help="secondary workloads to leave out")
     ap.add_argument("--general", action="store_true", help="piecewise3/4: also time the general map-based path")
     ap.add_argument("--workload", default="projective",

@@ -1191,10 +1191,17 @@ static int check_points(hg_ctx *c, const float *p, int n, const char *what)
 
 static int check_point_floats(hg_ctx *c, const float *p, size_t n_floats, const char *what)
 {
-    for (size_t i = 0; i < n_floats; ++i) {
-        const float v = p[i];
-        if (!(v >= -1048576.f && v <= 1048576.f))  // also rejects NaN / Inf
-            return fail(c, HG_ERR_UNSUPPORTED, "%s[%zu] = %g: piecewise points must be finite and |v| <= 2^20", what, i, (double)v);
+    // blocks of branch-free compares (the compiler vectorises them): a batch carries millions of coordinates and this
+    // runs on the host in front of every launch; only a failing block is searched for the offender
+    for (size_t b0 = 0; b0 < n_floats; b0 += 4096) {
+        const size_t b1 = b0 + 4096 < n_floats ? b0 + 4096 : n_floats;
+        unsigned bad = 0;
+        for (size_t i = b0; i < b1; ++i) bad |= (unsigned)!(p[i] >= -1048576.f && p[i] <= 1048576.f);  // also NaN / Inf
+        if (bad)
+            for (size_t i = b0; i < b1; ++i)
+                if (!(p[i] >= -1048576.f && p[i] <= 1048576.f))
+                    return fail(c, HG_ERR_UNSUPPORTED, "%s[%zu] = %g: piecewise points must be finite and |v| <= 2^20", what, i,
+                                (double)p[i]);
     }
     return HG_OK;
 }
@@ -1391,17 +1398,21 @@ static int pw_fused_launch(hg_ctx *c, const float *dst_dev, int nF, int max_ow, 
         a.map_pts = dst_dev;
         a.tris = (const uint32_t *)c->tris.p;
         a.rec = (TriRec *)c->rec.p;
-        a.invd_out = (double *)c->invd.p;
+        a.invd_out = (float *)c->invd.p;
         a.n_tris = c->n_tris;
         a.dst_stride = 2 * (size_t)c->n_pts;
         a.rec_stride = T;
         pw_setup_kernel<<<dim3((unsigned)((T + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>(a);
-        // warps per triangle: a mesh of T triangles over oH rows has triangles ~ oH / sqrt(T/2) rows tall
-        int split = (int)((double)max_oh / (32.0 * sqrt((double)T / 2.0 + 1.0)) + 0.5);
-        if (split < 1) split = 1;
-        if (split > 16) split = 16;
-        pw_span_bin_kernel<<<dim3((unsigned)((T * split + 3) / 4), (unsigned)nF), 128, 0, c->stream>>>(
-            (const FusedFrame *)c->fframes.p, split);
+        // lanes per triangle: a mesh of T triangles over oH rows has triangles ~ oH / sqrt(T/2) rows tall; about three rows
+        // per lane keep the lanes busy without leaving the machine empty for coarse meshes
+        const double rows_guess = (double)max_oh / sqrt((double)T / 2.0 + 1.0);
+        int lpt_log2 = 3;
+        while (lpt_log2 < 9 && (double)(1 << lpt_log2) * 3.0 < rows_guess) ++lpt_log2;
+        // ... and a coarse mesh spreads its triangles further until the launch fills the machine about twice
+        while (lpt_log2 < 9 && (double)(T << lpt_log2) * nF < 2.0 * 2048.0 * c->sm_count && (double)(1 << lpt_log2) < rows_guess) ++lpt_log2;
+        const size_t span_threads = T << lpt_log2;
+        pw_span_bin_kernel<<<dim3((unsigned)((span_threads + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>(
+            (const FusedFrame *)c->fframes.p, lpt_log2);
         c->launches += 2;
         CU(c, cudaGetLastError());
     }
@@ -1435,7 +1446,7 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         if (fr[f].oH > max_oh) max_oh = fr[f].oH;
     }
     TRY(ensure(c, c->rec, sizeof(TriRec) * T * nF));
-    TRY(ensure(c, c->invd, sizeof(double) * 6 * T * nF));
+    TRY(ensure(c, c->invd, sizeof(float) * 8 * T * nF));
     // + one row group of slack: the pixel kernel's bin pointers may step (and read, but never use) past the last row
     const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
     TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * (total_bins + slack)));
@@ -1448,7 +1459,7 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         FusedFrame &F = ff[(size_t)f];
         F.src = fr[f].src; F.out = fr[f].out;
         F.rec = (const TriRec *)c->rec.p + T * f;
-        F.inv = (const double *)c->invd.p + 6 * T * f;
+        F.inv = (const float *)c->invd.p + 8 * T * f;
         F.bin_cnt = (unsigned *)c->bin_cnt.p + bin0;
         F.bin_ent = (unsigned *)c->bin_ent.p + bin0 * PW_BIN_CAP;
         F.bin_run = (uint4 *)c->bin_run.p + 2 * bin0;
@@ -2114,7 +2125,7 @@ int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int6
     const size_t T = (size_t)c->n_tris, pts_per_frame = 2 * (size_t)c->n_pts;
     const size_t slot_px = hg_stream_slot_bytes(max_out_w, max_out_h) / 4;
     const size_t bin_stride = (size_t)pwf_bins_x(max_out_w) * (size_t)max_out_h;
-    TRY(upload_dst_points(c, dst_pts, (size_t)n_frames));
+    TRY(ensure(c, c->dst_pts, sizeof(float) * pts_per_frame * (size_t)n_frames));
     c->map32_current = false;
     c->last_inv_len = -1;
     // chunk: frames in flight never share a ring slot, and the per-frame scratch stays below ~1.5 GB
@@ -2133,7 +2144,7 @@ int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int6
     const bool fused = !c->force_general && c->n_tris < PW_MAX_TRIS;
     const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
     TRY(ensure(c, c->rec, sizeof(TriRec) * (T ? T : 1) * (size_t)chunk));
-    TRY(ensure(c, c->invd, sizeof(double) * 6 * (T ? T : 1) * (size_t)chunk));
+    TRY(ensure(c, c->invd, sizeof(float) * 8 * (T ? T : 1) * (size_t)chunk));
     TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * (bin_stride * chunk + slack)));
     TRY(ensure(c, c->bin_ent, sizeof(unsigned) * (bin_stride * chunk + slack) * PW_BIN_CAP));
     TRY(ensure(c, c->bin_run, sizeof(uint4) * 2 * (bin_stride * chunk + slack)));
@@ -2166,14 +2177,18 @@ int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int6
     int prev_f0 = -1, prev_nf = 0, k = 0;
     for (int f0 = 0; f0 < n_frames; f0 += chunk, ++k) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
-        const float *dd = (const float *)c->dst_pts.p + pts_per_frame * (size_t)f0;
+        float *dd = (float *)c->dst_pts.p + pts_per_frame * (size_t)f0;
+        // this chunk's destiny points go up while the previous chunk computes (a pageable source is staged by the driver
+        // before the call returns; the copy itself is stream-ordered in front of this chunk's kernels)
+        CU(c, cudaMemcpyAsync(dd, dst_pts + pts_per_frame * (size_t)f0, sizeof(float) * pts_per_frame * (size_t)nf,
+                              cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * bin_stride * (size_t)nf, c->stream));
         CU(c, cudaMemsetAsync(c->fstatus.p, 0, sizeof(int) * (size_t)nf, c->stream));
         StreamArgs a{};
         a.dst_pts = dd; a.n_pts = c->n_pts; a.n_frames = nf; a.frame0 = (long long)first_frame + f0;
         a.src = src; a.src_stride_px = (size_t)W * H; a.n_src = n_src; a.W = W; a.H = H;
         a.out_ring = (uint32_t *)out_ring_dev; a.slot_px = slot_px; a.n_slots = n_slots; a.max_w = max_out_w; a.max_h = max_out_h;
-        a.rec = (const TriRec *)c->rec.p; a.invd = (const double *)c->invd.p;
+        a.rec = (const TriRec *)c->rec.p; a.invd = (const float *)c->invd.p;
         a.bin_cnt = (unsigned *)c->bin_cnt.p; a.bin_ent = (unsigned *)c->bin_ent.p; a.bin_run = (uint4 *)c->bin_run.p;
         a.status = (int *)c->fstatus.p; a.bin_stride = bin_stride;
         a.n_tris = c->n_tris; a.minSrcX = min_src_x; a.minSrcY = min_src_y;

@@ -38,7 +38,7 @@ struct PwSetupArgs {
     TriRec *rec;
     float *fwd_out;         // optional dense copies (T*6)
     float *inv_out;
-    double *invd_out;       // optional: inverse matrices widened to double (T*6 per frame), for the fused kernel
+    float *invd_out;        // optional: inverse matrices as 32-byte records (T*8 floats per frame), for the fused kernel
     int n_tris;
     size_t dst_stride;      // frame stride (floats) for batched calls, indexed by blockIdx.y
     size_t rec_stride;
@@ -102,8 +102,9 @@ __global__ void pw_setup_kernel(PwSetupArgs a)
         for (int k = 0; k < 6; ++k) a.inv_out[(f * a.n_tris + t) * 6 + k] = r.inv[k];
     }
     if (a.invd_out) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) a.invd_out[(f * a.n_tris + t) * 6 + k] = (double)r.inv[k];
+        float4 *o = reinterpret_cast<float4 *>(a.invd_out + (f * a.n_tris + t) * 8);
+        o[0] = make_float4(r.inv[0], r.inv[1], r.inv[2], r.inv[3]);
+        o[1] = make_float4(r.inv[4], r.inv[5], 0.f, 0.f);
     }
 }
 

@@ -35,7 +35,7 @@ struct FusedFrame {
     const uint32_t *src;
     uint32_t *out;
     const TriRec *rec;     // n_tris records of this frame (edges + row range)
-    const double *inv;     // n_tris * 6 doubles: the f32-rounded inverse matrices, widened
+    const float *inv;      // n_tris * 8 floats: the f32-rounded inverse matrices, one 32-byte record each
     unsigned *bin_cnt;     // oH * bins_x counters (zeroed before the span kernel)
     unsigned *bin_ent;     // oH * bins_x * PW_BIN_CAP packed entries  (t << 14 | c1 << 7 | c0)
     uint4 *bin_run;        // oH * bins_x run records (pw_bin_runs_kernel): what the pixel kernel reads
@@ -43,55 +43,78 @@ struct FusedFrame {
     int W, H, xOff, yOff, oW, oH, minSrcX, minSrcY, n_tris, bins_x;
 };
 
-// `split` warps per triangle (tall triangles of small meshes would otherwise leave the machine empty); the lanes of
-// those warps stride over the triangle's rows
-__global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *frames, int split)
+// `lpt` lanes per triangle (a power of two: 8 .. 512), chosen on the host from the mesh so that a triangle's rows fill
+// its lanes about three times over — short triangles of fine meshes share a warp, tall triangles of coarse meshes spread
+// over several warps.  Lane l of a triangle takes its rows l, l + lpt, ...
+// Per row: the exact interval [S, E) of TypedArray.fill (IEEE edge intersections, Math.round, relative-index clamping:
+// H.js:1111-1126, 1172-1197), cut at map-row boundaries, one entry per 64-column bin it touches.  All flat indices are
+// below 2^31 (checked on the host), so the piece arithmetic is 32-bit.
+__global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *frames, int lpt_log2)
 {
     const FusedFrame &F = frames[blockIdx.y];
-    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int t = gw / split;
+    const unsigned gid = blockIdx.x * 128u + threadIdx.x;
+    const int t = (int)(gid >> lpt_log2);
     if (t >= F.n_tris) return;
-    const int lane = (threadIdx.x & 31) + 32 * (gw - t * split);
-    const int stride = 32 * split;
+    const int lane = (int)(gid & ((1u << lpt_log2) - 1u)), stride = 1 << lpt_log2;
     const TriRec &r = F.rec[t];
-    const long long len = (long long)F.oW * F.oH;
-    const double mw = (double)F.oW, yoff = (double)F.yOff;
-    for (long long i = lane;; i += stride) {
-        const double y = (double)r.y0 + (double)i;
-        if (!(y < r.maxY)) break;  // also ends on NaN
+    const unsigned oW = (unsigned)F.oW, len = oW * (unsigned)F.oH;
+    const double mw = (double)F.oW, yoff = (double)F.yOff, dlen = (double)len;
+    const double y00 = (double)r.y0, maxY = r.maxY;
+    for (int i = lane;; i += stride) {
+        const double y = y00 + (double)i;
+        if (!(y < maxY)) break;  // also ends on NaN
         double xo, xd;
         predict_x_limits(r, y, xo, xd);
         const double rowbase = __dmul_rn(__dsub_rn(y, yoff), mw);
-        long long k0 = js_fill_bound(__dadd_rn(rowbase, js_round(xo)), len);
-        const long long k1 = js_fill_bound(__dadd_rn(rowbase, js_round(xd)), len);
+        const double rel0 = __dadd_rn(rowbase, js_round(xo)), rel1 = __dadd_rn(rowbase, js_round(xd));
+        unsigned k0, k1;
+        if (rel0 >= 0.0 && rel0 < dlen && rel1 >= 0.0) {
+            // the usual case: both relative indices are non-negative integers (a product and a sum of small integers),
+            // fill() clamps the end to the length
+            k0 = (unsigned)(int)rel0;
+            k1 = rel1 < dlen ? (unsigned)(int)rel1 : len;
+        } else {  // negative (counted from the end), infinite or NaN indices: the general rule
+            k0 = (unsigned)js_fill_bound(rel0, (long long)len);
+            k1 = (unsigned)js_fill_bound(rel1, (long long)len);
+        }
+        if (k0 >= k1) continue;
+        unsigned row = k0 / oW, c0 = k0 - row * oW;
         int pieces = 0;
         while (k0 < k1) {
             if (++pieces > PW_MAX_PIECES) { atomicOr(F.status, 1); break; }
-            const long long row = k0 / F.oW;
-            const long long row_end = (row + 1) * F.oW;
-            const long long e = k1 < row_end ? k1 : row_end;
-            const int c0 = (int)(k0 - row * F.oW), c1 = (int)(e - row * F.oW);
-            // eight bins at a time: the slot reservations (independent atomics) go out back to back, the entry
-            // stores that depend on them follow
-            const int b_last = (c1 - 1) / PW_BIN_W;
-            for (int b0 = c0 / PW_BIN_W; b0 <= b_last; b0 += 8) {
-                unsigned slot[8];
-                const size_t bin0 = (size_t)row * F.bins_x + b0;
+            const unsigned room = oW - c0, want = k1 - k0, n = want < room ? want : room;
+            const unsigned c1 = c0 + n;  // the piece covers columns [c0, c1) of map row `row`
+            const unsigned b_first = c0 / PW_BIN_W, b_last = (c1 - 1u) / PW_BIN_W;
+            unsigned *cnt = F.bin_cnt + (size_t)row * F.bins_x;
+            unsigned *ent = F.bin_ent + (size_t)row * F.bins_x * PW_BIN_CAP;
+            const unsigned tt = (unsigned)t << 14;
+            if (b_first == b_last) {
+                const unsigned slot = atomicAdd(cnt + b_first, 1u);
+                if (slot < PW_BIN_CAP) ent[b_first * PW_BIN_CAP + slot] = tt | ((c1 - b_first * PW_BIN_W) << 7) | (c0 - b_first * PW_BIN_W);
+                else atomicOr(F.status, 1);
+            } else {
+                // four bins at a time: the slot reservations (independent atomics) go out back to back, the entry stores
+                // that depend on them follow
+                for (unsigned b0 = b_first; b0 <= b_last; b0 += 4) {
+                    unsigned slot[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (b0 + i <= b_last) slot[i] = atomicAdd(F.bin_cnt + bin0 + i, 1u);
+                    for (int j = 0; j < 4; ++j)
+                        if (b0 + j <= b_last) slot[j] = atomicAdd(cnt + b0 + j, 1u);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (b0 + i <= b_last) {
-                        const int b = b0 + i;
-                        const int lo = max(c0, b * PW_BIN_W) - b * PW_BIN_W;
-                        const int hi = min(c1, (b + 1) * PW_BIN_W) - b * PW_BIN_W;
-                        if (slot[i] < PW_BIN_CAP) F.bin_ent[(bin0 + i) * PW_BIN_CAP + slot[i]] = ((unsigned)t << 14) | ((unsigned)hi << 7) | (unsigned)lo;
-                        else atomicOr(F.status, 1);
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned b = b0 + j;
+                        if (b <= b_last) {
+                            const unsigned lo = b == b_first ? c0 - b * PW_BIN_W : 0u;
+                            const unsigned hi = b == b_last ? c1 - b * PW_BIN_W : (unsigned)PW_BIN_W;
+                            if (slot[j] < PW_BIN_CAP) ent[b * PW_BIN_CAP + slot[j]] = tt | (hi << 7) | lo;
+                            else atomicOr(F.status, 1);
+                        }
                     }
                 }
             }
-            k0 = e;
+            k0 += n;
+            ++row;
+            c0 = 0u;
         }
     }
 }
@@ -110,7 +133,10 @@ __device__ __forceinline__ int pwf_map_id(int raw, int n_tris)
 //     record = { start mask (bit c: a run begins at column c), up to PW_RUN_CAP ids as int16, in column order }
 // so the pixel kernel finds a pixel's triangle with two popcounts instead of scanning the entries: run index =
 // popc(mask & bits[0..c]) - 1.  Adjacent runs with the same final id are merged; more than PW_RUN_CAP runs in one bin
-// flags the frame for the general path.
+// flags the frame for the general path.  Bins with no entry or a single entry (most bins of a coarse mesh) take a
+// short cut.  (Measured and dropped: sorting the entries by id through a register network and painting them from the
+// highest id down with 64-bit column masks — 33 % slower than scanning the entries per candidate column: bins hold two
+// or three entries, the fixed cost of eight-wide masks does not pay.)
 constexpr int PW_RUN_CAP = 8;
 
 __global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *frames)
@@ -120,49 +146,66 @@ __global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *fram
     const size_t bin = (size_t)blockIdx.x * 128 + threadIdx.x;
     if (bin >= nbins) return;
     const unsigned cnt = min(F.bin_cnt[bin], (unsigned)PW_BIN_CAP);
-    unsigned ent[PW_BIN_CAP];
-    {
-        const uint4 *pe = reinterpret_cast<const uint4 *>(F.bin_ent) + 2 * bin;
-        const uint4 a = cnt > 0 ? pe[0] : make_uint4(0, 0, 0, 0), b = cnt > 4 ? pe[1] : make_uint4(0, 0, 0, 0);
-        ent[0] = a.x; ent[1] = a.y; ent[2] = a.z; ent[3] = a.w; ent[4] = b.x; ent[5] = b.y; ent[6] = b.z; ent[7] = b.w;
-    }
-    // candidate run starts: column 0 and every interval end point inside the bin.  Typical bins hold 1-3 entries: the
-    // loops stop at cnt instead of running predicated over all PW_BIN_CAP slots
-    unsigned long long cand = 1ull;
-#pragma unroll
-    for (int e = 0; e < PW_BIN_CAP; ++e) {
-        if ((unsigned)e >= cnt) break;
-        const unsigned lo = ent[e] & 127u, hi = (ent[e] >> 7) & 127u;
-        cand |= 1ull << lo;          // lo <= 63
-        if (hi < 64u) cand |= 1ull << hi;
-    }
-    unsigned long long mask = 0ull;
+    unsigned long long mask = 1ull;
     unsigned ids[PW_RUN_CAP / 2] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // int16 pairs, -1 = no triangle
-    int runs = 0, prev = -2;
-    while (cand) {
-        const int c = __ffsll((long long)cand) - 1;
-        cand &= cand - 1;
-        int raw = -1;
+    if (cnt == 1u) {
+        const unsigned e = F.bin_ent[bin * PW_BIN_CAP];
+        const unsigned lo = e & 127u, hi = (e >> 7) & 127u;
+        const unsigned id = (unsigned)pwf_map_id((int)(e >> 14), F.n_tris) & 0xFFFFu;
+        if (id != 0xFFFFu) {
+            // runs: [nothing, 0..lo) [t, lo..hi) [nothing, hi..64)
+            if (lo == 0u) {
+                ids[0] = 0xFFFF0000u | id;
+            } else {
+                mask |= 1ull << lo;
+                ids[0] = (id << 16) | 0xFFFFu;
+            }
+            if (hi < 64u) mask |= 1ull << hi;  // its id (-1) is already in place
+        }
+    } else if (cnt > 1u) {
+        unsigned ent[PW_BIN_CAP];
+        {
+            const uint4 *pe = reinterpret_cast<const uint4 *>(F.bin_ent) + 2 * bin;
+            const uint4 a = pe[0], b = cnt > 4 ? pe[1] : make_uint4(0, 0, 0, 0);
+            ent[0] = a.x; ent[1] = a.y; ent[2] = a.z; ent[3] = a.w; ent[4] = b.x; ent[5] = b.y; ent[6] = b.z; ent[7] = b.w;
+        }
+        // candidate run starts: column 0 and every interval end point inside the bin.  Typical bins hold 2-3 entries: the
+        // loops stop at cnt instead of running predicated over all PW_BIN_CAP slots
+        unsigned long long cand = 1ull;
 #pragma unroll
         for (int e = 0; e < PW_BIN_CAP; ++e) {
             if ((unsigned)e >= cnt) break;
-            // lo <= c < hi  <=>  (unsigned)(c - lo) < (unsigned)(hi - lo)
-            const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u);
-            if ((unsigned)(c - lo) < (unsigned)(hi - lo)) raw = max(raw, (int)(ent[e] >> 14));
+            const unsigned lo = ent[e] & 127u, hi = (ent[e] >> 7) & 127u;
+            cand |= 1ull << lo;          // lo <= 63
+            if (hi < 64u) cand |= 1ull << hi;
         }
-        const int id = pwf_map_id(raw, F.n_tris);
-        if (id != prev) {
-            if (runs == PW_RUN_CAP) {
-                atomicOr(F.status, 1);
-                break;
-            }
-            const unsigned h = (unsigned)id & 0xFFFFu;
+        mask = 0ull;
+        int runs = 0, prev = -2;
+        while (cand) {
+            const int c = __ffsll((long long)cand) - 1;
+            cand &= cand - 1;
+            int raw = -1;
 #pragma unroll
-            for (int w = 0; w < PW_RUN_CAP / 2; ++w)
-                if (w == (runs >> 1)) ids[w] = (runs & 1) ? ((ids[w] & 0x0000FFFFu) | (h << 16)) : ((ids[w] & 0xFFFF0000u) | h);
-            mask |= 1ull << c;
-            prev = id;
-            ++runs;
+            for (int e = 0; e < PW_BIN_CAP; ++e) {
+                if ((unsigned)e >= cnt) break;
+                // lo <= c < hi  <=>  (unsigned)(c - lo) < (unsigned)(hi - lo)
+                const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u);
+                if ((unsigned)(c - lo) < (unsigned)(hi - lo)) raw = max(raw, (int)(ent[e] >> 14));
+            }
+            const int id = pwf_map_id(raw, F.n_tris);
+            if (id != prev) {
+                if (runs == PW_RUN_CAP) {
+                    atomicOr(F.status, 1);
+                    break;
+                }
+                const unsigned h = (unsigned)id & 0xFFFFu;
+#pragma unroll
+                for (int w = 0; w < PW_RUN_CAP / 2; ++w)
+                    if (w == (runs >> 1)) ids[w] = (runs & 1) ? ((ids[w] & 0x0000FFFFu) | (h << 16)) : ((ids[w] & 0xFFFF0000u) | h);
+                mask |= 1ull << c;
+                prev = id;
+                ++runs;
+            }
         }
     }
     F.bin_run[2 * bin] = make_uint4((unsigned)mask, (unsigned)(mask >> 32), 0u, 0u);
@@ -192,11 +235,13 @@ __host__ __device__ inline int pwf_bins_x(int oW) { return (oW + PW_BIN_W - 1) /
 __host__ __device__ inline int pwf_tiles_x(int oW) { return ((oW & 3) ? (oW + 3 + PW_BIN_W - 1) : (oW + PW_BIN_W - 1)) / PW_BIN_W; }
 __host__ __device__ inline int pwf_tiles_y(int oH, int niter) { return (oH + PWF_GROUP_ROWS * niter - 1) / (PWF_GROUP_ROWS * niter); }
 
-__device__ __forceinline__ void pwf_load_matrix(const double *inv, int t, double (&m)[6])
+// the f32-rounded inverse matrix of triangle t: one 32-byte record (six floats + padding = exactly one sector), widened
+// to double once, when a quad moves to another triangle — the pixel loop has no conversions
+__device__ __forceinline__ void pwf_load_matrix(const float *inv, int t, double (&m)[6])
 {
-    const double2 *p = reinterpret_cast<const double2 *>(inv + 6 * (size_t)t);
-    const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    m[0] = a.x; m[1] = a.y; m[2] = b.x; m[3] = b.y; m[4] = c.x; m[5] = c.y;
+    const float4 *p = reinterpret_cast<const float4 *>(inv + 8 * (size_t)t);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    m[0] = (double)a.x; m[1] = (double)a.y; m[2] = (double)a.z; m[3] = (double)a.w; m[4] = (double)b.x; m[5] = (double)b.y;
 }
 
 // coordinates -> flat source index or HG_OUTSIDE: window test [minSrc, W+minSrc) x [minSrc, H+minSrc) on the unrounded
@@ -387,13 +432,11 @@ __device__ __forceinline__ void pwf_body(const FusedFrame &F, int niter, int til
 //   * the doubled-coordinate decode of warp_geo.cuh with its warp-uniform "end pixels inside => quad inside" shortcut
 //     (both source coordinates are monotone along the quad: one triangle, one affine map), loads predicated directly.
 //   * run ids through one PRMT; the gathers of a quad carry no per-pixel predicate when its whole warp reads inside;
-//     pixel registers double-buffered (stores two iterations behind their gathers) and run records L2-prefetched: with
-//     ~30 % fewer instructions than the first generation the loop was latency-bound (ncu: issue-active 47 %, the store
-//     stage waiting on its gathers) until two row groups of gathers were kept in flight per thread.
+//     gathers as asynchronous copies into a shared-memory ring (see pwf_issue) and the CTA's run records staged in
+//     shared memory once: with ~30 % fewer instructions than the first generation the loop was latency-bound (ncu:
+//     issue-active 47 %) until no register load but the matrix fetch was left in it.
 constexpr int PWF_QCAP = 1024;
-#ifndef PWF_PREFETCH
-#define PWF_PREFETCH 3   // run records are L2-prefetched this many row groups ahead
-#endif  // per warp: 16 row groups x 32 lanes x 2 quads, the most a CTA can ever queue
+  // per warp: 16 row groups x 32 lanes x 2 quads, the most a CTA can ever queue
 
 // id of run r (0..7) from the eight packed int16 ids: one byte permute, sign-extended
 __device__ __forceinline__ int pwf_run_id2(const uint4 &ids, unsigned r)
@@ -410,30 +453,52 @@ __device__ __forceinline__ int pwf_run_id2(const uint4 &ids, unsigned r)
 template <bool ZERO_OFF>
 struct PwfCtx {
     const uint32_t *src;
-    const double *inv;
+    const float *inv;
     unsigned W, npx_src, W2, H2, Wi, Hi, kflat;
     int oW, oH, yOff, base0;
     double xs[2][4];
     unsigned vmask[2];
     unsigned long long below[2], inner[2];
-    bool prev_bin, has_bin;
+    bool prev_bin, has_bin, src_aligned;
     int lane;
     unsigned lt_mask;
     // pipeline state
-    uint4 be0, be1;      // run record (S0 -> S1)
     int t0[2];           // triangle of each quad's first pixel (S1 -> S2)
+    int tm[2];           // triangle whose matrix mq[q] holds
     double mq[2][6];     // its inverse matrix (S1 -> S2)
     int qn;              // warp-uniform: entries in this warp's queue
 };
 
+// The gathers do not land in registers: every pixel is an ASYNCHRONOUS 4-byte copy global -> shared (cp.async, SASS
+// LDGSTS) into the thread's own slot of a ring of PWF_NST row groups, committed as one group per row group and awaited
+// (cp.async.wait_group) only when the row group is stored, PWF_DEPTH iterations later.  Why: ptxas tracks every LDG of
+// this loop with ONE scoreboard barrier (all gathers and the matrix loads: wr=5 in the SASS), so the first use of any
+// loaded register — the next matrix, a pixel to store — waited for ALL loads in flight, the just-issued gathers included
+// (ncu: 35 % of the stall samples on the instruction in front of the matrix loads).  Asynchronous copies are not
+// scoreboarded at all: PWF_DEPTH row groups of gathers (24 per thread) are in flight behind the arithmetic, and the
+// matrix loads are the only register loads left in the loop.  A pixel outside the window is a copy of zero source
+// bytes: the hardware fills the slot with zeros (H.js:1047: the output stays transparent).
+constexpr int PWF_DEPTH = 3;            // row groups of gathers in flight
+constexpr int PWF_NST = PWF_DEPTH + 1;  // ring slots per thread (the slot being stored is not the one being filled)
+// Ring layout: 32-bit words [slot][quad][pixel k][thread] — the 32 lanes of one copy instruction write 32 consecutive
+// words (no bank conflict; the [thread][k] layout that a 16-byte read would like is a 4-way conflict for every copy).
+constexpr uint32_t PWF_KSTEP = 4u * 128u;   // bytes between pixel k and k+1 of a thread's quad (PWF_THREADS words)
+
+__device__ __forceinline__ void pwf_copy4(uint32_t smem_dst, const uint32_t *src, bool take)
+{
+    const int n = take ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(src), "r"(n) : "memory");
+}
+
 // S2: coordinates (H.js:1046), window test and Math.round (H.js:1047-1048), flat gather (H.js:1049-1052) of one row group
 template <bool ZERO_OFF>
-__device__ __forceinline__ void pwf_issue(PwfCtx<ZERO_OFF> &C, const FusedFrame &F, int g, uint32_t (&px)[2][4])
+__device__ __forceinline__ void pwf_issue(PwfCtx<ZERO_OFF> &C, const FusedFrame &F, int g, uint32_t slot)
 {
     const int row = C.base0 + g * PWF_GROUP_ROWS;
     const double y = (double)(C.yOff + row);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
+        const uint32_t dst = slot + 4u * (uint32_t)(q * 4 * PWF_THREADS);   // word [q][k][thread]: pixel k at dst + k * PWF_KSTEP
         const bool live = (C.t0[q] >= 0) && (row < C.oH) && (C.vmask[q] != 0u);
         const double r0 = __dmul_rn(C.mq[q][2], y), r1 = __dmul_rn(C.mq[q][3], y);
         if (ZERO_OFF) {
@@ -443,20 +508,20 @@ __device__ __forceinline__ void pwf_issue(PwfCtx<ZERO_OFF> &C, const FusedFrame 
                 hx[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(C.mq[q][0], C.xs[q][k], r0, C.mq[q][4]), 2.0, HG_MAGIC + 1.0));
                 hy[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(C.mq[q][1], C.xs[q][k], r1, C.mq[q][5]), 2.0, HG_MAGIC + 1.0));
             }
+            unsigned flat[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) flat[k] = (hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat;
             const unsigned cz = (unsigned)(HG_HI_ZERO + 2);
             const bool ends_inside = live && ((hx[0] - cz) < C.Wi) & ((hy[0] - cz) < C.Hi) & ((hx[3] - cz) < C.Wi) & ((hy[3] - cz) < C.Hi);
             if (__all_sync(0xffffffffu, ends_inside)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) px[q][k] = __ldg(C.src + ((hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat));
+                for (int k = 0; k < 4; ++k) pwf_copy4(dst + PWF_KSTEP * k, C.src + flat[k], true);
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const unsigned flat = (hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat;
                     const bool in = live & ((hx[k] - (unsigned)(HG_HI_ZERO + 1)) < C.W2) & ((hy[k] - (unsigned)(HG_HI_ZERO + 1)) < C.H2) &
-                                    (flat < C.npx_src);
-                    uint32_t v = 0u;
-                    if (in) v = __ldg(C.src + flat);
-                    px[q][k] = v;
+                                    (flat[k] < C.npx_src);
+                    pwf_copy4(dst + PWF_KSTEP * k, C.src + (in ? flat[k] : 0u), in);
                 }
             }
         } else {
@@ -466,7 +531,7 @@ __device__ __forceinline__ void pwf_issue(PwfCtx<ZERO_OFF> &C, const FusedFrame 
                 if (live)
                     f = pwf_decode<false>(affine_coord_exact(C.mq[q][0], C.xs[q][k], r0, C.mq[q][4]),
                                           affine_coord_exact(C.mq[q][1], C.xs[q][k], r1, C.mq[q][5]), F, C.npx_src);
-                px[q][k] = ldg_or_zero(C.src, f);
+                pwf_copy4(dst + PWF_KSTEP * k, C.src + (f != HG_OUTSIDE ? f : 0u), f != HG_OUTSIDE);
             }
         }
     }
@@ -474,16 +539,22 @@ __device__ __forceinline__ void pwf_issue(PwfCtx<ZERO_OFF> &C, const FusedFrame 
 
 // S1: triangle of each quad's first pixel from the run record of row group g, its matrix; note cut quads in the queue
 template <bool ZERO_OFF>
-__device__ __forceinline__ void pwf_resolve(PwfCtx<ZERO_OFF> &C, int g, unsigned short *wq)
+__device__ __forceinline__ void pwf_resolve(PwfCtx<ZERO_OFF> &C, int g, unsigned short *wq, const uint4 *rec)
 {
     const bool row_ok = C.base0 + g * PWF_GROUP_ROWS < C.oH;
-    const unsigned long long m64 = ((unsigned long long)C.be0.y << 32) | (unsigned long long)C.be0.x;
+    const uint4 be0 = rec[0], be1 = rec[1];   // shared memory: the record of this thread's row in group g
+    const unsigned long long m64 = ((unsigned long long)be0.y << 32) | (unsigned long long)be0.x;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const unsigned r = (unsigned)__popcll(m64 & C.below[q]) - 1u;
-        const int t = pwf_run_id2(C.be1, r);
+        const int t = pwf_run_id2(be1, r);
+        // rows of one triangle follow each other: the matrix is fetched only when the quad has moved to another triangle
+        // (the registers still hold the last triangle's; "no triangle" does not disturb them)
+        if (t >= 0 && t != C.tm[q]) {
+            pwf_load_matrix(C.inv, t, C.mq[q]);
+            C.tm[q] = t;
+        }
         C.t0[q] = t;
-        if (t >= 0) pwf_load_matrix(C.inv, t, C.mq[q]);
         const bool cut = row_ok && (C.vmask[q] != 0u) && (((m64 & C.inner[q]) != 0ull) || (q == 0 && C.prev_bin));
         const unsigned bal = __ballot_sync(0xffffffffu, cut);
         if (cut) wq[C.qn + __popc(bal & C.lt_mask)] = (unsigned short)((g << 6) | (C.lane << 1) | q);
@@ -491,26 +562,30 @@ __device__ __forceinline__ void pwf_resolve(PwfCtx<ZERO_OFF> &C, int g, unsigned
     }
 }
 
-// S3: stores of one row group
+// S3: stores of one row group: its copies have landed (the caller waited for its commit group), each quad is one
+// 16-byte shared-memory read and one 128-bit store
 template <bool ZERO_OFF>
-__device__ __forceinline__ void pwf_retire(const PwfCtx<ZERO_OFF> &C, int g, uint32_t *p_out, const uint32_t (&px)[2][4])
+__device__ __forceinline__ void pwf_retire(const PwfCtx<ZERO_OFF> &C, int g, uint32_t *p_out, const uint32_t *slot)
 {
     if (C.base0 + g * PWF_GROUP_ROWS >= C.oH) return;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         uint32_t *dst = p_out + 32 * q;
+        const uint32_t *w = slot + q * 4 * PWF_THREADS;
+        const uint32_t px[4] = {w[0], w[PWF_THREADS], w[2 * PWF_THREADS], w[3 * PWF_THREADS]};
         if (C.vmask[q] == 0xFu) {
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(px[q][0], px[q][1], px[q][2], px[q][3]);
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(px[0], px[1], px[2], px[3]);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (C.vmask[q] & (1u << k)) dst[k] = px[q][k];
+                if (C.vmask[q] & (1u << k)) dst[k] = px[k];
         }
     }
 }
 
 template <bool ZERO_OFF>
-__device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int tile_x, int row0, unsigned short *wq)
+__device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int tile_x, int row0, unsigned short *wq, uint4 (*s_rec)[2],
+                                          uint32_t (*s_px)[2][4][PWF_THREADS])
 {
     const int warp_id = threadIdx.x >> 5;
     const int tx = threadIdx.x & (PWF_TX - 1), ty = threadIdx.x / PWF_TX;
@@ -518,6 +593,7 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
     C.lane = threadIdx.x & 31;
     C.lt_mask = (1u << C.lane) - 1u;
     C.src = F.src;
+    C.src_aligned = ((unsigned long long)(uintptr_t)F.src & 15ull) == 0ull;
     C.inv = F.inv;
     C.oW = F.oW;
     C.oH = F.oH;
@@ -553,117 +629,162 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
     }
     // pixels of quad 0 left of the tile belong to the previous bin (only when they are pixels of the image at all)
     C.prev_bin = (a > 0) && (tx == 0) && (tile_x > 0);
-    C.be0 = make_uint4(1u, 0u, 0u, 0u);
-    C.be1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     C.t0[0] = C.t0[1] = -1;
+    C.tm[0] = C.tm[1] = -1;
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int k = 0; k < 6; ++k) C.mq[q][k] = 0.0;
     C.qn = 0;
 
-    const uint4 *p_run = F.bin_run + 2 * ((size_t)C.base0 * F.bins_x + tile_x);
-    const size_t run_step = 2 * (size_t)PWF_GROUP_ROWS * F.bins_x;
+    // S0, once per CTA: the run records of all its rows (16 * ngroups records of 32 bytes, one 64-column bin each) go to
+    // shared memory through cp.async — the dependent chain record -> triangle id -> matrix then starts from a 30-cycle
+    // shared-memory read instead of a DRAM / L2 round trip in every iteration (ncu of the register-staged variant: 25 % of
+    // the stall samples on the first use of the record)
+    {
+        const int nrec = PWF_GROUP_ROWS * ngroups;
+        for (int i = threadIdx.x; i < 2 * nrec; i += PWF_THREADS) {
+            const int rr = i >> 1, h = i & 1, row = row0 + rr;
+            uint4 *dst = &s_rec[rr][h];
+            if (C.has_bin && row < oH) {
+                const uint4 *srcp = F.bin_run + 2 * ((size_t)row * F.bins_x + tile_x) + h;
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(srcp) : "memory");
+            } else {
+                *dst = h ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint4(1u, 0u, 0u, 0u);
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+    }
+
     uint32_t *p_out = F.out + ((long long)C.base0 * oW + xx00);
     const long long out_step = (long long)PWF_GROUP_ROWS * oW;
 
-    // S0: the run record of row group g (L2-prefetched PWF_PREFETCH groups earlier: the records of a frame were written
-    // by the run kernel just before and mostly sit in DRAM by now)
-    auto load_record = [&](int g) {
-        if (g >= ngroups) return;
-        if (C.has_bin && C.base0 + g * PWF_GROUP_ROWS < oH) {
-            C.be0 = __ldg(p_run);
-            C.be1 = __ldg(p_run + 1);
-            if (g + PWF_PREFETCH < ngroups && C.base0 + (g + PWF_PREFETCH) * PWF_GROUP_ROWS < oH && tx == 0)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p_run + PWF_PREFETCH * run_step));
-        } else {
-            C.be0 = make_uint4(1u, 0u, 0u, 0u);
-            C.be1 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        }
-        p_run += run_step;
-    };
-    if (C.has_bin && tx == 0) {
-#pragma unroll
-        for (int g = 1; g < PWF_PREFETCH; ++g)
-            if (g < ngroups && C.base0 + g * PWF_GROUP_ROWS < oH) asm volatile("prefetch.global.L2 [%0];" ::"l"(p_run + g * run_step));
-    }
-
-    // FOUR STAGES, the pixel registers double-buffered (the loop is unrolled by two so that pa / pb alternate without
-    // moves): the gathers of a row group are stored TWO iterations after they were issued, so two groups of gathers
-    // (16 loads per thread) are in flight while the arithmetic of the following groups runs.
-    //   iteration g:  S3 store group g-4 | S2 coordinates + gathers of g-2 | S1 ids + matrix loads of g-1 | S0 record of g
-    uint32_t pa[2][4], pb[2][4];
+    // THREE STAGES; iteration `it`:  S3 store row group it-1-DEPTH | S2 coordinates + asynchronous gathers of it-1 |
+    // S1 ids + matrix loads of it.  Every iteration commits exactly one copy group (an empty one when it issues nothing),
+    // so "all but the newest DEPTH-1 groups have landed" is the condition for storing row group it-1-DEPTH.
+    const uint32_t px_base = (uint32_t)__cvta_generic_to_shared(&s_px[0][0][0][threadIdx.x]);
+    constexpr uint32_t px_stage_bytes = 2u * 4u * PWF_THREADS * 4u;
 #pragma unroll 1
-    for (int it = 0; it < ngroups + 4; it += 2) {
-        // even step: group it-2 gathers into pa, which group it-4 has just left
-        if (it >= 4) {
-            pwf_retire(C, it - 4, p_out, pa);
+    for (int it = 0; it < ngroups + 1 + PWF_DEPTH; ++it) {
+        if (it >= 1 + PWF_DEPTH) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(PWF_DEPTH - 1) : "memory");
+            const int g = it - 1 - PWF_DEPTH;
+            pwf_retire(C, g, p_out, &s_px[g % PWF_NST][0][0][threadIdx.x]);
             p_out += out_step;
         }
-        if (it >= 2 && it - 2 < ngroups) pwf_issue(C, F, it - 2, pa);
-        if (it >= 1 && it - 1 < ngroups) pwf_resolve(C, it - 1, wq);
-        load_record(it);
-        // odd step: the same with pb
-        const int i1 = it + 1;
-        if (i1 >= 4 && i1 - 4 < ngroups) {
-            pwf_retire(C, i1 - 4, p_out, pb);
-            p_out += out_step;
-        }
-        if (i1 >= 2 && i1 - 2 < ngroups) pwf_issue(C, F, i1 - 2, pb);
-        if (i1 - 1 < ngroups) pwf_resolve(C, i1 - 1, wq);
-        load_record(i1);
+        if (it >= 1 && it - 1 < ngroups) pwf_issue(C, F, it - 1, px_base + (uint32_t)((it - 1) % PWF_NST) * px_stage_bytes);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (it < ngroups) pwf_resolve(C, it, wq, s_rec[it * PWF_GROUP_ROWS + ty]);
     }
 
-    // ---- the queued quads again, one QUAD per lane, every pixel with the triangle of its own run (H.js:1044-1052
-    // verbatim): the run record(s) once, then up to four matrices, four gathers and one 128-bit store
+    // ---- the queued quads again, one QUAD per lane and TWO quads per lane and pass, every pixel with the triangle of its
+    // own run (H.js:1044-1052 verbatim).  The pass is written in phases over both quads so that its three dependent
+    // round trips overlap across the 2 x 4 pixels: run record(s) -> ids of all pixels -> the (at most two, as a rule)
+    // distinct matrices of each quad, loaded back to back -> all flat indices -> all gathers -> two 128-bit stores.
     __syncwarp();  // also orders the provisional stores above before the final ones below
     const int qn = C.qn;
-    for (int e0 = 0; e0 < qn; e0 += 32) {
-        const int e = e0 + C.lane;
-        if (e >= qn) continue;
-        const unsigned ent = wq[e];
-        const int qq = (int)(ent & 1u), sl = (int)((ent >> 1) & 31u), g = (int)(ent >> 6);
-        const int row = row0 + warp_id * 4 + (sl >> 3) + g * PWF_GROUP_ROWS;
-        const int ae = (oW & 3) ? (int)(((unsigned)row * (unsigned)oW) & 3u) : 0;
-        const int X0 = tile_x * PW_BIN_W + 4 * (sl & 7) + 32 * qq - ae;
-        const double y = (double)(F.yOff + row);
-        // the quad lies in one bin, except a first quad that reaches back into the previous one
-        const int binA = X0 < 0 ? 0 : (X0 >> 6), binB = (X0 + 3) >> 6;
-        const uint4 *pr = F.bin_run + 2 * ((size_t)row * F.bins_x + binA);
-        const uint4 a0 = __ldg(pr), a1 = __ldg(pr + 1);
-        uint4 b0 = a0, b1 = a1;
-        if (binB != binA && binB < F.bins_x) {
-            b0 = __ldg(pr + 2);
-            b1 = __ldg(pr + 3);
-        }
-        uint32_t v[4];
-        int t_prev = -2;
-        double m[6];
+    for (int e0 = 0; e0 < qn; e0 += 64) {
+        int row[2], X0[2], tk[2][4], tA[2], tB[2];
+        float4 mA[2][2], mB[2][2];
+        unsigned idx[2][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int X = X0 + k;
-            v[k] = 0u;
-            if (X < 0 || X >= oW) continue;
-            const bool inB = (X >> 6) != binA;
-            const uint4 &r0 = inB ? b0 : a0, &r1 = inB ? b1 : a1;
-            const unsigned long long m64 = ((unsigned long long)r0.y << 32) | (unsigned long long)r0.x;
-            const int t = pwf_run_id2(r1, (unsigned)__popcll(m64 & ((2ull << (X & 63)) - 1ull)) - 1u);
-            if (t < 0) continue;
-            if (t != t_prev) {
-                pwf_load_matrix(F.inv, t, m);
-                t_prev = t;
+        for (int u = 0; u < 2; ++u) {
+            const int e = e0 + 32 * u + C.lane;
+            row[u] = -1;
+            X0[u] = 0;
+            tA[u] = tB[u] = -1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tk[u][k] = -1;
+            if (e >= qn) continue;
+            const unsigned ent = wq[e];
+            const int qq = (int)(ent & 1u), sl = (int)((ent >> 1) & 31u), g = (int)(ent >> 6);
+            row[u] = row0 + warp_id * 4 + (sl >> 3) + g * PWF_GROUP_ROWS;
+            const int ae = (oW & 3) ? (int)(((unsigned)row[u] * (unsigned)oW) & 3u) : 0;
+            X0[u] = tile_x * PW_BIN_W + 4 * (sl & 7) + 32 * qq - ae;
+            // the quad lies in one bin, except a first quad that reaches back into the previous one
+            const int binA = X0[u] < 0 ? 0 : (X0[u] >> 6), binB = (X0[u] + 3) >> 6;
+            const int rr = row[u] - row0;
+            uint4 a0, a1;
+            if (binA == tile_x) {
+                a0 = s_rec[rr][0];
+                a1 = s_rec[rr][1];
+            } else {   // the previous bin (a first quad reaching back over the tile's left edge)
+                const uint4 *pr = F.bin_run + 2 * ((size_t)row[u] * F.bins_x + binA);
+                a0 = __ldg(pr);
+                a1 = __ldg(pr + 1);
             }
-            const double x = (double)(F.xOff + X);
-            v[k] = ldg_or_zero(C.src, pwf_decode<ZERO_OFF>(affine_coord_exact(m[0], x, __dmul_rn(m[2], y), m[4]),
-                                                          affine_coord_exact(m[1], x, __dmul_rn(m[3], y), m[5]), F, C.npx_src));
-        }
-        uint32_t *dst = F.out + ((long long)row * oW + X0);
-        if (X0 >= 0 && X0 + 3 < oW) {
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
-        } else {
+            uint4 b0 = a0, b1 = a1;
+            if (binB != binA && binB < F.bins_x) {   // binB == tile_x
+                b0 = s_rec[rr][0];
+                b1 = s_rec[rr][1];
+            }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (X0 + k >= 0 && X0 + k < oW) dst[k] = v[k];
+            for (int k = 0; k < 4; ++k) {
+                const int X = X0[u] + k;
+                if (X < 0 || X >= oW) continue;
+                const bool inB = (X >> 6) != binA;
+                const uint4 &r0 = inB ? b0 : a0, &r1 = inB ? b1 : a1;
+                const unsigned long long m64 = ((unsigned long long)r0.y << 32) | (unsigned long long)r0.x;
+                const int t = pwf_run_id2(r1, (unsigned)__popcll(m64 & ((2ull << (X & 63)) - 1ull)) - 1u);
+                tk[u][k] = t;
+                if (t >= 0 && tA[u] < 0) tA[u] = t;
+                else if (t >= 0 && t != tA[u] && tB[u] < 0) tB[u] = t;
+            }
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            mA[u][0] = mA[u][1] = mB[u][0] = mB[u][1] = z;
+            if (tA[u] >= 0) {
+                const float4 *pm = reinterpret_cast<const float4 *>(F.inv + 8 * (size_t)tA[u]);
+                mA[u][0] = __ldg(pm);
+                mA[u][1] = __ldg(pm + 1);
+            }
+            if (tB[u] >= 0) {
+                const float4 *pm = reinterpret_cast<const float4 *>(F.inv + 8 * (size_t)tB[u]);
+                mB[u][0] = __ldg(pm);
+                mB[u][1] = __ldg(pm + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const double y = (double)(F.yOff + row[u]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int t = tk[u][k];
+                idx[u][k] = HG_OUTSIDE;
+                if (t < 0) continue;
+                float4 p0 = mA[u][0], p1 = mA[u][1];
+                if (t != tA[u]) {
+                    if (t == tB[u]) {
+                        p0 = mB[u][0];
+                        p1 = mB[u][1];
+                    } else {   // a third triangle inside one quad: fetched on the spot
+                        const float4 *pm = reinterpret_cast<const float4 *>(F.inv + 8 * (size_t)t);
+                        p0 = __ldg(pm);
+                        p1 = __ldg(pm + 1);
+                    }
+                }
+                const double x = (double)(F.xOff + X0[u] + k);
+                idx[u][k] = pwf_decode<ZERO_OFF>(affine_coord_exact((double)p0.x, x, __dmul_rn((double)p0.z, y), (double)p1.x),
+                                                 affine_coord_exact((double)p0.y, x, __dmul_rn((double)p0.w, y), (double)p1.y), F, C.npx_src);
+            }
+        }
+        uint32_t v[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[u][k] = ldg_or_zero(C.src, idx[u][k]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (row[u] < 0) continue;
+            uint32_t *dst = F.out + ((long long)row[u] * oW + X0[u]);
+            if (X0[u] >= 0 && X0[u] + 3 < oW) {
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(v[u][0], v[u][1], v[u][2], v[u][3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (X0[u] + k >= 0 && X0[u] + k < oW) dst[k] = v[u][k];
+            }
         }
     }
 }
@@ -678,9 +799,11 @@ __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel
     const int tile_x = blockIdx.x - tile_y * tiles_x;
     const int row0 = tile_y * PWF_GROUP_ROWS * niter;
     if (row0 >= F.oH) return;
+    __shared__ uint4 s_rec[PWF_GROUP_ROWS * 16][2];   // run records of the CTA's rows (niter <= 16)
+    __shared__ uint32_t s_px[PWF_NST][2][4][PWF_THREADS];   // gathered pixels: a ring of row groups, [quad][pixel][thread]
     unsigned short *wq = s_q[threadIdx.x >> 5];
-    if (F.minSrcX == 0 && F.minSrcY == 0) pwf_body2<true>(F, niter, tile_x, row0, wq);
-    else pwf_body2<false>(F, niter, tile_x, row0, wq);
+    if (F.minSrcX == 0 && F.minSrcY == 0) pwf_body2<true>(F, niter, tile_x, row0, wq, s_rec, s_px);
+    else pwf_body2<false>(F, niter, tile_x, row0, wq, s_rec, s_px);
 }
 
 // first-generation kernel, kept for A/B runs (HG_PWF_V1=1); needs oW-wide rows of bins == tiles

@@ -32,7 +32,7 @@ struct StreamArgs {
     size_t slot_px;
     int n_slots, max_w, max_h;
     const TriRec *rec;
-    const double *invd;
+    const float *invd;
     unsigned *bin_cnt, *bin_ent;
     uint4 *bin_run;
     int *status;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(128) pw_stream_frames_kernel(const StreamArgs 
     F.src = a.src + (a.n_src > 1 ? (size_t)(g % a.n_src) * a.src_stride_px : 0);
     F.out = a.out_ring + (size_t)slot * a.slot_px;
     F.rec = a.rec + (size_t)a.n_tris * f;
-    F.inv = a.invd + 6 * (size_t)a.n_tris * f;
+    F.inv = a.invd + 8 * (size_t)a.n_tris * f;
     F.bin_cnt = a.bin_cnt + a.bin_stride * f;
     F.bin_ent = a.bin_ent + a.bin_stride * f * PW_BIN_CAP;
     F.bin_run = a.bin_run + 2 * a.bin_stride * f;

@@ -637,8 +637,17 @@ __device__ __forceinline__ void geo_flush_queue(const GeoFrame &F, const double 
             if (FAST) {
                 const double MG = HG_MAGIC + 1.0 + (double)HG_NEAR_DELTA2 / 4294967296.0;
                 const double rc = rcp_newton1(dn);
-                const int jx = exact_doubled_floor(__fma_rn(__dadd_rn(nx, nx), rc, MG), nx, dn);
-                const int jy = exact_doubled_floor(__fma_rn(__dadd_rn(ny, ny), rc, MG), ny, dn);
+                const double Tx = __fma_rn(__dadd_rn(nx, nx), rc, MG), Ty = __fma_rn(__dadd_rn(ny, ny), rc, MG);
+                const int jx = exact_doubled_floor(Tx, nx, dn), jy = exact_doubled_floor(Ty, ny, dn);
+                // Most queued pixels sit EXACTLY on a decision boundary ("nice" points: whole columns of them) and resolve
+                // to the value the loop already stored: the exact integers equal the ones an approximate quotient decodes
+                // to.  The loop's quotient and this one differ by < 2^-20, so unless one of them lies just BELOW an integer
+                // (low word within 4 delta of 2^32: the two could then sit on different sides of it) both decode to the
+                // same integer part, and the provisional pixel is the reference's — no gather, no store.
+                const unsigned top = 0u - 4u * HG_NEAR_DELTA2;
+                if (jx == __double2hiint(Tx) - HG_HI_ZERO && jy == __double2hiint(Ty) - HG_HI_ZERO &&
+                    (unsigned)__double2loint(Tx) < top && (unsigned)__double2loint(Ty) < top)
+                    continue;
                 const unsigned flat = (unsigned)(jy >> 1) * W + (unsigned)(jx >> 1);
                 const bool in = ((unsigned)(jx - 1) < 2u * W) & ((unsigned)(jy - 1) < 2u * H) & (flat < npx_src);
                 v = in ? __ldg(F.src + flat) : 0u;

@@ -110,3 +110,15 @@ def video_stream(n_frames: int, w: int = 1920, h: int = 1080, seed: int = 5):
     dy = 0.03 * h * np.cos(0.07 * f + theta[None, :])
     dst = (src[None, :, :].astype(np.float64) + np.stack([dx, dy], axis=2)).astype(np.float32)
     return src, dst, tris
+
+
+def u64_to_halves(v: int):
+    """A 64-bit checksum as two 32-bit halves (low, high): what an int64 all-reduce can sum over ranks without overflow
+    (at most 2^32 * world per half)."""
+    v &= 0xFFFFFFFFFFFFFFFF
+    return v & 0xFFFFFFFF, v >> 32
+
+
+def halves_to_u64(lo_sum: int, hi_sum: int) -> int:
+    """Sum mod 2^64 of the checksums whose halves were summed separately."""
+    return (lo_sum + (hi_sum << 32)) & 0xFFFFFFFFFFFFFFFF

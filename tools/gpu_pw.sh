@@ -1,9 +1,13 @@
 #!/bin/bash
-# piecewise loop: targeted parity tests + the piecewise bench lines.  Usage under gpurun: bash tools/gpu_pw.sh [tag]
+# piecewise loop: parity tests + the piecewise bench lines.  Usage under gpurun: bash tools/gpu_pw.sh [tag] [all]
 tag=${1:-pw}
 out=gpurun_out/$tag
 mkdir -p $out
-python -m pytest tests -m gpu -x -q -k "piecewise or stream or fused or flows or config or pipe or mesh or index" 2>&1 | tail -15 | tee $out/pytest.txt
+if [ "$2" = "all" ]; then
+  python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $out/pytest.txt
+else
+  python -m pytest tests -m gpu -x -q -k "piecewise or stream or fused or flows or config or pipe or mesh or index" 2>&1 | tail -15 | tee $out/pytest.txt
+fi
 for w in piecewise3 piecewise4 config5; do
   extra=""; [ $w = config5 ] && extra="--c5-frames 2048"
   python bench.py --workload $w --steps 10 --warmup 3 $extra > $out/$w.json 2> $out/$w.err || tail -5 $out/$w.err
