@@ -489,7 +489,7 @@ def sec_config5(env, frames: int, steps: int, warmup: int):
     ctx.image_set_device(image.data_ptr(), w, h)
     ctx.piecewise_set_mesh(src_pts, tris)
     smm = [int(np.floor(v + 0.5)) for v in (float(src_pts[:, 0].min()), float(src_pts[:, 1].min()))]
-    n_slots = 64
+    n_slots = 256                                            # 2.4 GB of output ring: chunks of 128 frames per launch chain
     max_w, max_h = int(w * 1.07) + 8, int(h * 1.07) + 8      # points move by +-3 % of the frame
     slot = ctx.stream_slot_bytes(max_w, max_h)
     ring = torch.zeros(n_slots * slot, dtype=torch.uint8, device=env.dev)

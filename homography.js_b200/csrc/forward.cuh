@@ -63,6 +63,7 @@ struct FwdArgs {
     //   x = ixx * (X - rx) + ixy * (Y - ry),  y = iyx * (X - rx) + iyy * (Y - ry)     (integer inverse of the permutation)
     int lattice;             // 1: this frame takes the lattice kernel
     int ixx, ixy, iyx, iyy, rx, ry;
+    int shift_copy;          // lattice frame that is a pure translation with 16-byte aligned rows on both sides
 };
 
 struct FwdParams {
@@ -163,6 +164,26 @@ __device__ __forceinline__ void lattice_quad_load(const FwdArgs &a, const uint32
 {
     int Y = p0 / a.oW;
     int X = p0 - Y * a.oW;
+    if (a.shift_copy) {
+        // a translation between images whose rows are whole 16-byte groups: the quad is four consecutive source pixels
+        // x0 .. x0+3 of one row — the aligned group that holds x0 and (unless x0 is aligned itself) the next one, i.e. one
+        // or two 128-bit loads instead of four 32-bit ones through the same sectors
+        const int y = Y - a.ry, x0 = X - a.rx;
+        if ((unsigned)y < (unsigned)a.H && x0 >= 0 && x0 + 7 < a.W) {
+            const uint4 *g = reinterpret_cast<const uint4 *>(src + (size_t)y * a.W + (x0 & ~3));
+            const uint4 A = __ldg(g);
+            const int off = x0 & 3;   // the same for every quad of the frame
+            if (off == 0) {
+                px[0] = A.x; px[1] = A.y; px[2] = A.z; px[3] = A.w;
+            } else {
+                const uint4 B = __ldg(g + 1);
+                if (off == 1) { px[0] = A.y; px[1] = A.z; px[2] = A.w; px[3] = B.x; }
+                else if (off == 2) { px[0] = A.z; px[1] = A.w; px[2] = B.x; px[3] = B.y; }
+                else { px[0] = A.w; px[1] = B.x; px[2] = B.y; px[3] = B.z; }
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int u = X - a.rx, v = Y - a.ry;

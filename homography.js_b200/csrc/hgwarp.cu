@@ -96,6 +96,8 @@ struct hg_ctx {
     bool no_tall = false;           // HG_GEO_NO_TALL: never pick the tall thread layout (A/B runs)
     bool bilinear_v1 = false;       // HG_BILINEAR_V1: first-generation bilinear kernel (A/B runs)
     bool pwf_v1 = false;            // HG_PWF_V1: first-generation fused piecewise pixel kernel (A/B runs)
+    bool geo_async = false;         // HG_GEO_ASYNC: affine / projective pixel loop with asynchronous gathers (A/B runs)
+    bool pwf_records_inline = false;  // HG_PWF_RECORDS_INLINE: the pixel kernel builds the run records of aligned frames itself (A/B runs)
     CUtensorMap img_tm[GEO_NBOX];
     bool img_tm_ok = false;
     DevBuf tm_dev;                   // TM_CACHE_SLOTS x GEO_NBOX tensor maps
@@ -409,6 +411,9 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
         const size_t smem = (size_t)P.stages * (size_t)(GEO_HDR_BYTES + P.box_bytes);
         if (kind == HG_AFFINE) warp_inverse_geo_staged_kernel<0><<<(unsigned)ctas, GEO_STAGED_THREADS, smem, stream>>>(P);
         else warp_inverse_geo_staged_kernel<1><<<(unsigned)ctas, GEO_STAGED_THREADS, smem, stream>>>(P);
+    } else if (c->geo_async) {
+        if (kind == HG_AFFINE) warp_inverse_geo_async_kernel<0><<<grid, GEO_THREADS, 0, stream>>>(P);
+        else warp_inverse_geo_async_kernel<1><<<grid, GEO_THREADS, 0, stream>>>(P);
     } else {
         if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, 0, stream>>>(P);
         else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, 0, stream>>>(P);
@@ -522,6 +527,8 @@ int hg_ctx_create(int device, hg_ctx **out)
         c->no_tall = getenv("HG_GEO_NO_TALL") != nullptr;
         c->bilinear_v1 = getenv("HG_BILINEAR_V1") != nullptr;
         c->pwf_v1 = getenv("HG_PWF_V1") != nullptr;
+        c->geo_async = getenv("HG_GEO_ASYNC") != nullptr;
+        c->pwf_records_inline = getenv("HG_PWF_RECORDS_INLINE") != nullptr;
         // the ring must fit a CTA's shared memory: shrink the depth (the CTA count follows from the occupancy below)
         const size_t cta_max = prop.sharedMemPerBlockOptin;
         auto ring = [&]() { return (size_t)c->geo_stages * (size_t)(GEO_HDR_BYTES + c->geo_box_bytes); };
@@ -886,6 +893,7 @@ static bool forward_lattice_plan(FwdArgs &a)
     a.lattice = 1;
     a.ixx = sxx; a.ixy = syx; a.iyx = sxy; a.iyy = syy;  // inverse of a signed permutation = its transpose
     a.rx = (int)rx; a.ry = (int)ry;
+    a.shift_copy = (sxx == 1 && syy == 1 && (a.oW & 3) == 0 && (a.W & 3) == 0 && ((uintptr_t)a.src & 15) == 0) ? 1 : 0;
     return true;
 }
 
@@ -1384,7 +1392,7 @@ static int pw_inverse_general_frame(hg_ctx *c, const float *dst_dev, const PwFra
 // the kernel chain of the fused path over the nF FusedFrame descriptors in c->fframes (written by the host or by
 // pw_stream_frames_kernel); bin counters and status flags are already zeroed.  Grids are sized for a max_ow x max_oh
 // window: CTAs beyond a smaller frame's extent exit at once.
-static int pw_fused_launch(hg_ctx *c, const float *dst_dev, int nF, int max_ow, int max_oh, size_t max_bins)
+static int pw_fused_launch(hg_ctx *c, const float *dst_dev, int nF, int max_ow, int max_oh, size_t max_bins, bool widths_aligned)
 {
     const size_t T = (size_t)c->n_tris;
     // rows per CTA = 16 * niter: long-lived CTAs amortise their start-up and keep the software pipeline full
@@ -1416,12 +1424,20 @@ static int pw_fused_launch(hg_ctx *c, const float *dst_dev, int nF, int max_ow, 
         c->launches += 2;
         CU(c, cudaGetLastError());
     }
-    pw_bin_runs_kernel<<<dim3((unsigned)((max_bins + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
-    c->launches++;
-    CU(c, cudaGetLastError());
+    // the run records: a pass of their own, unless every frame of the launch has a width that is a multiple of four — then
+    // the pixel kernel builds the records of its rows in shared memory itself (no record array written and read back)
+    // (measured on B200, 64 4K frames per launch: building them inside the pixel kernel costs the 162-triangle mesh as much
+    // as the pass it saves and the 7,938-triangle mesh 11 % more — the record builder's instructions land in a kernel that is
+    // already bound by its instruction and L1 rates — so it is opt-in: HG_PWF_RECORDS_INLINE=1)
+    const bool records_inline = widths_aligned && !c->pwf_v1 && c->pwf_records_inline;
+    if (!records_inline) {
+        pw_bin_runs_kernel<<<dim3((unsigned)((max_bins + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
     TRY(prof_begin(c));
     if (c->pwf_v1) pw_warp_fused_v1_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p, niter);
-    else pw_warp_fused_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p, niter);
+    else pw_warp_fused_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p, niter, records_inline ? 1 : 0);
     c->launches++;
     CU(c, cudaGetLastError());
     TRY(prof_end(c));
@@ -1479,7 +1495,9 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         const size_t nb = (size_t)pwf_bins_x(fr[f].oW) * fr[f].oH;
         if (nb > max_bins) max_bins = nb;
     }
-    return pw_fused_launch(c, dst_dev, nF, max_ow, max_oh, max_bins);
+    bool aligned = true;
+    for (int f = 0; f < nF; ++f) aligned = aligned && (fr[f].oW & 3) == 0;
+    return pw_fused_launch(c, dst_dev, nF, max_ow, max_oh, max_bins, aligned);
 }
 
 static bool pw_fused_possible(hg_ctx *c, const PwFrameHost &f)
@@ -1603,7 +1621,8 @@ int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *dst_pts, const hg_fr
     }
     const size_t pts_per_frame = 2 * (size_t)c->n_pts;
     TRY(check_point_floats(c, dst_pts, pts_per_frame * (size_t)n_frames, "dst_pts"));
-    TRY(upload_dst_points(c, dst_pts, (size_t)n_frames));
+    TRY(ensure(c, c->dst_pts, sizeof(float) * pts_per_frame * (size_t)n_frames));
+    TRY(ensure_pinned(c, sizeof(int) * (size_t)n_frames));
     c->map32_current = false;
     c->last_inv_len = -1;
     // chunk so that the per-frame scratch (triangle records, inverse matrices, bins) stays below ~1.5 GB
@@ -1614,18 +1633,23 @@ int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *dst_pts, const hg_fr
     }
     int chunk = (int)((1500ull << 20) / (per_frame ? per_frame : 1));
     if (chunk < 1) chunk = 1;
-    if (chunk > 1024) chunk = 1024;
-    std::vector<int> status((size_t)n_frames, 0);
+    // ... and at most 32 frames, so that a larger batch runs as a pipeline: the host stages the destiny points and frame
+    // descriptors of chunk k+1 while chunk k computes (the status flags come back through pinned memory, so nothing
+    // below blocks before the one synchronisation at the end)
+    if (chunk > 32) chunk = 32;
+    int *status = (int *)c->pin_big;
     const bool fused = pw_fused_possible(c, fr[0]);
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
-        const float *dd = (const float *)c->dst_pts.p + pts_per_frame * (size_t)f0;
+        float *dd = (float *)c->dst_pts.p + pts_per_frame * (size_t)f0;
+        CU(c, cudaMemcpyAsync(dd, dst_pts + pts_per_frame * (size_t)f0, sizeof(float) * pts_per_frame * (size_t)nf,
+                              cudaMemcpyHostToDevice, c->stream));
         if (fused) {
             TRY(pw_inverse_fused_chunk(c, dd, fr.data() + f0, nf, min_src_x, min_src_y));
             // the scratch is reused by the next chunk: collect this chunk's status first (stream-ordered copy)
-            CU(c, cudaMemcpyAsync(status.data() + f0, c->fstatus.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaMemcpyAsync(status + f0, c->fstatus.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
         } else {
-            for (int f = 0; f < nf; ++f) status[(size_t)(f0 + f)] = 1;
+            for (int f = 0; f < nf; ++f) status[f0 + f] = 1;
         }
     }
     CU(c, cudaStreamSynchronize(c->stream));
@@ -2197,7 +2221,7 @@ int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int6
         pw_stream_frames_kernel<<<(unsigned)((nf + 3) / 4), 128, 0, c->stream>>>(a);
         c->launches++;
         CU(c, cudaGetLastError());
-        if (fused) TRY(pw_fused_launch(c, dd, nf, max_out_w, max_out_h, bin_stride));
+        if (fused) TRY(pw_fused_launch(c, dd, nf, max_out_w, max_out_h, bin_stride, false));  // windows are decided on the device
         // the scratch is reused by the next chunk: collect this chunk's status and windows first (stream-ordered copies)
         CU(c, cudaMemcpyAsync(h_status + f0, c->fstatus.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(h_info + f0, (StreamInfo *)c->sinfo.p + f0, sizeof(StreamInfo) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));

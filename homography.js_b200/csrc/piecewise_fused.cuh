@@ -139,12 +139,9 @@ __device__ __forceinline__ int pwf_map_id(int raw, int n_tris)
 // or three entries, the fixed cost of eight-wide masks does not pay.)
 constexpr int PW_RUN_CAP = 8;
 
-__global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *frames)
+// the run record of one bin from its span entries
+__device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin, uint4 &rec0, uint4 &rec1)
 {
-    const FusedFrame &F = frames[blockIdx.y];
-    const size_t nbins = (size_t)F.bins_x * F.oH;
-    const size_t bin = (size_t)blockIdx.x * 128 + threadIdx.x;
-    if (bin >= nbins) return;
     const unsigned cnt = min(F.bin_cnt[bin], (unsigned)PW_BIN_CAP);
     unsigned long long mask = 1ull;
     unsigned ids[PW_RUN_CAP / 2] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // int16 pairs, -1 = no triangle
@@ -208,8 +205,24 @@ __global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *fram
             }
         }
     }
-    F.bin_run[2 * bin] = make_uint4((unsigned)mask, (unsigned)(mask >> 32), 0u, 0u);
-    F.bin_run[2 * bin + 1] = make_uint4(ids[0], ids[1], ids[2], ids[3]);
+    rec0 = make_uint4((unsigned)mask, (unsigned)(mask >> 32), 0u, 0u);
+    rec1 = make_uint4(ids[0], ids[1], ids[2], ids[3]);
+}
+
+// the records as a pass of their own: frames whose width is not a multiple of four (their first quads reach back into
+// the previous bin, whose record the pixel kernel then needs as well), the general-path comparison runs and the
+// first-generation pixel kernel read them from global memory; for the other frames the pixel kernel builds the records
+// of its rows itself, straight into shared memory (pw_warp_fused_kernel, records_inline)
+__global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *frames)
+{
+    const FusedFrame &F = frames[blockIdx.y];
+    const size_t nbins = (size_t)F.bins_x * F.oH;
+    const size_t bin = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (bin >= nbins) return;
+    uint4 r0, r1;
+    pwf_make_record(F, bin, r0, r1);
+    F.bin_run[2 * bin] = r0;
+    F.bin_run[2 * bin + 1] = r1;
 }
 
 // id of run r (0..7) from the packed int16 ids
@@ -465,7 +478,7 @@ struct PwfCtx {
     // pipeline state
     int t0[2];           // triangle of each quad's first pixel (S1 -> S2)
     int tm[2];           // triangle whose matrix mq[q] holds
-    double mq[2][6];     // its inverse matrix (S1 -> S2)
+    float4 mqa[2], mqb[2];  // its inverse matrix as loaded (S1 -> S2): (m0..m3), (m4, m5, -, -); widened where it is used
     int qn;              // warp-uniform: entries in this warp's queue
 };
 
@@ -500,13 +513,15 @@ __device__ __forceinline__ void pwf_issue(PwfCtx<ZERO_OFF> &C, const FusedFrame 
     for (int q = 0; q < 2; ++q) {
         const uint32_t dst = slot + 4u * (uint32_t)(q * 4 * PWF_THREADS);   // word [q][k][thread]: pixel k at dst + k * PWF_KSTEP
         const bool live = (C.t0[q] >= 0) && (row < C.oH) && (C.vmask[q] != 0u);
-        const double r0 = __dmul_rn(C.mq[q][2], y), r1 = __dmul_rn(C.mq[q][3], y);
+        const double m0 = (double)C.mqa[q].x, m1 = (double)C.mqa[q].y, m2 = (double)C.mqa[q].z, m3 = (double)C.mqa[q].w,
+                     m4 = (double)C.mqb[q].x, m5 = (double)C.mqb[q].y;
+        const double r0 = __dmul_rn(m2, y), r1 = __dmul_rn(m3, y);
         if (ZERO_OFF) {
             unsigned hx[4], hy[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                hx[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(C.mq[q][0], C.xs[q][k], r0, C.mq[q][4]), 2.0, HG_MAGIC + 1.0));
-                hy[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(C.mq[q][1], C.xs[q][k], r1, C.mq[q][5]), 2.0, HG_MAGIC + 1.0));
+                hx[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(m0, C.xs[q][k], r0, m4), 2.0, HG_MAGIC + 1.0));
+                hy[k] = (unsigned)__double2hiint(__fma_rd(affine_coord_exact(m1, C.xs[q][k], r1, m5), 2.0, HG_MAGIC + 1.0));
             }
             unsigned flat[4];
 #pragma unroll
@@ -529,8 +544,7 @@ __device__ __forceinline__ void pwf_issue(PwfCtx<ZERO_OFF> &C, const FusedFrame 
             for (int k = 0; k < 4; ++k) {
                 unsigned f = HG_OUTSIDE;
                 if (live)
-                    f = pwf_decode<false>(affine_coord_exact(C.mq[q][0], C.xs[q][k], r0, C.mq[q][4]),
-                                          affine_coord_exact(C.mq[q][1], C.xs[q][k], r1, C.mq[q][5]), F, C.npx_src);
+                    f = pwf_decode<false>(affine_coord_exact(m0, C.xs[q][k], r0, m4), affine_coord_exact(m1, C.xs[q][k], r1, m5), F, C.npx_src);
                 pwf_copy4(dst + PWF_KSTEP * k, C.src + (f != HG_OUTSIDE ? f : 0u), f != HG_OUTSIDE);
             }
         }
@@ -551,7 +565,9 @@ __device__ __forceinline__ void pwf_resolve(PwfCtx<ZERO_OFF> &C, int g, unsigned
         // rows of one triangle follow each other: the matrix is fetched only when the quad has moved to another triangle
         // (the registers still hold the last triangle's; "no triangle" does not disturb them)
         if (t >= 0 && t != C.tm[q]) {
-            pwf_load_matrix(C.inv, t, C.mq[q]);
+            const float4 *pm = reinterpret_cast<const float4 *>(C.inv + 8 * (size_t)t);
+            C.mqa[q] = __ldg(pm);       // no use of the loaded values in this stage: the next stage widens them, one
+            C.mqb[q] = __ldg(pm + 1);   // iteration later, when they have long arrived
             C.tm[q] = t;
         }
         C.t0[q] = t;
@@ -585,7 +601,7 @@ __device__ __forceinline__ void pwf_retire(const PwfCtx<ZERO_OFF> &C, int g, uin
 
 template <bool ZERO_OFF>
 __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int tile_x, int row0, unsigned short *wq, uint4 (*s_rec)[2],
-                                          uint32_t (*s_px)[2][4][PWF_THREADS])
+                                          uint32_t (*s_px)[2][4][PWF_THREADS], bool records_inline)
 {
     const int warp_id = threadIdx.x >> 5;
     const int tx = threadIdx.x & (PWF_TX - 1), ty = threadIdx.x / PWF_TX;
@@ -631,10 +647,7 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
     C.prev_bin = (a > 0) && (tx == 0) && (tile_x > 0);
     C.t0[0] = C.t0[1] = -1;
     C.tm[0] = C.tm[1] = -1;
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int k = 0; k < 6; ++k) C.mq[q][k] = 0.0;
+    C.mqa[0] = C.mqa[1] = C.mqb[0] = C.mqb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     C.qn = 0;
 
     // S0, once per CTA: the run records of all its rows (16 * ngroups records of 32 bytes, one 64-column bin each) go to
@@ -647,6 +660,12 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
             const int rr = i >> 1, h = i & 1, row = row0 + rr;
             uint4 *dst = &s_rec[rr][h];
             if (C.has_bin && row < oH) {
+                if (records_inline) {
+                    // no run-record pass ran for this launch: resolve the bin's span entries here (one thread per record;
+                    // the h == 1 thread of the pair idles)
+                    if (h == 0) pwf_make_record(F, (size_t)row * F.bins_x + tile_x, s_rec[rr][0], s_rec[rr][1]);
+                    continue;
+                }
                 const uint4 *srcp = F.bin_run + 2 * ((size_t)row * F.bins_x + tile_x) + h;
                 const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(srcp) : "memory");
@@ -789,7 +808,7 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
     }
 }
 
-__global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel(const FusedFrame *frames, int niter)
+__global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel(const FusedFrame *frames, int niter, int records_inline)
 {
     __shared__ unsigned short s_q[PWF_THREADS / 32][PWF_QCAP];
     const FusedFrame F = frames[blockIdx.y];
@@ -802,8 +821,10 @@ __global__ void __launch_bounds__(PWF_THREADS, HG_PWF_MINB) pw_warp_fused_kernel
     __shared__ uint4 s_rec[PWF_GROUP_ROWS * 16][2];   // run records of the CTA's rows (niter <= 16)
     __shared__ uint32_t s_px[PWF_NST][2][4][PWF_THREADS];   // gathered pixels: a ring of row groups, [quad][pixel][thread]
     unsigned short *wq = s_q[threadIdx.x >> 5];
-    if (F.minSrcX == 0 && F.minSrcY == 0) pwf_body2<true>(F, niter, tile_x, row0, wq, s_rec, s_px);
-    else pwf_body2<false>(F, niter, tile_x, row0, wq, s_rec, s_px);
+    // (a frame of unaligned width always has its records in global memory: the host ran the record pass for the launch)
+    const bool inl = records_inline != 0 && (F.oW & 3) == 0;
+    if (F.minSrcX == 0 && F.minSrcY == 0) pwf_body2<true>(F, niter, tile_x, row0, wq, s_rec, s_px, inl);
+    else pwf_body2<false>(F, niter, tile_x, row0, wq, s_rec, s_px, inl);
 }
 
 // first-generation kernel, kept for A/B runs (HG_PWF_V1=1); needs oW-wide rows of bins == tiles

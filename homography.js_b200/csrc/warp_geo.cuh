@@ -356,11 +356,28 @@ struct GeoFastCtx {
     double xs[4];
     double c0, c1, c2, c3, c4, c5, c6, c7;  // affine: m0..m5; projective: 2h0, 2h1, 2h2, 2h3, 2h4, 2h5, h6, h7
     int xOff, yOff, s;
+    uint32_t ring;           // ASYNC: shared-memory byte address of this thread's word in slot 0 of the gather ring
 };
 
+// ASYNC variant of the pixel loop (warp_inverse_geo_async_kernel): the gathers are 4-byte asynchronous copies global ->
+// shared (cp.async) into a ring of two row groups, words [slot][row j][pixel k][thread] (the 32 lanes of one copy write
+// 32 consecutive words), committed as one group per row group and awaited only where the row group is stored.  ptxas
+// tracks every LDG of the register variant with ONE scoreboard barrier, so storing a row group waits for the gathers of
+// the NEXT one as well (issued a moment before); asynchronous copies carry no register scoreboard.  A pixel outside the
+// image is a copy of zero source bytes (the slot is zero-filled).
+constexpr uint32_t GEO_RING_K = 4u * GEO_THREADS;                          // bytes between pixel k and k+1
+constexpr uint32_t GEO_RING_J = 4u * GEO_RING_K;                           // bytes between row j and j+1
+constexpr uint32_t GEO_RING_SLOT = GEO_ROWS_PER_THREAD * GEO_RING_J;       // bytes per ring slot
+
+__device__ __forceinline__ void geo_copy4(uint32_t smem_dst, const uint32_t *src, bool take)
+{
+    const int n = take ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(src), "r"(n) : "memory");
+}
+
 // arithmetic + gathers of one row group
-template <int KIND>
-__device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g, int base, int *qn)
+template <int KIND, bool ASYNC = false>
+__device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g, int base, int *qn, uint32_t slot = 0u)
 {
     constexpr int R = GEO_ROWS_PER_THREAD;
     const double MG = (KIND == 0) ? (HG_MAGIC + 1.0) : (HG_MAGIC + 1.0 + (double)HG_NEAR_DELTA2 / 4294967296.0);
@@ -430,7 +447,11 @@ __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g,
         // both variants
         if (__all_sync(__activemask(), ends_inside)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) g.px[j][k] = __ldg(C.srcv + ((hy[k] >> 1) * C.W + ((hx[k] >> 1) + C.nkflat)));
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t *p = C.srcv + ((hy[k] >> 1) * C.W + ((hx[k] >> 1) + C.nkflat));
+                if (ASYNC) geo_copy4(C.ring + slot + GEO_RING_J * j + GEO_RING_K * k, p, true);
+                else g.px[j][k] = __ldg(p);
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -438,23 +459,37 @@ __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g,
                 // 0 <= v < W on the unrounded coordinate, and the flat index inside the image (Q2: past the end reads 0)
                 const bool in = ((hx[k] - (unsigned)(HG_HI_ZERO + 1)) < C.W2) & ((hy[k] - (unsigned)(HG_HI_ZERO + 1)) < C.H2) &
                                 (flat < C.npx);
-                uint32_t v = 0u;
-                if (in) v = __ldg(C.src + flat);
-                g.px[j][k] = v;
+                if (ASYNC) {
+                    geo_copy4(C.ring + slot + GEO_RING_J * j + GEO_RING_K * k, C.src + (in ? flat : 0u), in);
+                } else {
+                    uint32_t v = 0u;
+                    if (in) v = __ldg(C.src + flat);
+                    g.px[j][k] = v;
+                }
             }
         }
     }
+    if (ASYNC) asm volatile("cp.async.commit_group;" ::: "memory");
     g.qpos = 0;
     if (KIND == 1 && g.redo) g.qpos = atomicAdd(qn, 1);  // consumed when the group retires
 }
 
 // queue entry (or in-place exact resolution when the queue is full), then the stores of one row group
-template <int KIND>
+template <int KIND, bool ASYNC = false>
 __device__ __forceinline__ void geo_fast_retire(const GeoFrame &F, const double (&m)[8], const GeoFastCtx<KIND> &C, GeoGroup &g,
-                                                int x_first, unsigned mask, uint2 *q)
+                                                int x_first, unsigned mask, uint2 *q, const uint32_t *slot = nullptr, int pending = 0)
 {
     constexpr int R = GEO_ROWS_PER_THREAD;
     if (g.base < 0) return;
+    if (ASYNC) {
+        // the copies of this row group have landed once at most `pending` newer groups are still in flight
+        if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) g.px[j][k] = slot[(j * 4 + k) * GEO_THREADS];
+    }
     if (KIND == 1 && g.redo) {
         if (g.qpos < GEO_QCAP) {
             q[g.qpos] = make_uint2((unsigned)(x_first + 4), (g.redo << 17) | (unsigned)g.base);
@@ -495,11 +530,14 @@ __device__ __forceinline__ void geo_fast_retire(const GeoFrame &F, const double 
     g.base = -1;
 }
 
-template <int KIND>
+template <int KIND, bool ASYNC = false>
 __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&m)[8], int base0, int niter, int s,
-                                              int x_first, unsigned mask, uint2 *q, int *qn, int group_rows)
+                                              int x_first, unsigned mask, uint2 *q, int *qn, int group_rows,
+                                              uint32_t *ring = nullptr)
 {
     GeoFastCtx<KIND> C;
+    C.ring = ASYNC ? (uint32_t)__cvta_generic_to_shared(ring + threadIdx.x) : 0u;
+    const uint32_t *ring_a = ring + threadIdx.x, *ring_b = ring + threadIdx.x + GEO_RING_SLOT / 4;
     C.src = F.src;
     C.W = (unsigned)F.W;
     C.H = (unsigned)F.H;
@@ -535,15 +573,15 @@ __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&
     for (int it = 0; it < niter; it += 2) {
         const int b0 = base0 + it * group_rows, b1 = b0 + group_rows;
         if (b0 >= oH) break;
-        geo_fast_issue<KIND>(C, ga, b0, qn);
-        geo_fast_retire<KIND>(F, m, C, gb, x_first, mask, q);
+        geo_fast_issue<KIND, ASYNC>(C, ga, b0, qn, 0u);
+        geo_fast_retire<KIND, ASYNC>(F, m, C, gb, x_first, mask, q, ring_b, 1);   // ga's copies stay in flight
         if (it + 1 < niter && b1 < oH) {
-            geo_fast_issue<KIND>(C, gb, b1, qn);
-            geo_fast_retire<KIND>(F, m, C, ga, x_first, mask, q);
+            geo_fast_issue<KIND, ASYNC>(C, gb, b1, qn, GEO_RING_SLOT);
+            geo_fast_retire<KIND, ASYNC>(F, m, C, ga, x_first, mask, q, ring_a, 1);
         }
     }
-    geo_fast_retire<KIND>(F, m, C, ga, x_first, mask, q);
-    geo_fast_retire<KIND>(F, m, C, gb, x_first, mask, q);
+    geo_fast_retire<KIND, ASYNC>(F, m, C, ga, x_first, mask, q, ring_a, 0);
+    geo_fast_retire<KIND, ASYNC>(F, m, C, gb, x_first, mask, q, ring_b, 0);
 }
 
 // CTA-uniform: may the projective frame run geo_fast_body?  The denominator h6 x + h7 y + 1 is affine in (x, y), so
@@ -661,8 +699,25 @@ __device__ __forceinline__ void geo_flush_queue(const GeoFrame &F, const double 
 
 // The default kernel: one CTA per (tile, frame), source pixels gathered directly from global memory through L1 / L2
 // (geo_fast_body; geo_tile_body for the projective frames geo_fast_mode rejects).
+template <int KIND, bool ASYNC>
+__device__ __forceinline__ void warp_inverse_geo_impl(const GeoParams &P, uint32_t *ring);
+
 template <int KIND>
 __global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG_GEO_MINB) warp_inverse_geo_kernel(const GeoParams P)
+{
+    warp_inverse_geo_impl<KIND, false>(P, nullptr);
+}
+
+// the same kernel with asynchronous gathers (see GeoFastCtx): opt-in / default per launch_geo
+template <int KIND>
+__global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG_GEO_MINB) warp_inverse_geo_async_kernel(const GeoParams P)
+{
+    __shared__ uint32_t s_ring[2 * GEO_RING_SLOT / 4];
+    warp_inverse_geo_impl<KIND, true>(P, s_ring);
+}
+
+template <int KIND, bool ASYNC>
+__device__ __forceinline__ void warp_inverse_geo_impl(const GeoParams &P, uint32_t *ring)
 {
     // per-warp queue of pixels whose quotient must be resolved exactly (projective only)
     __shared__ uint2 s_q[KIND == 1 ? GEO_THREADS / 32 : 1][KIND == 1 ? GEO_QCAP : 1];
@@ -715,10 +770,10 @@ __global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG
     const bool fast = (KIND == 1) && geo_fast_mode(F, m);  // CTA-uniform: from the matrix and the frame window
     if (active) {
         if (KIND == 0) {
-            geo_fast_body<0>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows);
+            geo_fast_body<0, ASYNC>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows, ring);
         } else {
             if (m[6] == 0.0 && m[7] == 0.0) geo_tile_body<1, 2>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows);
-            else if (fast) geo_fast_body<1>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows);
+            else if (fast) geo_fast_body<1, ASYNC>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows, ring);
             else geo_tile_body<1, 0>(F, m, base, P.niter, s, x_first, mask, q, qn, group_rows);
         }
     }

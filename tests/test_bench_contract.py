@@ -34,3 +34,23 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_stay_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_headline_frames_have_distinct_points_and_one_window():
+    """bench.py's per-frame destiny points (a different transform per frame, as in test/benchmark.js:96-113) all produce the
+    1728 x 1080 window of BASELINE config 2, frame 0 being exactly config 2 — checked with the oracle's limits."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    import homography_js_b200 as hg
+    from oracle import oracle as O
+    O.build()
+    wl = hg.workloads.projective_1080p()
+    pts = bench.headline_points(wl, 130, 0)
+    assert np.array_equal(pts[0], np.asarray(wl["dst"], np.float64))
+    assert len({tuple(p) for p in pts[:64]}) == 64 and np.array_equal(pts[64], pts[0])   # period 64
+    for f in (0, 1, 17, 63, 129):
+        lim = O.transform_limits(O.projective_from_squares(wl["src"], pts[f]), wl["W"], wl["H"])
+        assert [int(v) for v in lim] == [wl["x_off"], wl["y_off"], wl["o_w"], wl["o_h"]], (f, lim)
+    # both arms print the same config dictionary (the driver compares them)
+    assert bench.config_dict(wl) == bench.config_dict(hg.workloads.projective_1080p())

@@ -310,3 +310,17 @@ def test_piecewise_pipe_frames_bit_exact(ctx):
 def test_pcie_probe_reports_three_positive_rates(ctx):
     a, b, c2 = ctx.pcie_probe(8 << 20, 4)
     assert a > 0.5 and b > 0.5 and c2 > 0.5
+
+
+def test_forward_translation_shift_copy_every_alignment(ctx):
+    """Translations between images with 16-byte aligned rows take the 128-bit shifted-copy form of the lattice kernel: every
+    source alignment (x0 mod 4), windows hanging over every image edge, half-pixel translations."""
+    W, H = 64, 20
+    img = _rand_img(12, W, H)
+    ctx.image_set(img, W, H)
+    for e in list(range(-9, 10)) + [2.5, -3.5, 70, -70]:
+        for f_, yo, oW, oH in ((0, 0, 64, 20), (3, -2, 72, 28), (-1.5, 5, 32, 12)):
+            m = np.array([1, 0, 0, 1, e, f_], np.float32)
+            got = ctx.warp_forward_matrix(m, 0, yo, oW, oH)
+            want = O.warp_forward_geometric(img, W, H, m, 0, yo, oW, oH)
+            assert _diff(got, want) == 0, (e, f_, yo, oW, oH)
