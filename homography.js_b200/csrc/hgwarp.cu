@@ -97,6 +97,7 @@ struct hg_ctx {
     bool bilinear_v1 = false;       // HG_BILINEAR_V1: first-generation bilinear kernel (A/B runs)
     bool pwf_v1 = false;            // HG_PWF_V1: first-generation fused piecewise pixel kernel (A/B runs)
     bool geo_async = false;         // HG_GEO_ASYNC: affine / projective pixel loop with asynchronous gathers (A/B runs)
+    int pw_chunk = 64;              // HG_PW_CHUNK: frames per pipelined chunk of hg_warp_piecewise_inverse_batch (A/B runs)
     bool pwf_records_inline = false;  // HG_PWF_RECORDS_INLINE: the pixel kernel builds the run records of aligned frames itself (A/B runs)
     CUtensorMap img_tm[GEO_NBOX];
     bool img_tm_ok = false;
@@ -529,6 +530,7 @@ int hg_ctx_create(int device, hg_ctx **out)
         c->pwf_v1 = getenv("HG_PWF_V1") != nullptr;
         c->geo_async = getenv("HG_GEO_ASYNC") != nullptr;
         c->pwf_records_inline = getenv("HG_PWF_RECORDS_INLINE") != nullptr;
+        env_int("HG_PW_CHUNK", 1, 1024, c->pw_chunk);
         // the ring must fit a CTA's shared memory: shrink the depth (the CTA count follows from the occupancy below)
         const size_t cta_max = prop.sharedMemPerBlockOptin;
         auto ring = [&]() { return (size_t)c->geo_stages * (size_t)(GEO_HDR_BYTES + c->geo_box_bytes); };
@@ -1419,8 +1421,9 @@ static int pw_fused_launch(hg_ctx *c, const float *dst_dev, int nF, int max_ow, 
         // ... and a coarse mesh spreads its triangles further until the launch fills the machine about twice
         while (lpt_log2 < 9 && (double)(T << lpt_log2) * nF < 2.0 * 2048.0 * c->sm_count && (double)(1 << lpt_log2) < rows_guess) ++lpt_log2;
         const size_t span_threads = T << lpt_log2;
-        pw_span_bin_kernel<<<dim3((unsigned)((span_threads + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>(
-            (const FusedFrame *)c->fframes.p, lpt_log2);
+        const dim3 sg((unsigned)((span_threads + 127) / 128), (unsigned)nF);
+        if (rows_guess >= 96.0) pw_span_bin_kernel<true><<<sg, 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p, lpt_log2);
+        else pw_span_bin_kernel<false><<<sg, 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p, lpt_log2);
         c->launches += 2;
         CU(c, cudaGetLastError());
     }
@@ -1465,7 +1468,7 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
     TRY(ensure(c, c->invd, sizeof(float) * 8 * T * nF));
     // + one row group of slack: the pixel kernel's bin pointers may step (and read, but never use) past the last row
     const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
-    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * (total_bins + slack)));
+    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * 2 * (total_bins + slack)));
     TRY(ensure(c, c->bin_ent, sizeof(unsigned) * (total_bins + slack) * PW_BIN_CAP));
     TRY(ensure(c, c->bin_run, sizeof(uint4) * 2 * (total_bins + slack)));
     TRY(ensure(c, c->fstatus, sizeof(int) * (size_t)nF));
@@ -1476,7 +1479,7 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         F.src = fr[f].src; F.out = fr[f].out;
         F.rec = (const TriRec *)c->rec.p + T * f;
         F.inv = (const float *)c->invd.p + 8 * T * f;
-        F.bin_cnt = (unsigned *)c->bin_cnt.p + bin0;
+        F.bin_cnt = (unsigned *)c->bin_cnt.p + 2 * bin0;
         F.bin_ent = (unsigned *)c->bin_ent.p + bin0 * PW_BIN_CAP;
         F.bin_run = (uint4 *)c->bin_run.p + 2 * bin0;
         F.status = (int *)c->fstatus.p + f;
@@ -1488,7 +1491,7 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         bin0 += (size_t)F.bins_x * fr[f].oH;
     }
     CU(c, cudaMemcpyAsync(c->fframes.p, ff.data(), sizeof(FusedFrame) * (size_t)nF, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * total_bins, c->stream));
+    CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * 2 * total_bins, c->stream));
     CU(c, cudaMemsetAsync(c->fstatus.p, 0, sizeof(int) * (size_t)nF, c->stream));
     size_t max_bins = 1;
     for (int f = 0; f < nF; ++f) {
@@ -1633,10 +1636,12 @@ int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *dst_pts, const hg_fr
     }
     int chunk = (int)((1500ull << 20) / (per_frame ? per_frame : 1));
     if (chunk < 1) chunk = 1;
-    // ... and at most 32 frames, so that a larger batch runs as a pipeline: the host stages the destiny points and frame
+    // ... and at most 64 frames, so that a larger batch runs as a pipeline: the host stages the destiny points and frame
     // descriptors of chunk k+1 while chunk k computes (the status flags come back through pinned memory, so nothing
-    // below blocks before the one synchronisation at the end)
-    if (chunk > 32) chunk = 32;
+    // below blocks before the one synchronisation at the end).  Measured on 64 4K frames: chunks of 16 / 32 / 64 frames ->
+    // 0.408 / 0.431 / 0.441 of the HBM bound for the whole step (162 triangles): launches this size are worth more than the
+    // overlap of a 2 MB upload.
+    if (chunk > c->pw_chunk) chunk = c->pw_chunk;
     int *status = (int *)c->pin_big;
     const bool fused = pw_fused_possible(c, fr[0]);
     for (int f0 = 0; f0 < n_frames; f0 += chunk) {
@@ -2169,7 +2174,7 @@ int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int6
     const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
     TRY(ensure(c, c->rec, sizeof(TriRec) * (T ? T : 1) * (size_t)chunk));
     TRY(ensure(c, c->invd, sizeof(float) * 8 * (T ? T : 1) * (size_t)chunk));
-    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * (bin_stride * chunk + slack)));
+    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * 2 * (bin_stride * chunk + slack)));
     TRY(ensure(c, c->bin_ent, sizeof(unsigned) * (bin_stride * chunk + slack) * PW_BIN_CAP));
     TRY(ensure(c, c->bin_run, sizeof(uint4) * 2 * (bin_stride * chunk + slack)));
     TRY(ensure(c, c->fstatus, sizeof(int) * (size_t)chunk));
@@ -2206,7 +2211,7 @@ int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int6
         // before the call returns; the copy itself is stream-ordered in front of this chunk's kernels)
         CU(c, cudaMemcpyAsync(dd, dst_pts + pts_per_frame * (size_t)f0, sizeof(float) * pts_per_frame * (size_t)nf,
                               cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * bin_stride * (size_t)nf, c->stream));
+        CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * 2 * bin_stride * (size_t)nf, c->stream));
         CU(c, cudaMemsetAsync(c->fstatus.p, 0, sizeof(int) * (size_t)nf, c->stream));
         StreamArgs a{};
         a.dst_pts = dd; a.n_pts = c->n_pts; a.n_frames = nf; a.frame0 = (long long)first_frame + f0;

@@ -36,7 +36,7 @@ struct FusedFrame {
     uint32_t *out;
     const TriRec *rec;     // n_tris records of this frame (edges + row range)
     const float *inv;      // n_tris * 8 floats: the f32-rounded inverse matrices, one 32-byte record each
-    unsigned *bin_cnt;     // oH * bins_x counters (zeroed before the span kernel)
+    unsigned *bin_cnt;     // oH * bins_x x {entry counter, highest whole-bin id + 1} (zeroed before the span kernel)
     unsigned *bin_ent;     // oH * bins_x * PW_BIN_CAP packed entries  (t << 14 | c1 << 7 | c0)
     uint4 *bin_run;        // oH * bins_x run records (pw_bin_runs_kernel): what the pixel kernel reads
     int *status;           // bit 0: not representable -> redo with the general path
@@ -49,17 +49,69 @@ struct FusedFrame {
 // Per row: the exact interval [S, E) of TypedArray.fill (IEEE edge intersections, Math.round, relative-index clamping:
 // H.js:1111-1126, 1172-1197), cut at map-row boundaries, one entry per 64-column bin it touches.  All flat indices are
 // below 2^31 (checked on the host), so the piece arithmetic is 32-bit.
-__global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *frames, int lpt_log2)
+// Bin state: two words per bin — [2 bin] a counter of entries, [2 bin + 1] the highest id + 1 among the intervals that cover
+// the WHOLE bin (0 = none).  A wide interval (coarse meshes: seven bins per row and triangle) covers its interior bins
+// completely: those need no entry, only a fire-and-forget atomic max (RED) — no slot to wait for.  Entries (slot
+// reservation with a returning atomic, then a store that depends on it) are left for the two ends of an interval, and
+// their stores are deferred until the next reservation goes out, so the atomic's round trip to L2 runs under the next
+// row's edge intersections instead of stalling the lane.
+#ifndef HG_SPAN_MINB
+#define HG_SPAN_MINB 10
+#endif
+struct PwPending {
+    unsigned *addr;   // entry slot base of the bin (bin * PW_BIN_CAP), nullptr = nothing pending
+    unsigned slot, value;
+};
+__device__ __forceinline__ void pw_pending_flush(PwPending &p, int *status)
+{
+    if (p.addr) {
+        if (p.slot < PW_BIN_CAP) p.addr[p.slot] = p.value;
+        else atomicOr(status, 1);
+        p.addr = nullptr;
+    }
+}
+template <bool DEFER>
+__device__ __forceinline__ void pw_emit_entry(PwPending &p, unsigned *cnt, unsigned *ent, unsigned b, unsigned value, int *status)
+{
+    if (!DEFER) {
+        const unsigned slot = atomicAdd(cnt + 2u * b, 1u);
+        if (slot < PW_BIN_CAP) ent[(size_t)b * PW_BIN_CAP + slot] = value;
+        else atomicOr(status, 1);
+        return;
+    }
+    pw_pending_flush(p, status);
+    p.slot = atomicAdd(cnt + 2u * b, 1u);
+    p.addr = ent + (size_t)b * PW_BIN_CAP;
+    p.value = value;
+}
+
+// DEFER: entry stores wait until the next reservation goes out (coarse meshes: few, tall triangles, the kernel is bound by
+// the latency of its atomics — 57 -> 37 us per 16 4K frames of the 162-triangle mesh); fine meshes have thousands of
+// triangles in flight to cover that latency and measured 15 % faster storing at once.
+template <bool DEFER>
+__global__ void __launch_bounds__(128, HG_SPAN_MINB) pw_span_bin_kernel(const FusedFrame *frames, int lpt_log2)
 {
     const FusedFrame &F = frames[blockIdx.y];
     const unsigned gid = blockIdx.x * 128u + threadIdx.x;
     const int t = (int)(gid >> lpt_log2);
     if (t >= F.n_tris) return;
     const int lane = (int)(gid & ((1u << lpt_log2) - 1u)), stride = 1 << lpt_log2;
-    const TriRec &r = F.rec[t];
+    TriRec r;
+    {
+        // the record through the read-only path into locals: the entry stores below may alias it as far as the compiler
+        // knows, and every row would otherwise wait for twelve edge doubles re-read behind them (40 warps per SM are worth
+        // more than keeping all of them in registers: the launch bound lets the compiler decide which to re-fetch)
+        const TriRec *__restrict__ g = F.rec + t;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { r.m[e] = __ldg(&g->m[e]); r.b[e] = __ldg(&g->b[e]); r.lo[e] = __ldg(&g->lo[e]); r.hi[e] = __ldg(&g->hi[e]); }
+        r.maxY = __ldg(&g->maxY);
+        r.y0 = __ldg(&g->y0);
+    }
     const unsigned oW = (unsigned)F.oW, len = oW * (unsigned)F.oH;
     const double mw = (double)F.oW, yoff = (double)F.yOff, dlen = (double)len;
     const double y00 = (double)r.y0, maxY = r.maxY;
+    const unsigned tt = (unsigned)t << 14;
+    PwPending pa{nullptr, 0u, 0u}, pb{nullptr, 0u, 0u};
     for (int i = lane;; i += stride) {
         const double y = y00 + (double)i;
         if (!(y < maxY)) break;  // also ends on NaN
@@ -85,38 +137,28 @@ __global__ void __launch_bounds__(128) pw_span_bin_kernel(const FusedFrame *fram
             const unsigned room = oW - c0, want = k1 - k0, n = want < room ? want : room;
             const unsigned c1 = c0 + n;  // the piece covers columns [c0, c1) of map row `row`
             const unsigned b_first = c0 / PW_BIN_W, b_last = (c1 - 1u) / PW_BIN_W;
-            unsigned *cnt = F.bin_cnt + (size_t)row * F.bins_x;
+            unsigned *cnt = F.bin_cnt + 2 * (size_t)row * F.bins_x;
             unsigned *ent = F.bin_ent + (size_t)row * F.bins_x * PW_BIN_CAP;
-            const unsigned tt = (unsigned)t << 14;
+            const unsigned lo = c0 - b_first * PW_BIN_W, hi = c1 - b_last * PW_BIN_W;
             if (b_first == b_last) {
-                const unsigned slot = atomicAdd(cnt + b_first, 1u);
-                if (slot < PW_BIN_CAP) ent[b_first * PW_BIN_CAP + slot] = tt | ((c1 - b_first * PW_BIN_W) << 7) | (c0 - b_first * PW_BIN_W);
-                else atomicOr(F.status, 1);
+                if (lo == 0u && hi == (unsigned)PW_BIN_W) atomicMax(cnt + 2u * b_first + 1u, (unsigned)t + 1u);
+                else pw_emit_entry<DEFER>(pa, cnt, ent, b_first, tt | (hi << 7) | lo, F.status);
             } else {
-                // four bins at a time: the slot reservations (independent atomics) go out back to back, the entry stores
-                // that depend on them follow
-                for (unsigned b0 = b_first; b0 <= b_last; b0 += 4) {
-                    unsigned slot[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (b0 + j <= b_last) slot[j] = atomicAdd(cnt + b0 + j, 1u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const unsigned b = b0 + j;
-                        if (b <= b_last) {
-                            const unsigned lo = b == b_first ? c0 - b * PW_BIN_W : 0u;
-                            const unsigned hi = b == b_last ? c1 - b * PW_BIN_W : (unsigned)PW_BIN_W;
-                            if (slot[j] < PW_BIN_CAP) ent[b * PW_BIN_CAP + slot[j]] = tt | (hi << 7) | lo;
-                            else atomicOr(F.status, 1);
-                        }
-                    }
-                }
+                // the first and the last bin of the piece are partial as a rule (an entry each), the bins between them are
+                // covered completely
+                if (lo == 0u) atomicMax(cnt + 2u * b_first + 1u, (unsigned)t + 1u);
+                else pw_emit_entry<DEFER>(pa, cnt, ent, b_first, tt | ((unsigned)PW_BIN_W << 7) | lo, F.status);
+                for (unsigned b = b_first + 1u; b < b_last; ++b) atomicMax(cnt + 2u * b + 1u, (unsigned)t + 1u);
+                if (hi == (unsigned)PW_BIN_W) atomicMax(cnt + 2u * b_last + 1u, (unsigned)t + 1u);
+                else pw_emit_entry<DEFER>(pb, cnt, ent, b_last, tt | (hi << 7), F.status);
             }
             k0 += n;
             ++row;
             c0 = 0u;
         }
     }
+    pw_pending_flush(pa, F.status);
+    pw_pending_flush(pb, F.status);
 }
 
 
@@ -142,10 +184,14 @@ constexpr int PW_RUN_CAP = 8;
 // the run record of one bin from its span entries
 __device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin, uint4 &rec0, uint4 &rec1)
 {
-    const unsigned cnt = min(F.bin_cnt[bin], (unsigned)PW_BIN_CAP);
+    const uint2 st = *reinterpret_cast<const uint2 *>(F.bin_cnt + 2 * bin);   // entries, highest whole-bin id + 1
+    const unsigned cnt = min(st.x, (unsigned)PW_BIN_CAP);
+    const int full_raw = (int)st.y - 1;   // -1: no interval covers the whole bin
     unsigned long long mask = 1ull;
     unsigned ids[PW_RUN_CAP / 2] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // int16 pairs, -1 = no triangle
-    if (cnt == 1u) {
+    if (cnt == 0u) {
+        ids[0] = 0xFFFF0000u | ((unsigned)pwf_map_id(full_raw, F.n_tris) & 0xFFFFu);
+    } else if (cnt == 1u && full_raw < 0) {
         const unsigned e = F.bin_ent[bin * PW_BIN_CAP];
         const unsigned lo = e & 127u, hi = (e >> 7) & 127u;
         const unsigned id = (unsigned)pwf_map_id((int)(e >> 14), F.n_tris) & 0xFFFFu;
@@ -159,7 +205,7 @@ __device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin,
             }
             if (hi < 64u) mask |= 1ull << hi;  // its id (-1) is already in place
         }
-    } else if (cnt > 1u) {
+    } else {
         unsigned ent[PW_BIN_CAP];
         {
             const uint4 *pe = reinterpret_cast<const uint4 *>(F.bin_ent) + 2 * bin;
@@ -181,7 +227,7 @@ __device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin,
         while (cand) {
             const int c = __ffsll((long long)cand) - 1;
             cand &= cand - 1;
-            int raw = -1;
+            int raw = full_raw;   // what covers the whole bin covers this column
 #pragma unroll
             for (int e = 0; e < PW_BIN_CAP; ++e) {
                 if ((unsigned)e >= cnt) break;
