@@ -71,88 +71,147 @@ struct FwdParams {
     const FwdArgs *many;     // device array, indexed by blockIdx.y
 };
 
+// pass 1.  A thread takes four consecutive source pixels of one row of the loop domain per step (one division per quad,
+// the row terms m2*y / m3*y once per quad; a piecewise quad fetches a triangle's forward matrix only when the triangle
+// changes).  Every product and sum is the reference's own (H.js:1382-1385 / 1401-1404): unfused, in its order.
 template <bool PIECEWISE>
 __global__ void __launch_bounds__(256) forward_scatter_kernel(const FwdParams P)
 {
     const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
     if (a.lattice) return;
-    const int n = a.domW * a.domH;  // < 2^31 (checked on the host)
+    const int domW = a.domW, nq_row = (domW + 3) >> 2;
+    const int nquads = nq_row * a.domH;  // < 2^31 (checked on the host)
     const long long npix_out = (long long)a.oW * a.oH;
     const int stride = (int)(gridDim.x * blockDim.x);
-    float mf[6];
-    if (!PIECEWISE) {
+    double m[8];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) mf[k] = (float)a.mat[k];
-    }
-    // key - stride may wrap past 2^31 only after the loop condition has failed: the unsigned compare ends the loop
-    for (unsigned key = blockIdx.x * blockDim.x + threadIdx.x; key < (unsigned)n; key += (unsigned)stride) {
-        const int yy = (int)(key / (unsigned)a.domW);
-        const int xx = (int)(key - (unsigned)yy * (unsigned)a.domW);
-        const double x = (double)(a.minX + xx), y = (double)(a.minY + yy);
-        double tx, ty;
+    for (int k = 0; k < 8; ++k) m[k] = PIECEWISE ? 0.0 : ((a.kind == 0 && k < 6) ? (double)(float)a.mat[k] : a.mat[k]);
+    int t_have = -1;
+    for (int q = (int)(blockIdx.x * blockDim.x + threadIdx.x); q < nquads; q += stride) {
+        const int yy = q / nq_row;
+        const int xx0 = (q - yy * nq_row) << 2;
+        const double y = (double)(a.minY + yy);
+        const long long key0 = (long long)yy * domW + xx0;
+        int tq[4] = {-1, -1, -1, -1};
         if (PIECEWISE) {
-            if ((long long)key >= a.map_len) continue;  // read past the map: undefined > -1 is false
-            const int raw = __ldg(a.map32 + key);
-            const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);  // Int16Array semantics
-            if (t < 0 || t >= a.n_tris) continue;
-            apply_affine_general(a.rec[t].fwd, x, y, tx, ty);
-        } else if (a.kind == 0) {
-            apply_affine_general(mf, x, y, tx, ty);
-        } else {
-            apply_projective_general(a.mat, x, y, tx, ty);
+            // map[key]: entries past the end read `undefined` (> -1 is false); Int16Array semantics of the stored id
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (xx0 + k < domW && key0 + k < a.map_len) {
+                    const int raw = __ldg(a.map32 + key0 + k);
+                    const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);
+                    tq[k] = (t >= 0 && t < a.n_tris) ? t : -1;
+                }
+            }
         }
-        const long long p = forward_target(tx, ty, a.xOff, a.yOff, a.oW, npix_out);
-        if (p >= 0) atomicMax(a.winner + p, (int)key);
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+        if (!PIECEWISE) {
+            if (a.kind == 0) {
+                r0 = __dmul_rn(m[2], y);
+                r1 = __dmul_rn(m[3], y);
+            } else {
+                r0 = __dmul_rn(m[1], y);
+                r1 = __dmul_rn(m[4], y);
+                r2 = __dmul_rn(m[7], y);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = xx0 + k;
+            if (xx >= domW) break;
+            const double x = (double)(a.minX + xx);
+            double tx, ty;
+            if (PIECEWISE) {
+                const int t = tq[k];
+                if (t < 0) continue;
+                if (t != t_have) {
+                    const float *f = a.rec[t].fwd;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) m[c] = (double)__ldg(f + c);
+                    t_have = t;
+                }
+                tx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[2], y)), m[4]);
+                ty = __dadd_rn(__dadd_rn(__dmul_rn(m[1], x), __dmul_rn(m[3], y)), m[5]);
+            } else if (a.kind == 0) {
+                tx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), r0), m[4]);
+                ty = __dadd_rn(__dadd_rn(__dmul_rn(m[1], x), r1), m[5]);
+            } else {
+                const double den = __dadd_rn(__dadd_rn(__dmul_rn(m[6], x), r2), 1.0);
+                tx = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[0], x), r0), m[2]), den);
+                ty = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[3], x), r1), m[5]), den);
+            }
+            const long long p = forward_target(tx, ty, a.xOff, a.yOff, a.oW, npix_out);
+            if (p >= 0) atomicMax(a.winner + p, (int)(key0 + k));
+        }
     }
 }
 
 // pass 2: every output pixel takes the source pixel of its winning key (or stays transparent) and hands the plane
-// entry back as -1
+// entry back as -1.  When the loop domain is the image itself (always for _geometricWarp; for _piecewiseAffineWarp when
+// the source points span the image) the key IS the flat source index: no division.
 __global__ void __launch_bounds__(256) forward_gather_kernel(const FwdParams P)
 {
     const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
     if (a.lattice) return;
-    const long long npix = (long long)a.oW * a.oH;
-    const long long nquad = (npix + 3) >> 2;
+    const int npix = a.oW * a.oH;  // < 2^31 (checked on the host)
+    const int nquad = (npix + 3) >> 2;
     const long long npx_src = (long long)a.W * a.H;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += stride) {
-        const long long p0 = q << 2;
-        int key[4];
-        if (p0 + 3 < npix) {
-            int4 *wp = reinterpret_cast<int4 *>(a.winner + p0);
-            const int4 kv = *wp;
-            key[0] = kv.x; key[1] = kv.y; key[2] = kv.z; key[3] = kv.w;
-            if ((kv.x & kv.y & kv.z & kv.w) != -1) *wp = make_int4(-1, -1, -1, -1);
-        } else {
+    const int stride = (int)(gridDim.x * blockDim.x);
+    const bool key_is_flat = a.domW == a.W && a.minX == 0 && a.minY == 0;
+    const uint32_t *__restrict__ src = a.src;
+    // two quads per thread and step, a grid stride apart: both plane reads go out first, then the eight gathers that depend
+    // on them, then the two stores (the pass is bound by this chain of dependent loads)
+    for (int q = (int)(blockIdx.x * blockDim.x + threadIdx.x); q < nquad; q += 2 * stride) {
+        int key[2][4];
+        uint32_t px[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int p0 = (q + u * stride) << 2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) key[u][k] = -1;
+            if (q + u * stride >= nquad) continue;
+            if (p0 + 3 < npix) {
+                int4 *wp = reinterpret_cast<int4 *>(a.winner + p0);
+                const int4 kv = *wp;
+                key[u][0] = kv.x; key[u][1] = kv.y; key[u][2] = kv.z; key[u][3] = kv.w;
+                if ((kv.x & kv.y & kv.z & kv.w) != -1) *wp = make_int4(-1, -1, -1, -1);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (p0 + k < npix) {
+                        key[u][k] = a.winner[p0 + k];
+                        if (key[u][k] != -1) a.winner[p0 + k] = -1;
+                    }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                key[k] = -1;
-                if (p0 + k < npix) {
-                    key[k] = a.winner[p0 + k];
-                    if (key[k] != -1) a.winner[p0 + k] = -1;
+                uint32_t v = 0u;
+                if (key[u][k] >= 0) {
+                    long long flat = key[u][k];
+                    if (!key_is_flat) {
+                        const int yy = key[u][k] / a.domW;
+                        const int xx = key[u][k] - yy * a.domW;
+                        // idx = y*(W<<2) + (x<<2): flat, so x >= W runs into the next row; outside the image -> 0
+                        flat = (long long)(a.minY + yy) * a.W + (a.minX + xx);
+                    }
+                    if (flat >= 0 && flat < npx_src) v = __ldg(src + flat);
                 }
+                px[u][k] = v;
             }
-        }
-        uint32_t px[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t v = 0u;
-            if (key[k] >= 0) {
-                const int yy = key[k] / a.domW;
-                const int xx = key[k] - yy * a.domW;
-                // idx = y*(W<<2) + (x<<2): flat, so x >= W runs into the next row; outside the image -> 0
-                const long long flat = (long long)(a.minY + yy) * a.W + (a.minX + xx);
-                if (flat >= 0 && flat < npx_src) v = __ldg(a.src + flat);
+        for (int u = 0; u < 2; ++u) {
+            const int p0 = (q + u * stride) << 2;
+            if (q + u * stride >= nquad) continue;
+            if (p0 + 3 < npix) {
+                *reinterpret_cast<uint4 *>(a.out + p0) = make_uint4(px[u][0], px[u][1], px[u][2], px[u][3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (p0 + k < npix) a.out[p0 + k] = px[u][k];
             }
-            px[k] = v;
-        }
-        if (p0 + 3 < npix) {
-            *reinterpret_cast<uint4 *>(a.out + p0) = make_uint4(px[0], px[1], px[2], px[3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (p0 + k < npix) a.out[p0 + k] = px[k];
         }
     }
 }

@@ -73,6 +73,8 @@ struct hg_ctx {
     bool winner_clean = false;  // every entry of `winner` is -1 (the gather pass hands the plane back clean)
     void *pin_big = nullptr;    // pinned host staging for per-frame status / info read-backs
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr};  // chunk boundaries of hg_warp_piecewise_stream
+    cudaStream_t stream2 = nullptr;                // second lane of forward batches (scatter of one sub-batch beside the gather of another)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     size_t pin_big_cap = 0;
     // parameters of the last inverse index map (rebuilt on demand for the aliasing forward read, Q8)
     std::vector<float> last_inv_pts;
@@ -570,6 +572,12 @@ int hg_ctx_destroy(hg_ctx *c)
     if (c->pin_big) cudaFreeHost(c->pin_big);
     for (cudaEvent_t e : c->ev_chunk)
         if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) {
+        cudaStreamSynchronize(c->stream2);
+        cudaStreamDestroy(c->stream2);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto &pr : c->prof_ev) {
@@ -961,11 +969,25 @@ static int run_forward_batch(hg_ctx *c, std::vector<FwdArgs> &fa, bool piecewise
     int planes = (int)((48ll << 20) / (max_npix * 4));
     if (planes < 1) planes = 1;
     if (planes > 8) planes = 8;
+    // two lanes of sub-batches on two streams, each with its own half of the planes: the scatter of one sub-batch (bound by
+    // the atomic rate) runs beside the gather of the other (bound by its dependent loads)
+    const bool two_lanes = planes >= 2;
+    const int half = two_lanes ? planes / 2 : planes;
     if (n_lattice < n_frames) {
         TRY(ensure_winner(c, (size_t)max_npix * planes));
+        if (two_lanes && !c->stream2) {
+            CU(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+            CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+        // sub-batch i = general frames [i * half, (i + 1) * half) in frame order; it uses planes (i % 2) * half + j
         int k = 0;
         for (auto &a : fa)
-            if (!a.lattice) a.winner = (int *)c->winner.p + (size_t)max_npix * (k++ % planes);
+            if (!a.lattice) {
+                const int sub = k / half, j = k % half;
+                a.winner = (int *)c->winner.p + (size_t)max_npix * ((two_lanes ? (sub & 1) * half : 0) + j);
+                ++k;
+            }
     }
     TRY(ensure(c, c->fwd_args, sizeof(FwdArgs) * (size_t)n_frames));
     // general frames first in device order? no: keep frame order, kernels skip frames of the other kind
@@ -986,27 +1008,37 @@ static int run_forward_batch(hg_ctx *c, std::vector<FwdArgs> &fa, bool piecewise
     }
     if (n_lattice < n_frames) {
         c->winner_clean = false;
-        // sub-batches of consecutive frames that together hold at most `planes` general frames
-        int f0 = 0;
+        if (two_lanes) {
+            CU(c, cudaEventRecord(c->ev_fork, c->stream));   // frame descriptors uploaded, planes clean
+            CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        }
+        // sub-batches of consecutive frames that together hold exactly `half` general frames (the last one fewer)
+        int f0 = 0, sub = 0;
         while (f0 < n_frames) {
             int f1 = f0, g = 0;
-            while (f1 < n_frames && f1 - f0 < 32768 && (g < planes || fa[(size_t)f1].lattice)) {
+            while (f1 < n_frames && f1 - f0 < 32768 && (g < half || fa[(size_t)f1].lattice)) {
                 if (!fa[(size_t)f1].lattice) g++;
                 f1++;
             }
             if (g > 0) {
                 const int nf = f1 - f0;
+                cudaStream_t st = (two_lanes && (sub & 1)) ? c->stream2 : c->stream;
                 FwdParams P{};
                 P.many = (const FwdArgs *)c->fwd_args.p + f0;
                 const dim3 gs(fwd_blocks(c, max_dom, nf), (unsigned)nf), gg(fwd_blocks(c, (max_npix + 3) / 4, nf), (unsigned)nf);
-                if (piecewise) forward_scatter_kernel<true><<<gs, 256, 0, c->stream>>>(P);
-                else forward_scatter_kernel<false><<<gs, 256, 0, c->stream>>>(P);
-                forward_gather_kernel<<<gg, 256, 0, c->stream>>>(P);
+                if (piecewise) forward_scatter_kernel<true><<<gs, 256, 0, st>>>(P);
+                else forward_scatter_kernel<false><<<gs, 256, 0, st>>>(P);
+                forward_gather_kernel<<<gg, 256, 0, st>>>(P);
                 c->launches += 2;
+                ++sub;
             }
             f0 = f1;
         }
         CU(c, cudaGetLastError());
+        if (two_lanes) {
+            CU(c, cudaEventRecord(c->ev_join, c->stream2));
+            CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        }
         c->winner_clean = true;
     }
     TRY(prof_end(c));
