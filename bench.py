@@ -903,6 +903,8 @@ def run_headline(env, wl_name: str, with_secondary: bool):
                     "pipe": {"value": pipe_val, "unit": "Mpix/s", "ms_per_step": pipe_ms / e2e_steps,
                              "api": "hg_pipe_submit per frame (H2D image + solve + warp + D2H result, 4 frames in flight) + hg_pipe_flush"},
                     "host_link": link,
+                    "frac_of_host_link": (class_val * 1e6 * bytes_per_px / 1e9) / link["bidir_GBps_all_gpus"]
+                    if link["bidir_GBps_all_gpus"] > 0 else None,
                     "pipe_frac_of_host_link": (pipe_val * 1e6 * bytes_per_px / 1e9) / link["bidir_GBps_all_gpus"]
                     if link["bidir_GBps_all_gpus"] > 0 else None},
             "gpu_launches": int(t["launches"]),
