@@ -33,7 +33,7 @@ SYMBOLS = [
     "hg_pipe_create", "hg_pipe_submit", "hg_pipe_wait", "hg_pipe_flush", "hg_pipe_destroy",
     "hg_pipe_create_piecewise", "hg_pipe_submit_piecewise",
     "hg_host_alloc_pinned_ex", "hg_pcie_probe",
-    "hg_debug_rcp_max_error", "hg_debug_quotient_at_least", "hg_debug_force_general", "hg_debug_piecewise_stats",
+    "hg_debug_rcp_max_error", "hg_debug_quotient_at_least", "hg_debug_force_general", "hg_debug_piecewise_binning", "hg_debug_piecewise_stats",
     "hg_dev_alloc", "hg_dev_free", "hg_host_alloc_pinned", "hg_host_free_pinned",
     "hg_memcpy_h2d", "hg_memcpy_d2h", "hg_output_device",
 ]
@@ -134,6 +134,7 @@ def load():
     L.hg_pipe_flush.argtypes = [vp]
     L.hg_pipe_destroy.argtypes = [vp]
     L.hg_debug_force_general.argtypes = [vp, i]
+    L.hg_debug_piecewise_binning.argtypes = [vp, i]
     L.hg_debug_piecewise_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.hg_debug_rcp_max_error.argtypes = [vp, i, i, C.POINTER(d)]
     L.hg_debug_quotient_at_least.argtypes = [vp, vp, vp, vp, i, vp]
@@ -241,6 +242,9 @@ class Context:
 
     def debug_force_general(self, on: bool):
         self._ck(self.L.hg_debug_force_general(self.h, int(on)))
+
+    def debug_piecewise_binning(self, mode: int):
+        self._ck(self.L.hg_debug_piecewise_binning(self.h, int(mode)))
 
     def dev_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()

@@ -69,6 +69,11 @@ struct hg_ctx {
     // mesh
     DevBuf src_pts, dst_pts, tris, rec, map32, map16, frames, mats, winner;
     DevBuf invd, bin_cnt, bin_ent, bin_run, fstatus, fframes;  // fused piecewise path
+    // second set of the fused path's per-chunk scratch: chunk k+1 is binned (stream_pre) while chunk k's pixels are written
+    DevBuf rec_b, invd_b, bin_cnt_b, bin_ent_b, bin_run_b, fstatus_b, fframes_b, yr_b;
+    DevBuf yr;                                     // row ranges of the triangles (band binning pass)
+    cudaStream_t stream_pre = nullptr;             // high-priority lane of the span / run passes
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_pix[2] = {nullptr, nullptr};
     DevBuf fwd_args, cs_frames, cs_out, sinfo, pts_batch;     // forward batches, checksums, stream bookkeeping, point batches
     bool winner_clean = false;  // every entry of `winner` is -1 (the gather pass hands the plane back clean)
     void *pin_big = nullptr;    // pinned host staging for per-frame status / info read-backs
@@ -99,7 +104,9 @@ struct hg_ctx {
     bool bilinear_v1 = false;       // HG_BILINEAR_V1: first-generation bilinear kernel (A/B runs)
     bool pwf_v1 = false;            // HG_PWF_V1: first-generation fused piecewise pixel kernel (A/B runs)
     bool geo_async = false;         // HG_GEO_ASYNC: affine / projective pixel loop with asynchronous gathers (A/B runs)
-    int pw_chunk = 64;              // HG_PW_CHUNK: frames per pipelined chunk of hg_warp_piecewise_inverse_batch (A/B runs)
+    int pw_chunk = 0;               // HG_PW_CHUNK: frames per pipelined chunk of the piecewise batch / stream calls (0: 64; 16 with two lanes)
+    int pw_binning = 0;             // HG_PW_BINNING / hg_debug_piecewise_binning: 0 auto, 1 span + run passes, 2 one band pass
+    bool pw_serial = true;          // unless HG_PW_LANES: one lane — every chunk's binning passes in front of its pixel kernel
     bool pwf_records_inline = false;  // HG_PWF_RECORDS_INLINE: the pixel kernel builds the run records of aligned frames itself (A/B runs)
     CUtensorMap img_tm[GEO_NBOX];
     bool img_tm_ok = false;
@@ -533,6 +540,9 @@ int hg_ctx_create(int device, hg_ctx **out)
         c->geo_async = getenv("HG_GEO_ASYNC") != nullptr;
         c->pwf_records_inline = getenv("HG_PWF_RECORDS_INLINE") != nullptr;
         env_int("HG_PW_CHUNK", 1, 1024, c->pw_chunk);
+        c->pw_serial = getenv("HG_PW_LANES") == nullptr;
+        env_int("HG_PW_BINNING", 0, 2, c->pw_binning);
+        CUC(cudaFuncSetAttribute(pw_band_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWB_SMEM));
         // the ring must fit a CTA's shared memory: shrink the depth (the CTA count follows from the occupancy below)
         const size_t cta_max = prop.sharedMemPerBlockOptin;
         auto ring = [&]() { return (size_t)c->geo_stages * (size_t)(GEO_HDR_BYTES + c->geo_box_bytes); };
@@ -565,6 +575,8 @@ int hg_ctx_destroy(hg_ctx *c)
     DevBuf *bufs[] = {&c->img_own, &c->out, &c->scratch, &c->src_pts, &c->dst_pts, &c->tris,
                       &c->rec, &c->map32, &c->map16, &c->frames, &c->mats, &c->winner,
                       &c->invd, &c->bin_cnt, &c->bin_ent, &c->bin_run, &c->fstatus, &c->fframes, &c->tm_dev,
+                      &c->rec_b, &c->invd_b, &c->bin_cnt_b, &c->bin_ent_b, &c->bin_run_b, &c->fstatus_b, &c->fframes_b,
+                      &c->yr, &c->yr_b,
                       &c->fwd_args, &c->cs_frames, &c->cs_out, &c->sinfo, &c->pts_batch};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -572,6 +584,14 @@ int hg_ctx_destroy(hg_ctx *c)
     if (c->pin_big) cudaFreeHost(c->pin_big);
     for (cudaEvent_t e : c->ev_chunk)
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_pre)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_pix)
+        if (e) cudaEventDestroy(e);
+    if (c->stream_pre) {
+        cudaStreamSynchronize(c->stream_pre);
+        cudaStreamDestroy(c->stream_pre);
+    }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream2) {
@@ -1423,28 +1443,90 @@ static int pw_inverse_general_frame(hg_ctx *c, const float *dst_dev, const PwFra
     return HG_OK;
 }
 
-// the kernel chain of the fused path over the nF FusedFrame descriptors in c->fframes (written by the host or by
-// pw_stream_frames_kernel); bin counters and status flags are already zeroed.  Grids are sized for a max_ow x max_oh
-// window: CTAs beyond a smaller frame's extent exit at once.
-static int pw_fused_launch(hg_ctx *c, const float *dst_dev, int nF, int max_ow, int max_oh, size_t max_bins, bool widths_aligned)
+// per-chunk scratch of the fused path; lane 1 exists so that the binning passes of one chunk run beside the pixel kernel of
+// the chunk before it
+struct PwScratch {
+    DevBuf *rec, *invd, *bin_cnt, *bin_ent, *bin_run, *fstatus, *fframes, *yr;
+};
+static PwScratch pw_scratch(hg_ctx *c, int lane)
+{
+    if (lane == 0) return PwScratch{&c->rec, &c->invd, &c->bin_cnt, &c->bin_ent, &c->bin_run, &c->fstatus, &c->fframes, &c->yr};
+    return PwScratch{&c->rec_b, &c->invd_b, &c->bin_cnt_b, &c->bin_ent_b, &c->bin_run_b, &c->fstatus_b, &c->fframes_b, &c->yr_b};
+}
+// One band pass (pw_band_bins_kernel) or the span + run passes?  Measured on B200, 64 4K frames per call, whole step against
+// the HBM bound: 162 triangles 0.475 (band) / 0.440 (span + runs); 7,938 triangles 0.212 / 0.242 — every band scans all row
+// ranges, evaluates a row of a triangle once per band it can reach and runs at 24 warps per SM, which a fine mesh (two
+// rows per lane and segment) does not repay.
+static bool pw_band_binning(const hg_ctx *c)
+{
+    if (c->pw_binning) return c->pw_binning == 2;
+    return c->n_tris <= 2048;
+}
+static int pw_scratch_ensure(hg_ctx *c, const PwScratch &S, size_t T, int nF, size_t total_bins)
+{
+    TRY(ensure(c, *S.yr, sizeof(int2) * (T ? T : 1) * (size_t)nF));
+    // + one row group of slack: the pixel kernel's bin pointers may step (and read, but never use) past the last row
+    const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
+    TRY(ensure(c, *S.rec, sizeof(TriRec) * (T ? T : 1) * (size_t)nF));
+    TRY(ensure(c, *S.invd, sizeof(float) * 8 * (T ? T : 1) * (size_t)nF));
+    TRY(ensure(c, *S.bin_cnt, sizeof(unsigned) * 2 * (total_bins + slack)));
+    TRY(ensure(c, *S.bin_ent, sizeof(unsigned) * (total_bins + slack) * PW_BIN_CAP));
+    TRY(ensure(c, *S.bin_run, sizeof(uint4) * 2 * (total_bins + slack)));
+    TRY(ensure(c, *S.fstatus, sizeof(int) * (size_t)nF));
+    TRY(ensure(c, *S.fframes, sizeof(FusedFrame) * (size_t)nF));
+    return HG_OK;
+}
+// the two lanes of a pipelined piecewise call: binning passes on a high-priority stream of their own (their CTAs are
+// placed as pixel CTAs of the previous chunk retire: the passes are bound by the latency of their atomics, the pixel
+// kernel by L1 and HBM, so they share the machine well), pixel kernels on the context stream
+static int pw_lanes_begin(hg_ctx *c)
+{
+    if (!c->stream_pre) {
+        int lo = 0, hi = 0;
+        CU(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(c, cudaStreamCreateWithPriority(&c->stream_pre, cudaStreamNonBlocking, hi));
+        for (auto &e : c->ev_pre) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : c->ev_pix) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // everything queued on the context stream so far (image upload, mesh) is visible to the binning lane
+    CU(c, cudaEventRecord(c->ev_pre[0], c->stream));
+    CU(c, cudaStreamWaitEvent(c->stream_pre, c->ev_pre[0], 0));
+    return HG_OK;
+}
+
+// the binning passes of the fused path over the nF FusedFrame descriptors in S.fframes (written by the host or by
+// pw_stream_frames_kernel) on stream `st`; bin counters and status flags are already zeroed.  Grids are sized for a
+// max_ow x max_oh window: CTAs beyond a smaller frame's extent exit at once.
+static int pw_fused_prepass(hg_ctx *c, const PwScratch &S, cudaStream_t st, const float *dst_dev, int nF, int max_ow, int max_oh,
+                            size_t max_bins, bool records_inline)
 {
     const size_t T = (size_t)c->n_tris;
-    // rows per CTA = 16 * niter: long-lived CTAs amortise their start-up and keep the software pipeline full
-    int niter = 16;
-    while (niter > 1 && (long long)pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter) * nF < (long long)c->sm_count * 16) niter >>= 1;
-    const int max_tiles = pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter);
+    const FusedFrame *frames = (const FusedFrame *)S.fframes->p;
     if (T > 0) {
         PwSetupArgs a{};
         a.src_pts = (const float *)c->src_pts.p;
         a.dst_pts = dst_dev;
         a.map_pts = dst_dev;
         a.tris = (const uint32_t *)c->tris.p;
-        a.rec = (TriRec *)c->rec.p;
-        a.invd_out = (float *)c->invd.p;
+        a.rec = (TriRec *)S.rec->p;
+        a.invd_out = (float *)S.invd->p;
+        a.yr_out = (int2 *)S.yr->p;
         a.n_tris = c->n_tris;
         a.dst_stride = 2 * (size_t)c->n_pts;
         a.rec_stride = T;
-        pw_setup_kernel<<<dim3((unsigned)((T + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>(a);
+        pw_setup_kernel<<<dim3((unsigned)((T + 127) / 128), (unsigned)nF), 128, 0, st>>>(a);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    if (pw_band_binning(c)) {
+        // bins, overlaps and run records of a band of map rows in one pass through shared memory
+        const int band_rows = pwb_band_rows(pwf_bins_x(max_ow));
+        pw_band_bins_kernel<<<dim3((unsigned)((max_oh + band_rows - 1) / band_rows), (unsigned)nF), PWB_THREADS, PWB_SMEM, st>>>(frames);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        return HG_OK;
+    }
+    if (T > 0) {
         // lanes per triangle: a mesh of T triangles over oH rows has triangles ~ oH / sqrt(T/2) rows tall; about three rows
         // per lane keep the lanes busy without leaving the machine empty for coarse meshes
         const double rows_guess = (double)max_oh / sqrt((double)T / 2.0 + 1.0);
@@ -1454,9 +1536,9 @@ static int pw_fused_launch(hg_ctx *c, const float *dst_dev, int nF, int max_ow, 
         while (lpt_log2 < 9 && (double)(T << lpt_log2) * nF < 2.0 * 2048.0 * c->sm_count && (double)(1 << lpt_log2) < rows_guess) ++lpt_log2;
         const size_t span_threads = T << lpt_log2;
         const dim3 sg((unsigned)((span_threads + 127) / 128), (unsigned)nF);
-        if (rows_guess >= 96.0) pw_span_bin_kernel<true><<<sg, 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p, lpt_log2);
-        else pw_span_bin_kernel<false><<<sg, 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p, lpt_log2);
-        c->launches += 2;
+        if (rows_guess >= 96.0) pw_span_bin_kernel<true><<<sg, 128, 0, st>>>(frames, lpt_log2);
+        else pw_span_bin_kernel<false><<<sg, 128, 0, st>>>(frames, lpt_log2);
+        c->launches++;
         CU(c, cudaGetLastError());
     }
     // the run records: a pass of their own, unless every frame of the launch has a width that is a multiple of four — then
@@ -1464,27 +1546,56 @@ static int pw_fused_launch(hg_ctx *c, const float *dst_dev, int nF, int max_ow, 
     // (measured on B200, 64 4K frames per launch: building them inside the pixel kernel costs the 162-triangle mesh as much
     // as the pass it saves and the 7,938-triangle mesh 11 % more — the record builder's instructions land in a kernel that is
     // already bound by its instruction and L1 rates — so it is opt-in: HG_PWF_RECORDS_INLINE=1)
-    const bool records_inline = widths_aligned && !c->pwf_v1 && c->pwf_records_inline;
     if (!records_inline) {
-        pw_bin_runs_kernel<<<dim3((unsigned)((max_bins + 127) / 128), (unsigned)nF), 128, 0, c->stream>>>((const FusedFrame *)c->fframes.p);
+        pw_bin_runs_kernel<<<dim3((unsigned)((max_bins + 127) / 128), (unsigned)nF), 128, 0, st>>>(frames);
         c->launches++;
         CU(c, cudaGetLastError());
     }
+    return HG_OK;
+}
+
+// the pixel kernel over the same descriptors, on the context stream
+static int pw_fused_pixels(hg_ctx *c, const PwScratch &S, int nF, int max_ow, int max_oh, bool records_inline)
+{
+    const FusedFrame *frames = (const FusedFrame *)S.fframes->p;
+    // rows per CTA = 16 * niter: long-lived CTAs amortise their start-up and keep the software pipeline full
+    int niter = 16;
+    while (niter > 1 && (long long)pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter) * nF < (long long)c->sm_count * 16) niter >>= 1;
+    const int max_tiles = pwf_tiles_x(max_ow) * pwf_tiles_y(max_oh, niter);
     TRY(prof_begin(c));
-    if (c->pwf_v1) pw_warp_fused_v1_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p, niter);
-    else pw_warp_fused_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>((const FusedFrame *)c->fframes.p, niter, records_inline ? 1 : 0);
+    if (c->pwf_v1) pw_warp_fused_v1_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>(frames, niter);
+    else pw_warp_fused_kernel<<<dim3((unsigned)max_tiles, (unsigned)nF), PWF_THREADS, 0, c->stream>>>(frames, niter, records_inline ? 1 : 0);
     c->launches++;
     CU(c, cudaGetLastError());
     TRY(prof_end(c));
     return HG_OK;
 }
 
-// fused (map-free) inverse piecewise warp of nF frames in four launches; status_dev[f] != 0 afterwards means
-// frame f could not be represented and must be redone with pw_inverse_general_frame
+// binning passes on `pre`, then the pixel kernel on the context stream; lane >= 0: the two are different streams, joined by
+// the lane's events (ev_pre: bins ready; ev_pix: scratch free again)
+static int pw_fused_launch(hg_ctx *c, const PwScratch &S, int lane, const float *dst_dev, int nF, int max_ow, int max_oh,
+                           size_t max_bins, bool widths_aligned)
+{
+    const bool records_inline = widths_aligned && !c->pwf_v1 && c->pwf_records_inline && !pw_band_binning(c);
+    cudaStream_t pre = lane >= 0 ? c->stream_pre : c->stream;
+    TRY(pw_fused_prepass(c, S, pre, dst_dev, nF, max_ow, max_oh, max_bins, records_inline));
+    if (lane >= 0) {
+        CU(c, cudaEventRecord(c->ev_pre[lane], pre));
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_pre[lane], 0));
+    }
+    return pw_fused_pixels(c, S, nF, max_ow, max_oh, records_inline);
+}
+
+// fused (map-free) inverse piecewise warp of nF frames in four launches; S.fstatus[f] != 0 afterwards means frame f could
+// not be represented and must be redone with pw_inverse_general_frame.  lane < 0: everything on the context stream with
+// scratch set 0; lane 0 / 1: binning on the high-priority stream with that lane's scratch (`lane_busy`: the lane's previous
+// pixel kernel has to finish first)
 static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrameHost *fr, int nF, int min_src_x,
-                                  int min_src_y)
+                                  int min_src_y, int lane = -1, bool lane_busy = false)
 {
     const size_t T = (size_t)c->n_tris;
+    const PwScratch S = pw_scratch(c, lane < 0 ? 0 : lane);
+    cudaStream_t pre = lane >= 0 ? c->stream_pre : c->stream;
     std::vector<FusedFrame> ff((size_t)nF);
     size_t total_bins = 0;
     for (int f = 0; f < nF; ++f) {
@@ -1496,25 +1607,18 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         if (fr[f].oW > max_ow) max_ow = fr[f].oW;
         if (fr[f].oH > max_oh) max_oh = fr[f].oH;
     }
-    TRY(ensure(c, c->rec, sizeof(TriRec) * T * nF));
-    TRY(ensure(c, c->invd, sizeof(float) * 8 * T * nF));
-    // + one row group of slack: the pixel kernel's bin pointers may step (and read, but never use) past the last row
-    const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
-    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * 2 * (total_bins + slack)));
-    TRY(ensure(c, c->bin_ent, sizeof(unsigned) * (total_bins + slack) * PW_BIN_CAP));
-    TRY(ensure(c, c->bin_run, sizeof(uint4) * 2 * (total_bins + slack)));
-    TRY(ensure(c, c->fstatus, sizeof(int) * (size_t)nF));
-    TRY(ensure(c, c->fframes, sizeof(FusedFrame) * (size_t)nF));
+    TRY(pw_scratch_ensure(c, S, T, nF, total_bins));
     size_t bin0 = 0;
     for (int f = 0; f < nF; ++f) {
         FusedFrame &F = ff[(size_t)f];
         F.src = fr[f].src; F.out = fr[f].out;
-        F.rec = (const TriRec *)c->rec.p + T * f;
-        F.inv = (const float *)c->invd.p + 8 * T * f;
-        F.bin_cnt = (unsigned *)c->bin_cnt.p + 2 * bin0;
-        F.bin_ent = (unsigned *)c->bin_ent.p + bin0 * PW_BIN_CAP;
-        F.bin_run = (uint4 *)c->bin_run.p + 2 * bin0;
-        F.status = (int *)c->fstatus.p + f;
+        F.rec = (const TriRec *)S.rec->p + T * f;
+        F.inv = (const float *)S.invd->p + 8 * T * f;
+        F.yr = (const int2 *)S.yr->p + T * f;
+        F.bin_cnt = (unsigned *)S.bin_cnt->p + 2 * bin0;
+        F.bin_ent = (unsigned *)S.bin_ent->p + bin0 * PW_BIN_CAP;
+        F.bin_run = (uint4 *)S.bin_run->p + 2 * bin0;
+        F.status = (int *)S.fstatus->p + f;
         F.W = fr[f].W; F.H = fr[f].H;
         F.xOff = fr[f].xOff; F.yOff = fr[f].yOff; F.oW = fr[f].oW; F.oH = fr[f].oH;
         F.minSrcX = min_src_x; F.minSrcY = min_src_y;
@@ -1522,9 +1626,10 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
         F.bins_x = pwf_bins_x(fr[f].oW);
         bin0 += (size_t)F.bins_x * fr[f].oH;
     }
-    CU(c, cudaMemcpyAsync(c->fframes.p, ff.data(), sizeof(FusedFrame) * (size_t)nF, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * 2 * total_bins, c->stream));
-    CU(c, cudaMemsetAsync(c->fstatus.p, 0, sizeof(int) * (size_t)nF, c->stream));
+    if (lane_busy) CU(c, cudaStreamWaitEvent(pre, c->ev_pix[lane], 0));
+    CU(c, cudaMemcpyAsync(S.fframes->p, ff.data(), sizeof(FusedFrame) * (size_t)nF, cudaMemcpyHostToDevice, pre));
+    if (!pw_band_binning(c)) CU(c, cudaMemsetAsync(S.bin_cnt->p, 0, sizeof(unsigned) * 2 * total_bins, pre));
+    CU(c, cudaMemsetAsync(S.fstatus->p, 0, sizeof(int) * (size_t)nF, pre));
     size_t max_bins = 1;
     for (int f = 0; f < nF; ++f) {
         const size_t nb = (size_t)pwf_bins_x(fr[f].oW) * fr[f].oH;
@@ -1532,7 +1637,7 @@ static int pw_inverse_fused_chunk(hg_ctx *c, const float *dst_dev, const PwFrame
     }
     bool aligned = true;
     for (int f = 0; f < nF; ++f) aligned = aligned && (fr[f].oW & 3) == 0;
-    return pw_fused_launch(c, dst_dev, nF, max_ow, max_oh, max_bins, aligned);
+    return pw_fused_launch(c, S, lane, dst_dev, nF, max_ow, max_oh, max_bins, aligned);
 }
 
 static bool pw_fused_possible(hg_ctx *c, const PwFrameHost &f)
@@ -1673,18 +1778,41 @@ int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *dst_pts, const hg_fr
     // below blocks before the one synchronisation at the end).  Measured on 64 4K frames: chunks of 16 / 32 / 64 frames ->
     // 0.408 / 0.431 / 0.441 of the HBM bound for the whole step (162 triangles): launches this size are worth more than the
     // overlap of a 2 MB upload.
-    if (chunk > c->pw_chunk) chunk = c->pw_chunk;
-    int *status = (int *)c->pin_big;
     const bool fused = pw_fused_possible(c, fr[0]);
-    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    // One lane by default: chunks of 16 / 32 / 64 frames gave 0.408 / 0.431 / 0.441 of the HBM bound on 64 4K frames.
+    // HG_PW_LANES=1 (opt-in, A/B runs): the binning passes of chunk k+1 run on a high-priority stream beside the pixel kernel
+    // of chunk k, each lane with its own scratch.  Measured and not adopted: the pixel kernel slows down by what the passes
+    // take (0.61 -> 0.47 of the bound while they share the SMs), the whole step ends at 0.413 / 0.429 (chunks of 16 / 32)
+    // against 0.438 in one lane — the passes are not idle latency the pixel kernel could fill, they compete for issue slots
+    // and L1.
+    const int want = c->pw_chunk > 0 ? c->pw_chunk : (c->pw_serial ? 64 : 16);
+    if (chunk > want) chunk = want;
+    const bool lanes = fused && !c->pw_serial && n_frames > chunk;
+    int *status = (int *)c->pin_big;
+    if (lanes) {
+        // both lanes sized for the largest chunk before anything is in flight
+        size_t most_bins = 0;
+        for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+            size_t b = 0;
+            for (int f = f0; f < n_frames && f < f0 + chunk; ++f) b += (size_t)pwf_bins_x(fr[(size_t)f].oW) * fr[(size_t)f].oH;
+            if (b > most_bins) most_bins = b;
+        }
+        for (int l = 0; l < 2; ++l) TRY(pw_scratch_ensure(c, pw_scratch(c, l), (size_t)c->n_tris, chunk, most_bins));
+        TRY(pw_lanes_begin(c));
+    }
+    int k = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++k) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         float *dd = (float *)c->dst_pts.p + pts_per_frame * (size_t)f0;
+        // the points go up in front of the lane's wait for its scratch: the host never blocks behind a pixel kernel
         CU(c, cudaMemcpyAsync(dd, dst_pts + pts_per_frame * (size_t)f0, sizeof(float) * pts_per_frame * (size_t)nf,
-                              cudaMemcpyHostToDevice, c->stream));
+                              cudaMemcpyHostToDevice, lanes ? c->stream_pre : c->stream));
         if (fused) {
-            TRY(pw_inverse_fused_chunk(c, dd, fr.data() + f0, nf, min_src_x, min_src_y));
-            // the scratch is reused by the next chunk: collect this chunk's status first (stream-ordered copy)
-            CU(c, cudaMemcpyAsync(status + f0, c->fstatus.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
+            TRY(pw_inverse_fused_chunk(c, dd, fr.data() + f0, nf, min_src_x, min_src_y, lanes ? (k & 1) : -1, k >= 2));
+            // the scratch is reused two chunks on: collect this chunk's status first (stream-ordered copy)
+            CU(c, cudaMemcpyAsync(status + f0, pw_scratch(c, lanes ? (k & 1) : 0).fstatus->p, sizeof(int) * (size_t)nf,
+                                  cudaMemcpyDeviceToHost, c->stream));
+            if (lanes) CU(c, cudaEventRecord(c->ev_pix[k & 1], c->stream));
         } else {
             for (int f = 0; f < nf; ++f) status[f0 + f] = 1;
         }
@@ -1707,6 +1835,13 @@ int hg_debug_piecewise_stats(hg_ctx *c, uint64_t *frames_fused, uint64_t *frames
     if (!c || !frames_fused || !frames_general) return HG_ERR_INVALID;
     *frames_fused = c->n_fused;
     *frames_general = c->n_general;
+    return HG_OK;
+}
+
+int hg_debug_piecewise_binning(hg_ctx *c, int mode)
+{
+    if (!c || mode < 0 || mode > 2) return HG_ERR_INVALID;
+    c->pw_binning = mode;
     return HG_OK;
 }
 
@@ -2203,27 +2338,33 @@ int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int6
     if (chunk > 1024) chunk = 1024;
     if (chunk < 1) chunk = 1;
     const bool fused = !c->force_general && c->n_tris < PW_MAX_TRIS;
-    const size_t slack = (size_t)PWF_GROUP_ROWS * 1024;
-    TRY(ensure(c, c->rec, sizeof(TriRec) * (T ? T : 1) * (size_t)chunk));
-    TRY(ensure(c, c->invd, sizeof(float) * 8 * (T ? T : 1) * (size_t)chunk));
-    TRY(ensure(c, c->bin_cnt, sizeof(unsigned) * 2 * (bin_stride * chunk + slack)));
-    TRY(ensure(c, c->bin_ent, sizeof(unsigned) * (bin_stride * chunk + slack) * PW_BIN_CAP));
-    TRY(ensure(c, c->bin_run, sizeof(uint4) * 2 * (bin_stride * chunk + slack)));
-    TRY(ensure(c, c->fstatus, sizeof(int) * (size_t)chunk));
-    TRY(ensure(c, c->fframes, sizeof(FusedFrame) * (size_t)chunk));
+    // two lanes, like hg_warp_piecewise_inverse_batch: chunk k+1 is binned beside the pixel kernel of chunk k
+    if (fused && !c->pw_serial && c->pw_chunk > 0 && chunk > c->pw_chunk) chunk = c->pw_chunk;
+    const bool lanes = fused && !c->pw_serial && n_frames > chunk;
+    for (int l = 0; l < (lanes ? 2 : 1); ++l) TRY(pw_scratch_ensure(c, pw_scratch(c, l), T, chunk, bin_stride * (size_t)chunk));
     TRY(ensure(c, c->sinfo, sizeof(StreamInfo) * (size_t)n_frames));
     TRY(ensure_pinned(c, (sizeof(StreamInfo) + sizeof(int)) * (size_t)n_frames));
     StreamInfo *h_info = (StreamInfo *)c->pin_big;
     int *h_status = (int *)((char *)c->pin_big + sizeof(StreamInfo) * (size_t)n_frames);
     for (auto &e : c->ev_chunk)
         if (!e) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (lanes) TRY(pw_lanes_begin(c));
+    cudaStream_t pre = lanes ? c->stream_pre : c->stream;
     // frames of chunk [f0, f0 + nf) the span bins could not express: the general, map-based path (exact for everything)
     bool any_general = false;
     auto redo_flagged = [&](int f0, int nf) -> int {
+        bool first = true;
         for (int f = f0; f < f0 + nf; ++f) {
             const StreamInfo &I = h_info[f];
             if (I.status == 2) continue;  // skipped: reported to the caller
             if (!fused || h_status[f] == 1) {
+                if (first && lanes) {
+                    // the general path writes scratch set 0 and the map from the context stream: nothing of a later chunk
+                    // may be in flight on either lane (rare: a frame the bins cannot express)
+                    CU(c, cudaStreamSynchronize(c->stream_pre));
+                    CU(c, cudaStreamSynchronize(c->stream));
+                }
+                first = false;
                 PwFrameHost g{src + (n_src > 1 ? (size_t)(((long long)first_frame + f) % n_src) * (size_t)W * H : 0),
                               (uint32_t *)out_ring_dev + (size_t)I.slot * slot_px, W, H, I.x_off, I.y_off, I.o_w, I.o_h};
                 TRY(pw_inverse_general_frame(c, (const float *)c->dst_pts.p + pts_per_frame * (size_t)f, g, min_src_x, min_src_y));
@@ -2233,36 +2374,41 @@ int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int6
                 c->n_fused++;
             }
         }
+        if (!first && lanes) CU(c, cudaStreamSynchronize(c->stream));
         return HG_OK;
     };
     int prev_f0 = -1, prev_nf = 0, k = 0;
     for (int f0 = 0; f0 < n_frames; f0 += chunk, ++k) {
         const int nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        const int lane = lanes ? (k & 1) : -1;
+        const PwScratch S = pw_scratch(c, lanes ? lane : 0);
         float *dd = (float *)c->dst_pts.p + pts_per_frame * (size_t)f0;
         // this chunk's destiny points go up while the previous chunk computes (a pageable source is staged by the driver
         // before the call returns; the copy itself is stream-ordered in front of this chunk's kernels)
         CU(c, cudaMemcpyAsync(dd, dst_pts + pts_per_frame * (size_t)f0, sizeof(float) * pts_per_frame * (size_t)nf,
-                              cudaMemcpyHostToDevice, c->stream));
-        CU(c, cudaMemsetAsync(c->bin_cnt.p, 0, sizeof(unsigned) * 2 * bin_stride * (size_t)nf, c->stream));
-        CU(c, cudaMemsetAsync(c->fstatus.p, 0, sizeof(int) * (size_t)nf, c->stream));
+                              cudaMemcpyHostToDevice, pre));
+        if (lanes && k >= 2) CU(c, cudaStreamWaitEvent(pre, c->ev_pix[lane], 0));  // the lane's scratch is free again
+        if (!pw_band_binning(c)) CU(c, cudaMemsetAsync(S.bin_cnt->p, 0, sizeof(unsigned) * 2 * bin_stride * (size_t)nf, pre));
+        CU(c, cudaMemsetAsync(S.fstatus->p, 0, sizeof(int) * (size_t)nf, pre));
         StreamArgs a{};
         a.dst_pts = dd; a.n_pts = c->n_pts; a.n_frames = nf; a.frame0 = (long long)first_frame + f0;
         a.src = src; a.src_stride_px = (size_t)W * H; a.n_src = n_src; a.W = W; a.H = H;
         a.out_ring = (uint32_t *)out_ring_dev; a.slot_px = slot_px; a.n_slots = n_slots; a.max_w = max_out_w; a.max_h = max_out_h;
-        a.rec = (const TriRec *)c->rec.p; a.invd = (const float *)c->invd.p;
-        a.bin_cnt = (unsigned *)c->bin_cnt.p; a.bin_ent = (unsigned *)c->bin_ent.p; a.bin_run = (uint4 *)c->bin_run.p;
-        a.status = (int *)c->fstatus.p; a.bin_stride = bin_stride;
+        a.rec = (const TriRec *)S.rec->p; a.invd = (const float *)S.invd->p; a.yr = (const int2 *)S.yr->p;
+        a.bin_cnt = (unsigned *)S.bin_cnt->p; a.bin_ent = (unsigned *)S.bin_ent->p; a.bin_run = (uint4 *)S.bin_run->p;
+        a.status = (int *)S.fstatus->p; a.bin_stride = bin_stride;
         a.n_tris = c->n_tris; a.minSrcX = min_src_x; a.minSrcY = min_src_y;
-        a.frames_out = (FusedFrame *)c->fframes.p;
+        a.frames_out = (FusedFrame *)S.fframes->p;
         a.info_out = (StreamInfo *)c->sinfo.p + f0;
-        pw_stream_frames_kernel<<<(unsigned)((nf + 3) / 4), 128, 0, c->stream>>>(a);
+        pw_stream_frames_kernel<<<(unsigned)((nf + 3) / 4), 128, 0, pre>>>(a);
         c->launches++;
         CU(c, cudaGetLastError());
-        if (fused) TRY(pw_fused_launch(c, dd, nf, max_out_w, max_out_h, bin_stride, false));  // windows are decided on the device
-        // the scratch is reused by the next chunk: collect this chunk's status and windows first (stream-ordered copies)
-        CU(c, cudaMemcpyAsync(h_status + f0, c->fstatus.p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
+        if (fused) TRY(pw_fused_launch(c, S, lane, dd, nf, max_out_w, max_out_h, bin_stride, false));  // windows are decided on the device
+        // the scratch is reused by a later chunk: collect this chunk's status and windows first (stream-ordered copies)
+        CU(c, cudaMemcpyAsync(h_status + f0, S.fstatus->p, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaMemcpyAsync(h_info + f0, (StreamInfo *)c->sinfo.p + f0, sizeof(StreamInfo) * (size_t)nf, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaEventRecord(c->ev_chunk[k & 1], c->stream));
+        if (lanes) CU(c, cudaEventRecord(c->ev_pix[lane], c->stream));
         // while this chunk runs, look at the previous one: its flagged frames are redone behind this chunk in stream
         // order, and their slots are not touched by it (a chunk covers at most half of the ring when the stream wraps)
         if (prev_f0 >= 0) {

@@ -39,6 +39,7 @@ struct PwSetupArgs {
     float *fwd_out;         // optional dense copies (T*6)
     float *inv_out;
     float *invd_out;        // optional: inverse matrices as 32-byte records (T*8 floats per frame), for the fused kernel
+    int2 *yr_out;           // optional: the rows [y0, y_end) each triangle's fill loop visits (T per frame), for the band binning pass
     int n_tris;
     size_t dst_stride;      // frame stride (floats) for batched calls, indexed by blockIdx.y
     size_t rec_stride;
@@ -101,6 +102,8 @@ __global__ void pw_setup_kernel(PwSetupArgs a)
 #pragma unroll
         for (int k = 0; k < 6; ++k) a.inv_out[(f * a.n_tris + t) * 6 + k] = r.inv[k];
     }
+    // H.js:1114-1116: for (y = y0; y < maxY; y++) with maxY = Math.ceil(max y), an integer below 2^21 (points are validated)
+    if (a.yr_out) a.yr_out[f * a.n_tris + t] = make_int2(r.y0, (r.maxY > (double)r.y0) ? (int)r.maxY : r.y0);
     if (a.invd_out) {
         float4 *o = reinterpret_cast<float4 *>(a.invd_out + (f * a.n_tris + t) * 8);
         o[0] = make_float4(r.inv[0], r.inv[1], r.inv[2], r.inv[3]);

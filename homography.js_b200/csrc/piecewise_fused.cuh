@@ -36,6 +36,7 @@ struct FusedFrame {
     uint32_t *out;
     const TriRec *rec;     // n_tris records of this frame (edges + row range)
     const float *inv;      // n_tris * 8 floats: the f32-rounded inverse matrices, one 32-byte record each
+    const int2 *yr;        // n_tris row ranges [y0, y_end) of the triangles (pw_band_bins_kernel scans these, not the records)
     unsigned *bin_cnt;     // oH * bins_x x {entry counter, highest whole-bin id + 1} (zeroed before the span kernel)
     unsigned *bin_ent;     // oH * bins_x * PW_BIN_CAP packed entries  (t << 14 | c1 << 7 | c0)
     uint4 *bin_run;        // oH * bins_x run records (pw_bin_runs_kernel): what the pixel kernel reads
@@ -181,20 +182,20 @@ __device__ __forceinline__ int pwf_map_id(int raw, int n_tris)
 // or three entries, the fixed cost of eight-wide masks does not pay.)
 constexpr int PW_RUN_CAP = 8;
 
-// the run record of one bin from its span entries
-__device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin, uint4 &rec0, uint4 &rec1)
+// the run record of one bin from its span entries (`ent`: 16-byte aligned, global or shared memory), their count and the
+// highest id among the intervals that cover the whole bin (-1: none)
+__device__ __forceinline__ void pwf_make_record_from(const unsigned *ent_p, unsigned cnt_raw, int full_raw, int n_tris, int *status,
+                                                     uint4 &rec0, uint4 &rec1)
 {
-    const uint2 st = *reinterpret_cast<const uint2 *>(F.bin_cnt + 2 * bin);   // entries, highest whole-bin id + 1
-    const unsigned cnt = min(st.x, (unsigned)PW_BIN_CAP);
-    const int full_raw = (int)st.y - 1;   // -1: no interval covers the whole bin
+    const unsigned cnt = min(cnt_raw, (unsigned)PW_BIN_CAP);
     unsigned long long mask = 1ull;
     unsigned ids[PW_RUN_CAP / 2] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // int16 pairs, -1 = no triangle
     if (cnt == 0u) {
-        ids[0] = 0xFFFF0000u | ((unsigned)pwf_map_id(full_raw, F.n_tris) & 0xFFFFu);
+        ids[0] = 0xFFFF0000u | ((unsigned)pwf_map_id(full_raw, n_tris) & 0xFFFFu);
     } else if (cnt == 1u && full_raw < 0) {
-        const unsigned e = F.bin_ent[bin * PW_BIN_CAP];
+        const unsigned e = ent_p[0];
         const unsigned lo = e & 127u, hi = (e >> 7) & 127u;
-        const unsigned id = (unsigned)pwf_map_id((int)(e >> 14), F.n_tris) & 0xFFFFu;
+        const unsigned id = (unsigned)pwf_map_id((int)(e >> 14), n_tris) & 0xFFFFu;
         if (id != 0xFFFFu) {
             // runs: [nothing, 0..lo) [t, lo..hi) [nothing, hi..64)
             if (lo == 0u) {
@@ -208,7 +209,7 @@ __device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin,
     } else {
         unsigned ent[PW_BIN_CAP];
         {
-            const uint4 *pe = reinterpret_cast<const uint4 *>(F.bin_ent) + 2 * bin;
+            const uint4 *pe = reinterpret_cast<const uint4 *>(ent_p);
             const uint4 a = pe[0], b = cnt > 4 ? pe[1] : make_uint4(0, 0, 0, 0);
             ent[0] = a.x; ent[1] = a.y; ent[2] = a.z; ent[3] = a.w; ent[4] = b.x; ent[5] = b.y; ent[6] = b.z; ent[7] = b.w;
         }
@@ -235,10 +236,10 @@ __device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin,
                 const int lo = (int)(ent[e] & 127u), hi = (int)((ent[e] >> 7) & 127u);
                 if ((unsigned)(c - lo) < (unsigned)(hi - lo)) raw = max(raw, (int)(ent[e] >> 14));
             }
-            const int id = pwf_map_id(raw, F.n_tris);
+            const int id = pwf_map_id(raw, n_tris);
             if (id != prev) {
                 if (runs == PW_RUN_CAP) {
-                    atomicOr(F.status, 1);
+                    atomicOr(status, 1);
                     break;
                 }
                 const unsigned h = (unsigned)id & 0xFFFFu;
@@ -255,6 +256,12 @@ __device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin,
     rec1 = make_uint4(ids[0], ids[1], ids[2], ids[3]);
 }
 
+__device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin, uint4 &rec0, uint4 &rec1)
+{
+    const uint2 st = *reinterpret_cast<const uint2 *>(F.bin_cnt + 2 * bin);   // entries, highest whole-bin id + 1
+    pwf_make_record_from(F.bin_ent + bin * PW_BIN_CAP, st.x, (int)st.y - 1, F.n_tris, F.status, rec0, rec1);
+}
+
 // the records as a pass of their own: frames whose width is not a multiple of four (their first quads reach back into
 // the previous bin, whose record the pixel kernel then needs as well), the general-path comparison runs and the
 // first-generation pixel kernel read them from global memory; for the other frames the pixel kernel builds the records
@@ -269,6 +276,218 @@ __global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *fram
     pwf_make_record(F, bin, r0, r1);
     F.bin_run[2 * bin] = r0;
     F.bin_run[2 * bin + 1] = r1;
+}
+
+// ---- ONE binning pass (pw_band_bins_kernel) instead of  memset + pw_span_bin_kernel + pw_bin_runs_kernel  ----------------
+// A CTA owns a BAND of map rows (as many as fit PWB_NB_MAX bins: 17 rows of a 4K map) and keeps the band's bins — counter,
+// whole-bin id, eight entries each — in SHARED memory: the entry slots come from shared-memory atomics (no round trip to
+// L2 per entry, the latency that bounded pw_span_bin_kernel), and the run records are built from shared memory straight
+// into F.bin_run.  The global counter / entry arrays, their memset and the run pass's read-back are gone.
+//
+//   A  scan the triangles' row ranges (8 bytes each) for (triangle, row) pairs that can reach the band,
+//   B  evaluate those pairs exactly like pw_span_bin_kernel (eight lanes per triangle), clip the interval to the band, bin it,
+//   C  one run record per bin (pwf_make_record_from).
+//
+// Which pairs "can reach the band": the reference's relative index is  (y - yOff) * oW + X  with X = Math.round(x limit)
+// NOT offset by xOff, so row y of a triangle lands in map row  r + d,  r = y - yOff,  d = floor(X / oW)  (or, for a negative
+// index, oH rows further down: TypedArray.fill counts those from the end).  For X in [xOff - 1, xOff + oW + 1] — one more
+// than the window the points' extrema define — d lies in [dlo, dhi] below, and the band evaluates the rows r with
+// r + d or r + oH + d inside it.  That assumption is CHECKED, not trusted: every evaluated pair whose interval leaves the
+// rows it was assumed to reach flags the frame for the general path, and the (few, as a rule none) rows of triangles no
+// band would evaluate at all are evaluated by band 0 for that check alone.  A pair is evaluated by every band it can reach
+// ((rows + dhi - dlo) / rows times on average: 19 / 17 for a 4K frame at xOff = 0).
+#ifndef HG_PWB_THREADS
+#define HG_PWB_THREADS 256
+#endif
+#ifndef HG_PWB_MINB
+#define HG_PWB_MINB 3
+#endif
+#ifndef HG_PWB_NB
+#define HG_PWB_NB 1024
+#endif
+constexpr int PWB_THREADS = HG_PWB_THREADS;
+constexpr int PWB_NB_MAX = HG_PWB_NB;     // bins of one band (40 bytes each)
+constexpr int PWB_WORK_CAP = 2048;   // (triangle, candidate row range) segments waiting for evaluation
+constexpr int PWB_TRI_STEP = PWB_THREADS;    // triangles scanned between two looks at the worklist (at most four segments each)
+constexpr int PWB_LPS = 8;           // lanes per segment
+constexpr int PWB_MAX_ROWS = 64;     // rows per band at most
+constexpr int PWB_CHECK_ROWS = 64;   // rows of one triangle outside every band's reach that band 0 still evaluates
+constexpr size_t PWB_SMEM = (size_t)PWB_NB_MAX * (8 + 4 * PW_BIN_CAP) + (size_t)PWB_WORK_CAP * 4 + 16;
+
+__host__ __device__ inline int pwb_band_rows(int bins_x)
+{
+    const int r = PWB_NB_MAX / (bins_x > 0 ? bins_x : 1);
+    return r > PWB_MAX_ROWS ? PWB_MAX_ROWS : (r < 1 ? 1 : r);
+}
+__host__ __device__ inline int pwb_floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }   // b > 0
+
+__global__ void __launch_bounds__(PWB_THREADS, HG_PWB_MINB) pw_band_bins_kernel(const FusedFrame *frames)
+{
+    extern __shared__ uint4 pwb_smem[];
+    const FusedFrame &G = frames[blockIdx.y];
+    const int oW = G.oW, oH = G.oH;
+    if (oW <= 0 || oH <= 0) return;
+    const int bins_x = G.bins_x;
+    if (bins_x > PWB_NB_MAX) {   // the host does not launch this kernel for such frames
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(G.status, 1);
+        return;
+    }
+    const int BR = pwb_band_rows(bins_x), R0 = (int)blockIdx.x * BR;
+    if (R0 >= oH) return;
+    const int rows = min(BR, oH - R0), nb = rows * bins_x, tid = (int)threadIdx.x;
+    unsigned *s_ent = reinterpret_cast<unsigned *>(pwb_smem);
+    unsigned *s_cnt = s_ent + PWB_NB_MAX * PW_BIN_CAP, *s_full = s_cnt + PWB_NB_MAX, *s_work = s_full + PWB_NB_MAX;
+    unsigned *s_n = s_work + PWB_WORK_CAP;
+    for (int i = tid; i < nb; i += PWB_THREADS) {
+        s_cnt[i] = 0u;
+        s_full[i] = 0u;
+    }
+    if (tid == 0) *s_n = 0u;
+    const int xOff = G.xOff, yOff = G.yOff, T = G.n_tris;
+    int *status = G.status;
+    const TriRec *rec = G.rec;
+    const int2 *yr = G.yr;
+    const int dlo = pwb_floor_div(xOff - 1, oW), dhi = pwb_floor_div(xOff + oW, oW);
+    // candidate rows (inclusive, in y): A = rows that reach the band directly, B = through an index counted from the end
+    int ya0 = yOff + R0 - dhi, ya1 = yOff + R0 + rows - 1 - dlo, yb0 = ya0 - oH, yb1 = ya1 - oH;
+    if (yb1 >= ya0 - 1) {   // the two ranges meet (maps of a few rows): one range, no pair evaluated twice
+        ya0 = yb0;
+        yb1 = yb0 - 1;
+    }
+    const bool check_band = blockIdx.x == 0;
+    const int yc = yOff - oH - dhi;   // rows y < yc  and ...
+    const int yd = yOff + oH - dlo;   // ... rows y >= yd reach no band under the assumption: band 0 verifies that
+    const unsigned band_k0 = (unsigned)R0 * (unsigned)oW, band_k1 = (unsigned)(R0 + rows) * (unsigned)oW;
+    const unsigned len = (unsigned)oW * (unsigned)oH;
+    const double mw = (double)oW, yoff = (double)yOff, dlen = (double)len;
+    __syncthreads();
+
+    for (int tb = 0; tb < T; tb += PWB_TRI_STEP) {
+        // ---- A: segments of the next PWB_TRI_STEP triangles
+#pragma unroll
+        for (int u = 0; u < PWB_TRI_STEP / PWB_THREADS; ++u) {
+            const int t = tb + u * PWB_THREADS + tid;
+            if (t >= T) break;
+            const int2 b = __ldg(yr + t);   // rows [b.x, b.y)
+            if (max(b.x, ya0) <= min(b.y - 1, ya1)) s_work[atomicAdd(s_n, 1u)] = (unsigned)t;
+            if (max(b.x, yb0) <= min(b.y - 1, yb1)) s_work[atomicAdd(s_n, 1u)] = (unsigned)t | (1u << 17);
+            if (check_band) {
+                const int nc = min(b.y, yc) - b.x, nd = b.y - max(b.x, yd);
+                if (nc > PWB_CHECK_ROWS || nd > PWB_CHECK_ROWS) atomicOr(status, 1);   // a window far smaller than the mesh
+                else {
+                    if (nc > 0) s_work[atomicAdd(s_n, 1u)] = (unsigned)t | (2u << 17);
+                    if (nd > 0) s_work[atomicAdd(s_n, 1u)] = (unsigned)t | (3u << 17);
+                }
+            }
+        }
+        __syncthreads();
+        const int n_work = (int)*s_n;
+        __syncthreads();   // everyone has read the count before the next step appends to it
+        if (n_work <= PWB_WORK_CAP - 4 * PWB_TRI_STEP && tb + PWB_TRI_STEP < T) continue;   // room for another step (CTA-uniform)
+        // ---- B: evaluate, `lps` lanes per segment (8 .. 32: as many as keep the CTA's threads busy with the segments at hand)
+        int lps = PWB_LPS;
+        while (lps < 32 && n_work * lps < PWB_THREADS) lps <<= 1;
+        for (int sg = tid / lps; sg < n_work; sg += PWB_THREADS / lps) {
+            const unsigned w = s_work[sg];
+            const int t = (int)(w & 0x1FFFFu), which = (int)(w >> 17);
+            const int2 b = __ldg(yr + t);
+            int lo, hi;
+            if (which == 0) { lo = max(b.x, ya0); hi = min(b.y - 1, ya1); }
+            else if (which == 1) { lo = max(b.x, yb0); hi = min(b.y - 1, yb1); }
+            else if (which == 2) { lo = b.x; hi = min(b.y, yc) - 1; }
+            else { lo = max(b.x, yd); hi = b.y - 1; }
+            TriRec r;
+            {
+                const TriRec *__restrict__ g = rec + t;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) { r.m[e] = __ldg(&g->m[e]); r.b[e] = __ldg(&g->b[e]); r.lo[e] = __ldg(&g->lo[e]); r.hi[e] = __ldg(&g->hi[e]); }
+            }
+            const unsigned tt = (unsigned)t << 14;
+            for (int yy = lo + (tid & (lps - 1)); yy <= hi; yy += lps) {
+                const double y = (double)yy;
+                double xo, xd;
+                predict_x_limits(r, y, xo, xd);
+                const double rowbase = __dmul_rn(__dsub_rn(y, yoff), mw);
+                const double rel0 = __dadd_rn(rowbase, js_round(xo)), rel1 = __dadd_rn(rowbase, js_round(xd));
+                unsigned k0, k1;
+                if (rel0 >= 0.0 && rel0 < dlen && rel1 >= 0.0) {
+                    k0 = (unsigned)(int)rel0;
+                    k1 = rel1 < dlen ? (unsigned)(int)rel1 : len;
+                } else {
+                    k0 = (unsigned)js_fill_bound(rel0, (long long)len);
+                    k1 = (unsigned)js_fill_bound(rel1, (long long)len);
+                }
+                if (k0 >= k1) continue;
+                // the interval must stay inside the rows this pair was assumed to reach (see above)
+                const int rr = yy - yOff, ra = (int)(k0 / (unsigned)oW), rz = (int)((k1 - 1u) / (unsigned)oW);
+                const bool direct = ra >= rr + dlo && rz <= rr + dhi, wrapped = ra >= rr + oH + dlo && rz <= rr + oH + dhi;
+                if (!(direct || wrapped)) {
+                    atomicOr(status, 1);
+                    continue;
+                }
+                unsigned a = max(k0, band_k0);
+                const unsigned z = min(k1, band_k1);
+                if (a >= z) continue;
+                unsigned row = a / (unsigned)oW, c0 = a - row * (unsigned)oW;
+                while (a < z) {
+                    const unsigned room = (unsigned)oW - c0, want = z - a, n = want < room ? want : room;
+                    const unsigned c1 = c0 + n;
+                    const unsigned base = (row - (unsigned)R0) * (unsigned)bins_x;
+                    const unsigned b_first = c0 / PW_BIN_W, b_last = (c1 - 1u) / PW_BIN_W;
+                    const unsigned blo = c0 - b_first * PW_BIN_W, bhi = c1 - b_last * PW_BIN_W;
+                    unsigned e_bin[2], e_val[2];
+                    int ne = 0;
+                    if (b_first == b_last) {
+                        if (blo == 0u && bhi == (unsigned)PW_BIN_W) atomicMax(s_full + base + b_first, (unsigned)t + 1u);
+                        else { e_bin[ne] = base + b_first; e_val[ne++] = tt | (bhi << 7) | blo; }
+                    } else {
+                        if (blo == 0u) atomicMax(s_full + base + b_first, (unsigned)t + 1u);
+                        else { e_bin[ne] = base + b_first; e_val[ne++] = tt | ((unsigned)PW_BIN_W << 7) | blo; }
+                        for (unsigned bb = b_first + 1u; bb < b_last; ++bb) atomicMax(s_full + base + bb, (unsigned)t + 1u);
+                        if (bhi == (unsigned)PW_BIN_W) atomicMax(s_full + base + b_last, (unsigned)t + 1u);
+                        else { e_bin[ne] = base + b_last; e_val[ne++] = tt | (bhi << 7); }
+                    }
+                    for (int e = 0; e < ne; ++e) {
+                        const unsigned slot = atomicAdd(s_cnt + e_bin[e], 1u);
+                        if (slot < (unsigned)PW_BIN_CAP) s_ent[e_bin[e] * PW_BIN_CAP + slot] = e_val[e];
+                        else atomicOr(status, 1);
+                    }
+                    a += n;
+                    ++row;
+                    c0 = 0u;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) *s_n = 0u;
+        __syncthreads();
+    }
+
+    // ---- C: the run records of the band.  Bins without an entry, or with one entry and nothing behind it (most bins of a
+    // coarse mesh), are encoded on the spot; the others are collected and resolved in a second, dense sweep — otherwise
+    // every warp walks the general path for the few of its lanes that need it.
+    uint4 *out = G.bin_run + 2 * (size_t)R0 * (size_t)bins_x;
+    for (int i = tid; i < nb; i += PWB_THREADS) {
+        const unsigned cnt = s_cnt[i];
+        const int full_raw = (int)s_full[i] - 1;
+        if (cnt == 0u || (cnt == 1u && full_raw < 0)) {
+            uint4 r0, r1;
+            pwf_make_record_from(s_ent + (size_t)i * PW_BIN_CAP, cnt, full_raw, T, status, r0, r1);
+            out[2 * i] = r0;
+            out[2 * i + 1] = r1;
+        } else {
+            s_work[atomicAdd(s_n, 1u)] = (unsigned)i;   // nb <= PWB_NB_MAX <= PWB_WORK_CAP
+        }
+    }
+    __syncthreads();
+    const int n_gen = (int)*s_n;
+    for (int j = tid; j < n_gen; j += PWB_THREADS) {
+        const int i = (int)s_work[j];
+        uint4 r0, r1;
+        pwf_make_record_from(s_ent + (size_t)i * PW_BIN_CAP, s_cnt[i], (int)s_full[i] - 1, T, status, r0, r1);
+        out[2 * i] = r0;
+        out[2 * i + 1] = r1;
+    }
 }
 
 // id of run r (0..7) from the packed int16 ids

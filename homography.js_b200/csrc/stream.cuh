@@ -33,6 +33,7 @@ struct StreamArgs {
     int n_slots, max_w, max_h;
     const TriRec *rec;
     const float *invd;
+    const int2 *yr;
     unsigned *bin_cnt, *bin_ent;
     uint4 *bin_run;
     int *status;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(128) pw_stream_frames_kernel(const StreamArgs 
     F.out = a.out_ring + (size_t)slot * a.slot_px;
     F.rec = a.rec + (size_t)a.n_tris * f;
     F.inv = a.invd + 8 * (size_t)a.n_tris * f;
+    F.yr = a.yr + (size_t)a.n_tris * f;
     F.bin_cnt = a.bin_cnt + 2 * a.bin_stride * f;
     F.bin_ent = a.bin_ent + a.bin_stride * f * PW_BIN_CAP;
     F.bin_run = a.bin_run + 2 * a.bin_stride * f;

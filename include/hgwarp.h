@@ -267,6 +267,9 @@ int hg_debug_rcp_max_error(hg_ctx *ctx, int biased_exponent, int negative, doubl
 int hg_debug_quotient_at_least(hg_ctx *ctx, const double *N, const double *D, const double *b, int n, int *out);
 /* on != 0: inverse piecewise warps always take the general map-based path (tests compare it with the fused one) */
 int hg_debug_force_general(hg_ctx *ctx, int on);
+/* how the fused path bins a frame's triangle rows: 0 = automatic, 1 = span + run passes over global bins, 2 = one pass per
+ * band of map rows through shared memory (tests run every frame through both and compare) */
+int hg_debug_piecewise_binning(hg_ctx *ctx, int mode);
 /* how many inverse piecewise frames were finished by the fused (map-free) path / by the general map-based path */
 int hg_debug_piecewise_stats(hg_ctx *ctx, uint64_t *frames_fused, uint64_t *frames_general);
 

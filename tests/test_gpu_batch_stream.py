@@ -241,6 +241,20 @@ def test_stream_windows_and_pixels_bit_exact(ctx):
     assert _stream_case(ctx, n_frames=12, n_slots=16) == 12
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_stream_under_both_binning_passes(ctx, mode):
+    """span + run passes over global bins (1) and the one-pass band binning through shared memory (2): same bytes, and
+    neither hands a frame to the map-based path."""
+    ctx.debug_piecewise_binning(mode)
+    try:
+        f0, g0 = ctx.debug_piecewise_stats()
+        assert _stream_case(ctx, n_frames=23, n_slots=8, n_src=3, first=7) == 8
+        f1, g1 = ctx.debug_piecewise_stats()
+        assert (f1 - f0, g1 - g0) == (23, 0)
+    finally:
+        ctx.debug_piecewise_binning(0)
+
+
 def test_stream_wraps_the_ring_and_reads_a_source_ring(ctx):
     assert _stream_case(ctx, n_frames=23, n_slots=8, n_src=3, first=1000) == 8
 

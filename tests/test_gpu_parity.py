@@ -440,29 +440,34 @@ def test_forward_piecewise_bit_exact(ctx, seed):
 
 
 # ------------------------------------------------------------------ fused (map-free) piecewise path
-def _pw_case(ctx, img, src, dst, tris, force_general=False):
+BINNINGS = {"span": 1, "band": 2}   # hg_debug_piecewise_binning: the two ways the fused path bins triangle rows
+
+
+def _pw_case(ctx, img, src, dst, tris, force_general=False, binning=None, window=None):
     H, W = img.shape[:2]
     mm = O.minmax_xy(dst)
-    xo, yo, oW, oH = int(mm[0]), int(mm[1]), int(mm[2] - mm[0]), int(mm[3] - mm[1])
+    xo, yo, oW, oH = window or (int(mm[0]), int(mm[1]), int(mm[2] - mm[0]), int(mm[3] - mm[1]))
     if oW < 1 or oH < 1:
         return
     smm = O.minmax_xy(src)
     ctx.image_set(img, W, H)
     ctx.piecewise_set_mesh(src, tris)
     ctx.debug_force_general(force_general)
+    ctx.debug_piecewise_binning(BINNINGS.get(binning, 0))
     try:
         got = ctx.warp_piecewise_inverse(dst, xo, yo, oW, oH, int(smm[0]), int(smm[1]))
     finally:
         ctx.debug_force_general(False)
+        ctx.debug_piecewise_binning(0)
     fwd = O.piecewise_matrices(src, dst, tris)
     imap = O.build_index_map(dst, tris, oW, yo, oW * oH)
     want = O.warp_inverse_piecewise(img, W, H, imap, O.inverse_matrices(fwd), xo, yo, oW, oH, int(smm[0]), int(smm[1]), threads=4)
-    assert _diff(got, want) == 0, f"{_diff(got, want)} of {oW * oH} pixels differ (force_general={force_general})"
+    assert _diff(got, want) == 0, f"{_diff(got, want)} of {oW * oH} pixels differ (force_general={force_general}, binning={binning})"
 
 
 @pytest.mark.parametrize("seed", range(10))
-@pytest.mark.parametrize("force_general", [False, True])
-def test_piecewise_irregular_frames_fused_and_general(ctx, seed, force_general):
+@pytest.mark.parametrize("path", ["span", "band", "general"])
+def test_piecewise_irregular_frames_fused_and_general(ctx, seed, path):
     """Offsets != 0 (Q4: spans spill over row ends), ~~minY < round(minY) (Q5: fills wrap to the END of the map),
     negative coordinates, non-multiple-of-4 widths, folded meshes with many overlaps (bin overflow -> fallback)."""
     rng = np.random.default_rng(700 + seed)
@@ -481,7 +486,24 @@ def test_piecewise_irregular_frames_fused_and_general(ctx, seed, force_general):
         dst = dst * [1.117, 0.93] + [0.6, 0.7]
     else:              # minification far below 1/1.2
         dst = dst * 0.31 + [3.3, 2.2]
-    _pw_case(ctx, img, src, dst.astype(np.float32), tris, force_general)
+    _pw_case(ctx, img, src, dst.astype(np.float32), tris, path == "general", path)
+
+
+@pytest.mark.parametrize("binning", ["span", "band"])
+def test_piecewise_windows_unrelated_to_the_mesh(ctx, binning):
+    """The C ABI takes any window: cropped inside the mesh, far to its right / below it (spans land many rows away from
+    their own, or nowhere), a one-row and a one-column map, a window whose width is smaller than the mesh offset."""
+    rng = np.random.default_rng(4242)
+    W, H = 200, 150
+    img = _rand_img(17, W, H)
+    src, tris = _grid_mesh(7, 6, W, H)
+    dst = (src * 1.1 + rng.uniform(-4, 4, src.shape) + [25.3, 11.6]).astype(np.float32)
+    f0, g0 = ctx.debug_piecewise_stats()
+    for window in ((60, 40, 90, 70), (0, 0, 300, 200), (-40, -30, 120, 100), (150, 100, 64, 300), (30, 50, 1, 80),
+                   (30, 50, 130, 1), (200, 12, 17, 160), (26, 12, 7, 5), (-500, 0, 800, 90), (0, -400, 250, 700)):
+        _pw_case(ctx, img, src, dst, tris, binning=binning, window=window)
+    f1, g1 = ctx.debug_piecewise_stats()
+    assert f1 - f0 >= 3, "every window fell back to the map-based path"
 
 
 def test_piecewise_random_triangle_soup(ctx):
@@ -492,17 +514,21 @@ def test_piecewise_random_triangle_soup(ctx):
     src = rng.uniform(0, [W, H], (14, 2)).astype(np.float32)
     dst = (src + rng.uniform(-25, 25, src.shape) + 12).astype(np.float32)
     tris = rng.integers(0, 14, (20, 3)).astype(np.uint32)
-    for fg in (False, True):
-        _pw_case(ctx, img, src, dst, tris, fg)
+    for fg, binning in ((False, "span"), (False, "band"), (True, None)):
+        _pw_case(ctx, img, src, dst, tris, fg, binning)
 
 
-def test_config4_mesh_one_frame_4k(ctx):
+@pytest.mark.parametrize("binning", ["span", "band"])
+def test_config4_mesh_one_frame_4k(ctx, binning):
     """Config 4 mesh (64x64 points, 7,938 triangles) on a 3840x2160 frame, one frame, all pixels."""
     import homography_js_b200 as hgm
     w, h = 3840, 2160
     img = _rand_img(4, w, h)
     src, dst, tris = hgm.workloads.piecewise_sinusoid(64, 64, w, h, phase=0.7)
-    _pw_case(ctx, img, src, dst, tris)
+    f0, g0 = ctx.debug_piecewise_stats()
+    _pw_case(ctx, img, src, dst, tris, binning=binning)
+    f1, g1 = ctx.debug_piecewise_stats()
+    assert (f1 - f0, g1 - g0) == (1, 0), "the frame fell back to the general path"
 
 
 def test_piecewise_batch_matches_oracle(ctx):
