@@ -71,68 +71,77 @@ struct FwdParams {
     const FwdArgs *many;     // device array, indexed by blockIdx.y
 };
 
-// pass 1.  A thread takes four consecutive source pixels of one row of the loop domain per step (one division per quad,
-// the row terms m2*y / m3*y once per quad; a piecewise quad fetches a triangle's forward matrix only when the triangle
-// changes).  Every product and sum is the reference's own (H.js:1382-1385 / 1401-1404): unfused, in its order.
-template <bool PIECEWISE>
+// pass 1.  A WARP takes 128 consecutive source pixels of one row of the loop domain per step, lane l the pixels l, l + 32,
+// l + 64, l + 96: the 32 atomics of one instruction then land on 32 neighbouring targets for maps near the identity (four
+// 32-byte sectors, i.e. four requests to the L2 atomic units) instead of 32 targets four pixels apart (sixteen).  One
+// division per warp step, the row terms m2*y / m3*y once per step; a piecewise lane fetches a triangle's forward matrix only
+// when the triangle changes.  The frame's constants are copied to registers first: through the descriptor reference every
+// field would be re-read after each atomic (the compiler must assume the atomic wrote it) — 8 % of the first version's
+// instructions were such loads.  Every product and sum is the reference's own (H.js:1382-1385 / 1401-1404): unfused, in
+// its order.  MODE: 0 affine, 1 projective (host-dispatched: a batch has one kind), 2 piecewise.
+template <int MODE>
 __global__ void __launch_bounds__(256) forward_scatter_kernel(const FwdParams P)
 {
-    const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
-    if (a.lattice) return;
-    const int domW = a.domW, nq_row = (domW + 3) >> 2;
-    const int nquads = nq_row * a.domH;  // < 2^31 (checked on the host)
-    const long long npix_out = (long long)a.oW * a.oH;
-    const int stride = (int)(gridDim.x * blockDim.x);
+    const FwdArgs &g = P.many ? P.many[blockIdx.y] : P.one;
+    if (g.lattice) return;
+    const int domW = g.domW, domH = g.domH, minX = g.minX, minY = g.minY, oW = g.oW, xOff = g.xOff, yOff = g.yOff, n_tris = g.n_tris;
+    int *const winner = g.winner;
+    const int *const map32 = g.map32;
+    const TriRec *const rec = g.rec;
+    const long long map_len = g.map_len;
+    const long long npix_out = (long long)oW * g.oH;
     double m[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = PIECEWISE ? 0.0 : ((a.kind == 0 && k < 6) ? (double)(float)a.mat[k] : a.mat[k]);
+    for (int k = 0; k < 8; ++k) m[k] = MODE == 2 ? 0.0 : ((MODE == 0 && k < 6) ? (double)(float)g.mat[k] : g.mat[k]);
+    const int nseg_row = (domW + 127) >> 7;
+    const int nseg = nseg_row * domH;  // 128-pixel steps; loop-domain pixels < 2^31 (checked on the host)
+    const int lane = (int)(threadIdx.x & 31u);
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
     int t_have = -1;
-    for (int q = (int)(blockIdx.x * blockDim.x + threadIdx.x); q < nquads; q += stride) {
-        const int yy = q / nq_row;
-        const int xx0 = (q - yy * nq_row) << 2;
-        const double y = (double)(a.minY + yy);
-        const long long key0 = (long long)yy * domW + xx0;
+    for (int sg = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); sg < nseg; sg += nwarps) {
+        const int yy = sg / nseg_row;
+        const int xx0 = ((sg - yy * nseg_row) << 7) + lane;
+        const double y = (double)(minY + yy);
+        const int key0 = yy * domW + xx0;
         int tq[4] = {-1, -1, -1, -1};
-        if (PIECEWISE) {
+        if (MODE == 2) {
             // map[key]: entries past the end read `undefined` (> -1 is false); Int16Array semantics of the stored id
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (xx0 + k < domW && key0 + k < a.map_len) {
-                    const int raw = __ldg(a.map32 + key0 + k);
+                if (xx0 + 32 * k < domW && (long long)key0 + 32 * k < map_len) {
+                    const int raw = __ldg(map32 + key0 + 32 * k);
                     const int t = (raw < 0) ? -1 : (int)(short)(unsigned short)(raw & 0xFFFF);
-                    tq[k] = (t >= 0 && t < a.n_tris) ? t : -1;
+                    tq[k] = (t >= 0 && t < n_tris) ? t : -1;
                 }
             }
         }
         double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-        if (!PIECEWISE) {
-            if (a.kind == 0) {
-                r0 = __dmul_rn(m[2], y);
-                r1 = __dmul_rn(m[3], y);
-            } else {
-                r0 = __dmul_rn(m[1], y);
-                r1 = __dmul_rn(m[4], y);
-                r2 = __dmul_rn(m[7], y);
-            }
+        if (MODE == 0) {
+            r0 = __dmul_rn(m[2], y);
+            r1 = __dmul_rn(m[3], y);
+        } else if (MODE == 1) {
+            r0 = __dmul_rn(m[1], y);
+            r1 = __dmul_rn(m[4], y);
+            r2 = __dmul_rn(m[7], y);
         }
+        const double x_first = (double)(minX + xx0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int xx = xx0 + k;
-            if (xx >= domW) break;
-            const double x = (double)(a.minX + xx);
+            if (xx0 + 32 * k >= domW) break;
+            const double x = __dadd_rn(x_first, (double)(32 * k));   // exact: small integers
             double tx, ty;
-            if (PIECEWISE) {
+            if (MODE == 2) {
                 const int t = tq[k];
                 if (t < 0) continue;
                 if (t != t_have) {
-                    const float *f = a.rec[t].fwd;
+                    const float *f = rec[t].fwd;
 #pragma unroll
                     for (int c = 0; c < 6; ++c) m[c] = (double)__ldg(f + c);
                     t_have = t;
                 }
                 tx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[2], y)), m[4]);
                 ty = __dadd_rn(__dadd_rn(__dmul_rn(m[1], x), __dmul_rn(m[3], y)), m[5]);
-            } else if (a.kind == 0) {
+            } else if (MODE == 0) {
                 tx = __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), r0), m[4]);
                 ty = __dadd_rn(__dadd_rn(__dmul_rn(m[1], x), r1), m[5]);
             } else {
@@ -140,8 +149,8 @@ __global__ void __launch_bounds__(256) forward_scatter_kernel(const FwdParams P)
                 tx = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[0], x), r0), m[2]), den);
                 ty = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[3], x), r1), m[5]), den);
             }
-            const long long p = forward_target(tx, ty, a.xOff, a.yOff, a.oW, npix_out);
-            if (p >= 0) atomicMax(a.winner + p, (int)(key0 + k));
+            const long long p = forward_target(tx, ty, xOff, yOff, oW, npix_out);
+            if (p >= 0) atomicMax(winner + p, key0 + 32 * k);
         }
     }
 }
@@ -149,23 +158,29 @@ __global__ void __launch_bounds__(256) forward_scatter_kernel(const FwdParams P)
 // pass 2: every output pixel takes the source pixel of its winning key (or stays transparent) and hands the plane
 // entry back as -1.  When the loop domain is the image itself (always for _geometricWarp; for _piecewiseAffineWarp when
 // the source points span the image) the key IS the flat source index: no division.
+#ifndef HG_FWD_GATHER_U
+#define HG_FWD_GATHER_U 2
+#endif
+constexpr int FWD_GU = HG_FWD_GATHER_U;   // quads per thread and step of the gather pass
 __global__ void __launch_bounds__(256) forward_gather_kernel(const FwdParams P)
 {
-    const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
-    if (a.lattice) return;
-    const int npix = a.oW * a.oH;  // < 2^31 (checked on the host)
+    const FwdArgs &g = P.many ? P.many[blockIdx.y] : P.one;
+    if (g.lattice) return;
+    // the frame's constants in registers (the stores below may alias the descriptor as far as the compiler knows)
+    struct { int *winner; uint32_t *out; int domW, W, minX, minY; } a = {g.winner, g.out, g.domW, g.W, g.minX, g.minY};
+    const int npix = g.oW * g.oH;  // < 2^31 (checked on the host)
     const int nquad = (npix + 3) >> 2;
-    const long long npx_src = (long long)a.W * a.H;
+    const long long npx_src = (long long)g.W * g.H;
     const int stride = (int)(gridDim.x * blockDim.x);
-    const bool key_is_flat = a.domW == a.W && a.minX == 0 && a.minY == 0;
-    const uint32_t *__restrict__ src = a.src;
+    const bool key_is_flat = g.domW == g.W && g.minX == 0 && g.minY == 0;
+    const uint32_t *__restrict__ src = g.src;
     // two quads per thread and step, a grid stride apart: both plane reads go out first, then the eight gathers that depend
     // on them, then the two stores (the pass is bound by this chain of dependent loads)
-    for (int q = (int)(blockIdx.x * blockDim.x + threadIdx.x); q < nquad; q += 2 * stride) {
-        int key[2][4];
-        uint32_t px[2][4];
+    for (int q = (int)(blockIdx.x * blockDim.x + threadIdx.x); q < nquad; q += FWD_GU * stride) {
+        int key[FWD_GU][4];
+        uint32_t px[FWD_GU][4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < FWD_GU; ++u) {
             const int p0 = (q + u * stride) << 2;
 #pragma unroll
             for (int k = 0; k < 4; ++k) key[u][k] = -1;
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(256) forward_gather_kernel(const FwdParams P)
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < FWD_GU; ++u)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 uint32_t v = 0u;
@@ -202,7 +217,7 @@ __global__ void __launch_bounds__(256) forward_gather_kernel(const FwdParams P)
                 px[u][k] = v;
             }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < FWD_GU; ++u) {
             const int p0 = (q + u * stride) << 2;
             if (q + u * stride >= nquad) continue;
             if (p0 + 3 < npix) {

@@ -105,6 +105,7 @@ struct hg_ctx {
     bool pwf_v1 = false;            // HG_PWF_V1: first-generation fused piecewise pixel kernel (A/B runs)
     bool geo_async = false;         // HG_GEO_ASYNC: affine / projective pixel loop with asynchronous gathers (A/B runs)
     int pw_chunk = 0;               // HG_PW_CHUNK: frames per pipelined chunk of the piecewise batch / stream calls (0: 64; 16 with two lanes)
+    int fwd_plane_mb = 48;          // HG_FWD_PLANE_MB: budget of the forward batches' winner planes (kept L2-resident)
     int pw_binning = 0;             // HG_PW_BINNING / hg_debug_piecewise_binning: 0 auto, 1 span + run passes, 2 one band pass
     bool pw_serial = true;          // unless HG_PW_LANES: one lane — every chunk's binning passes in front of its pixel kernel
     bool pwf_records_inline = false;  // HG_PWF_RECORDS_INLINE: the pixel kernel builds the run records of aligned frames itself (A/B runs)
@@ -542,6 +543,7 @@ int hg_ctx_create(int device, hg_ctx **out)
         env_int("HG_PW_CHUNK", 1, 1024, c->pw_chunk);
         c->pw_serial = getenv("HG_PW_LANES") == nullptr;
         env_int("HG_PW_BINNING", 0, 2, c->pw_binning);
+        env_int("HG_FWD_PLANE_MB", 1, 4096, c->fwd_plane_mb);
         CUC(cudaFuncSetAttribute(pw_band_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWB_SMEM));
         // the ring must fit a CTA's shared memory: shrink the depth (the CTA count follows from the occupancy below)
         const size_t cta_max = prop.sharedMemPerBlockOptin;
@@ -958,8 +960,9 @@ static int run_forward(hg_ctx *c, FwdArgs &a, bool piecewise, uint32_t *dst, siz
     TRY(prof_begin(c));
     if (n > 0) {
         const dim3 g(fwd_blocks(c, n, 1), 1);
-        if (piecewise) forward_scatter_kernel<true><<<g, 256, 0, c->stream>>>(P);
-        else forward_scatter_kernel<false><<<g, 256, 0, c->stream>>>(P);
+        if (piecewise) forward_scatter_kernel<2><<<g, 256, 0, c->stream>>>(P);
+        else if (a.kind == 0) forward_scatter_kernel<0><<<g, 256, 0, c->stream>>>(P);
+        else forward_scatter_kernel<1><<<g, 256, 0, c->stream>>>(P);
         c->launches++;
         CU(c, cudaGetLastError());
     }
@@ -986,7 +989,7 @@ static int run_forward_batch(hg_ctx *c, std::vector<FwdArgs> &fa, bool piecewise
     }
     max_npix = (max_npix + 3) & ~3LL;  // planes start 16-byte aligned (the gather pass reads and resets them four at a time)
     // planes: as many as fit ~48 MB (they are read, reset and re-used while L2-resident), between 1 and 8
-    int planes = (int)((48ll << 20) / (max_npix * 4));
+    int planes = (int)(((long long)c->fwd_plane_mb << 20) / (max_npix * 4));
     if (planes < 1) planes = 1;
     if (planes > 8) planes = 8;
     // two lanes of sub-batches on two streams, each with its own half of the planes: the scatter of one sub-batch (bound by
@@ -1046,8 +1049,9 @@ static int run_forward_batch(hg_ctx *c, std::vector<FwdArgs> &fa, bool piecewise
                 FwdParams P{};
                 P.many = (const FwdArgs *)c->fwd_args.p + f0;
                 const dim3 gs(fwd_blocks(c, max_dom, nf), (unsigned)nf), gg(fwd_blocks(c, (max_npix + 3) / 4, nf), (unsigned)nf);
-                if (piecewise) forward_scatter_kernel<true><<<gs, 256, 0, st>>>(P);
-                else forward_scatter_kernel<false><<<gs, 256, 0, st>>>(P);
+                if (piecewise) forward_scatter_kernel<2><<<gs, 256, 0, st>>>(P);
+                else if (fa[0].kind == 0) forward_scatter_kernel<0><<<gs, 256, 0, st>>>(P);   // one kind per batch
+                else forward_scatter_kernel<1><<<gs, 256, 0, st>>>(P);
                 forward_gather_kernel<<<gg, 256, 0, st>>>(P);
                 c->launches += 2;
                 ++sub;
