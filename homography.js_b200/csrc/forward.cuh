@@ -281,7 +281,8 @@ __device__ __forceinline__ void lattice_quad_store(uint32_t *out, int p0, int np
 
 __global__ void __launch_bounds__(256) forward_lattice_kernel(const FwdParams P)
 {
-    const FwdArgs &a = P.many ? P.many[blockIdx.y] : P.one;
+    // by value: through a reference every field would be re-read after each store (which may alias the descriptor)
+    const FwdArgs a = P.many ? P.many[blockIdx.y] : P.one;
     if (!a.lattice) return;
     const int npix = a.oW * a.oH;  // < 2^31 (checked on the host)
     const int nquad = (npix + 3) >> 2;

@@ -92,7 +92,7 @@ __device__ __forceinline__ void pw_emit_entry(PwPending &p, unsigned *cnt, unsig
 template <bool DEFER>
 __global__ void __launch_bounds__(128, HG_SPAN_MINB) pw_span_bin_kernel(const FusedFrame *frames, int lpt_log2)
 {
-    const FusedFrame &F = frames[blockIdx.y];
+    const FusedFrame F = frames[blockIdx.y];   // by value: the atomics below may alias the descriptor as far as the compiler knows
     const unsigned gid = blockIdx.x * 128u + threadIdx.x;
     const int t = (int)(gid >> lpt_log2);
     if (t >= F.n_tris) return;
@@ -268,7 +268,7 @@ __device__ __forceinline__ void pwf_make_record(const FusedFrame &F, size_t bin,
 // of its rows itself, straight into shared memory (pw_warp_fused_kernel, records_inline)
 __global__ void __launch_bounds__(128) pw_bin_runs_kernel(const FusedFrame *frames)
 {
-    const FusedFrame &F = frames[blockIdx.y];
+    const FusedFrame F = frames[blockIdx.y];
     const size_t nbins = (size_t)F.bins_x * F.oH;
     const size_t bin = (size_t)blockIdx.x * 128 + threadIdx.x;
     if (bin >= nbins) return;
