@@ -387,7 +387,7 @@ def sec_config4(env, frames: int, steps: int, warmup: int):
     """BASELINE config 4: piecewise sinusoid over a 64x64 grid (7,938 triangles), 3840x2160, `frames` frames per GPU per step
     (4096 over 8 GPUs), frame f of the whole job using phase 2 pi f / total (distinct destiny points, matrices and triangle
     map per frame, H.js:1033-1038), streamed through hg_warp_piecewise_stream: output windows on the device, sources from a
-    ring of 8 distinct images per GPU, outputs into a ring of 32 slots (> 1 GB)."""
+    ring of 8 distinct images per GPU, outputs into a ring of 128 slots (4.8 GB: chunks of 64 frames per launch chain)."""
     torch, hg, ctx = env.torch, env.hg, env.ctx
     w, h, nx = 3840, 2160, 64
     total = frames * env.world
@@ -400,7 +400,7 @@ def sec_config4(env, frames: int, steps: int, warmup: int):
     dst_all = np.repeat(src[None, :, :], F, axis=0).copy()
     dst_all[:, :, 1] = (A + src[None, :, 1].astype(np.float64) + A * np.sin(2 * math.pi * 2 * xs[None, :] / w + ph[:, None])).astype(np.float32)
     ctx.piecewise_set_mesh(src, tris)
-    n_src, n_slots = 8, 32
+    n_src, n_slots = 8, 128
     max_w, max_h = w + 8, int(h + 2 * A) + 16
     slot = ctx.stream_slot_bytes(max_w, max_h)
     g = torch.Generator(device=env.dev)
@@ -852,6 +852,7 @@ def run_headline(env, wl_name: str, with_secondary: bool):
             raise SystemExit("parity gate failed: host-to-host output differs from the oracle")
     pipe.close()
     # (c) the ceiling of the host link, all ranks probing at the same moment: raw pinned copies, both directions at once
+    ctx.pcie_probe(64 << 20, 1)       # the context pins the probe's buffers once: the timed call below starts copying at once
     env.barrier()
     p_h2d, p_d2h, p_bi = ctx.pcie_probe(64 << 20, 6)
     env.barrier()

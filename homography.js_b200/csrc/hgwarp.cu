@@ -81,6 +81,11 @@ struct hg_ctx {
     cudaStream_t stream2 = nullptr;                // second lane of forward batches (scatter of one sub-batch beside the gather of another)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     size_t pin_big_cap = 0;
+    // hg_pcie_probe keeps its buffers between calls (see there)
+    void *probe_h[2] = {nullptr, nullptr}, *probe_d[2] = {nullptr, nullptr};
+    cudaStream_t probe_s[2] = {nullptr, nullptr};
+    cudaEvent_t probe_e[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t probe_bytes = 0;
     // parameters of the last inverse index map (rebuilt on demand for the aliasing forward read, Q8)
     std::vector<float> last_inv_pts;
     double last_inv_mw = 0, last_inv_yoff = 0;
@@ -569,11 +574,21 @@ int hg_ctx_create(int device, hg_ctx **out)
     return HG_OK;
 }
 
+static void hg_pcie_probe_release(hg_ctx *c)
+{
+    for (auto &ev : c->probe_e) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    for (auto &st : c->probe_s) { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } st = nullptr; }
+    for (auto &p : c->probe_d) { if (p) cudaFree(p); p = nullptr; }
+    for (auto &p : c->probe_h) { if (p) cudaFreeHost(p); p = nullptr; }
+    c->probe_bytes = 0;
+}
+
 int hg_ctx_destroy(hg_ctx *c)
 {
     if (!c) return HG_ERR_INVALID;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    hg_pcie_probe_release(c);
     DevBuf *bufs[] = {&c->img_own, &c->out, &c->scratch, &c->src_pts, &c->dst_pts, &c->tris,
                       &c->rec, &c->map32, &c->map16, &c->frames, &c->mats, &c->winner,
                       &c->invd, &c->bin_cnt, &c->bin_ent, &c->bin_run, &c->fstatus, &c->fframes, &c->tm_dev,
@@ -2526,22 +2541,30 @@ int hg_pcie_probe(hg_ctx *c, size_t bytes, int iters, double *h2d_gbs, double *d
     BIND(c);
     NEED(c, h2d_gbs && d2h_gbs && bidir_gbs, "NULL argument");
     NEED(c, bytes >= 4096 && bytes <= (1ull << 31) && iters >= 1 && iters <= 4096, "bytes in [4 KiB, 2 GiB], iters in [1, 4096]");
-    void *h_a = nullptr, *h_b = nullptr, *d_a = nullptr, *d_b = nullptr;
-    cudaStream_t s1 = nullptr, s2 = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; return r == cudaSuccess; };
-    ok(cudaHostAlloc(&h_a, bytes, cudaHostAllocDefault));
-    ok(cudaHostAlloc(&h_b, bytes, cudaHostAllocDefault));
-    ok(cudaMalloc(&d_a, bytes));
-    ok(cudaMalloc(&d_b, bytes));
-    ok(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
-    ok(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-    ok(cudaEventCreate(&e0)); ok(cudaEventCreate(&e1)); ok(cudaEventCreate(&e2)); ok(cudaEventCreate(&e3));
+    // buffers, streams and events are kept by the context: pinning 2 x 64 MiB takes tens of milliseconds and as long again
+    // to release, so ranks that probe "at the same moment" (a barrier in front of the call) would otherwise drift apart by
+    // about one copy phase and measure each other's idle link.  A first call allocates; calls after it start copying at once.
+    if (c->probe_bytes < bytes) {
+        hg_pcie_probe_release(c);
+        ok(cudaHostAlloc(&c->probe_h[0], bytes, cudaHostAllocDefault));
+        ok(cudaHostAlloc(&c->probe_h[1], bytes, cudaHostAllocDefault));
+        ok(cudaMalloc(&c->probe_d[0], bytes));
+        ok(cudaMalloc(&c->probe_d[1], bytes));
+        for (auto &st : c->probe_s) ok(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (auto &ev : c->probe_e) ok(cudaEventCreate(&ev));
+        if (e == cudaSuccess) {
+            c->probe_bytes = bytes;
+            memset(c->probe_h[0], 1, bytes);
+            memset(c->probe_h[1], 2, bytes);
+            ok(cudaMemsetAsync(c->probe_d[1], 3, bytes, c->probe_s[1]));
+        }
+    }
     if (e == cudaSuccess) {
-        memset(h_a, 1, bytes);
-        memset(h_b, 2, bytes);
-        ok(cudaMemsetAsync(d_b, 3, bytes, s2));
+        void *h_a = c->probe_h[0], *h_b = c->probe_h[1], *d_a = c->probe_d[0], *d_b = c->probe_d[1];
+        cudaStream_t s1 = c->probe_s[0], s2 = c->probe_s[1];
+        cudaEvent_t e0 = c->probe_e[0], e1 = c->probe_e[1], e2 = c->probe_e[2], e3 = c->probe_e[3];
         // warm-up of both directions
         ok(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s1));
         ok(cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s2));
@@ -2571,18 +2594,9 @@ int hg_pcie_probe(hg_ctx *c, size_t bytes, int iters, double *h2d_gbs, double *d
         if (ok(cudaEventElapsedTime(&ma, e0, e1)) && ok(cudaEventElapsedTime(&mb, e2, e3)))
             *bidir_gbs = 2.0 * (double)bytes * iters / ((ma > mb ? ma : mb) * 1e-3) / 1e9;
     }
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    if (e2) cudaEventDestroy(e2);
-    if (e3) cudaEventDestroy(e3);
-    if (s1) cudaStreamDestroy(s1);
-    if (s2) cudaStreamDestroy(s2);
-    if (d_a) cudaFree(d_a);
-    if (d_b) cudaFree(d_b);
-    if (h_a) cudaFreeHost(h_a);
-    if (h_b) cudaFreeHost(h_b);
     if (e != cudaSuccess) {
         cudaGetLastError();
+        hg_pcie_probe_release(c);
         return fail(c, HG_ERR_CUDA, "hg_pcie_probe: %s", cudaGetErrorString(e));
     }
     return HG_OK;

@@ -18,12 +18,12 @@ cap geo_projective   'warp_inverse_geo_kernel'    4 --workload projective
 cap geo_affine       'warp_inverse_geo_kernel'    4 --workload affine
 cap geo_rot90        'warp_inverse_geo_kernel'    4 --workload affine_rot90
 cap pw3_pixel        'pw_warp_fused_kernel'       3 --workload piecewise3 --pw-frames 16
-cap pw3_span         'pw_span_bin_kernel'         3 --workload piecewise3 --pw-frames 16
-cap pw3_runs         'pw_bin_runs_kernel'         3 --workload piecewise3 --pw-frames 16
+cap pw3_band         'pw_band_bins_kernel'        3 --workload piecewise3 --pw-frames 16
 cap pw4_pixel        'pw_warp_fused_kernel'       3 --workload piecewise4 --pw-frames 16
 cap pw4_span         'pw_span_bin_kernel'         3 --workload piecewise4 --pw-frames 16
 cap pw4_runs         'pw_bin_runs_kernel'         3 --workload piecewise4 --pw-frames 16
 cap c5_pixel         'pw_warp_fused_kernel'       8 --workload config5 --c5-frames 1024
+cap c5_band          'pw_band_bins_kernel'        8 --workload config5 --c5-frames 1024
 cap bilinear         'bilinear2_kernel'           4 --workload projective_bilinear
 cap fwd_lattice      'forward_lattice_kernel'     4 --workload affine_forward
 cap fwd_scatter      'forward_scatter_kernel'    20 --workload affine_forward_general
