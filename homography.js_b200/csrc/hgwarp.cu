@@ -81,6 +81,11 @@ struct hg_ctx {
     cudaStream_t stream2 = nullptr;                // second lane of forward batches (scatter of one sub-batch beside the gather of another)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     size_t pin_big_cap = 0;
+    // hg_solve_with_limits runs on a stream and scratch of its own: it depends on nothing queued on the context stream, and
+    // the class surface calls it between setImage() (an asynchronous upload) and warp() — the solve's round trip and the
+    // host work around it then run beside the upload instead of behind it
+    cudaStream_t stream_aux = nullptr;
+    DevBuf scratch_aux;   // 4 KiB, same layout as `scratch`
     // hg_pcie_probe keeps its buffers between calls (see there)
     void *probe_h[2] = {nullptr, nullptr}, *probe_d[2] = {nullptr, nullptr};
     cudaStream_t probe_s[2] = {nullptr, nullptr};
@@ -440,9 +445,9 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
     return HG_OK;
 }
 
-int launch_solve(hg_ctx *c, const SolveArgs &a)
+int launch_solve(hg_ctx *c, const SolveArgs &a, cudaStream_t st = nullptr)
 {
-    solve_kernel<<<(a.n + 63) / 64, 64, 0, c->stream>>>(a);
+    solve_kernel<<<(a.n + 63) / 64, 64, 0, st ? st : c->stream>>>(a);
     c->launches++;
     CU(c, cudaGetLastError());
     return HG_OK;
@@ -589,6 +594,11 @@ int hg_ctx_destroy(hg_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     hg_pcie_probe_release(c);
+    if (c->stream_aux) {
+        cudaStreamSynchronize(c->stream_aux);
+        cudaStreamDestroy(c->stream_aux);
+    }
+    if (c->scratch_aux.p) cudaFree(c->scratch_aux.p);
     DevBuf *bufs[] = {&c->img_own, &c->out, &c->scratch, &c->src_pts, &c->dst_pts, &c->tris,
                       &c->rec, &c->map32, &c->map16, &c->frames, &c->mats, &c->winner,
                       &c->invd, &c->bin_cnt, &c->bin_ent, &c->bin_run, &c->fstatus, &c->fframes, &c->tm_dev,
@@ -804,24 +814,29 @@ int hg_solve_with_limits(hg_ctx *c, int kind, const double *src, const double *d
     NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
     const size_t pb = kind == HG_AFFINE ? 48 : 64;
     const size_t mb = kind == HG_AFFINE ? 24 : 64;
-    TRY(upload_small(c, SC_SRC, src, pb));
-    TRY(upload_small(c, SC_DST, dst, pb));
+    if (!c->stream_aux) {
+        CU(c, cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking));
+        TRY(ensure(c, c->scratch_aux, 4096));
+    }
+    cudaStream_t st = c->stream_aux;
+    char *sc = (char *)c->scratch_aux.p;
+    CU(c, cudaMemcpyAsync(sc + SC_SRC, src, pb, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(sc + SC_DST, dst, pb, cudaMemcpyHostToDevice, st));
     SolveArgs a{};
-    a.src = (const double *)((char *)c->scratch.p + SC_SRC);
-    a.dst = (const double *)((char *)c->scratch.p + SC_DST);
-    a.out_f = (float *)((char *)c->scratch.p + SC_MAT);
-    a.out_d = (double *)((char *)c->scratch.p + SC_MAT);
+    a.src = (const double *)(sc + SC_SRC);
+    a.dst = (const double *)(sc + SC_DST);
+    a.out_f = (float *)(sc + SC_MAT);
+    a.out_d = (double *)(sc + SC_MAT);
     a.n = 1;
     a.op = kind == HG_AFFINE ? 0 : 1;
-    TRY(launch_solve(c, a));
-    limits_kernel<<<1, 32, 0, c->stream>>>(kind, (char *)c->scratch.p + SC_MAT, w, h,
-                                           (double *)((char *)c->scratch.p + SC_LIM));
+    TRY(launch_solve(c, a, st));
+    limits_kernel<<<1, 32, 0, st>>>(kind, sc + SC_MAT, w, h, (double *)(sc + SC_LIM));
     c->launches++;
     CU(c, cudaGetLastError());
-    // one D2H for matrix + limits (contiguous in scratch: [SC_MAT, SC_LIM+32))
-    char *pin = (char *)c->pinned;
-    CU(c, cudaMemcpyAsync(pin, (char *)c->scratch.p + SC_MAT, SC_LIM + 32 - SC_MAT, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    // one D2H for matrix + limits (contiguous in scratch: [SC_MAT, SC_LIM+32)), into the upper half of the pinned page
+    char *pin = (char *)c->pinned + 2048;
+    CU(c, cudaMemcpyAsync(pin, sc + SC_MAT, SC_LIM + 32 - SC_MAT, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
     memcpy(matrix_out, pin, mb);
     memcpy(limits_out, pin + (SC_LIM - SC_MAT), 32);
     return HG_OK;
@@ -878,17 +893,16 @@ int hg_warp_inverse_points(hg_ctx *c, int kind, const double *dst_pts, const dou
     NEED(c, dst_pts && src_pts, "NULL points");
     NEED(c, kind == HG_AFFINE || kind == HG_PROJECTIVE, "kind must be HG_AFFINE or HG_PROJECTIVE");
     const size_t pb = kind == HG_AFFINE ? 48 : 64;
-    // inverse matrix = calculateTransformMatrix(kind, dstPoints, srcPoints)  (H.js:994)
-    TRY(upload_small(c, SC_SRC, dst_pts, pb));
-    TRY(upload_small(c, SC_DST, src_pts, pb));
-    SolveArgs a{};
-    a.src = (const double *)((char *)c->scratch.p + SC_SRC);
-    a.dst = (const double *)((char *)c->scratch.p + SC_DST);
-    a.out_f = (float *)((char *)c->scratch.p + SC_MAT);
-    a.out_d = (double *)((char *)c->scratch.p + SC_MAT);
-    a.n = 1;
-    a.op = kind == HG_AFFINE ? 0 : 1;
-    TRY(launch_solve(c, a));
+    // inverse matrix = calculateTransformMatrix(kind, dstPoints, srcPoints)  (H.js:994).  The points travel as kernel
+    // parameters: a copy from pageable memory would make the host wait for everything queued on the stream — the image
+    // upload of a preceding hg_image_set — before the solve and the pixel loop could even be queued behind it.
+    SolvePoints sp{};
+    memcpy(sp.src, dst_pts, pb);
+    memcpy(sp.dst, src_pts, pb);
+    solve_points_kernel<<<1, 32, 0, c->stream>>>(sp, kind == HG_AFFINE ? 0 : 1, (float *)((char *)c->scratch.p + SC_MAT),
+                                                 (double *)((char *)c->scratch.p + SC_MAT));
+    c->launches++;
+    CU(c, cudaGetLastError());
     // inverse map: dst -> src
     return warp_inverse_common(c, kind, nullptr, true, x_off, y_off, o_w, o_h, out_host, out_dev, points_map_is_rotated(dst_pts, src_pts));
 }
