@@ -498,8 +498,11 @@ __device__ __forceinline__ int pwf_run_id(const uint4 &ids, unsigned r)
     return (int)(short)(unsigned short)((r & 1u) ? (w >> 16) : w);
 }
 
+// CTAs per SM the pixel kernels are compiled for.  4 (128 registers, 132 KB of the SM's shared memory, the rest L1) against
+// 5 (96 registers): the same on the 4K configs (0.610 / 0.452), +3.5 % on the 1080p video stream (pixel kernel 0.564 ->
+// 0.584, whole step 0.447 -> 0.460); 3 loses 12-15 % everywhere, 6 lost 20 %.
 #ifndef HG_PWF_MINB
-#define HG_PWF_MINB 5
+#define HG_PWF_MINB 4
 #endif
 constexpr int PWF_TX = 8;                       // threads across one 64-column bin: each owns quads tx and tx+8
 constexpr int PWF_TY = 16;                      // thread rows per CTA
@@ -756,7 +759,10 @@ struct PwfCtx {
 // scoreboarded at all: PWF_DEPTH row groups of gathers (24 per thread) are in flight behind the arithmetic, and the
 // matrix loads are the only register loads left in the loop.  A pixel outside the window is a copy of zero source
 // bytes: the hardware fills the slot with zeros (H.js:1047: the output stays transparent).
-constexpr int PWF_DEPTH = 3;            // row groups of gathers in flight
+#ifndef HG_PWF_DEPTH
+#define HG_PWF_DEPTH 3
+#endif
+constexpr int PWF_DEPTH = HG_PWF_DEPTH;   // row groups of gathers in flight
 constexpr int PWF_NST = PWF_DEPTH + 1;  // ring slots per thread (the slot being stored is not the one being filled)
 // Ring layout: 32-bit words [slot][quad][pixel k][thread] — the 32 lanes of one copy instruction write 32 consecutive
 // words (no bank conflict; the [thread][k] layout that a 16-byte read would like is a 4-way conflict for every copy).
