@@ -259,6 +259,39 @@ def test_stream_wraps_the_ring_and_reads_a_source_ring(ctx):
     assert _stream_case(ctx, n_frames=23, n_slots=8, n_src=3, first=1000) == 8
 
 
+def test_two_lane_chunk_pipeline_gives_the_same_frames(monkeypatch):
+    """HG_PW_LANES=1 (opt-in, measured slower): binning passes of chunk k+1 on a second stream beside the pixel kernel of chunk
+    k, two scratch sets.  Chunks of two frames so that a short stream / batch runs through both lanes several times, ring wrap
+    and skipped frames included; both binning passes."""
+    monkeypatch.setenv("HG_PW_LANES", "1")
+    monkeypatch.setenv("HG_PW_CHUNK", "2")
+    c = hg.Context(0)
+    try:
+        for mode in (2, 1):
+            c.debug_piecewise_binning(mode)
+            assert _stream_case(c, n_frames=11, n_slots=8, n_src=2, first=3) == 8
+            assert _stream_case(c, n_frames=7, n_slots=16, bad=(4,)) == 6
+        c.debug_piecewise_binning(0)
+        # the batch entry point: nine 4:3 frames with their own windows
+        w, h, n = 160, 120, 9
+        img = _rand_img(77, w, h)
+        src_pts, dst_all, tris = hg.workloads.video_stream(n, w, h, seed=9)
+        smm = [int(O.js_round(float(src_pts[:, 0].min()))), int(O.js_round(float(src_pts[:, 1].min())))]
+        c.image_set(img, w, h)
+        c.piecewise_set_mesh(src_pts, tris)
+        wins = [hg.workloads.piecewise_extent(dst_all[f]) for f in range(n)]
+        outs = [torch.zeros(wn[2] * wn[3] * 4, dtype=torch.uint8, device="cuda") for wn in wins]
+        torch.cuda.synchronize()
+        frames = [hg.HgFrame(None, outs[f].data_ptr(), 0, 0, *wins[f]) for f in range(n)]
+        c.warp_piecewise_inverse_batch(dst_all, frames, smm[0], smm[1])
+        for f in range(n):
+            win, want = _oracle_piecewise(img, w, h, src_pts, dst_all[f], tris, smm)
+            assert tuple(win) == tuple(wins[f])
+            assert _diff(outs[f].cpu().numpy(), want) == 0, f
+    finally:
+        c.close()
+
+
 def test_stream_skips_frames_without_a_window(ctx):
     assert _stream_case(ctx, n_frames=6, n_slots=6, bad=(2,)) == 5
 
