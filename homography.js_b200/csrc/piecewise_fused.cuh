@@ -735,7 +735,7 @@ template <bool ZERO_OFF>
 struct PwfCtx {
     const uint32_t *src;
     const float *inv;
-    unsigned W, npx_src, W2, H2, Wi, Hi, kflat;
+    unsigned W, npx_src, W2, H2, Wi, Hi, nkflat;   // nkflat = -(HG_HI_ZERO >> 1) * (W + 1): flat = (hy >> 1) * W + (hx >> 1) + nkflat
     int oW, oH, yOff, base0;
     double xs[2][4];
     unsigned vmask[2];
@@ -796,7 +796,7 @@ __device__ __forceinline__ void pwf_issue(PwfCtx<ZERO_OFF> &C, const FusedFrame 
             }
             unsigned flat[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) flat[k] = (hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat;
+            for (int k = 0; k < 4; ++k) flat[k] = (hy[k] >> 1) * C.W + ((hx[k] >> 1) + C.nkflat);   // (a >> 1) + b is one LEA.HI
             const unsigned cz = (unsigned)(HG_HI_ZERO + 2);
             const bool ends_inside = live && ((hx[0] - cz) < C.Wi) & ((hy[0] - cz) < C.Hi) & ((hx[3] - cz) < C.Wi) & ((hy[3] - cz) < C.Hi);
             if (__all_sync(0xffffffffu, ends_inside)) {
@@ -897,7 +897,7 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
     C.H2 = 2u * H;
     C.Wi = C.W2 >= 3u ? C.W2 - 3u : 0u;
     C.Hi = C.H2 >= 3u ? C.H2 - 3u : 0u;
-    C.kflat = (unsigned)(HG_HI_ZERO >> 1) * (C.W + 1u);
+    C.nkflat = 0u - (unsigned)(HG_HI_ZERO >> 1) * (C.W + 1u);
     int xx00 = 0;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -961,10 +961,10 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
         if (it >= 1 + PWF_DEPTH) {
             asm volatile("cp.async.wait_group %0;" ::"n"(PWF_DEPTH - 1) : "memory");
             const int g = it - 1 - PWF_DEPTH;
-            pwf_retire(C, g, p_out, &s_px[g % PWF_NST][0][0][threadIdx.x]);
+            pwf_retire(C, g, p_out, &s_px[(unsigned)g % (unsigned)PWF_NST][0][0][threadIdx.x]);
             p_out += out_step;
         }
-        if (it >= 1 && it - 1 < ngroups) pwf_issue(C, F, it - 1, px_base + (uint32_t)((it - 1) % PWF_NST) * px_stage_bytes);
+        if (it >= 1 && it - 1 < ngroups) pwf_issue(C, F, it - 1, px_base + ((uint32_t)(it - 1) % (uint32_t)PWF_NST) * px_stage_bytes);
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (it < ngroups) pwf_resolve(C, it, wq, s_rec[it * PWF_GROUP_ROWS + ty]);
     }
