@@ -740,7 +740,7 @@ struct PwfCtx {
     double xs[2][4];
     unsigned vmask[2];
     unsigned long long below[2], inner[2];
-    bool prev_bin, has_bin, src_aligned;
+    bool prev_bin, has_bin, src_aligned, warp_prev;
     int lane;
     unsigned lt_mask;
     // pipeline state
@@ -828,6 +828,29 @@ __device__ __forceinline__ void pwf_resolve(PwfCtx<ZERO_OFF> &C, int g, unsigned
 {
     const bool row_ok = C.base0 + g * PWF_GROUP_ROWS < C.oH;
     const uint4 be0 = rec[0], be1 = rec[1];   // shared memory: the record of this thread's row in group g
+    // ONE RUN over the whole bin in all four rows of the warp (most row groups of a coarse mesh): both quads belong to run 0,
+    // nothing cuts them — no popcounts, no id permute, no cut test; only a first quad that reaches back into the previous
+    // bin (frames of unaligned width) is still queued
+    if (__all_sync(0xffffffffu, (be0.x == 1u) & (be0.y == 0u))) {
+        const int t = (int)(short)(unsigned short)(be1.x & 0xFFFFu);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (t >= 0 && t != C.tm[q]) {
+                const float4 *pm = reinterpret_cast<const float4 *>(C.inv + 8 * (size_t)t);
+                C.mqa[q] = __ldg(pm);
+                C.mqb[q] = __ldg(pm + 1);
+                C.tm[q] = t;
+            }
+            C.t0[q] = t;
+        }
+        if (C.warp_prev) {   // warp-uniform: some lane of the warp owns a quad that starts in the previous bin
+            const bool cut = row_ok && (C.vmask[0] != 0u) && C.prev_bin;
+            const unsigned bal = __ballot_sync(0xffffffffu, cut);
+            if (cut) wq[C.qn + __popc(bal & C.lt_mask)] = (unsigned short)((g << 6) | (C.lane << 1));
+            C.qn += __popc(bal);
+        }
+        return;
+    }
     const unsigned long long m64 = ((unsigned long long)be0.y << 32) | (unsigned long long)be0.x;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -916,6 +939,7 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
     }
     // pixels of quad 0 left of the tile belong to the previous bin (only when they are pixels of the image at all)
     C.prev_bin = (a > 0) && (tx == 0) && (tile_x > 0);
+    C.warp_prev = __any_sync(0xffffffffu, C.prev_bin);
     C.t0[0] = C.t0[1] = -1;
     C.tm[0] = C.tm[1] = -1;
     C.mqa[0] = C.mqa[1] = C.mqb[0] = C.mqb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
