@@ -10,16 +10,18 @@
 //   bin (row R, 64-column block B)  ->  up to PW_BIN_CAP entries  (t, c0, c1)   "triangle t covers columns
 //                                                                               [c0,c1) of this block in row R"
 //
-// (~1/64 of the map's size; a few entries per bin for any non-folded mesh).  A second pass (pw_bin_runs_kernel, one
-// thread per bin) resolves the overlaps — highest id wins — and run-length encodes each bin as a 64-bit start mask +
-// up to 8 int16 ids.  The warp kernel finds t with two popcounts, then does what H.js:1046-1052 does: inverse 2x3 of
-// the triangle, window test, Math.round, flat gather, 128-bit store.
+// (~1/64 of the map's size; a few entries per bin for any non-folded mesh).  The overlaps are then resolved — highest id
+// wins — and each bin is run-length encoded as a 64-bit start mask + up to 8 int16 ids.  Two ways to get there: meshes of
+// up to 2,048 triangles take ONE pass per band of map rows that keeps the band's bins in shared memory and writes the run
+// records directly (pw_band_bins_kernel); finer meshes bin into global memory (pw_span_bin_kernel) and encode in a second
+// pass (pw_bin_runs_kernel, one thread per bin).  The warp kernel finds t with two popcounts, then does what
+// H.js:1046-1052 does: inverse 2x3 of the triangle, window test, Math.round, flat gather, 128-bit store.
 //
 // Exactness: every quirk of the reference's map (no x offset -> spans spilling into the next row, negative
 // relative fill indices landing at the END of the map, last-writer-wins overlaps, int16 wrap of ids) is inherited
 // from the exact interval computation.  A frame that cannot be represented (a bin with more than PW_BIN_CAP
-// entries or runs, an interval crossing more than PW_MAX_PIECES rows, >= 2^17 triangles) raises a status flag and is redone
-// by the general map-based path — never approximated.
+// entries or runs, an interval crossing more than PW_MAX_PIECES rows or leaving the rows the band pass assumed it could reach,
+// >= 2^17 triangles) raises a status flag and is redone by the general map-based path — never approximated.
 #pragma once
 #include "piecewise.cuh"
 #include "warp_geo.cuh"
