@@ -328,10 +328,10 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
 //   projective  the numerators use doubled coefficients (an exact scaling) and ONE fma each with a per-row constant —
 //               a different association than the reference's (and one add per pixel along the quad), off by <= 8 ulp of the
 //               largest term, which geo_fast_mode bounds below 2^-25 pixel — and the reciprocal of the denominator (MUFU.RCP64H + one
-//               Newton step, 2^-39.9 relative).  Total error of 2v < 2^-20.9 < delta = 2^-19.  Both coordinates are
-//               tested with one multiply: umulhi(lo_x, lo_y) < 2 delta holds whenever either factor is < 2 delta
-//               (false positives, both within 2^-9 of a boundary, only cost a trip through the exact path).  Flagged
-//               pixels go to the warp queue and are redone by geo_flush_queue with the reference's own arithmetic.
+//               Newton step, 2^-39.9 relative).  Total error of 2v < 2^-20.9 < delta = 2^-19.  The eight fractions of a
+//               quad are tested with ONE compare of their minimum (a three-input minimum per pixel); only a quad that has a
+//               fraction below 2 delta works out which of its pixels are flagged.  Flagged pixels go to the warp queue and
+//               are redone by geo_flush_queue with the reference's own arithmetic.
 // Two-stage software pipeline, unrolled by two row groups: a group's gathers are issued right after its
 // arithmetic and stored one group later, so the loads of 8 pixels per thread stay in flight across a full group of
 // arithmetic of the same warp; the bounds predicate guards the load directly (no sentinel round trip).
@@ -403,6 +403,7 @@ __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g,
             dn = __fma_rn(C.c6, C.xs[0], r2);
         }
         unsigned hx[4], hy[4];
+        unsigned lx[4], ly[4], lomin = 0xFFFFFFFFu;   // projective: fractions of 2v + 1 + delta, and the smallest of the quad's eight
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             double tx, ty;
@@ -418,11 +419,21 @@ __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g,
                     ny = __dadd_rn(ny, C.c3);
                     dn = __dadd_rn(dn, C.c6);
                 }
-                const bool again = __umulhi((unsigned)__double2loint(tx), (unsigned)__double2loint(ty)) < 2u * HG_NEAR_DELTA2;
-                g.redo |= again ? (1u << (4 * j + k)) : 0u;
+                lx[k] = (unsigned)__double2loint(tx);
+                ly[k] = (unsigned)__double2loint(ty);
+                lomin = __vimin3_u32(lomin, lx[k], ly[k]);   // one three-input minimum per pixel
             }
             hx[k] = (unsigned)__double2hiint(tx);
             hy[k] = (unsigned)__double2hiint(ty);
+        }
+        // "within delta of a decision boundary" per QUAD first: one compare for eight fractions; the per-pixel flags are
+        // worked out only for the (rare) quad that has one
+        if (KIND == 1 && lomin < 2u * HG_NEAR_DELTA2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool again = (lx[k] < 2u * HG_NEAR_DELTA2) | (ly[k] < 2u * HG_NEAR_DELTA2);
+                g.redo |= again ? (1u << (4 * j + k)) : 0u;
+            }
         }
         // Along an output row both source coordinates are monotone in x (the denominator keeps its sign), so when the
         // quad's two END pixels lie at least one half-pixel step inside the image (2 <= n <= 2W - 2, same for y) the
