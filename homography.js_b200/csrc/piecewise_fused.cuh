@@ -995,47 +995,55 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
         if (it < ngroups) pwf_resolve(C, it, wq, s_rec[it * PWF_GROUP_ROWS + ty]);
     }
 
-    // ---- the queued quads again, one QUAD per lane and TWO quads per lane and pass, every pixel with the triangle of its
-    // own run (H.js:1044-1052 verbatim).  The pass is written in phases over both quads so that its three dependent
-    // round trips overlap across the 2 x 4 pixels: run record(s) -> ids of all pixels -> the (at most two, as a rule)
-    // distinct matrices of each quad, loaded back to back -> all flat indices -> all gathers -> two 128-bit stores.
+    // ---- the queued quads again, one QUAD per lane and TWO quads per lane and pass (H.js:1044-1052 verbatim, every pixel
+    // with the triangle of its own run).  The loop above has already stored the quad computed with ONE triangle — the run at
+    // its first column inside this bin — so only the pixels that belong to ANOTHER run (or to none) are computed again and
+    // stored over the provisional ones, one 32-bit store each: for the usual quad that one span boundary cuts that is half
+    // of its arithmetic, one matrix instead of two and two gathers instead of four.  Written in phases over both quads so
+    // that the dependent round trips overlap: run record(s) -> ids of all pixels -> matrices -> flat indices -> gathers -> stores.
     __syncwarp();  // also orders the provisional stores above before the final ones below
     const int qn = C.qn;
     for (int e0 = 0; e0 < qn; e0 += 64) {
-        int row[2], X0[2], tk[2][4], tA[2], tB[2];
-        float4 mA[2][2], mB[2][2];
+        int row[2], X0[2], tk[2][4], tB[2];
+        unsigned redo[2];   // bit k: pixel k is a pixel of the frame whose run is not the one the loop used
+        float4 mB[2][2];
         unsigned idx[2][4];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int e = e0 + 32 * u + C.lane;
             row[u] = -1;
             X0[u] = 0;
-            tA[u] = tB[u] = -1;
+            tB[u] = -1;
+            redo[u] = 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) tk[u][k] = -1;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            mB[u][0] = mB[u][1] = z;
             if (e >= qn) continue;
             const unsigned ent = wq[e];
             const int qq = (int)(ent & 1u), sl = (int)((ent >> 1) & 31u), g = (int)(ent >> 6);
             row[u] = row0 + warp_id * 4 + (sl >> 3) + g * PWF_GROUP_ROWS;
             const int ae = (oW & 3) ? (int)(((unsigned)row[u] * (unsigned)oW) & 3u) : 0;
-            X0[u] = tile_x * PW_BIN_W + 4 * (sl & 7) + 32 * qq - ae;
+            const int cq = 4 * (sl & 7) + 32 * qq - ae;     // first column of the quad inside this bin (negative: previous bin)
+            X0[u] = tile_x * PW_BIN_W + cq;
             // the quad lies in one bin, except a first quad that reaches back into the previous one
             const int binA = X0[u] < 0 ? 0 : (X0[u] >> 6), binB = (X0[u] + 3) >> 6;
             const int rr = row[u] - row0;
-            uint4 a0, a1;
-            if (binA == tile_x) {
-                a0 = s_rec[rr][0];
-                a1 = s_rec[rr][1];
-            } else {   // the previous bin (a first quad reaching back over the tile's left edge)
+            const uint4 t0r = s_rec[rr][0], t1r = s_rec[rr][1];   // this bin's record
+            uint4 a0 = t0r, a1 = t1r;
+            if (binA != tile_x) {   // the previous bin (a first quad reaching back over the tile's left edge)
                 const uint4 *pr = F.bin_run + 2 * ((size_t)row[u] * F.bins_x + binA);
                 a0 = __ldg(pr);
                 a1 = __ldg(pr + 1);
             }
             uint4 b0 = a0, b1 = a1;
             if (binB != binA && binB < F.bins_x) {   // binB == tile_x
-                b0 = s_rec[rr][0];
-                b1 = s_rec[rr][1];
+                b0 = t0r;
+                b1 = t1r;
             }
+            // the run the loop computed the whole quad with (pwf_resolve: the run at column max(cq, 0) of this bin)
+            const unsigned long long mt = ((unsigned long long)t0r.y << 32) | (unsigned long long)t0r.x;
+            const int t_main = pwf_run_id2(t1r, (unsigned)__popcll(mt & ((2ull << (cq < 0 ? 0 : cq)) - 1ull)) - 1u);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int X = X0[u] + k;
@@ -1045,15 +1053,10 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
                 const unsigned long long m64 = ((unsigned long long)r0.y << 32) | (unsigned long long)r0.x;
                 const int t = pwf_run_id2(r1, (unsigned)__popcll(m64 & ((2ull << (X & 63)) - 1ull)) - 1u);
                 tk[u][k] = t;
-                if (t >= 0 && tA[u] < 0) tA[u] = t;
-                else if (t >= 0 && t != tA[u] && tB[u] < 0) tB[u] = t;
-            }
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            mA[u][0] = mA[u][1] = mB[u][0] = mB[u][1] = z;
-            if (tA[u] >= 0) {
-                const float4 *pm = reinterpret_cast<const float4 *>(F.inv + 8 * (size_t)tA[u]);
-                mA[u][0] = __ldg(pm);
-                mA[u][1] = __ldg(pm + 1);
+                if (t != t_main) {
+                    redo[u] |= 1u << k;
+                    if (t >= 0 && tB[u] < 0) tB[u] = t;
+                }
             }
             if (tB[u] >= 0) {
                 const float4 *pm = reinterpret_cast<const float4 *>(F.inv + 8 * (size_t)tB[u]);
@@ -1068,17 +1071,12 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
             for (int k = 0; k < 4; ++k) {
                 const int t = tk[u][k];
                 idx[u][k] = HG_OUTSIDE;
-                if (t < 0) continue;
-                float4 p0 = mA[u][0], p1 = mA[u][1];
-                if (t != tA[u]) {
-                    if (t == tB[u]) {
-                        p0 = mB[u][0];
-                        p1 = mB[u][1];
-                    } else {   // a third triangle inside one quad: fetched on the spot
-                        const float4 *pm = reinterpret_cast<const float4 *>(F.inv + 8 * (size_t)t);
-                        p0 = __ldg(pm);
-                        p1 = __ldg(pm + 1);
-                    }
+                if (t < 0 || !(redo[u] & (1u << k))) continue;
+                float4 p0 = mB[u][0], p1 = mB[u][1];
+                if (t != tB[u]) {   // a third triangle inside one quad: fetched on the spot
+                    const float4 *pm = reinterpret_cast<const float4 *>(F.inv + 8 * (size_t)t);
+                    p0 = __ldg(pm);
+                    p1 = __ldg(pm + 1);
                 }
                 const double x = (double)(F.xOff + X0[u] + k);
                 idx[u][k] = pwf_decode<ZERO_OFF>(affine_coord_exact((double)p0.x, x, __dmul_rn((double)p0.z, y), (double)p1.x),
@@ -1092,15 +1090,11 @@ __device__ __forceinline__ void pwf_body2(const FusedFrame &F, int niter, int ti
             for (int k = 0; k < 4; ++k) v[u][k] = ldg_or_zero(C.src, idx[u][k]);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            if (row[u] < 0) continue;
+            if (redo[u] == 0u) continue;
             uint32_t *dst = F.out + ((long long)row[u] * oW + X0[u]);
-            if (X0[u] >= 0 && X0[u] + 3 < oW) {
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(v[u][0], v[u][1], v[u][2], v[u][3]);
-            } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (X0[u] + k >= 0 && X0[u] + k < oW) dst[k] = v[u][k];
-            }
+            for (int k = 0; k < 4; ++k)
+                if (redo[u] & (1u << k)) dst[k] = v[u][k];   // a pixel without a triangle stays transparent: v = 0
         }
     }
 }
