@@ -400,7 +400,7 @@ def sec_config4(env, frames: int, steps: int, warmup: int):
     dst_all = np.repeat(src[None, :, :], F, axis=0).copy()
     dst_all[:, :, 1] = (A + src[None, :, 1].astype(np.float64) + A * np.sin(2 * math.pi * 2 * xs[None, :] / w + ph[:, None])).astype(np.float32)
     ctx.piecewise_set_mesh(src, tris)
-    n_src, n_slots = 8, 128
+    n_src, n_slots = 8, env.args.c4_slots
     max_w, max_h = w + 8, int(h + 2 * A) + 16
     slot = ctx.stream_slot_bytes(max_w, max_h)
     g = torch.Generator(device=env.dev)
@@ -489,7 +489,9 @@ def sec_config5(env, frames: int, steps: int, warmup: int):
     ctx.image_set_device(image.data_ptr(), w, h)
     ctx.piecewise_set_mesh(src_pts, tris)
     smm = [int(np.floor(v + 0.5)) for v in (float(src_pts[:, 0].min()), float(src_pts[:, 1].min()))]
-    n_slots = 256                                            # 2.4 GB of output ring: chunks of 128 frames per launch chain
+    # output ring: 2,048 slots of 9.6 MB by default = chunks of 1,024 frames per launch chain (measured, 12,500 frames per step:
+    # 256 / 512 / 2,048 slots -> 0.499 / 0.519 / 0.528 of the HBM bound)
+    n_slots = env.args.c5_slots
     max_w, max_h = int(w * 1.07) + 8, int(h * 1.07) + 8      # points move by +-3 % of the frame
     slot = ctx.stream_slot_bytes(max_w, max_h)
     ring = torch.zeros(n_slots * slot, dtype=torch.uint8, device=env.dev)
@@ -925,9 +927,12 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="headline frames per step (per GPU)")
     ap.add_argument("--e2e-frames", type=int, default=16, help="frames per end-to-end step (per GPU)")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the CPU reference arm")
-    ap.add_argument("--pw-frames", type=int, default=64, help="frames per step per GPU of the piecewise3 / piecewise4 batches")
+    ap.add_argument("--pw-frames", type=int, default=128, help="frames per step per GPU of the piecewise3 / piecewise4 batches")
     ap.add_argument("--c4-frames", type=int, default=512, help="config 4: frames per GPU per step (4096 / 8)")
     ap.add_argument("--c5-frames", type=int, default=12500, help="config 5: frames per GPU per step (100000 / 8)")
+    ap.add_argument("--c4-slots", type=int, default=128, help="config 4: slots of the output ring (a launch chain covers half of it)")
+    ap.add_argument("--c5-slots", type=int, default=2048,
+                    help="config 5: slots of the output ring (19.6 GB; a launch chain covers half of it, at most 1,024 frames)")
     ap.add_argument("--fwd-frames", type=int, default=64, help="frames per step per GPU of the forward / bilinear lines")
     ap.add_argument("--secondary-steps", type=int, default=10, help="timed steps of each secondary workload (at most --steps)")
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU baseline work")

@@ -114,10 +114,11 @@ struct hg_ctx {
     bool bilinear_v1 = false;       // HG_BILINEAR_V1: first-generation bilinear kernel (A/B runs)
     bool pwf_v1 = false;            // HG_PWF_V1: first-generation fused piecewise pixel kernel (A/B runs)
     bool geo_async = false;         // HG_GEO_ASYNC: affine / projective pixel loop with asynchronous gathers (A/B runs)
-    int pw_chunk = 0;               // HG_PW_CHUNK: frames per pipelined chunk of the piecewise batch / stream calls (0: 64; 16 with two lanes)
+    int pw_chunk = 0;               // HG_PW_CHUNK: frames per pipelined chunk of the piecewise batch / stream calls (0: 128; 64 with two lanes)
     int fwd_plane_mb = 48;          // HG_FWD_PLANE_MB: budget of the forward batches' winner planes (kept L2-resident)
     int pw_binning = 0;             // HG_PW_BINNING / hg_debug_piecewise_binning: 0 auto, 1 span + run passes, 2 one band pass
-    bool pw_serial = true;          // unless HG_PW_LANES: one lane — every chunk's binning passes in front of its pixel kernel
+    int pw_lanes = -1;              // HG_PW_LANES: 0 one lane (every chunk's binning passes in front of its pixel kernel), 1 two lanes,
+                                    // unset: two lanes for meshes binned by the span + run passes, one for the band pass
     bool pwf_records_inline = false;  // HG_PWF_RECORDS_INLINE: the pixel kernel builds the run records of aligned frames itself (A/B runs)
     CUtensorMap img_tm[GEO_NBOX];
     bool img_tm_ok = false;
@@ -551,7 +552,7 @@ int hg_ctx_create(int device, hg_ctx **out)
         c->geo_async = getenv("HG_GEO_ASYNC") != nullptr;
         c->pwf_records_inline = getenv("HG_PWF_RECORDS_INLINE") != nullptr;
         env_int("HG_PW_CHUNK", 1, 1024, c->pw_chunk);
-        c->pw_serial = getenv("HG_PW_LANES") == nullptr;
+        env_int("HG_PW_LANES", 0, 1, c->pw_lanes);
         env_int("HG_PW_BINNING", 0, 2, c->pw_binning);
         env_int("HG_FWD_PLANE_MB", 1, 4096, c->fwd_plane_mb);
         CUC(cudaFuncSetAttribute(pw_band_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PWB_SMEM));
@@ -1495,6 +1496,11 @@ static bool pw_band_binning(const hg_ctx *c)
     if (c->pw_binning) return c->pw_binning == 2;
     return c->n_tris <= 2048;
 }
+// Two lanes (the binning passes of chunk k+1 on a high-priority stream beside the pixel kernel of chunk k)?  Measured on B200:
+// the band pass is bound by its instruction count and takes from the pixel kernel what it gains (config 3: 0.438 -> 0.413-0.429
+// of the HBM bound), the span pass is bound by its returning atomics and shares the machine (config 4, 512 frames streamed in
+// chunks of 64: 0.292 -> 0.301; chunks of 32: 0.298).
+static bool pw_two_lanes(const hg_ctx *c) { return c->pw_lanes >= 0 ? c->pw_lanes == 1 : !pw_band_binning(c); }
 static int pw_scratch_ensure(hg_ctx *c, const PwScratch &S, size_t T, int nF, size_t total_bins)
 {
     TRY(ensure(c, *S.yr, sizeof(int2) * (T ? T : 1) * (size_t)nF));
@@ -1806,21 +1812,17 @@ int hg_warp_piecewise_inverse_batch(hg_ctx *c, const float *dst_pts, const hg_fr
     }
     int chunk = (int)((1500ull << 20) / (per_frame ? per_frame : 1));
     if (chunk < 1) chunk = 1;
-    // ... and at most 64 frames, so that a larger batch runs as a pipeline: the host stages the destiny points and frame
-    // descriptors of chunk k+1 while chunk k computes (the status flags come back through pinned memory, so nothing
-    // below blocks before the one synchronisation at the end).  Measured on 64 4K frames: chunks of 16 / 32 / 64 frames ->
-    // 0.408 / 0.431 / 0.441 of the HBM bound for the whole step (162 triangles): launches this size are worth more than the
-    // overlap of a 2 MB upload.
+    // ... and at most 128 frames (64 with two lanes), so that a larger batch runs as a pipeline: the host stages the destiny
+    // points and frame descriptors of chunk k+1 while chunk k computes (the status flags come back through pinned memory, so
+    // nothing below blocks before the one synchronisation at the end).  Measured on 4K frames of the 162-triangle mesh, whole
+    // step against the HBM bound: chunks of 16 / 32 / 64 frames 0.408 / 0.431 / 0.441 (64 frames per call, earlier kernels);
+    // 64 / 128 frames 0.504 / 0.518 (128 frames per call) — launches this size are worth more than the overlap of a 2 MB upload.
     const bool fused = pw_fused_possible(c, fr[0]);
-    // One lane by default: chunks of 16 / 32 / 64 frames gave 0.408 / 0.431 / 0.441 of the HBM bound on 64 4K frames.
-    // HG_PW_LANES=1 (opt-in, A/B runs): the binning passes of chunk k+1 run on a high-priority stream beside the pixel kernel
-    // of chunk k, each lane with its own scratch.  Measured and not adopted: the pixel kernel slows down by what the passes
-    // take (0.61 -> 0.47 of the bound while they share the SMs), the whole step ends at 0.413 / 0.429 (chunks of 16 / 32)
-    // against 0.438 in one lane — the passes are not idle latency the pixel kernel could fill, they compete for issue slots
-    // and L1.
-    const int want = c->pw_chunk > 0 ? c->pw_chunk : (c->pw_serial ? 64 : 16);
+    // One lane or two: pw_two_lanes().  HG_PW_LANES=0 / 1 forces either.
+    const bool two = pw_two_lanes(c);
+    const int want = c->pw_chunk > 0 ? c->pw_chunk : (two ? 64 : 128);
     if (chunk > want) chunk = want;
-    const bool lanes = fused && !c->pw_serial && n_frames > chunk;
+    const bool lanes = fused && two && n_frames > chunk;
     int *status = (int *)c->pin_big;
     if (lanes) {
         // both lanes sized for the largest chunk before anything is in flight
@@ -2372,8 +2374,9 @@ int hg_warp_piecewise_stream(hg_ctx *c, const float *dst_pts, int n_frames, int6
     if (chunk < 1) chunk = 1;
     const bool fused = !c->force_general && c->n_tris < PW_MAX_TRIS;
     // two lanes, like hg_warp_piecewise_inverse_batch: chunk k+1 is binned beside the pixel kernel of chunk k
-    if (fused && !c->pw_serial && c->pw_chunk > 0 && chunk > c->pw_chunk) chunk = c->pw_chunk;
-    const bool lanes = fused && !c->pw_serial && n_frames > chunk;
+    const bool two = pw_two_lanes(c);
+    if (fused && two && chunk > (c->pw_chunk > 0 ? c->pw_chunk : 64)) chunk = c->pw_chunk > 0 ? c->pw_chunk : 64;
+    const bool lanes = fused && two && n_frames > chunk;
     for (int l = 0; l < (lanes ? 2 : 1); ++l) TRY(pw_scratch_ensure(c, pw_scratch(c, l), T, chunk, bin_stride * (size_t)chunk));
     TRY(ensure(c, c->sinfo, sizeof(StreamInfo) * (size_t)n_frames));
     TRY(ensure_pinned(c, (sizeof(StreamInfo) + sizeof(int)) * (size_t)n_frames));

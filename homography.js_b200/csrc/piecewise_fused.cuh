@@ -344,12 +344,18 @@ __global__ void __launch_bounds__(PWB_THREADS, HG_PWB_MINB) pw_band_bins_kernel(
         s_cnt[i] = 0u;
         s_full[i] = 0u;
     }
-    if (tid == 0) *s_n = 0u;
     const int xOff = G.xOff, yOff = G.yOff, T = G.n_tris;
+    if (tid == 0) {
+        *s_n = 0u;
+        // one thread divides for the CTA (two signed divisions per thread were 4 % of the pass's instructions)
+        s_n[1] = (unsigned)pwb_floor_div(xOff - 1, oW);
+        s_n[2] = (unsigned)pwb_floor_div(xOff + oW, oW);
+    }
+    __syncthreads();
     int *status = G.status;
     const TriRec *rec = G.rec;
     const int2 *yr = G.yr;
-    const int dlo = pwb_floor_div(xOff - 1, oW), dhi = pwb_floor_div(xOff + oW, oW);
+    const int dlo = (int)s_n[1], dhi = (int)s_n[2];
     // candidate rows (inclusive, in y): A = rows that reach the band directly, B = through an index counted from the end
     int ya0 = yOff + R0 - dhi, ya1 = yOff + R0 + rows - 1 - dlo, yb0 = ya0 - oH, yb1 = ya1 - oH;
     if (yb1 >= ya0 - 1) {   // the two ranges meet (maps of a few rows): one range, no pair evaluated twice
@@ -362,7 +368,6 @@ __global__ void __launch_bounds__(PWB_THREADS, HG_PWB_MINB) pw_band_bins_kernel(
     const unsigned band_k0 = (unsigned)R0 * (unsigned)oW, band_k1 = (unsigned)(R0 + rows) * (unsigned)oW;
     const unsigned len = (unsigned)oW * (unsigned)oH;
     const double mw = (double)oW, yoff = (double)yOff, dlen = (double)len;
-    __syncthreads();
 
     for (int tb = 0; tb < T; tb += PWB_TRI_STEP) {
         // ---- A: segments of the next PWB_TRI_STEP triangles
