@@ -337,6 +337,11 @@ __device__ __forceinline__ void geo_tile_body(const GeoFrame &F, const double (&
 // arithmetic of the same warp; the bounds predicate guards the load directly (no sentinel round trip).
 #define HG_NEAR_DELTA2 8192u  // 2^13 * 2^-32 = 2^-19 in units of 2v
 
+// The magic addends of the doubled-coordinate decode, read from the constant bank: a DFMA takes a constant-bank operand
+// directly, a 64-bit literal with a non-zero low word is two moves per row under the kernels' register caps.
+__constant__ double hg_mg_affine = HG_MAGIC + 1.0;
+__constant__ double hg_mg_projective = HG_MAGIC + 1.0 + (double)HG_NEAR_DELTA2 / 4294967296.0;
+
 struct GeoGroup {
     uint32_t px[GEO_ROWS_PER_THREAD][4];
     int base;        // first row of the group (-1: empty)
@@ -348,7 +353,8 @@ template <int KIND>
 struct GeoFastCtx {
     const uint32_t *src;
     unsigned W, H, W2, H2, npx;
-    unsigned Wi, Hi;         // 2W - 3, 2H - 3 (0 for a 1-pixel dimension): the strictly-inside range of the end-pixel test
+    unsigned Wi, Hi;         // 2W - 3, 2H - 3: the strictly-inside range of the end-pixel test (meaningless when !wide)
+    bool wide;               // W >= 2 and H >= 2; a 1-pixel dimension has no strictly-inside range (the test is then always false)
     unsigned kflat;          // flat = (hy >> 1) * W + (hx >> 1) - kflat
     unsigned nkflat;         // -kflat: (hx >> 1) + nkflat is one LEA.HI
     const uint32_t *srcv;    // src again, pinned to vector registers (the address multiply-add then takes an immediate 4)
@@ -380,27 +386,25 @@ template <int KIND, bool ASYNC = false>
 __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g, int base, int *qn, uint32_t slot = 0u)
 {
     constexpr int R = GEO_ROWS_PER_THREAD;
-    const double MG = (KIND == 0) ? (HG_MAGIC + 1.0) : (HG_MAGIC + 1.0 + (double)HG_NEAR_DELTA2 / 4294967296.0);
+    const double MG = (KIND == 0) ? hg_mg_affine : hg_mg_projective;
     g.base = base;
     g.redo = 0u;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const double y = (double)(C.yOff + base + C.s * j);
-        double r0, r1, r2 = 0.0;
+        double r0 = 0.0, r1 = 0.0;
         if (KIND == 0) {
             r0 = __dmul_rn(C.c2, y);
             r1 = __dmul_rn(C.c3, y);
-        } else {
-            r0 = __fma_rn(C.c1, y, C.c2);
-            r1 = __fma_rn(C.c4, y, C.c5);
-            r2 = __fma_rn(C.c7, y, 1.0);
         }
-        // projective: numerators / denominator of the quad's first pixel, then one add per pixel (x advances by 1)
+        // projective: numerators / denominator of the quad's first pixel — ONE fma each: the thread's x never changes, so
+        // 2 h0 x + 2 h2, 2 h3 x + 2 h5 and h6 x + 1 are formed once per thread (C.xs[1..3]) —, then one add per pixel (x
+        // advances by 1)
         double nx = 0.0, ny = 0.0, dn = 0.0;
         if (KIND == 1) {
-            nx = __fma_rn(C.c0, C.xs[0], r0);
-            ny = __fma_rn(C.c3, C.xs[0], r1);
-            dn = __fma_rn(C.c6, C.xs[0], r2);
+            nx = __fma_rn(C.c1, y, C.xs[1]);
+            ny = __fma_rn(C.c4, y, C.xs[2]);
+            dn = __fma_rn(C.c7, y, C.xs[3]);
         }
         unsigned hx[4], hy[4];
         unsigned lx[4], ly[4], lomin = 0xFFFFFFFFu;   // projective: fractions of 2v + 1 + delta, and the smallest of the quad's eight
@@ -444,7 +448,7 @@ __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g,
             // L2 prefetch one group ahead: the row's first pixel moves by an almost constant flat stride from group to
             // group, so "this group's index + the stride since the last group" names the cache line the next group
             // will gather from.  A hint only: a wrong guess costs one useless line, never a wrong pixel.
-            const unsigned f0 = (hy[0] >> 1) * C.W + (hx[0] >> 1) - C.kflat;
+            const unsigned f0 = (hy[0] >> 1) * C.W + ((hx[0] >> 1) + C.nkflat);
             const unsigned pf = f0 + (f0 - C.last[j]);
             C.last[j] = f0;
             // only when the quad reads along one source row (a rotated map walks down a column: one line per pixel,
@@ -453,7 +457,7 @@ __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g,
         }
 #endif
         const unsigned cz = (unsigned)(HG_HI_ZERO + 2);
-        const bool ends_inside = ((hx[0] - cz) < C.Wi) & ((hy[0] - cz) < C.Hi) & ((hx[3] - cz) < C.Wi) & ((hy[3] - cz) < C.Hi);
+        const bool ends_inside = C.wide & ((hx[0] - cz) < C.Wi) & ((hy[0] - cz) < C.Hi) & ((hx[3] - cz) < C.Wi) & ((hy[3] - cz) < C.Hi);
         // decided per warp (the lanes that run the body stay together), so it is a real branch, not predication of
         // both variants
         if (__all_sync(__activemask(), ends_inside)) {
@@ -466,7 +470,7 @@ __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g,
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const unsigned flat = (hy[k] >> 1) * C.W + (hx[k] >> 1) - C.kflat;
+                const unsigned flat = (hy[k] >> 1) * C.W + ((hx[k] >> 1) + C.nkflat);
                 // 0 <= v < W on the unrounded coordinate, and the flat index inside the image (Q2: past the end reads 0)
                 const bool in = ((hx[k] - (unsigned)(HG_HI_ZERO + 1)) < C.W2) & ((hy[k] - (unsigned)(HG_HI_ZERO + 1)) < C.H2) &
                                 (flat < C.npx);
@@ -524,10 +528,13 @@ __device__ __forceinline__ void geo_fast_retire(const GeoFrame &F, const double 
             }
         }
     }
-    uint32_t *dst = F.out + ((long long)g.base * (long long)F.oW + x_first);
+    // pixel offsets in 32 bits: oW * oH < 2^31 (check_window), so the offset of every row that is stored fits an int
+    int off = (int)((unsigned)g.base * (unsigned)F.oW) + x_first;
+    const int row_step = (int)((unsigned)C.s * (unsigned)F.oW);
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         if (g.base + C.s * j < F.oH) {
+            uint32_t *dst = F.out + off;
             if (mask == 0xFu) {
                 *reinterpret_cast<uint4 *>(dst) = make_uint4(g.px[j][0], g.px[j][1], g.px[j][2], g.px[j][3]);
             } else {
@@ -536,7 +543,7 @@ __device__ __forceinline__ void geo_fast_retire(const GeoFrame &F, const double 
                     if (mask & (1u << k)) dst[k] = g.px[j][k];
             }
         }
-        dst += (long long)C.s * (long long)F.oW;
+        off = (int)((unsigned)off + (unsigned)row_step);
     }
     g.base = -1;
 }
@@ -554,11 +561,16 @@ __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&
     C.H = (unsigned)F.H;
     C.W2 = 2u * C.W;
     C.H2 = 2u * C.H;
+    // no select in these two: under register pressure ptxas re-derives them in every row of the loop (three instructions
+    // each with the "0 for a 1-pixel dimension" select, one without)
     C.Wi = C.W2 >= 3u ? C.W2 - 3u : 0u;
     C.Hi = C.H2 >= 3u ? C.H2 - 3u : 0u;
+    C.wide = true;
+    asm volatile("" : "+r"(C.Wi), "+r"(C.Hi));
     C.npx = C.W * C.H;
     C.kflat = (unsigned)(HG_HI_ZERO >> 1) * (C.W + 1u);
     C.nkflat = 0u - C.kflat;
+    asm volatile("" : "+r"(C.nkflat));   // one live constant: ptxas otherwise re-derives it from W in every row
     C.srcv = F.src;
     asm volatile("" : "+l"(C.srcv));
     C.xOff = F.xOff;
@@ -567,7 +579,7 @@ __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&
 #pragma unroll
     for (int j = 0; j < GEO_ROWS_PER_THREAD; ++j) C.last[j] = 0xFFFFFFFFu;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) C.xs[k] = (double)(F.xOff + x_first + (KIND == 0 ? k : 0));  // projective: xs[0] only
+    for (int k = 0; k < 4; ++k) C.xs[k] = (double)(F.xOff + x_first + (KIND == 0 ? k : 0));  // projective: replaced below
     if (KIND == 0) {
         C.c0 = m[0]; C.c1 = m[1]; C.c2 = m[2]; C.c3 = m[3]; C.c4 = m[4]; C.c5 = m[5]; C.c6 = 0.0; C.c7 = 0.0;
     } else {
@@ -576,6 +588,12 @@ __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&
         // keep the doubled coefficients in registers (the compiler would otherwise re-derive them from the kernel
         // parameters inside the loop)
         asm volatile("" : "+d"(C.c0), "+d"(C.c1), "+d"(C.c2), "+d"(C.c3), "+d"(C.c4), "+d"(C.c5));
+        // the x part of the numerators and of the denominator, once per thread (two roundings per value like the per-row
+        // association it replaces: the error bound of geo_fast_mode is unchanged)
+        const double x0 = C.xs[0];
+        C.xs[1] = __fma_rn(C.c0, x0, C.c2);
+        C.xs[2] = __fma_rn(C.c3, x0, C.c5);
+        C.xs[3] = __fma_rn(C.c6, x0, 1.0);
     }
     GeoGroup ga, gb;
     ga.base = gb.base = -1;
