@@ -437,7 +437,8 @@ int launch_geo(hg_ctx *c, int kind, GeoParams &P, int max_ow, int max_oh, int n_
         if (kind == HG_AFFINE) warp_inverse_geo_async_kernel<0><<<grid, GEO_THREADS, 0, stream>>>(P);
         else warp_inverse_geo_async_kernel<1><<<grid, GEO_THREADS, 0, stream>>>(P);
     } else {
-        if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, 0, stream>>>(P);
+        if (kind == HG_AFFINE && P.ltx == 1) warp_inverse_geo_affine_tall_kernel<<<grid, GEO_THREADS, 0, stream>>>(P);
+        else if (kind == HG_AFFINE) warp_inverse_geo_kernel<0><<<grid, GEO_THREADS, 0, stream>>>(P);
         else warp_inverse_geo_kernel<1><<<grid, GEO_THREADS, 0, stream>>>(P);
     }
     c->launches++;

@@ -81,7 +81,16 @@ constexpr int GEO_TY = 8;           // thread rows per CTA  -> 128 threads
 #define HG_GEO_MINB 6  // CTAs per SM the affine kernel is compiled for (80 registers)
 #endif
 #ifndef HG_GEO_MINB_PROJ
-#define HG_GEO_MINB_PROJ 5  // projective: 96 registers measured 3 % faster than 80 (no spills, freer scheduling)
+// projective: 7 CTAs per SM (72 registers, 8 bytes of spill outside the loop).  Measured on config 2 / generic points after the
+// last changes to the loop: 5 CTAs (96 registers) 0.782 / 0.798 of the HBM bound, 6 (80) 0.778 / 0.792, 7 (72) 0.796 / 0.806,
+// 8 (64, 128 bytes of spill loads) 0.764.  (Round 1's loop preferred 5 over 6 by 3 %.)
+#define HG_GEO_MINB_PROJ 7
+#endif
+#ifndef HG_GEO_MINB_TALL
+// affine maps near a quarter turn (tall thread layout, GeoParams::ltx == 1): their gathers walk down source columns and are
+// bound by latency, not by issue slots — 8 CTAs per SM (64 registers, no spills): 0.766 -> 0.819 of the HBM bound (7: 0.804);
+// the same 8 CTAs cost a translation-like map 3.7 % (0.946 -> 0.911), hence a kernel instance of its own
+#define HG_GEO_MINB_TALL 8
 #endif
 #ifndef HG_GEO_STAGED_MINB
 #define HG_GEO_STAGED_MINB 5
@@ -735,6 +744,12 @@ template <int KIND>
 __global__ void __launch_bounds__(GEO_THREADS, KIND == 1 ? HG_GEO_MINB_PROJ : HG_GEO_MINB) warp_inverse_geo_kernel(const GeoParams P)
 {
     warp_inverse_geo_impl<KIND, false>(P, nullptr);
+}
+
+// the affine kernel compiled for the tall thread layout (see HG_GEO_MINB_TALL)
+__global__ void __launch_bounds__(GEO_THREADS, HG_GEO_MINB_TALL) warp_inverse_geo_affine_tall_kernel(const GeoParams P)
+{
+    warp_inverse_geo_impl<0, false>(P, nullptr);
 }
 
 // the same kernel with asynchronous gathers (see GeoFastCtx): opt-in / default per launch_geo

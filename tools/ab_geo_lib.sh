@@ -1,12 +1,12 @@
 #!/bin/bash
 # A/B of library builds on the affine / projective pixel loop (HGWARP_LIB override) + the GPU suite on the default build.
-# Usage under gpurun: bash tools/ab_geo_lib.sh <tag> libA.so libB.so ...
+# Usage under gpurun: [SKIP_TESTS=1] [WORKLOADS="projective ..."] bash tools/ab_geo_lib.sh <tag> libA.so libB.so ...
 tag=$1; shift
 out=gpurun_out/$tag
 mkdir -p $out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee $out/pytest.txt
+[ -z "$SKIP_TESTS" ] && python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee $out/pytest.txt
 for lib in "$@"; do
-  for w in projective affine projective_generic affine_rot90; do
+  for w in ${WORKLOADS:-projective affine projective_generic affine_rot90}; do
     HGWARP_LIB=$PWD/homography.js_b200/$lib python bench.py --workload $w --steps 20 --warmup 5 --no-secondary --cpu-budget 1 --e2e-frames 2 > $out/${w}_$lib.json 2> $out/${w}_$lib.err || tail -3 $out/${w}_$lib.err
     python - <<PY | tee -a $out/ab.txt
 import json
