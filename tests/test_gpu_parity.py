@@ -111,6 +111,17 @@ def test_affine_inverse_warp_random(ctx, seed):
               int(rng.integers(1, 400)), int(rng.integers(1, 400)))
 
 
+@pytest.mark.parametrize("deg", [90.0, 97.5, 270.0, 262.0])
+def test_affine_quarter_turn_maps_take_the_tall_kernel(ctx, deg):
+    """Maps near a quarter turn run warp_inverse_geo_affine_tall_kernel (2 x 64 thread layout, 8 CTAs per SM): same pixels."""
+    W, H = 333, 251
+    img = _rand_img(int(deg), W, H)
+    a = math.radians(deg)
+    inv = np.array([math.cos(a), math.sin(a), -math.sin(a), math.cos(a), W / 2 + 3.25, H / 2 - 7.5], np.float32)
+    for oW, oH in ((260, 341), (257, 130), (3, 400)):
+        _geo_case(ctx, img, inv, -oW // 2, -oH // 2, oW, oH)
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_projective_inverse_warp_random(ctx, seed):
     rng = np.random.default_rng(200 + seed)
