@@ -260,8 +260,8 @@ def test_stream_wraps_the_ring_and_reads_a_source_ring(ctx):
 
 
 def test_two_lane_chunk_pipeline_gives_the_same_frames(monkeypatch):
-    """HG_PW_LANES=1 (opt-in, measured slower): binning passes of chunk k+1 on a second stream beside the pixel kernel of chunk
-    k, two scratch sets.  Chunks of two frames so that a short stream / batch runs through both lanes several times, ring wrap
+    """HG_PW_LANES=1 (the default for meshes binned by the span + run passes, forced here for both binning passes): binning
+    passes of chunk k+1 on a second stream beside the pixel kernel of chunk k, two scratch sets.  Chunks of two frames so that a short stream / batch runs through both lanes several times, ring wrap
     and skipped frames included; both binning passes."""
     monkeypatch.setenv("HG_PW_LANES", "1")
     monkeypatch.setenv("HG_PW_CHUNK", "2")
