@@ -292,6 +292,35 @@ def test_two_lane_chunk_pipeline_gives_the_same_frames(monkeypatch):
         c.close()
 
 
+def test_fine_mesh_stream_takes_two_lanes_by_default(ctx):
+    """A mesh of more than 2,048 triangles is binned by the span + run passes, and a stream longer than one chunk of 64 frames
+    then runs in two lanes without any switch set (pw_two_lanes): every frame against the oracle, none through the map path."""
+    w, h, n = 1100, 300, 70      # cells of 33 x 9 pixels: two cells per 64-column bin, well inside its eight entries
+    img = _rand_img(41, w, h)
+    src_pts, _, tris = hg.workloads.piecewise_sinusoid(34, 34, w, h)
+    assert len(tris) > 2048
+    dst_all = np.stack([hg.workloads.piecewise_sinusoid(34, 34, w, h, phase=2 * np.pi * f / n)[1] for f in range(n)])
+    smm = [0, 0]
+    max_w, max_h = w + 8, int(h * 1.1) + 16
+    slot = ctx.stream_slot_bytes(max_w, max_h)
+    n_slots = 80
+    ring = torch.zeros(n_slots * slot, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.image_set(img, w, h)
+    ctx.piecewise_set_mesh(src_pts, tris)
+    f0, g0 = ctx.debug_piecewise_stats()
+    info = ctx.warp_piecewise_stream(dst_all, 0, smm[0], smm[1], ring.data_ptr(), n_slots, max_w, max_h)
+    f1, g1 = ctx.debug_piecewise_stats()
+    assert (f1 - f0, g1 - g0) == (n, 0)
+    host = ring.cpu().numpy()
+    for f in range(n):
+        I = info[f]
+        assert I.status == 0 and I.slot == f
+        win, want = _oracle_piecewise(img, w, h, src_pts, dst_all[f], tris, smm)
+        assert (I.x_off, I.y_off, I.o_w, I.o_h) == win, (f, win)
+        assert _diff(host[I.slot * slot: I.slot * slot + win[2] * win[3] * 4], want) == 0, f
+
+
 def test_stream_skips_frames_without_a_window(ctx):
     assert _stream_case(ctx, n_frames=6, n_slots=6, bad=(2,)) == 5
 
