@@ -143,17 +143,51 @@ __global__ void __launch_bounds__(128, HG_SPAN_MINB) pw_span_bin_kernel(const Fu
             unsigned *cnt = F.bin_cnt + 2 * (size_t)row * F.bins_x;
             unsigned *ent = F.bin_ent + (size_t)row * F.bins_x * PW_BIN_CAP;
             const unsigned lo = c0 - b_first * PW_BIN_W, hi = c1 - b_last * PW_BIN_W;
-            if (b_first == b_last) {
-                if (lo == 0u && hi == (unsigned)PW_BIN_W) atomicMax(cnt + 2u * b_first + 1u, (unsigned)t + 1u);
-                else pw_emit_entry<DEFER>(pa, cnt, ent, b_first, tt | (hi << 7) | lo, F.status);
+            if (DEFER) {
+                if (b_first == b_last) {
+                    if (lo == 0u && hi == (unsigned)PW_BIN_W) atomicMax(cnt + 2u * b_first + 1u, (unsigned)t + 1u);
+                    else pw_emit_entry<DEFER>(pa, cnt, ent, b_first, tt | (hi << 7) | lo, F.status);
+                } else {
+                    // the first and the last bin of the piece are partial as a rule (an entry each), the bins between them are
+                    // covered completely
+                    if (lo == 0u) atomicMax(cnt + 2u * b_first + 1u, (unsigned)t + 1u);
+                    else pw_emit_entry<DEFER>(pa, cnt, ent, b_first, tt | ((unsigned)PW_BIN_W << 7) | lo, F.status);
+                    for (unsigned b = b_first + 1u; b < b_last; ++b) atomicMax(cnt + 2u * b + 1u, (unsigned)t + 1u);
+                    if (hi == (unsigned)PW_BIN_W) atomicMax(cnt + 2u * b_last + 1u, (unsigned)t + 1u);
+                    else pw_emit_entry<DEFER>(pb, cnt, ent, b_last, tt | (hi << 7), F.status);
+                }
             } else {
-                // the first and the last bin of the piece are partial as a rule (an entry each), the bins between them are
-                // covered completely
-                if (lo == 0u) atomicMax(cnt + 2u * b_first + 1u, (unsigned)t + 1u);
-                else pw_emit_entry<DEFER>(pa, cnt, ent, b_first, tt | ((unsigned)PW_BIN_W << 7) | lo, F.status);
-                for (unsigned b = b_first + 1u; b < b_last; ++b) atomicMax(cnt + 2u * b + 1u, (unsigned)t + 1u);
-                if (hi == (unsigned)PW_BIN_W) atomicMax(cnt + 2u * b_last + 1u, (unsigned)t + 1u);
-                else pw_emit_entry<DEFER>(pb, cnt, ent, b_last, tt | (hi << 7), F.status);
+                // The (at most two) entries of the piece are noted first and their slots reserved at ONE place, both
+                // reservations in front of both stores: the lanes of a warp take different branches above (one bin, partial
+                // first bin, partial last bin), and a reservation inside each branch runs with the few lanes of that branch
+                // and a round trip to L2 of its own — up to three per row instead of one.
+                unsigned e_bin[2] = {0u, 0u}, e_val[2] = {0u, 0u};
+                int ne = 0;
+                if (b_first == b_last) {
+                    if (lo == 0u && hi == (unsigned)PW_BIN_W) atomicMax(cnt + 2u * b_first + 1u, (unsigned)t + 1u);
+                    else { e_bin[0] = b_first; e_val[0] = tt | (hi << 7) | lo; ne = 1; }
+                } else {
+                    if (lo == 0u) atomicMax(cnt + 2u * b_first + 1u, (unsigned)t + 1u);
+                    else { e_bin[0] = b_first; e_val[0] = tt | ((unsigned)PW_BIN_W << 7) | lo; ne = 1; }
+                    for (unsigned b = b_first + 1u; b < b_last; ++b) atomicMax(cnt + 2u * b + 1u, (unsigned)t + 1u);
+                    if (hi == (unsigned)PW_BIN_W) atomicMax(cnt + 2u * b_last + 1u, (unsigned)t + 1u);
+                    else {
+                        if (ne == 0) { e_bin[0] = b_last; e_val[0] = tt | (hi << 7); }
+                        else { e_bin[1] = b_last; e_val[1] = tt | (hi << 7); }
+                        ++ne;
+                    }
+                }
+                unsigned s0 = 0u, s1 = 0u;
+                if (ne > 0) s0 = atomicAdd(cnt + 2u * e_bin[0], 1u);
+                if (ne > 1) s1 = atomicAdd(cnt + 2u * e_bin[1], 1u);
+                if (ne > 0) {
+                    if (s0 < (unsigned)PW_BIN_CAP) ent[(size_t)e_bin[0] * PW_BIN_CAP + s0] = e_val[0];
+                    else atomicOr(F.status, 1);
+                }
+                if (ne > 1) {
+                    if (s1 < (unsigned)PW_BIN_CAP) ent[(size_t)e_bin[1] * PW_BIN_CAP + s1] = e_val[1];
+                    else atomicOr(F.status, 1);
+                }
             }
             k0 += n;
             ++row;
