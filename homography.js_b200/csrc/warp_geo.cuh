@@ -362,8 +362,7 @@ template <int KIND>
 struct GeoFastCtx {
     const uint32_t *src;
     unsigned W, H, W2, H2, npx;
-    unsigned Wi, Hi;         // 2W - 3, 2H - 3: the strictly-inside range of the end-pixel test (meaningless when !wide)
-    bool wide;               // W >= 2 and H >= 2; a 1-pixel dimension has no strictly-inside range (the test is then always false)
+    unsigned Wi, Hi;         // 2W - 3, 2H - 3 (0 for a 1-pixel dimension): the strictly-inside range of the end-pixel test
     unsigned kflat;          // flat = (hy >> 1) * W + (hx >> 1) - kflat
     unsigned nkflat;         // -kflat: (hx >> 1) + nkflat is one LEA.HI
     const uint32_t *srcv;    // src again, pinned to vector registers (the address multiply-add then takes an immediate 4)
@@ -466,7 +465,7 @@ __device__ __forceinline__ void geo_fast_issue(GeoFastCtx<KIND> &C, GeoGroup &g,
         }
 #endif
         const unsigned cz = (unsigned)(HG_HI_ZERO + 2);
-        const bool ends_inside = C.wide & ((hx[0] - cz) < C.Wi) & ((hy[0] - cz) < C.Hi) & ((hx[3] - cz) < C.Wi) & ((hy[3] - cz) < C.Hi);
+        const bool ends_inside = ((hx[0] - cz) < C.Wi) & ((hy[0] - cz) < C.Hi) & ((hx[3] - cz) < C.Wi) & ((hy[3] - cz) < C.Hi);
         // decided per warp (the lanes that run the body stay together), so it is a real branch, not predication of
         // both variants
         if (__all_sync(__activemask(), ends_inside)) {
@@ -570,11 +569,10 @@ __device__ __forceinline__ void geo_fast_body(const GeoFrame &F, const double (&
     C.H = (unsigned)F.H;
     C.W2 = 2u * C.W;
     C.H2 = 2u * C.H;
-    // no select in these two: under register pressure ptxas re-derives them in every row of the loop (three instructions
-    // each with the "0 for a 1-pixel dimension" select, one without)
     C.Wi = C.W2 >= 3u ? C.W2 - 3u : 0u;
     C.Hi = C.H2 >= 3u ? C.H2 - 3u : 0u;
-    C.wide = true;
+    // pinned to registers: under the kernels' register caps ptxas otherwise re-derives both (subtract, compare, select) in
+    // every row of the loop
     asm volatile("" : "+r"(C.Wi), "+r"(C.Hi));
     C.npx = C.W * C.H;
     C.kflat = (unsigned)(HG_HI_ZERO >> 1) * (C.W + 1u);
